@@ -1,0 +1,153 @@
+/*
+ * mllp_b200.h -- C ABI of the B200-native primal-dual LP iteration for HAHHHD/mllp.
+ *
+ * The reference is pure Python and has no FFI; the boundary it offers is "a free function
+ * in linear_program_methods.py called per instance with the loader's tuple" (SURVEY.md
+ * section 8b).  Each entry point below names the reference interface it sits behind:
+ *
+ *   mllp_lp_create        <- the CSR arrays produced by linear_program_data.py:75-77
+ *                            (scipy.sparse.load_npz -> .indptr/.indices/.data; float64 + int32)
+ *                            in the argument order of
+ *                            build_graph_from_weights_sets(constrs, constr_weights, rhs, coefs,
+ *                            device), linear_program_methods.py:89
+ *   mllp_pdhg_run / _host <- the "solve an LP, return (objective, solution)" convention of
+ *                            ortools_max_covering / gurobi_max_covering,
+ *                            linear_program_methods.py:477 / :542 (the reference's only LP solve
+ *                            call sites; the iteration itself is new)
+ *   mllp_pdhg_solve       <- same, run to a tolerance instead of a fixed iteration count
+ *   mllp_spmv             <- the A-traversal of build_graph_from_weights_sets,
+ *                            linear_program_methods.py:93-96 (exposed for unit parity)
+ *   mllp_batch_*          <- the per-instance loop of linear_program_experiment.py:123
+ *                            (for name, constrs, constr_weights, coefs, rhs, basis_opt in ...)
+ *                            packed into one launch
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Every function returns 0 on
+ * success or a non-zero status (CUDA error code, or MLLP_E_*); mllp_last_error() returns the
+ * message of the last failure on the calling thread.  "d_" pointers are device pointers owned
+ * by the caller (e.g. torch tensors' data_ptr()), "h_" pointers are host pointers.  `stream` is
+ * a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous on
+ * that stream unless noted.  A handle is bound to one device and is not re-entrant.
+ * All vectors are in the caller's (reference) row/column order; internal reordering is hidden.
+ */
+#ifndef MLLP_B200_H
+#define MLLP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLLP_E_INVALID 1001  /* bad argument */
+#define MLLP_E_NOMEM 1002    /* host allocation failed */
+#define MLLP_E_STATE 1003    /* handle in the wrong state / unsupported configuration */
+
+/* number of doubles written by the *_run / *_solve calls into their `scalars` output */
+#define MLLP_NUM_SCALARS 16
+/* scalars[0] pobj=c'x  [1] dobj  [2] ||primal res||_2  [3] ||dual res||_2  [4] ||b||_2
+ * [5] ||c||_2  [6] ||x||_2  [7] ||y||_2  [8] relative KKT error  [9] |pobj-dobj|
+ * [10] iterations done  [11] restarts  [12] converged flag  [13] final primal weight
+ * [14] last fixed-point error  [15] reserved
+ * (same definitions as oracle_kkt in oracle/pdhg_oracle.c) */
+
+typedef struct mllp_lp *mllp_lp_t;
+typedef struct mllp_batch *mllp_batch_t;
+
+/* creation flags */
+#define MLLP_F_DEFAULT 0u
+#define MLLP_F_NO_SMEM_RESIDENT 1u /* stream the matrix from L2/HBM even if it fits on-chip */
+#define MLLP_F_GRAPH_MODE 2u       /* one kernel launch per half-iteration (CUDA graph) instead
+                                      of the persistent cooperative kernel */
+
+const char *mllp_last_error(void);
+int mllp_version(void);
+
+/* Host-only self check of the format builder (no GPU needed): builds the tiled images of A
+ * and A' for a grid of `num_ctas` CTAs and replays the kernel's tile walk on the CPU against
+ * the plain CSR dot products.  out8[0] = worst relative row error, [1]/[2] tiles of A/A',
+ * [3]/[4] padding factors, [5] split rows of A, [6]/[7] largest per-CTA step counts.
+ * Returns 0 if every row is produced exactly once and the format is well formed. */
+int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr,
+                          const int32_t *indices, const double *values, int32_t num_ctas,
+                          int32_t pref_steps, int32_t max_steps, double *out8);
+
+/* Device facts the host side needs: out[0]=SM count, out[1]=L2 bytes, out[2]=max smem/CTA. */
+int mllp_device_info(int device, int64_t *out3);
+
+/*
+ * Build the device-resident formats of A (m x n, CSR, host pointers) and A' on `device`.
+ * h_lb / h_ub (n) may be NULL => l = 0, u = +inf (the dataset's standard form).
+ * h_ylo / h_yhi (m) may be NULL => all rows are equalities (dual free).
+ * Synchronous.  The input arrays are not referenced after return.
+ */
+int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t *h_indptr,
+                   const int32_t *h_indices, const double *h_values, const double *h_lb,
+                   const double *h_ub, const double *h_ylo, const double *h_yhi, int device,
+                   uint32_t flags, mllp_lp_t *out);
+int mllp_lp_destroy(mllp_lp_t lp);
+
+/* Geometry of the built formats: out[0]=m, [1]=n, [2]=nnz, [3]=tiles(A), [4]=tiles(A'),
+ * [5]=padded entries(A), [6]=padded entries(A'), [7]=split rows(A), [8]=split rows(A'),
+ * [9]=grid CTAs, [10]=threads per CTA, [11]=smem-resident bytes per CTA (0 if streaming),
+ * [12]=algorithmic bytes per iteration (24 nnz + 36 m + 44 n + 8, +16 n with bounds,
+ * +16 m with row senses), [13..15] reserved. */
+int mllp_lp_info(mllp_lp_t lp, int64_t *out16);
+
+/* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */
+int mllp_spmv(mllp_lp_t lp, int trans, const double *d_in, double *d_out, void *stream);
+
+/* sigma_max(A) by `iters` power-iteration steps on A'A from 1/sqrt(n); synchronous. */
+int mllp_estimate_norm(mllp_lp_t lp, int iters, double *h_sigma_max, void *stream);
+
+/*
+ * Parity mode: `num_iters` fixed-step iterations
+ *     g = c - A'y;  x+ = clip(x - tau g, l, u);  xbar = 2x+ - x;  y+ = clip(y + sigma(b - A xbar))
+ * in place on d_x (n) and d_y (m).  If d_scalars != NULL the KKT scalars of the final
+ * (x, y) are written there (MLLP_NUM_SCALARS doubles, device memory).  No host sync.
+ */
+int mllp_pdhg_run(mllp_lp_t lp, double *d_x, double *d_y, const double *d_b, const double *d_c,
+                  double tau, double sigma, int32_t num_iters, double *d_scalars, void *stream);
+
+/* Same, with HOST buffers: copies b, c, x, y in, runs, copies x, y and the scalars out,
+ * and synchronises the stream before returning (the end-to-end entry the Python
+ * pdhg_linear_program() uses for numpy inputs). */
+int mllp_pdhg_run_host(mllp_lp_t lp, double *h_x, double *h_y, const double *h_b,
+                       const double *h_c, double tau, double sigma, int32_t num_iters,
+                       double *h_scalars, void *stream);
+
+/*
+ * Solve mode: reflected restarted Halpern PDHG with fixed step eta (tau = eta/w,
+ * sigma = eta*w, w0 the initial primal weight), KKT check and restart test every
+ * `check_every` iterations, all decided on the device; stops at rel. KKT error <= tol or
+ * max_iters.  Spec: oracle_pdhg_solve in oracle/pdhg_oracle.c.  No host sync.
+ */
+int mllp_pdhg_solve(mllp_lp_t lp, double *d_x, double *d_y, const double *d_b,
+                    const double *d_c, double eta, double w0, int32_t max_iters,
+                    int32_t check_every, double tol, double *d_scalars, void *stream);
+
+/*
+ * Batched mode: `count` independent LPs in one launch (one CTA per LP, the whole LP held
+ * in shared memory).  Instance k has shape m[k] x n[k]; its CSR arrays are the slices
+ * [indptr_off[k], ...) of the concatenated host arrays, exactly as np.concatenate of the
+ * loader's per-instance arrays.  Vectors are concatenated in instance order
+ * (x: sum n[k], y: sum m[k]).  If `shared_matrix` != 0 only instance 0's matrix is given and
+ * all `count` instances use it with their own b, c (the perturbed-instance workload).
+ */
+int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t *h_m,
+                      const int32_t *h_n, const int64_t *h_indptr_off,
+                      const int64_t *h_nnz_off, const int32_t *h_indptr,
+                      const int32_t *h_indices, const double *h_values, int device,
+                      uint32_t flags, mllp_batch_t *out);
+int mllp_batch_destroy(mllp_batch_t bt);
+/* per-instance tau[k], sigma[k] (device arrays of `count`); scalars: count*MLLP_NUM_SCALARS */
+int mllp_batch_run(mllp_batch_t bt, double *d_x, double *d_y, const double *d_b,
+                   const double *d_c, const double *d_tau, const double *d_sigma,
+                   int32_t num_iters, double *d_scalars, void *stream);
+int mllp_batch_solve(mllp_batch_t bt, double *d_x, double *d_y, const double *d_b,
+                     const double *d_c, const double *d_eta, double w0, int32_t max_iters,
+                     int32_t check_every, double tol, double *d_scalars, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLLP_B200_H */

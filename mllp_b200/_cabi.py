@@ -1,0 +1,70 @@
+"""ctypes binding of the C ABI in include/mllp_b200.h.
+
+There is NO fallback: if libmllp_b200.so is missing or cannot be loaded this module raises,
+and every compute entry raises RuntimeError on any non-zero status from the library.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "csrc", "libmllp_b200.so")
+
+NUM_SCALARS = 16
+F_DEFAULT, F_NO_SMEM_RESIDENT, F_GRAPH_MODE = 0, 1, 2
+
+_vp = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_i64 = ctypes.c_int64
+_dbl = ctypes.c_double
+
+# name -> (restype, argtypes); mirrors include/mllp_b200.h one to one
+SIGNATURES = {
+    "mllp_last_error": (ctypes.c_char_p, []),
+    "mllp_version": (ctypes.c_int, []),
+    "mllp_format_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "mllp_device_info": (ctypes.c_int, [ctypes.c_int, _vp]),
+    "mllp_lp_create": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
+                                      ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "mllp_lp_destroy": (ctypes.c_int, [_vp]),
+    "mllp_lp_info": (ctypes.c_int, [_vp, _vp]),
+    "mllp_spmv": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
+    "mllp_estimate_norm": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_dbl), _vp]),
+    "mllp_pdhg_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),
+    "mllp_pdhg_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),
+    "mllp_pdhg_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _i32, _i32, _dbl, _vp, _vp]),
+    "mllp_batch_create": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
+                                         ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "mllp_batch_destroy": (ctypes.c_int, [_vp]),
+    "mllp_batch_info": (ctypes.c_int, [_vp, _vp]),
+    "mllp_batch_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "mllp_batch_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _dbl, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the library (once).  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                "mllp_b200: %s is missing; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for this path)" % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    msg = lib().mllp_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("mllp_b200: %s failed (status %d): %s" % (what, rc, last_error()))

@@ -1,0 +1,440 @@
+// cabi.cu -- the C ABI of include/mllp_b200.h for the single-instance path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mllp_b200.h"
+#include "lp_format.h"
+#include "pdhg_host.h"
+#include "pdhg_kernels.cuh"
+
+using namespace mllp;
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+}  // namespace
+
+#define CUDA_OK(call)                                           \
+    do {                                                        \
+        cudaError_t e_ = (call);                                \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);     \
+    } while (0)
+#define RC_OK(call)                                                                   \
+    do {                                                                              \
+        int rc_ = (call);                                                             \
+        if (rc_ != 0) {                                                               \
+            if (rc_ < 1000) return cuda_fail((cudaError_t)rc_, #call);                \
+            return rc_;                                                               \
+        }                                                                             \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct mllp_lp {
+    int device = 0;
+    int m = 0, n = 0;
+    int64_t nnz = 0;
+    uint32_t flags = 0;
+    bool bounds = false;
+    int G = 0, threads = 0;
+    DevLP d{};
+    std::vector<void*> allocs;
+    int32_t* d_orderX = nullptr;  // internal position k holds original column order[k]
+    int32_t* d_orderY = nullptr;
+    double* tmp_n = nullptr;
+    double* tmp_m = nullptr;
+    double* tmp_n2 = nullptr;
+    double* d_b = nullptr;        // writable aliases of d.b / d.c
+    double* d_c = nullptr;
+    double* u_x = nullptr;        // user-order staging for the *_host entry
+    double* u_y = nullptr;
+    double* u_b = nullptr;
+    double* u_c = nullptr;
+    double* d_scal = nullptr;     // MLLP_NUM_SCALARS
+    double* d_norm2 = nullptr;
+    int64_t info[16] = {0};
+    cudaGraphExec_t graph = nullptr;  // graph mode: GRAPH_UNROLL iterations
+};
+constexpr int GRAPH_UNROLL = 32;
+
+namespace {
+
+template <class T>
+int dev_alloc(mllp_lp* lp, T** out, size_t count)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    lp->allocs.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+template <class T>
+int dev_upload(mllp_lp* lp, T** out, const T* host, size_t count)
+{
+    RC_OK(dev_alloc(lp, out, count));
+    if (count) CUDA_OK(cudaMemcpy(*out, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+template <class T>
+int dev_zeros(mllp_lp* lp, T** out, size_t count)
+{
+    RC_OK(dev_alloc(lp, out, count));
+    CUDA_OK(cudaMemset(*out, 0, (count ? count : 1) * sizeof(T)));
+    return 0;
+}
+
+int upload_mat(mllp_lp* lp, const HostMat& H, DevMat& D)
+{
+    double* vals; int32_t* idx; Tile* tiles; uint32_t* cb; uint32_t* csb; SplitRow* sp;
+    RC_OK(dev_upload(lp, &vals, H.vals.data(), H.vals.size()));
+    RC_OK(dev_upload(lp, &idx, H.idx.data(), H.idx.size()));
+    RC_OK(dev_upload(lp, &tiles, H.tiles.data(), H.tiles.size()));
+    RC_OK(dev_upload(lp, &cb, H.cta_begin.data(), H.cta_begin.size()));
+    RC_OK(dev_upload(lp, &csb, H.cta_step_begin.data(), H.cta_step_begin.size()));
+    RC_OK(dev_upload(lp, &sp, H.splits.data(), H.splits.size()));
+    RC_OK(dev_zeros(lp, &D.partials, (size_t)H.num_partials));
+    RC_OK(dev_zeros(lp, &D.counters, H.splits.size()));
+    D.vals = reinterpret_cast<const double2*>(vals);
+    D.idx = reinterpret_cast<const int2*>(idx);
+    D.tiles = tiles;
+    D.cta_begin = cb;
+    D.cta_step_begin = csb;
+    D.splits = sp;
+    D.nrows = H.nrows;
+    D.ncols = H.ncols;
+    return 0;
+}
+
+std::vector<double> permuted(const double* src, const std::vector<int32_t>& order)
+{
+    std::vector<double> out(order.size());
+    for (size_t k = 0; k < order.size(); ++k) out[k] = src[order[k]];
+    return out;
+}
+
+int build_graph(mllp_lp* lp)
+{
+    cudaStream_t cs;
+    CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int i = 0; i < GRAPH_UNROLL && rc == 0; ++i) {
+        rc = launch_primal(lp->d, lp->bounds, lp->G, lp->threads, cs);
+        if (rc == 0) rc = launch_dual(lp->d, lp->bounds, lp->G, lp->threads, cs);
+    }
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    if (rc != 0 || e != cudaSuccess) {
+        cudaStreamDestroy(cs);
+        return rc != 0 ? cuda_fail((cudaError_t)rc, "graph capture") : cuda_fail(e, "cudaStreamEndCapture");
+    }
+    e = cudaGraphInstantiate(&lp->graph, g, 0);
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mllp_last_error(void) { return g_err.c_str(); }
+int mllp_version(void) { return 100; }
+
+int mllp_device_info(int device, int64_t* out3)
+{
+    if (!out3) return fail(MLLP_E_INVALID, "mllp_device_info: null output");
+    cudaDeviceProp p;
+    CUDA_OK(cudaGetDeviceProperties(&p, device));
+    out3[0] = p.multiProcessorCount;
+    out3[1] = p.l2CacheSize;
+    out3[2] = (int64_t)p.sharedMemPerBlockOptin;
+    return 0;
+}
+
+int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, const int32_t* h_indices,
+                   const double* h_values, const double* h_lb, const double* h_ub, const double* h_ylo,
+                   const double* h_yhi, int device, uint32_t flags, mllp_lp_t* out)
+{
+    if (!out) return fail(MLLP_E_INVALID, "mllp_lp_create: null output handle");
+    *out = nullptr;
+    if (m < 0 || n < 0 || nnz < 0 || !h_indptr || (nnz > 0 && (!h_indices || !h_values)))
+        return fail(MLLP_E_INVALID, "mllp_lp_create: bad shape or null CSR arrays");
+    if (h_indptr[0] != 0 || (int64_t)h_indptr[m] != nnz)
+        return fail(MLLP_E_INVALID, "mllp_lp_create: indptr[0] must be 0 and indptr[m] == nnz");
+    for (int i = 0; i < m; ++i)
+        if (h_indptr[i + 1] < h_indptr[i]) return fail(MLLP_E_INVALID, "mllp_lp_create: indptr not monotone");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (h_indices[k] < 0 || h_indices[k] >= n) return fail(MLLP_E_INVALID, "mllp_lp_create: column index out of range");
+    if ((h_lb == nullptr) != (h_ub == nullptr) || (h_ylo == nullptr) != (h_yhi == nullptr))
+        return fail(MLLP_E_INVALID, "mllp_lp_create: lb/ub (ylo/yhi) must be given together");
+
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MLLP_E_INVALID, "mllp_lp_create: no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(MLLP_E_STATE, "mllp_lp_create: this library is built for sm_100a (B200) only");
+
+    mllp_lp* lp = new (std::nothrow) mllp_lp();
+    if (!lp) return fail(MLLP_E_NOMEM, "mllp_lp_create: out of host memory");
+    lp->device = device;
+    lp->m = m; lp->n = n; lp->nnz = nnz; lp->flags = flags;
+    lp->bounds = (h_lb != nullptr) || (h_ylo != nullptr);
+
+    // launch geometry of the persistent grid
+    lp->threads = env_int("MLLP_THREADS", 512);
+    if (lp->threads < 32 || lp->threads > 1024 || (lp->threads & 31)) lp->threads = 512;
+    int bpsm = persistent_max_blocks_per_sm(lp->threads, lp->bounds);
+    if (bpsm <= 0) { delete lp; return fail(MLLP_E_STATE, "mllp_lp_create: persistent kernel cannot be resident"); }
+    const int want = env_int("MLLP_CTAS_PER_SM", 0);
+    if (want > 0 && want < bpsm) bpsm = want;
+    lp->G = prop.multiProcessorCount * bpsm;
+
+    BuildParams bp;
+    bp.num_ctas = lp->G;
+    bp.pref_steps = env_int("MLLP_PREF_STEPS", 4);
+    bp.max_steps = env_int("MLLP_MAX_STEPS", 4);
+    if (bp.pref_steps < 1) bp.pref_steps = 1;
+    if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
+    if (bp.max_steps > 1024) bp.max_steps = 1024;
+
+    int rc = 0;
+    try {
+        std::vector<int32_t> tptr, tind;
+        std::vector<double> tval;
+        csr_transpose(m, n, h_indptr, h_indices, h_values, tptr, tind, tval);
+        std::vector<int32_t> orderY, posY, orderX, posX;
+        plan_row_order(m, h_indptr, bp, orderY, posY);
+        plan_row_order(n, tptr.data(), bp, orderX, posX);
+        HostMat HA, HAT;
+        build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, HA);
+        build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
+
+        auto body = [&]() -> int {
+            RC_OK(upload_mat(lp, HA, lp->d.A));
+            RC_OK(upload_mat(lp, HAT, lp->d.AT));
+            RC_OK(dev_upload(lp, &lp->d_orderX, orderX.data(), orderX.size()));
+            RC_OK(dev_upload(lp, &lp->d_orderY, orderY.data(), orderY.size()));
+            lp->d.m = m; lp->d.n = n;
+            RC_OK(dev_zeros(lp, &lp->d_b, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->d_c, (size_t)n));
+            lp->d.b = lp->d_b; lp->d.c = lp->d_c;
+            if (lp->bounds) {
+                // general form: every box array is materialised (missing ones get +-inf / 0)
+                std::vector<double> lb((size_t)n, 0.0), ub((size_t)n, INFINITY), ylo((size_t)m, -INFINITY), yhi((size_t)m, INFINITY);
+                if (h_lb) { lb = permuted(h_lb, orderX); ub = permuted(h_ub, orderX); }
+                if (h_ylo) { ylo = permuted(h_ylo, orderY); yhi = permuted(h_yhi, orderY); }
+                double *p1, *p2, *p3, *p4;
+                RC_OK(dev_upload(lp, &p1, lb.data(), lb.size()));
+                RC_OK(dev_upload(lp, &p2, ub.data(), ub.size()));
+                RC_OK(dev_upload(lp, &p3, ylo.data(), ylo.size()));
+                RC_OK(dev_upload(lp, &p4, yhi.data(), yhi.size()));
+                lp->d.lb = p1; lp->d.ub = p2; lp->d.ylo = p3; lp->d.yhi = p4;
+            }
+            RC_OK(dev_zeros(lp, &lp->d.x, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->d.y, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->d.xbar, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->d.x0, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->d.y0, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->d.red, (size_t)RED_BUFFERS * lp->G * NRED));
+            RC_OK(dev_zeros(lp, &lp->d.barrier, 4));
+            RC_OK(dev_zeros(lp, &lp->d.ctrl, CTRL_SIZE));
+            RC_OK(dev_zeros(lp, &lp->tmp_n, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->tmp_n2, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->tmp_m, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->u_x, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->u_y, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->u_b, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->u_c, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->d_scal, MLLP_NUM_SCALARS));
+            RC_OK(dev_zeros(lp, &lp->d_norm2, 2));
+            if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
+            return 0;
+        };
+        rc = body();
+
+        int64_t* I = lp->info;
+        I[0] = m; I[1] = n; I[2] = nnz;
+        I[3] = (int64_t)HA.tiles.size(); I[4] = (int64_t)HAT.tiles.size();
+        I[5] = (int64_t)HA.total_steps * 64; I[6] = (int64_t)HAT.total_steps * 64;
+        I[7] = (int64_t)HA.splits.size(); I[8] = (int64_t)HAT.splits.size();
+        I[9] = lp->G; I[10] = lp->threads; I[11] = 0;
+        I[12] = 24 * nnz + 36 * (int64_t)m + 44 * (int64_t)n + 8 + (h_lb ? 16 * (int64_t)n : 0) + (h_ylo ? 16 * (int64_t)m : 0);
+        I[13] = HA.max_cta_steps; I[14] = HAT.max_cta_steps; I[15] = bpsm;
+    } catch (const std::bad_alloc&) {
+        rc = fail(MLLP_E_NOMEM, "mllp_lp_create: out of host memory");
+    }
+    if (rc != 0) {
+        const std::string keep = g_err;
+        mllp_lp_destroy(lp);
+        g_err = keep;
+        return rc;
+    }
+    *out = lp;
+    return 0;
+}
+
+int mllp_lp_destroy(mllp_lp_t lp)
+{
+    if (!lp) return 0;
+    DeviceGuard guard(lp->device);
+    if (lp->graph) cudaGraphExecDestroy(lp->graph);
+    for (void* p : lp->allocs) cudaFree(p);
+    delete lp;
+    return 0;
+}
+
+int mllp_lp_info(mllp_lp_t lp, int64_t* out16)
+{
+    if (!lp || !out16) return fail(MLLP_E_INVALID, "mllp_lp_info: null argument");
+    memcpy(out16, lp->info, sizeof(lp->info));
+    return 0;
+}
+
+int mllp_spmv(mllp_lp_t lp, int trans, const double* d_in, double* d_out, void* stream)
+{
+    if (!lp || !d_in || !d_out) return fail(MLLP_E_INVALID, "mllp_spmv: null argument");
+    DeviceGuard guard(lp->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!trans) {
+        RC_OK(launch_gather(lp->tmp_n, d_in, lp->d_orderX, lp->n, s));
+        RC_OK(launch_spmv(lp->d.A, lp->tmp_n, lp->tmp_m, lp->G, lp->threads, s));
+        RC_OK(launch_scatter(d_out, lp->tmp_m, lp->d_orderY, lp->m, s));
+    } else {
+        RC_OK(launch_gather(lp->tmp_m, d_in, lp->d_orderY, lp->m, s));
+        RC_OK(launch_spmv(lp->d.AT, lp->tmp_m, lp->tmp_n, lp->G, lp->threads, s));
+        RC_OK(launch_scatter(d_out, lp->tmp_n, lp->d_orderX, lp->n, s));
+    }
+    return 0;
+}
+
+int mllp_estimate_norm(mllp_lp_t lp, int iters, double* h_sigma_max, void* stream)
+{
+    if (!lp || !h_sigma_max || iters < 1) return fail(MLLP_E_INVALID, "mllp_estimate_norm: bad argument");
+    DeviceGuard guard(lp->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // v (tmp_n) = 1/sqrt(n); order does not matter for a constant vector
+    RC_OK(launch_fill(lp->tmp_n, lp->n > 0 ? 1.0 / sqrt((double)lp->n) : 0.0, lp->n, s));
+    for (int it = 0; it < iters; ++it) {
+        RC_OK(launch_spmv(lp->d.A, lp->tmp_n, lp->tmp_m, lp->G, lp->threads, s));
+        RC_OK(launch_spmv(lp->d.AT, lp->tmp_m, lp->tmp_n2, lp->G, lp->threads, s));
+        RC_OK(launch_sumsq(lp->tmp_n2, lp->n, lp->d_norm2, s));
+        RC_OK(launch_scale_by_invnorm(lp->tmp_n, lp->tmp_n2, lp->d_norm2, lp->n, s));
+    }
+    double nz2 = 0.0;
+    CUDA_OK(cudaMemcpyAsync(&nz2, lp->d_norm2, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    *h_sigma_max = sqrt(sqrt(nz2));
+    return 0;
+}
+
+static int load_problem(mllp_lp* lp, const double* d_x, const double* d_y, const double* d_b, const double* d_c,
+                        cudaStream_t s)
+{
+    RC_OK(launch_gather(lp->d.x, d_x, lp->d_orderX, lp->n, s));
+    RC_OK(launch_gather(lp->d.y, d_y, lp->d_orderY, lp->m, s));
+    RC_OK(launch_gather(lp->d_b, d_b, lp->d_orderY, lp->m, s));
+    RC_OK(launch_gather(lp->d_c, d_c, lp->d_orderX, lp->n, s));
+    return 0;
+}
+static int store_solution(mllp_lp* lp, double* d_x, double* d_y, cudaStream_t s)
+{
+    RC_OK(launch_scatter(d_x, lp->d.x, lp->d_orderX, lp->n, s));
+    RC_OK(launch_scatter(d_y, lp->d.y, lp->d_orderY, lp->m, s));
+    return 0;
+}
+
+int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, const double* d_c, double tau,
+                  double sigma, int32_t num_iters, double* d_scalars, void* stream)
+{
+    if (!lp || !d_x || !d_y || !d_b || !d_c || num_iters < 0)
+        return fail(MLLP_E_INVALID, "mllp_pdhg_run: null argument or negative iteration count");
+    DeviceGuard guard(lp->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    RC_OK(load_problem(lp, d_x, d_y, d_b, d_c, s));
+    if (lp->flags & MLLP_F_GRAPH_MODE) {
+        const double ts[2] = {tau, sigma};
+        CUDA_OK(cudaMemcpyAsync(lp->d.ctrl, ts, sizeof(ts), cudaMemcpyHostToDevice, s));
+        int left = num_iters;
+        for (; left >= GRAPH_UNROLL; left -= GRAPH_UNROLL) CUDA_OK(cudaGraphLaunch(lp->graph, s));
+        for (; left > 0; --left) {
+            RC_OK(launch_primal(lp->d, lp->bounds, lp->G, lp->threads, s));
+            RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));
+        }
+    } else if (num_iters > 0) {
+        RC_OK(launch_pdhg_persistent(lp->d, lp->bounds, lp->G, lp->threads, tau, sigma, num_iters, s));
+    }
+    if (d_scalars) RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, (double)num_iters, s));
+    RC_OK(store_solution(lp, d_x, d_y, s));
+    return 0;
+}
+
+int mllp_pdhg_run_host(mllp_lp_t lp, double* h_x, double* h_y, const double* h_b, const double* h_c, double tau,
+                       double sigma, int32_t num_iters, double* h_scalars, void* stream)
+{
+    if (!lp || !h_x || !h_y || !h_b || !h_c) return fail(MLLP_E_INVALID, "mllp_pdhg_run_host: null argument");
+    DeviceGuard guard(lp->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(lp->u_x, h_x, sizeof(double) * lp->n, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(lp->u_y, h_y, sizeof(double) * lp->m, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(lp->u_b, h_b, sizeof(double) * lp->m, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(lp->u_c, h_c, sizeof(double) * lp->n, cudaMemcpyHostToDevice, s));
+    RC_OK(mllp_pdhg_run(lp, lp->u_x, lp->u_y, lp->u_b, lp->u_c, tau, sigma, num_iters,
+                        h_scalars ? lp->d_scal : nullptr, stream));
+    CUDA_OK(cudaMemcpyAsync(h_x, lp->u_x, sizeof(double) * lp->n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(h_y, lp->u_y, sizeof(double) * lp->m, cudaMemcpyDeviceToHost, s));
+    if (h_scalars)
+        CUDA_OK(cudaMemcpyAsync(h_scalars, lp->d_scal, sizeof(double) * MLLP_NUM_SCALARS, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int mllp_pdhg_solve(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, const double* d_c, double eta,
+                    double w0, int32_t max_iters, int32_t check_every, double tol, double* d_scalars, void* stream)
+{
+    if (!lp || !d_x || !d_y || !d_b || !d_c || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 > 0.0) ||
+        !(eta > 0.0))
+        return fail(MLLP_E_INVALID, "mllp_pdhg_solve: bad argument");
+    if (lp->flags & MLLP_F_GRAPH_MODE) return fail(MLLP_E_STATE, "mllp_pdhg_solve: needs the persistent kernel (handle was created with MLLP_F_GRAPH_MODE)");
+    DeviceGuard guard(lp->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    RC_OK(load_problem(lp, d_x, d_y, d_b, d_c, s));
+    // scalars of the starting point (also what is returned when max_iters == 0)
+    RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, 0.0, s));
+    if (max_iters > 0)
+        RC_OK(launch_solve_persistent(lp->d, lp->bounds, lp->G, lp->threads, eta, w0, max_iters, check_every, tol,
+                                      d_scalars, s));
+    RC_OK(store_solution(lp, d_x, d_y, s));
+    return 0;
+}
+
+}  // extern "C"

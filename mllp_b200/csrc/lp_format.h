@@ -1,0 +1,79 @@
+// lp_format.h -- device-resident sparse format of A and A' for the fused PDHG kernels.
+//
+// Format ("warp-tiled SELL"): the rows of a matrix are re-ordered internally and cut into
+// TILES, each processed by one warp.  A tile covers 32/L consecutive (internal order) rows
+// with L lanes per row (L = 1,2,4,...,32: thread-per-row SELL-32 for the short rows of A',
+// warp-per-row for long rows), padded to `nsteps` steps of 2 entries per lane.  Storage is
+// step-major so that one step of one warp is a single contiguous 512 B run of values
+// (32 x double2, 128-bit loads) and a 256 B run of indices (32 x int2); within a step the
+// entries are arranged so that ONE gather instruction covers L consecutive entries of a row
+// (entry e of a step sits in lane e % L, half e / L).  Rows longer than 64*max_steps entries
+// are split into chunks (one tile each, L = 32) whose partial dot products meet in a
+// scratch array; the last chunk to arrive sums them in a fixed order, so results are
+// deterministic and no fp64 atomics are used.
+//
+// Tiles are dealt to the CTAs of the persistent grid at build time (cost-balanced) and the
+// storage is CTA-major, so a CTA's share of the matrix is one contiguous range that it can
+// keep resident in shared memory across iterations.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace mllp {
+
+struct Tile {            // 16 bytes, loaded as one int4
+    uint32_t off;        // first warp-step of this tile (64 entries per warp-step)
+    uint32_t row_base;   // first internal row; for a split chunk: chunk index within its row
+    uint16_t nsteps;     // steps of 2 entries per lane
+    uint8_t logL;        // log2(lanes per row)
+    uint8_t nrows;       // valid rows in this tile (1 .. 32 >> logL)
+    int32_t split;       // -1, or index into the split-row table
+};
+static_assert(sizeof(Tile) == 16, "Tile must be 16 bytes");
+
+struct SplitRow {        // 16 bytes
+    uint32_t row;        // internal row id
+    uint32_t first_slot; // first partial slot of this row
+    uint32_t nchunks;
+    uint32_t pad;
+};
+
+struct BuildParams {
+    int num_ctas = 148;      // CTAs of the persistent grid
+    int pref_steps = 4;      // choose L so a row needs at most this many steps
+    int max_steps = 4;       // rows longer than 64*max_steps entries are split
+};
+
+// Host-side image of one matrix in the tiled format.
+struct HostMat {
+    int nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    std::vector<double> vals;          // 64 * total_steps
+    std::vector<int32_t> idx;          // 64 * total_steps (internal column ids)
+    std::vector<Tile> tiles;           // CTA-major
+    std::vector<uint32_t> cta_begin;   // num_ctas + 1 (tile index)
+    std::vector<uint32_t> cta_step_begin; // num_ctas + 1 (warp-step index)
+    std::vector<SplitRow> splits;
+    uint32_t num_partials = 0;
+    uint64_t total_steps = 0;
+    int max_cta_steps = 0;             // largest per-CTA warp-step count
+    int max_cta_tiles = 0;
+};
+
+// Internal ordering of the rows of a CSR matrix, derived from row lengths only.
+// order[k] = original row at internal position k; pos[r] = internal position of row r.
+void plan_row_order(int nrows, const int32_t* ptr, const BuildParams& bp,
+                    std::vector<int32_t>& order, std::vector<int32_t>& pos);
+
+// Emit the tiled image of a CSR matrix whose rows follow `order`/`pos` and whose column
+// ids are renamed through `colpos` (the other matrix's pos[]).
+void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
+                    const double* val, const std::vector<int32_t>& order,
+                    const std::vector<int32_t>& colpos, const BuildParams& bp, HostMat& out);
+
+// CSR transpose (counting sort); outputs sized by the callee.
+void csr_transpose(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
+                   const double* val, std::vector<int32_t>& tptr, std::vector<int32_t>& tind,
+                   std::vector<double>& tval);
+
+}  // namespace mllp

@@ -1,0 +1,24 @@
+// pdhg_host.h -- host-visible launchers of pdhg_kernels.cu (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mllp {
+struct DevMat;
+struct DevLP;
+
+int launch_gather(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
+int launch_scatter(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
+int launch_fill(double* dst, double v, int n, cudaStream_t s);
+int launch_sumsq(const double* v, int n, double* out, cudaStream_t s);
+int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2, int n, cudaStream_t s);
+int launch_spmv(const DevMat& M, const double* in, double* out, int G, int threads, cudaStream_t s);
+int launch_primal(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
+int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
+int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s);
+int persistent_max_blocks_per_sm(int threads, bool bounds);
+int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, double tau, double sigma, int iters,
+                           cudaStream_t s);
+int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, double eta, double w0, int max_iters,
+                            int check_every, double tol, double* out, cudaStream_t s);
+}  // namespace mllp

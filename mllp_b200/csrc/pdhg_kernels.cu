@@ -1,0 +1,352 @@
+// pdhg_kernels.cu -- kernels and launchers of the single-instance PDHG path (sm_100a).
+#include "pdhg_host.h"
+#include "pdhg_kernels.cuh"
+
+namespace mllp {
+
+// ---------------------------------------------------------------------------------------
+// small utility kernels (boundary reordering, not on the per-iteration path)
+__global__ void k_gather(double* __restrict__ dst, const double* __restrict__ src,
+                         const int32_t* __restrict__ order, int n)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        dst[k] = src[order[k]];
+}
+__global__ void k_scatter(double* __restrict__ dst, const double* __restrict__ src,
+                          const int32_t* __restrict__ order, int n)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        dst[order[k]] = src[k];
+}
+__global__ void k_fill(double* dst, double v, int n)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[k] = v;
+}
+// single block: out[0] = sum v^2 (fixed order)
+__global__ void k_sumsq(const double* __restrict__ v, int n, double* out)
+{
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s += v[k] * v[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (threadIdx.x == 0) out[0] = s;
+    }
+}
+// dst = src / sqrt(sqrt-free norm2[0])   (dst = src * rsqrt(norm2))
+__global__ void k_scale_by_invnorm(double* __restrict__ dst, const double* __restrict__ src,
+                                   const double* norm2, int n)
+{
+    const double nz = sqrt(norm2[0]);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        dst[k] = nz > 0.0 ? src[k] / nz : src[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// phase kernels (graph mode, evaluation, unit SpMV).  Grid = the persistent grid G: the tile
+// to CTA assignment is fixed at build time.
+__global__ void __launch_bounds__(1024, 1) k_spmv(DevMat M, const double* in, double* out)
+{
+    SpmvOp op{in, out};
+    double acc[NRED];
+    run_phase(M, op, acc, M.vals, M.idx, 0u);
+}
+
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_primal(DevLP lp)
+{
+    PrimalOp<BOUNDS> op{lp, __ldcg(lp.ctrl + CTRL_TAU)};
+    double acc[NRED];
+    run_phase(lp.AT, op, acc, lp.AT.vals, lp.AT.idx, 0u);
+}
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_dual(DevLP lp)
+{
+    DualOp<BOUNDS> op{lp, __ldcg(lp.ctrl + CTRL_SIGMA)};
+    double acc[NRED];
+    run_phase(lp.A, op, acc, lp.A.vals, lp.A.idx, 0u);
+}
+
+template <bool BOUNDS>
+__device__ __forceinline__ void eval_phases(const DevLP& lp, double* red_p, double* red_d, double* smem)
+{
+    {
+        EvalPrimalOp<BOUNDS> op{lp};
+        double acc[NRED];
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+        run_phase(lp.AT, op, acc, lp.AT.vals, lp.AT.idx, 0u);
+        cta_reduce_store<6>(acc, red_p + (size_t)blockIdx.x * NRED, smem);
+    }
+    {
+        EvalDualOp<BOUNDS> op{lp};
+        double acc[NRED];
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+        run_phase(lp.A, op, acc, lp.A.vals, lp.A.idx, 0u);
+        cta_reduce_store<5>(acc, red_d + (size_t)blockIdx.x * NRED, smem);
+    }
+}
+
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_eval(DevLP lp, int G)
+{
+    __shared__ double smem[32 * NRED];
+    eval_phases<BOUNDS>(lp, lp.red + (size_t)RED_EVALP * G * NRED, lp.red + (size_t)RED_EVALD * G * NRED, smem);
+}
+
+// Turn the summed eval partials into the public scalars (calling warp, all lanes).
+__device__ __forceinline__ void kkt_from_sums(const double* red_p, const double* red_d, int G, double* s /*[10]*/)
+{
+    const double pobj = grid_sum(red_p, G, 0);
+    const double dbnd = grid_sum(red_p, G, 1);
+    const double dr2 = grid_sum(red_p, G, 2);
+    const double nc2 = grid_sum(red_p, G, 3);
+    const double nx2 = grid_sum(red_p, G, 4);
+    const double by = grid_sum(red_d, G, 0);
+    const double pr2 = grid_sum(red_d, G, 1);
+    const double nb2 = grid_sum(red_d, G, 2);
+    const double ny2 = grid_sum(red_d, G, 3);
+    const double dobj = by + dbnd;
+    s[0] = pobj; s[1] = dobj; s[2] = sqrt(pr2); s[3] = sqrt(dr2);
+    s[4] = sqrt(nb2); s[5] = sqrt(nc2); s[6] = sqrt(nx2); s[7] = sqrt(ny2);
+    const double gap = fabs(pobj - dobj);
+    double e = s[2] / (1.0 + s[4]);
+    e = fmax(e, s[3] / (1.0 + s[5]));
+    e = fmax(e, gap / (1.0 + fabs(pobj) + fabs(dobj)));
+    s[8] = e; s[9] = gap;
+}
+
+__global__ void k_eval_finalize(DevLP lp, int G, double* out, double iters)
+{
+    double s[10];
+    kkt_from_sums(lp.red + (size_t)RED_EVALP * G * NRED, lp.red + (size_t)RED_EVALD * G * NRED, G, s);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 10; ++k) out[k] = s[k];
+        out[10] = iters; out[11] = 0.0; out[12] = 0.0; out[13] = 1.0; out[14] = 0.0; out[15] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// persistent cooperative kernel, parity mode: `iters` full iterations in one launch,
+// two grid barriers per iteration, no host involvement.
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double tau, double sigma, int iters)
+{
+    unsigned target = 0;
+    PrimalOp<BOUNDS> pop{lp, tau};
+    DualOp<BOUNDS> dop{lp, sigma};
+    double acc[NRED];
+    for (int it = 0; it < iters; ++it) {
+        run_phase(lp.AT, pop, acc, lp.AT.vals, lp.AT.idx, 0u);
+        grid_barrier(lp.barrier, target);
+        run_phase(lp.A, dop, acc, lp.A.vals, lp.A.idx, 0u);
+        grid_barrier(lp.barrier, target);
+    }
+}
+
+// persistent cooperative kernel, solve mode (reflected restarted Halpern PDHG).
+// Control state is replicated: every CTA derives it from the same global partial sums with
+// the same arithmetic, so all CTAs take identical branches.
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, double eta, double w0, int max_iters,
+                                                              int check_every, double tol, double* out)
+{
+    __shared__ double smem[32 * NRED];
+    __shared__ double bc[16];
+    unsigned target = 0;
+    const size_t RS = (size_t)G * NRED;  // one reduction buffer
+    // x0 = x, y0 = y
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < lp.n; k += gridDim.x * blockDim.x) lp.x0[k] = __ldcg(lp.x + k);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < lp.m; k += gridDim.x * blockDim.x) lp.y0[k] = __ldcg(lp.y + k);
+    grid_barrier(lp.barrier, target);
+
+    double w = w0, fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
+    int k = 0, it = 0, restarts = 0, converged = 0;
+    double kk[10];
+    for (int q = 0; q < 10; ++q) kk[q] = 0.0;
+
+    while (it < max_iters) {
+        const double tau = eta / w, sigma = eta * w;
+        const double lam = (double)(k + 1) / (double)(k + 2);
+        const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iters);
+        const bool need_fpe = check || fpe_restart < 0.0;
+        double* redp = lp.red + (size_t)((it & 1) * 4 + RED_STEPP) * RS;
+        double* redd = lp.red + (size_t)((it & 1) * 4 + RED_STEPD) * RS;
+        {
+            PrimalHalpernOp<BOUNDS> op{lp, tau, lam};
+            double acc[NRED];
+            acc[0] = 0.0;
+            run_phase(lp.AT, op, acc, lp.AT.vals, lp.AT.idx, 0u);
+            if (need_fpe) cta_reduce_store<1>(acc, redp + (size_t)blockIdx.x * NRED, smem);
+        }
+        grid_barrier(lp.barrier, target);
+        {
+            DualHalpernOp<BOUNDS> op{lp, sigma, lam};
+            double acc[NRED];
+            acc[0] = 0.0;
+            run_phase(lp.A, op, acc, lp.A.vals, lp.A.idx, 0u);
+            if (need_fpe) cta_reduce_store<1>(acc, redd + (size_t)blockIdx.x * NRED, smem);
+        }
+        if (check) {
+            // KKT at the new iterate needs the complete x and y
+            grid_barrier(lp.barrier, target);
+            eval_phases<BOUNDS>(lp, lp.red + (size_t)((it & 1) * 4 + RED_EVALP) * RS,
+                                lp.red + (size_t)((it & 1) * 4 + RED_EVALD) * RS, smem);
+        }
+        grid_barrier(lp.barrier, target);
+        ++it; ++k;
+        if (need_fpe) {
+            if (threadIdx.x < 32) {
+                const double dx2 = grid_sum(redp, G, 0), dy2 = grid_sum(redd, G, 0);
+                if (threadIdx.x == 0) bc[0] = sqrt(w * dx2 + dy2 / w);
+            }
+            __syncthreads();
+            fpe = bc[0];
+            __syncthreads();
+            if (fpe_restart < 0.0) fpe_restart = fpe;
+        }
+        if (check) {
+            const double* ep = lp.red + (size_t)(((it - 1) & 1) * 4 + RED_EVALP) * RS;
+            const double* ed = lp.red + (size_t)(((it - 1) & 1) * 4 + RED_EVALD) * RS;
+            if (threadIdx.x < 32) {
+                double s[10];
+                kkt_from_sums(ep, ed, G, s);
+                const double ddx2 = grid_sum(ep, G, 5), ddy2 = grid_sum(ed, G, 4);
+                if (threadIdx.x == 0) {
+                    for (int q = 0; q < 10; ++q) bc[q] = s[q];
+                    bc[10] = ddx2; bc[11] = ddy2;
+                }
+            }
+            __syncthreads();
+            for (int q = 0; q < 10; ++q) kk[q] = bc[q];
+            const double ddx = sqrt(bc[10]), ddy = sqrt(bc[11]);
+            __syncthreads();
+            if (kk[8] <= tol) { converged = 1; break; }
+            const bool do_restart = (fpe <= 0.2 * fpe_restart) || (fpe <= 0.8 * fpe_restart && fpe > fpe_prev) ||
+                                    ((double)k >= 0.36 * (double)it);
+            fpe_prev = fpe;
+            if (do_restart) {
+                if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
+                for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lp.n; q += gridDim.x * blockDim.x) lp.x0[q] = __ldcg(lp.x + q);
+                for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lp.m; q += gridDim.x * blockDim.x) lp.y0[q] = __ldcg(lp.y + q);
+                grid_barrier(lp.barrier, target);
+                k = 0; fpe_restart = -1.0; fpe_prev = INFINITY;
+                ++restarts;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int q = 0; q < 10; ++q) out[q] = kk[q];
+        out[10] = (double)it; out[11] = (double)restarts; out[12] = (double)converged;
+        out[13] = w; out[14] = fpe; out[15] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) return (int)e_;    \
+    } while (0)
+
+static inline int blocks_for(int n) { return n <= 0 ? 1 : (n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256; }
+
+int launch_gather(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    k_gather<<<blocks_for(n), 256, 0, s>>>(dst, src, order, n);
+    return (int)cudaGetLastError();
+}
+int launch_scatter(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    k_scatter<<<blocks_for(n), 256, 0, s>>>(dst, src, order, n);
+    return (int)cudaGetLastError();
+}
+int launch_fill(double* dst, double v, int n, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    k_fill<<<blocks_for(n), 256, 0, s>>>(dst, v, n);
+    return (int)cudaGetLastError();
+}
+int launch_sumsq(const double* v, int n, double* out, cudaStream_t s)
+{
+    k_sumsq<<<1, 1024, 0, s>>>(v, n, out);
+    return (int)cudaGetLastError();
+}
+int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2, int n, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    k_scale_by_invnorm<<<blocks_for(n), 256, 0, s>>>(dst, src, norm2, n);
+    return (int)cudaGetLastError();
+}
+
+int launch_spmv(const DevMat& M, const double* in, double* out, int G, int threads, cudaStream_t s)
+{
+    k_spmv<<<G, threads, 0, s>>>(M, in, out);
+    return (int)cudaGetLastError();
+}
+
+int launch_primal(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s)
+{
+    if (bounds) k_primal<true><<<G, threads, 0, s>>>(lp);
+    else k_primal<false><<<G, threads, 0, s>>>(lp);
+    return (int)cudaGetLastError();
+}
+int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s)
+{
+    if (bounds) k_dual<true><<<G, threads, 0, s>>>(lp);
+    else k_dual<false><<<G, threads, 0, s>>>(lp);
+    return (int)cudaGetLastError();
+}
+int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s)
+{
+    if (bounds) k_eval<true><<<G, threads, 0, s>>>(lp, G);
+    else k_eval<false><<<G, threads, 0, s>>>(lp, G);
+    CK(cudaGetLastError());
+    k_eval_finalize<<<1, 32, 0, s>>>(lp, G, out, iters);
+    return (int)cudaGetLastError();
+}
+
+int persistent_max_blocks_per_sm(int threads, bool bounds)
+{
+    int nb = 0;
+    cudaError_t e = bounds ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pdhg_persistent<true>, threads, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pdhg_persistent<false>, threads, 0);
+    if (e != cudaSuccess) return -(int)e;
+    int nb2 = 0;
+    e = bounds ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_solve_persistent<true>, threads, 0)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_solve_persistent<false>, threads, 0);
+    if (e != cudaSuccess) return -(int)e;
+    return nb < nb2 ? nb : nb2;
+}
+
+int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, double tau, double sigma, int iters,
+                           cudaStream_t s)
+{
+    CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
+    DevLP lpv = lp;
+    void* args[] = {&lpv, &tau, &sigma, &iters};
+    const void* fn = bounds ? (const void*)k_pdhg_persistent<true> : (const void*)k_pdhg_persistent<false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, 0, s));
+    return 0;
+}
+
+int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, double eta, double w0, int max_iters,
+                            int check_every, double tol, double* out, cudaStream_t s)
+{
+    CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
+    DevLP lpv = lp;
+    void* args[] = {&lpv, &G, &eta, &w0, &max_iters, &check_every, &tol, &out};
+    const void* fn = bounds ? (const void*)k_solve_persistent<true> : (const void*)k_solve_persistent<false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, 0, s));
+    return 0;
+}
+
+}  // namespace mllp

@@ -1,0 +1,291 @@
+"""Host side of the B200 primal-dual LP path, in the calling convention of the reference's
+``linear_program_methods.py``.
+
+The reference has no LP iteration of its own; these functions are the new
+entry points the north star asks for, shaped after what the reference does have:
+
+* argument order ``(constrs, constr_weights, rhs, coefs, ...)`` as in
+  ``build_graph_from_weights_sets(constrs, constr_weights, rhs, coefs, device)``
+  (reference linear_program_methods.py:89), fed by the loader tuple
+  ``(file, constrs, constrs_weights, coefs, rhs, basis_opt)`` (linear_program_data.py:78);
+* return convention ``(objective, solution, ...)`` and "tensors in => tensors out on the same
+  device" as in ``gurobi_max_covering`` (linear_program_methods.py:542-553, :603-607);
+* non-convergence is reported, not raised (linear_program_methods.py:537-539); bad arguments
+  raise ``ValueError`` (linear_program_experiment.py:39).
+
+All arithmetic happens in hand-written sm_100a kernels behind the C ABI
+(include/mllp_b200.h); there is no CPU or PyTorch fallback -- a missing library or GPU raises.
+"""
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import _cabi
+
+__all__ = [
+    "DeviceLP", "device_lp", "pdhg_linear_program", "solve_linear_program", "estimate_step_size",
+    "csr_from_constrs", "SCALAR_NAMES",
+]
+
+SCALAR_NAMES = ("pobj", "dobj", "primal_res", "dual_res", "norm_b", "norm_c", "norm_x", "norm_y",
+                "rel_kkt", "gap", "iters", "restarts", "converged", "primal_weight", "fixed_point_err",
+                "reserved")
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _np_f64(a, size, name):
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    if a.shape[0] != size:
+        raise ValueError("%s has %d entries, expected %d" % (name, a.shape[0], size))
+    return a
+
+
+def csr_from_constrs(constrs, constr_weights, num_cols):
+    """CSR arrays from the loader's representation (linear_program_data.py:75-77):
+    ``constrs`` = per-row column-index arrays (np.split of scipy's indices by indptr) or a scipy
+    sparse matrix, ``constr_weights`` = the flat CSR data."""
+    if hasattr(constrs, "tocsr"):
+        A = constrs.tocsr()
+        A.sort_indices()
+        if A.shape[1] != num_cols:
+            raise ValueError("constraint matrix has %d columns, coefs has %d" % (A.shape[1], num_cols))
+        return (np.ascontiguousarray(A.indptr, dtype=np.int32), np.ascontiguousarray(A.indices, dtype=np.int32),
+                np.ascontiguousarray(A.data, dtype=np.float64))
+    m = len(constrs)
+    lens = np.fromiter((len(r) for r in constrs), dtype=np.int64, count=m)
+    indptr = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    if indptr[-1] >= 2 ** 31:
+        raise ValueError("more than 2^31-1 nonzeros")
+    indices = (np.concatenate([np.asarray(r, dtype=np.int32) for r in constrs])
+               if m and indptr[-1] else np.zeros(0, dtype=np.int32))
+    values = np.ascontiguousarray(constr_weights, dtype=np.float64).reshape(-1)
+    if values.shape[0] != indptr[-1]:
+        raise ValueError("constr_weights has %d entries, constrs lists %d" % (values.shape[0], indptr[-1]))
+    if indices.size and (indices.min() < 0 or indices.max() >= num_cols):
+        raise ValueError("column index out of range")
+    return indptr.astype(np.int32), np.ascontiguousarray(indices, dtype=np.int32), values
+
+
+def _device_index(device):
+    if device is None:
+        return 0
+    if isinstance(device, int):
+        return device
+    s = str(device)
+    if s == "cuda":
+        return 0
+    if s.startswith("cuda:"):
+        return int(s.split(":")[1])
+    raise ValueError("mllp_b200 runs on CUDA devices only (got device=%r); there is no CPU path" % (device,))
+
+
+class DeviceLP:
+    """Device-resident tiled formats of A and A' for one LP instance (built once, in the
+    loader).  Wraps an ``mllp_lp_t`` handle."""
+
+    def __init__(self, constrs, constr_weights, num_rows, num_cols, lb=None, ub=None, ylo=None, yhi=None,
+                 device=0, flags=_cabi.F_DEFAULT):
+        L = _cabi.lib()
+        self.m, self.n = int(num_rows), int(num_cols)
+        indptr, indices, values = csr_from_constrs(constrs, constr_weights, self.n)
+        if indptr.shape[0] != self.m + 1:
+            raise ValueError("constrs has %d rows, rhs has %d" % (indptr.shape[0] - 1, self.m))
+        self.nnz = int(indptr[-1])
+        self.device = _device_index(device)
+        self.flags = int(flags)
+        lb = None if lb is None else _np_f64(lb, self.n, "lb")
+        ub = None if ub is None else _np_f64(ub, self.n, "ub")
+        ylo = None if ylo is None else _np_f64(ylo, self.m, "ylo")
+        yhi = None if yhi is None else _np_f64(yhi, self.m, "yhi")
+        if (lb is None) != (ub is None) or (ylo is None) != (yhi is None):
+            raise ValueError("lb/ub and ylo/yhi must be given in pairs")
+        h = ctypes.c_void_p()
+        rc = L.mllp_lp_create(self.m, self.n, self.nnz, _ptr(indptr), _ptr(indices), _ptr(values), _ptr(lb),
+                              _ptr(ub), _ptr(ylo), _ptr(yhi), self.device, self.flags, ctypes.byref(h))
+        _cabi.check(rc, "mllp_lp_create")
+        self._h = h
+        self._finalizer = weakref.finalize(self, L.mllp_lp_destroy, h)
+        self._sigma_max = None
+
+    def close(self):
+        self._finalizer()
+        self._h = None
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("DeviceLP is closed")
+        return self._h
+
+    def info(self):
+        out = (ctypes.c_int64 * 16)()
+        _cabi.check(_cabi.lib().mllp_lp_info(self.handle, out), "mllp_lp_info")
+        keys = ("m", "n", "nnz", "tiles_A", "tiles_AT", "padded_A", "padded_AT", "split_rows_A", "split_rows_AT",
+                "grid_ctas", "threads", "smem_resident_bytes", "bytes_per_iter", "max_cta_steps_A",
+                "max_cta_steps_AT", "ctas_per_sm")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def sigma_max(self, iters=50, stream=None):
+        """||A||_2 estimate by power iteration on the device (cached)."""
+        if self._sigma_max is None:
+            s = ctypes.c_double(0.0)
+            _cabi.check(_cabi.lib().mllp_estimate_norm(self.handle, int(iters), ctypes.byref(s), stream),
+                        "mllp_estimate_norm")
+            self._sigma_max = s.value
+        return self._sigma_max
+
+    # -- torch-tensor level helpers (device pointers, caller's stream) --------------------------
+    def spmv(self, v, trans=False):
+        import torch
+        self._check_tensor(v, self.m if trans else self.n, "v")
+        out = torch.empty(self.n if trans else self.m, dtype=torch.float64, device=v.device)
+        _cabi.check(_cabi.lib().mllp_spmv(self.handle, int(bool(trans)), v.data_ptr(), out.data_ptr(),
+                                          _torch_stream(v.device)), "mllp_spmv")
+        return out
+
+    def _check_tensor(self, t, size, name):
+        import torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                and t.numel() == size and t.device.index == self.device):
+            raise ValueError("%s must be a contiguous float64 CUDA tensor of %d entries on cuda:%d"
+                             % (name, size, self.device))
+
+
+def _torch_stream(device):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# handles built by the loader (or lazily here), keyed by the identity of the weights array
+_HANDLES = {}
+
+
+def device_lp(constrs, constr_weights, rhs, coefs, lb=None, ub=None, ylo=None, yhi=None, device=0,
+              flags=_cabi.F_DEFAULT, cache=True):
+    """Return the DeviceLP of this instance, building (and caching) it on first use.  The cache
+    is keyed on the identity of ``constr_weights`` -- the loader's tuple keeps that array alive."""
+    key = (id(constr_weights), _device_index(device), int(flags), lb is not None, ylo is not None)
+    if cache:
+        hit = _HANDLES.get(key)
+        if hit is not None and hit[0]() is constr_weights:
+            return hit[1]
+    lp = DeviceLP(constrs, constr_weights, len(rhs), len(coefs), lb, ub, ylo, yhi, device, flags)
+    if cache:
+        try:
+            ref = weakref.ref(constr_weights, lambda _r, k=key: _HANDLES.pop(k, None))
+            _HANDLES[key] = (ref, lp)
+        except TypeError:
+            pass  # not weak-referenceable (e.g. a list): no caching
+    return lp
+
+
+def estimate_step_size(lp, safety=0.9, iters=50):
+    """eta = safety / sigma_max(A) (0.9/sigma_max by 50 power-iteration steps)."""
+    s = lp.sigma_max(iters)
+    return safety / s if s > 0 else 1.0
+
+
+def _info_dict(scal):
+    d = {k: float(v) for k, v in zip(SCALAR_NAMES, scal)}
+    for k in ("iters", "restarts"):
+        d[k] = int(d[k])
+    d["converged"] = bool(d["converged"])
+    del d["reserved"]
+    return d
+
+
+def _is_tensor(a):
+    return type(a).__module__.startswith("torch") and hasattr(a, "data_ptr")
+
+
+def pdhg_linear_program(constrs, constr_weights, rhs, coefs, *, num_iters, lb=None, ub=None, ylo=None, yhi=None,
+                        x0=None, y0=None, tau=None, sigma=None, device=0, handle=None, flags=_cabi.F_DEFAULT,
+                        verbose=False):
+    """Parity mode: ``num_iters`` fixed-step PDHG iterations on  min c'x, Ax=b (or row senses via
+    ylo/yhi), l<=x<=u  from (x0, y0) (default 0):
+
+        g = c - A'y;  x+ = clip(x - tau g, l, u);  xbar = 2x+ - x;  y+ = clip(y + sigma (b - A xbar))
+
+    Returns ``(objective, x, y, info)``.  numpy inputs give numpy outputs (host buffers go
+    through ``mllp_pdhg_run_host``, copies included); float64 CUDA tensors for rhs/coefs give
+    tensors on the same device with no host synchronisation (``mllp_pdhg_run`` on the current
+    stream; ``objective`` is then a 0-d tensor).  ``tau``/``sigma`` default to
+    0.9/sigma_max(A).  ``handle`` = a DeviceLP built earlier (e.g. by the loader)."""
+    if num_iters < 0:
+        raise ValueError("num_iters must be >= 0")
+    lp = handle if handle is not None else device_lp(constrs, constr_weights, rhs, coefs, lb, ub, ylo, yhi,
+                                                     device, flags)
+    if tau is None or sigma is None:
+        eta = estimate_step_size(lp)
+        tau = eta if tau is None else tau
+        sigma = eta if sigma is None else sigma
+    L = _cabi.lib()
+    if _is_tensor(rhs) or _is_tensor(coefs):
+        import torch
+        dev = torch.device("cuda", lp.device)
+        b = rhs if _is_tensor(rhs) else torch.as_tensor(np.asarray(rhs, dtype=np.float64), device=dev)
+        c = coefs if _is_tensor(coefs) else torch.as_tensor(np.asarray(coefs, dtype=np.float64), device=dev)
+        lp._check_tensor(b, lp.m, "rhs")
+        lp._check_tensor(c, lp.n, "coefs")
+        x = torch.zeros(lp.n, dtype=torch.float64, device=dev) if x0 is None else x0.clone()
+        y = torch.zeros(lp.m, dtype=torch.float64, device=dev) if y0 is None else y0.clone()
+        lp._check_tensor(x, lp.n, "x0")
+        lp._check_tensor(y, lp.m, "y0")
+        scal = torch.empty(_cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
+        _cabi.check(L.mllp_pdhg_run(lp.handle, x.data_ptr(), y.data_ptr(), b.data_ptr(), c.data_ptr(), float(tau),
+                                    float(sigma), int(num_iters), scal.data_ptr(), _torch_stream(dev)),
+                    "mllp_pdhg_run")
+        info = {"scalars": scal, "tau": float(tau), "sigma": float(sigma), "handle": lp}
+        return scal[0], x, y, info
+    b = _np_f64(rhs, lp.m, "rhs")
+    c = _np_f64(coefs, lp.n, "coefs")
+    x = np.zeros(lp.n) if x0 is None else _np_f64(x0, lp.n, "x0").copy()
+    y = np.zeros(lp.m) if y0 is None else _np_f64(y0, lp.m, "y0").copy()
+    scal = np.zeros(_cabi.NUM_SCALARS)
+    _cabi.check(L.mllp_pdhg_run_host(lp.handle, _ptr(x), _ptr(y), _ptr(b), _ptr(c), float(tau), float(sigma),
+                                     int(num_iters), _ptr(scal), None), "mllp_pdhg_run_host")
+    info = _info_dict(scal)
+    info.update(tau=float(tau), sigma=float(sigma), handle=lp)
+    if verbose:
+        print("pdhg: %d iters  pobj %.9g  dobj %.9g  rel_kkt %.3e" % (num_iters, scal[0], scal[1], scal[8]))
+    return float(scal[0]), x, y, info
+
+
+def solve_linear_program(constrs, constr_weights, rhs, coefs, *, tol=1e-6, max_iters=200000, check_every=64,
+                         lb=None, ub=None, ylo=None, yhi=None, x0=None, y0=None, eta=None, primal_weight=1.0,
+                         device=0, handle=None, flags=_cabi.F_DEFAULT, verbose=False):
+    """Solve mode: reflected restarted Halpern PDHG on the device until the relative KKT error is
+    <= ``tol`` (spec: oracle_pdhg_solve).  Returns ``(objective, x, y, info)``; numpy in/out.
+    Non-convergence within ``max_iters`` is reported in ``info['converged']``, not raised."""
+    import torch
+    lp = handle if handle is not None else device_lp(constrs, constr_weights, rhs, coefs, lb, ub, ylo, yhi,
+                                                     device, flags)
+    if eta is None:
+        eta = estimate_step_size(lp, safety=0.99)
+    dev = torch.device("cuda", lp.device)
+    as_t = lambda a, n, name: torch.as_tensor(_np_f64(a, n, name), device=dev)
+    tensors_in = _is_tensor(rhs)
+    b = rhs if tensors_in else as_t(rhs, lp.m, "rhs")
+    c = coefs if _is_tensor(coefs) else as_t(coefs, lp.n, "coefs")
+    x = torch.zeros(lp.n, dtype=torch.float64, device=dev) if x0 is None else (x0.clone() if _is_tensor(x0) else as_t(x0, lp.n, "x0"))
+    y = torch.zeros(lp.m, dtype=torch.float64, device=dev) if y0 is None else (y0.clone() if _is_tensor(y0) else as_t(y0, lp.m, "y0"))
+    for t, n, nm in ((b, lp.m, "rhs"), (c, lp.n, "coefs"), (x, lp.n, "x0"), (y, lp.m, "y0")):
+        lp._check_tensor(t, n, nm)
+    scal = torch.empty(_cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
+    _cabi.check(_cabi.lib().mllp_pdhg_solve(lp.handle, x.data_ptr(), y.data_ptr(), b.data_ptr(), c.data_ptr(),
+                                            float(eta), float(primal_weight), int(max_iters), int(check_every),
+                                            float(tol), scal.data_ptr(), _torch_stream(dev)), "mllp_pdhg_solve")
+    if tensors_in:
+        return scal[0], x, y, {"scalars": scal, "eta": float(eta), "handle": lp}
+    s = scal.cpu().numpy()
+    info = _info_dict(s)
+    info.update(eta=float(eta), handle=lp)
+    if verbose:
+        print("solve: %d iters, %d restarts, converged=%s, pobj %.9g, rel_kkt %.3e"
+              % (info["iters"], info["restarts"], info["converged"], s[0], s[8]))
+    return float(s[0]), x.cpu().numpy(), y.cpu().numpy(), info
