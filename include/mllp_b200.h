@@ -139,6 +139,10 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t *h_m,
                       const int32_t *h_indices, const double *h_values, int device,
                       uint32_t flags, mllp_batch_t *out);
 int mllp_batch_destroy(mllp_batch_t bt);
+/* out[0]=count, [1]=sum m, [2]=sum n, [3]=sum nnz (shared: nnz of the one matrix), [4]=CTAs,
+ * [5]=threads per CTA, [6]=dynamic smem bytes per CTA, [7]=algorithmic bytes per batch iteration,
+ * [8]=instances per CTA, [9..15] reserved. */
+int mllp_batch_info(mllp_batch_t bt, int64_t *out16);
 /* per-instance tau[k], sigma[k] (device arrays of `count`); scalars: count*MLLP_NUM_SCALARS */
 int mllp_batch_run(mllp_batch_t bt, double *d_x, double *d_y, const double *d_b,
                    const double *d_c, const double *d_tau, const double *d_sigma,

@@ -1,0 +1,205 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): iterates within 1e-9 relative L2 after a fixed iteration count;
+objective / KKT scalars within 1e-6 relative.  fp64 throughout.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mllp_b200 as M
+import mllp_b200.linear_program_data as D
+from mllp_b200 import _cabi
+from mllp_b200.linear_program_methods import SCALAR_NAMES
+from oracle import pdhg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HIGHS = json.load(open(os.path.join(GOLD, "highs_objectives.json")))
+ITER_TOL = 1e-9
+SCAL_TOL = 1e-6
+
+# (instance, iterations): every BASELINE.json config instance
+CASES = [("afiro", 5000), ("sc50a", 1000), ("sc105", 1000), ("adlittle", 1000), ("blend", 1000), ("share2b", 1000),
+         ("kb2", 1000), ("25fv47", 1000), ("pilot87", 1000), ("d2q06c", 1000), ("dfl001", 1000), ("ken-18", 1000),
+         ("osa-60", 300), ("pds-20", 1000)]
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def scal_close(info, kk):
+    for k in range(10):
+        ref = kk[k]
+        assert abs(info[SCALAR_NAMES[k]] - ref) <= SCAL_TOL * (1 + abs(ref)), (SCALAR_NAMES[k], info[SCALAR_NAMES[k]], ref)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch
+
+
+@pytest.mark.parametrize("name", ["afiro", "25fv47", "pilot87", "ken-18", "osa-60", "pds-20"])
+def test_spmv_parity_and_adjointness(name, torch_cuda):
+    torch = torch_cuda
+    A, _, _ = D.load_csr(name)
+    m, n = A.shape
+    lp = M.DeviceLP(A, A.data, m, n)
+    rng = np.random.default_rng(1)
+    v, w = rng.standard_normal(n), rng.standard_normal(m)
+    Av = lp.spmv(torch.tensor(v, device="cuda")).cpu().numpy()
+    Atw = lp.spmv(torch.tensor(w, device="cuda"), trans=True).cpu().numpy()
+    assert rel(Av, O.spmv(A, v)) < 1e-13 and rel(Atw, O.spmv(A, w, trans=True)) < 1e-13
+    # size-independent properties: adjointness and linearity
+    assert abs(w @ Av - v @ Atw) <= 1e-11 * (np.linalg.norm(w) * np.linalg.norm(Av) + 1)
+    v2 = rng.standard_normal(n)
+    lin = lp.spmv(torch.tensor(2.0 * v - 3.0 * v2, device="cuda")).cpu().numpy()
+    Av2 = lp.spmv(torch.tensor(v2, device="cuda")).cpu().numpy()
+    assert rel(lin, 2.0 * Av - 3.0 * Av2) < 1e-12
+    lp.close()
+
+
+@pytest.mark.parametrize("name,K", CASES)
+def test_parity_mode_iterates(name, K):
+    A, b, c = D.load_csr(name)
+    m, n = A.shape
+    constrs = np.split(A.indices, A.indptr)[1:-1]
+    lp = M.DeviceLP(constrs, A.data, m, n)
+    sig = O.power_iteration(A, 50)
+    assert abs(lp.sigma_max() - sig) <= 1e-10 * sig
+    eta = 0.9 / sig
+    obj, x, y, info = M.pdhg_linear_program(constrs, A.data, b, c, num_iters=K, tau=eta, sigma=eta, handle=lp)
+    xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, K)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    scal_close(info, O.kkt(A, b, c, xo, yo))
+    assert info["iters"] == K and abs(obj - c @ xo) <= SCAL_TOL * (1 + abs(c @ xo))
+    lp.close()
+
+
+def test_golden_fixture_afiro():
+    g = np.load(os.path.join(GOLD, "afiro_parity_K200.npz"))
+    A, b, c = D.load_csr("afiro")
+    eta = float(g["eta"])
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=200, tau=eta, sigma=eta)
+    assert rel(x, g["x"]) < ITER_TOL and rel(y, g["y"]) < ITER_TOL
+    scal_close(info, g["kkt"])
+
+
+@pytest.mark.parametrize("name", ["sc105", "25fv47", "pilot87"])
+def test_general_form_bounds_and_row_senses(name):
+    A, b, c = D.load_csr(name)
+    m, n = A.shape
+    rng = np.random.default_rng(7)
+    lb = np.where(rng.random(n) < 0.3, -np.inf, rng.uniform(-1, 0, n))
+    ub = np.where(rng.random(n) < 0.3, np.inf, rng.uniform(0.5, 2, n))
+    kind = rng.integers(0, 3, m)
+    ylo = np.where(kind == 1, 0.0, -np.inf)
+    yhi = np.where(kind == 2, 0.0, np.inf)
+    x0, y0 = rng.uniform(0, 0.4, n), np.clip(rng.standard_normal(m), ylo, yhi)
+    eta = 0.9 / O.power_iteration(A, 50)
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=400, tau=eta, sigma=0.5 * eta, lb=lb, ub=ub,
+                                            ylo=ylo, yhi=yhi, x0=x0, y0=y0, handle=None)
+    xo, yo = O.pdhg_run(A, b, c, x0, y0, eta, 0.5 * eta, 400, lb, ub, ylo, yhi)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    scal_close(info, O.kkt(A, b, c, xo, yo, lb, ub, ylo, yhi))
+    assert np.all(x >= lb) and np.all(x <= ub) and np.all(y >= ylo) and np.all(y <= yhi)
+
+
+def test_zero_iterations_and_warm_start(torch_cuda):
+    A, b, c = D.load_csr("blend")
+    m, n = A.shape
+    rng = np.random.default_rng(2)
+    x0, y0 = np.abs(rng.standard_normal(n)), rng.standard_normal(m)
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=0, tau=0.1, sigma=0.1, x0=x0, y0=y0)
+    assert np.array_equal(x, x0) and np.array_equal(y, y0)
+    scal_close(info, O.kkt(A, b, c, x0, y0))
+    # K iterations == K/2 + K/2 with a warm start (bitwise: same kernels, same order)
+    _, xa, ya, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=100, tau=0.1, sigma=0.1, x0=x0, y0=y0)
+    _, xh, yh, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=50, tau=0.1, sigma=0.1, x0=x0, y0=y0)
+    _, xb, yb, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=50, tau=0.1, sigma=0.1, x0=xh, y0=yh)
+    assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+
+
+@pytest.mark.parametrize("name", ["afiro", "pilot87", "osa-60"])
+def test_graph_mode_is_bitwise_identical_to_persistent(name):
+    A, b, c = D.load_csr(name)
+    m, n = A.shape
+    eta = 0.9 / O.power_iteration(A, 50)
+    K = 70  # not a multiple of the graph unroll
+    _, x1, y1, i1 = M.pdhg_linear_program(A, A.data, b, c, num_iters=K, tau=eta, sigma=eta)
+    lpg = M.DeviceLP(A, A.data, m, n, flags=_cabi.F_GRAPH_MODE)
+    _, x2, y2, i2 = M.pdhg_linear_program(A, A.data, b, c, num_iters=K, tau=eta, sigma=eta, handle=lpg)
+    assert np.array_equal(x1, x2) and np.array_equal(y1, y2) and i1["pobj"] == i2["pobj"]
+
+
+def test_torch_tensor_interface_no_host_sync(torch_cuda):
+    torch = torch_cuda
+    A, b, c = D.load_csr("25fv47")
+    m, n = A.shape
+    eta = 0.9 / O.power_iteration(A, 50)
+    bt, ct = torch.tensor(b, device="cuda"), torch.tensor(c, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        obj, x, y, info = M.pdhg_linear_program(A, A.data, bt, ct, num_iters=300, tau=eta, sigma=eta)
+    s.synchronize()
+    assert x.is_cuda and y.is_cuda and obj.is_cuda
+    xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, 300)
+    assert rel(x.cpu().numpy(), xo) < ITER_TOL and rel(y.cpu().numpy(), yo) < ITER_TOL
+
+
+@pytest.mark.parametrize("name", ["afiro", "sc50a", "sc105", "adlittle", "blend", "share2b"])
+def test_solve_mode_objective_matches_highs_and_oracle(name):
+    A, b, c = D.load_csr(name)
+    m, n = A.shape
+    obj, x, y, info = M.solve_linear_program(A, A.data, b, c, tol=1e-6, max_iters=400000)
+    assert info["converged"] and info["rel_kkt"] <= 1e-6
+    assert abs(obj - HIGHS[name]) <= 1e-4 * (1 + abs(HIGHS[name]))
+    # returned scalars describe the returned point
+    kk = O.kkt(A, b, c, x, y)
+    assert abs(kk[0] - obj) <= SCAL_TOL * (1 + abs(obj)) and abs(kk[8] - info["rel_kkt"]) <= 1e-9
+    if name in ("afiro", "sc50a", "sc105"):
+        xs, ys, ks, si = O.pdhg_solve(A, b, c, np.zeros(n), np.zeros(m), info["eta"], max_iters=400000, tol=1e-6)
+        assert abs(ks[0] - obj) <= SCAL_TOL * (1 + abs(obj))
+        assert abs(ks[8] - info["rel_kkt"]) <= SCAL_TOL
+
+
+def test_solve_mode_max_iters_reports_nonconvergence():
+    A, b, c = D.load_csr("share2b")
+    obj, x, y, info = M.solve_linear_program(A, A.data, b, c, tol=1e-12, max_iters=200)
+    assert not info["converged"] and info["iters"] == 200
+
+
+def test_error_paths():
+    A, b, c = D.load_csr("afiro")
+    with pytest.raises(ValueError):
+        M.pdhg_linear_program(A, A.data, b[:-1], c, num_iters=1, tau=0.1, sigma=0.1)
+    bad = A.copy()
+    with pytest.raises(ValueError):
+        M.DeviceLP(bad, bad.data, 27, 50)  # wrong column count
+    lpg = M.DeviceLP(A, A.data, 27, 51, flags=_cabi.F_GRAPH_MODE)
+    with pytest.raises(RuntimeError, match="persistent"):
+        M.solve_linear_program(A, A.data, b, c, handle=lpg)
+
+
+def test_random_skewed_matrix_with_empty_rows():
+    """ragged input: empty rows/columns, a few very long rows (split path), random values."""
+    rng = np.random.default_rng(11)
+    rows = [sp.random(1, 5000, density=d, random_state=int(10000 * d) + 3, format="csr")
+            for d in (0.0, 0.0004, 0.002, 0.01, 0.05, 0.2, 0.8)]
+    A = sp.vstack(rows * 9).tocsr()
+    A.data[:] = rng.standard_normal(A.nnz)
+    A.sort_indices()
+    m, n = A.shape
+    b, c = rng.standard_normal(m), rng.standard_normal(n)
+    eta = 0.9 / O.power_iteration(A, 50)
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=200, tau=eta, sigma=eta)
+    xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, 200)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
