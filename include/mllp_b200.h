@@ -71,6 +71,14 @@ int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indp
                           const int32_t *indices, const double *values, int32_t num_ctas,
                           int32_t pref_steps, int32_t max_steps, double *out8);
 
+/* Host-only statistic of the built format: distinct 128-byte lines touched by the warp-wide
+ * gather instructions (the gather cost model).  out6: [0]/[1] total lines A / A', [2]/[3] the
+ * largest per-CTA sum, [4]/[5] gather instructions.  `cluster` = cluster rows inside length
+ * classes (the default of mllp_lp_create). */
+int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr,
+                             const int32_t *indices, const double *values, int32_t num_ctas,
+                             int32_t pref_steps, int32_t max_steps, int32_t cluster, double *out6);
+
 /* Device facts the host side needs: out[0]=SM count, out[1]=L2 bytes, out[2]=max smem/CTA. */
 int mllp_device_info(int device, int64_t *out3);
 
@@ -88,9 +96,10 @@ int mllp_lp_destroy(mllp_lp_t lp);
 
 /* Geometry of the built formats: out[0]=m, [1]=n, [2]=nnz, [3]=tiles(A), [4]=tiles(A'),
  * [5]=padded entries(A), [6]=padded entries(A'), [7]=split rows(A), [8]=split rows(A'),
- * [9]=grid CTAs, [10]=threads per CTA, [11]=smem-resident bytes per CTA (0 if streaming),
+ * [9]=grid CTAs, [10]=threads per CTA, [11]=dynamic shared memory per CTA (bytes),
  * [12]=algorithmic bytes per iteration (24 nnz + 36 m + 44 n + 8, +16 n with bounds,
- * +16 m with row senses), [13..15] reserved. */
+ * +16 m with row senses), [13]/[14]=per-CTA cap of shared-memory resident warp-steps of A/A',
+ * [15]=CTAs per SM. */
 int mllp_lp_info(mllp_lp_t lp, int64_t *out16);
 
 /* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */

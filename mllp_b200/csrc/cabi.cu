@@ -1,6 +1,7 @@
 // cabi.cu -- the C ABI of include/mllp_b200.h for the single-instance path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,6 +63,7 @@ struct mllp_lp {
     uint32_t flags = 0;
     bool bounds = false;
     int G = 0, threads = 0;
+    size_t dyn_smem = 0;          // dynamic shared memory of the persistent kernels
     DevLP d{};
     std::vector<void*> allocs;
     int32_t* d_orderX = nullptr;  // internal position k holds original column order[k]
@@ -112,12 +114,17 @@ int dev_zeros(mllp_lp* lp, T** out, size_t count)
 int upload_mat(mllp_lp* lp, const HostMat& H, DevMat& D)
 {
     double* vals; int32_t* idx; Tile* tiles; uint32_t* cb; uint32_t* csb; SplitRow* sp;
+    LocalSplit* lsp; uint32_t* clb; uint32_t* cns;
     RC_OK(dev_upload(lp, &vals, H.vals.data(), H.vals.size()));
     RC_OK(dev_upload(lp, &idx, H.idx.data(), H.idx.size()));
     RC_OK(dev_upload(lp, &tiles, H.tiles.data(), H.tiles.size()));
     RC_OK(dev_upload(lp, &cb, H.cta_begin.data(), H.cta_begin.size()));
     RC_OK(dev_upload(lp, &csb, H.cta_step_begin.data(), H.cta_step_begin.size()));
     RC_OK(dev_upload(lp, &sp, H.splits.data(), H.splits.size()));
+    RC_OK(dev_upload(lp, &lsp, H.lsplits.data(), H.lsplits.size()));
+    RC_OK(dev_upload(lp, &clb, H.cta_lsplit_begin.data(), H.cta_lsplit_begin.size()));
+    RC_OK(dev_upload(lp, &cns, H.cta_nsplit.data(), H.cta_nsplit.size()));
+    D.lsplits = lsp; D.cta_lsplit_begin = clb; D.cta_nsplit = cns;
     RC_OK(dev_zeros(lp, &D.partials, (size_t)H.num_partials));
     RC_OK(dev_zeros(lp, &D.counters, H.splits.size()));
     D.vals = reinterpret_cast<const double2*>(vals);
@@ -210,22 +217,25 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
     lp->m = m; lp->n = n; lp->nnz = nnz; lp->flags = flags;
     lp->bounds = (h_lb != nullptr) || (h_ylo != nullptr);
 
-    // launch geometry of the persistent grid
-    lp->threads = env_int("MLLP_THREADS", 512);
-    if (lp->threads < 32 || lp->threads > 1024 || (lp->threads & 31)) lp->threads = 512;
-    int bpsm = persistent_max_blocks_per_sm(lp->threads, lp->bounds);
+    // launch geometry of the persistent grid.  Resident mode (default): one 1024-thread CTA per
+    // SM whose share of A and A' lives in shared memory; streaming mode: 2 x 512.
+    const bool resident = !(flags & (MLLP_F_NO_SMEM_RESIDENT | MLLP_F_GRAPH_MODE));
+    lp->threads = env_int("MLLP_THREADS", 1024);
+    if (lp->threads < 32 || lp->threads > 1024 || (lp->threads & 31)) lp->threads = 1024;
+    int bpsm = persistent_max_blocks_per_sm(lp->threads, lp->bounds, 0);
     if (bpsm <= 0) { delete lp; return fail(MLLP_E_STATE, "mllp_lp_create: persistent kernel cannot be resident"); }
-    const int want = env_int("MLLP_CTAS_PER_SM", 0);
+    const int want = env_int("MLLP_CTAS_PER_SM", 1);
     if (want > 0 && want < bpsm) bpsm = want;
     lp->G = prop.multiProcessorCount * bpsm;
 
     BuildParams bp;
     bp.num_ctas = lp->G;
     bp.pref_steps = env_int("MLLP_PREF_STEPS", 4);
-    bp.max_steps = env_int("MLLP_MAX_STEPS", 4);
+    bp.max_steps = env_int("MLLP_MAX_STEPS", 8);
     if (bp.pref_steps < 1) bp.pref_steps = 1;
     if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
     if (bp.max_steps > 1024) bp.max_steps = 1024;
+    bp.cluster = env_int("MLLP_CLUSTER", 1) != 0;
 
     int rc = 0;
     try {
@@ -233,8 +243,7 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
         std::vector<double> tval;
         csr_transpose(m, n, h_indptr, h_indices, h_values, tptr, tind, tval);
         std::vector<int32_t> orderY, posY, orderX, posX;
-        plan_row_order(m, h_indptr, bp, orderY, posY);
-        plan_row_order(n, tptr.data(), bp, orderX, posX);
+        plan_orders(m, n, h_indptr, h_indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
         HostMat HA, HAT;
         build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, HA);
         build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
@@ -260,9 +269,9 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
                 RC_OK(dev_upload(lp, &p4, yhi.data(), yhi.size()));
                 lp->d.lb = p1; lp->d.ub = p2; lp->d.ylo = p3; lp->d.yhi = p4;
             }
-            RC_OK(dev_zeros(lp, &lp->d.x, (size_t)n));
-            RC_OK(dev_zeros(lp, &lp->d.y, (size_t)m));
-            RC_OK(dev_zeros(lp, &lp->d.xbar, (size_t)n));
+            RC_OK(dev_zeros(lp, &lp->d.x, (size_t)n + 1));
+            RC_OK(dev_zeros(lp, &lp->d.y, (size_t)m + 1));
+            RC_OK(dev_zeros(lp, &lp->d.xbar, (size_t)n + 1));
             RC_OK(dev_zeros(lp, &lp->d.x0, (size_t)n));
             RC_OK(dev_zeros(lp, &lp->d.y0, (size_t)m));
             RC_OK(dev_zeros(lp, &lp->d.red, (size_t)RED_BUFFERS * lp->G * NRED));
@@ -278,6 +287,33 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
             RC_OK(dev_zeros(lp, &lp->d_scal, MLLP_NUM_SCALARS));
             RC_OK(dev_zeros(lp, &lp->d_norm2, 2));
             if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
+            // shared-memory residency of the matrix slices
+            const size_t desc_bytes = 16 * ((size_t)HA.max_cta_tiles + (size_t)HAT.max_cta_tiles);
+            lp->dyn_smem = desc_bytes;
+            lp->d.res_steps_A = 0; lp->d.res_steps_AT = 0;
+            if (resident) {
+                const size_t per_cta = (size_t)prop.sharedMemPerMultiprocessor / (size_t)bpsm;
+                size_t budget = std::min<size_t>(per_cta - 1024, (size_t)prop.sharedMemPerBlockOptin);
+                budget -= std::min<size_t>(budget, 6144);  // static shared memory of the kernels + slack
+                budget -= std::min<size_t>(budget, desc_bytes);
+                // The gathered vectors are read through L1 (the grid barrier invalidates it), so part of
+                // the SM's 228 KB stays L1: cap the shared-memory share of the matrix.
+                budget = std::min<size_t>(budget, (size_t)env_int("MLLP_RES_KB", 96) * 1024);
+                // what is left keeps (a prefix of) each CTA's share of A' and A resident
+                const size_t cap = budget / 768;
+                size_t a = (size_t)HA.max_cta_steps, at = (size_t)HAT.max_cta_steps;
+                if (a + at > cap) {   // A' first: its tiles are the short, latency-dominated ones
+                    at = std::min(at, cap);
+                    a = std::min(a, cap - at);
+                }
+                const int lim = env_int("MLLP_RES_STEPS", -1);  // dev knob: cap the resident steps
+                if (lim >= 0) { a = std::min<size_t>(a, (size_t)lim); at = std::min<size_t>(at, (size_t)lim); }
+                lp->d.res_steps_A = (uint32_t)a; lp->d.res_steps_AT = (uint32_t)at;
+                lp->dyn_smem = desc_bytes + 768 * (a + at);
+            }
+            if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(persistent_set_smem(lp->bounds, lp->dyn_smem));
+            if (persistent_max_blocks_per_sm(lp->threads, lp->bounds, lp->dyn_smem) < bpsm)
+                return fail(MLLP_E_STATE, "mllp_lp_create: persistent grid does not fit with the chosen shared memory");
             return 0;
         };
         rc = body();
@@ -287,9 +323,9 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
         I[3] = (int64_t)HA.tiles.size(); I[4] = (int64_t)HAT.tiles.size();
         I[5] = (int64_t)HA.total_steps * 64; I[6] = (int64_t)HAT.total_steps * 64;
         I[7] = (int64_t)HA.splits.size(); I[8] = (int64_t)HAT.splits.size();
-        I[9] = lp->G; I[10] = lp->threads; I[11] = 0;
+        I[9] = lp->G; I[10] = lp->threads; I[11] = (int64_t)lp->dyn_smem;
         I[12] = 24 * nnz + 36 * (int64_t)m + 44 * (int64_t)n + 8 + (h_lb ? 16 * (int64_t)n : 0) + (h_ylo ? 16 * (int64_t)m : 0);
-        I[13] = HA.max_cta_steps; I[14] = HAT.max_cta_steps; I[15] = bpsm;
+        I[13] = lp->d.res_steps_A; I[14] = lp->d.res_steps_AT; I[15] = bpsm;
     } catch (const std::bad_alloc&) {
         rc = fail(MLLP_E_NOMEM, "mllp_lp_create: out of host memory");
     }
@@ -391,10 +427,31 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
             RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));
         }
     } else if (num_iters > 0) {
-        RC_OK(launch_pdhg_persistent(lp->d, lp->bounds, lp->G, lp->threads, tau, sigma, num_iters, s));
+        RC_OK(launch_pdhg_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, num_iters, s));
     }
     if (d_scalars) RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, (double)num_iters, s));
     RC_OK(store_solution(lp, d_x, d_y, s));
+    return 0;
+}
+
+// Dev tool (not in the public header): run `iters` parity iterations on the current internal
+// state with barrier tracing; h_out receives iters*G*4 timestamps (ns): per CTA
+// [A' phase done, barrier released, A phase done, barrier released].
+int mllp_debug_trace(mllp_lp_t lp, double tau, double sigma, int32_t iters, unsigned long long* h_out)
+{
+    if (!lp || !h_out || iters < 1) return fail(MLLP_E_INVALID, "mllp_debug_trace: bad argument");
+    DeviceGuard guard(lp->device);
+    unsigned long long* d_tr = nullptr;
+    const size_t cnt = (size_t)iters * lp->G * 4;
+    CUDA_OK(cudaMalloc(&d_tr, cnt * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(d_tr, 0, cnt * sizeof(unsigned long long)));
+    DevLP d = lp->d;
+    d.trace = d_tr;
+    int rc = launch_pdhg_persistent(d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, iters, 0);
+    if (rc == 0) rc = (int)cudaDeviceSynchronize();
+    if (rc == 0) rc = (int)cudaMemcpy(h_out, d_tr, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_tr);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "mllp_debug_trace");
     return 0;
 }
 
@@ -431,7 +488,7 @@ int mllp_pdhg_solve(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, c
     // scalars of the starting point (also what is returned when max_iters == 0)
     RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, 0.0, s));
     if (max_iters > 0)
-        RC_OK(launch_solve_persistent(lp->d, lp->bounds, lp->G, lp->threads, eta, w0, max_iters, check_every, tol,
+        RC_OK(launch_solve_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, eta, w0, max_iters, check_every, tol,
                                       d_scalars, s));
     RC_OK(store_solution(lp, d_x, d_y, s));
     return 0;

@@ -36,6 +36,25 @@ RowClass classify(int len, const BuildParams& bp)
     return rc;
 }
 
+// Raise max_steps (the split threshold and chunk length) until no CTA gets more than
+// SPLIT_SLOTS split chunks.  Deterministic in (row lengths, bp), so the row-order planner and
+// the emitter agree.
+BuildParams effective_params(int nrows, const int32_t* ptr, BuildParams bp)
+{
+    const int G = std::max(1, bp.num_ctas);
+    if (bp.pref_steps < 1) bp.pref_steps = 1;
+    if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
+    for (;; bp.max_steps *= 2) {
+        const int64_t cap = 64LL * bp.max_steps;
+        int64_t chunks = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const int64_t len = ptr[r + 1] - ptr[r];
+            if (len > cap) chunks += (len + cap - 1) / cap;
+        }
+        if ((chunks + G - 1) / G <= SPLIT_SLOTS || bp.max_steps >= 16384) return bp;
+    }
+}
+
 }  // namespace
 
 void csr_transpose(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
@@ -57,9 +76,10 @@ void csr_transpose(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
         }
 }
 
-void plan_row_order(int nrows, const int32_t* ptr, const BuildParams& bp,
+void plan_row_order(int nrows, const int32_t* ptr, const BuildParams& bp_in,
                     std::vector<int32_t>& order, std::vector<int32_t>& pos)
 {
+    const BuildParams bp = effective_params(nrows, ptr, bp_in);
     const int S = std::max(bp.pref_steps, bp.max_steps) + 1;
     const int nkeys = 1 + 6 * S;
     std::vector<int32_t> key((size_t)nrows);
@@ -81,46 +101,99 @@ void plan_row_order(int nrows, const int32_t* ptr, const BuildParams& bp,
     }
 }
 
+namespace {
+
+// Re-sort `order` inside every class: rows are compared by their sorted lists of mapped entry
+// ids (otherpos).  Split rows (class key 0) keep their place.
+void cluster_within_classes(int nrows, const int32_t* ptr, const int32_t* ind, const BuildParams& bp_in,
+                            const std::vector<int32_t>& otherpos, std::vector<int32_t>& order,
+                            std::vector<int32_t>& pos)
+{
+    const BuildParams bp = effective_params(nrows, ptr, bp_in);
+    // mapped, sorted entry lists (flat)
+    std::vector<int32_t> keys((size_t)ptr[nrows]);
+    for (int r = 0; r < nrows; ++r) {
+        for (int32_t k = ptr[r]; k < ptr[r + 1]; ++k) keys[k] = otherpos[ind[k]];
+        std::sort(keys.begin() + ptr[r], keys.begin() + ptr[r + 1]);
+    }
+    auto cls = [&](int r) {
+        const RowClass rc = classify(ptr[r + 1] - ptr[r], bp);
+        return rc.nchunks > 1 ? -1 : rc.logL * 65536 + rc.nsteps;
+    };
+    size_t a = 0;
+    while (a < (size_t)nrows) {
+        size_t b = a + 1;
+        const int ca = cls(order[a]);
+        while (b < (size_t)nrows && cls(order[b]) == ca) ++b;
+        if (ca >= 0)
+            std::stable_sort(order.begin() + a, order.begin() + b, [&](int32_t r1, int32_t r2) {
+                return std::lexicographical_compare(keys.begin() + ptr[r1], keys.begin() + ptr[r1 + 1],
+                                                    keys.begin() + ptr[r2], keys.begin() + ptr[r2 + 1]);
+            });
+        a = b;
+    }
+    for (int p = 0; p < nrows; ++p) pos[order[p]] = p;
+}
+
+}  // namespace
+
+void plan_orders(int m, int n, const int32_t* ptr, const int32_t* ind, const int32_t* tptr, const int32_t* tind,
+                 const BuildParams& bp, std::vector<int32_t>& orderY, std::vector<int32_t>& posY,
+                 std::vector<int32_t>& orderX, std::vector<int32_t>& posX)
+{
+    plan_row_order(m, ptr, bp, orderY, posY);
+    plan_row_order(n, tptr, bp, orderX, posX);
+    if (bp.cluster) {
+        cluster_within_classes(n, tptr, tind, bp, posY, orderX, posX);   // columns by the rows they touch
+        cluster_within_classes(m, ptr, ind, bp, posX, orderY, posY);     // rows by the columns they touch
+    }
+}
+
 void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
                     const double* val, const std::vector<int32_t>& order,
-                    const std::vector<int32_t>& colpos, const BuildParams& bp, HostMat& out)
+                    const std::vector<int32_t>& colpos, const BuildParams& bp_in, HostMat& out)
 {
+    const BuildParams bp = effective_params(nrows, ptr, bp_in);
     out = HostMat();
     out.nrows = nrows;
     out.ncols = ncols;
     out.nnz = ptr[nrows];
+    const int G = std::max(1, bp.num_ctas);
 
-    // ---- 1. cut the internal row order into tiles --------------------------------------
     struct ProtoTile {
         uint32_t row_base;  // internal row (first of the tile, or the split row)
         uint16_t nsteps;
         uint8_t logL, nrows;
         int32_t split;      // split table index or -1
-        uint32_t chunk;     // chunk index for split rows
-        uint32_t chunk_len; // entries per chunk (split rows)
+        uint32_t e0, e1;    // entry range of the row (split chunks)
     };
-    std::vector<ProtoTile> proto;
-    int p = 0;
-    while (p < nrows) {
+
+    // ---- 1a. split rows (they lead the internal order): one chunk sequence ---------------
+    int nsplit_rows = 0;
+    while (nsplit_rows < nrows) {
+        const int r = order[nsplit_rows];
+        if (classify(ptr[r + 1] - ptr[r], bp).nchunks <= 1) break;
+        ++nsplit_rows;
+    }
+    const int chunk_steps = bp.max_steps;  // effective_params() bounds the chunks per CTA
+    std::vector<ProtoTile> chunks;
+    for (int p = 0; p < nsplit_rows; ++p) {
         const int r = order[p];
         const int len = ptr[r + 1] - ptr[r];
-        const RowClass rc = classify(len, bp);
-        if (rc.nchunks > 1) {
-            SplitRow sr{(uint32_t)p, out.num_partials, (uint32_t)rc.nchunks, 0};
-            const uint32_t chunk_len = 64u * (uint32_t)rc.nsteps;
-            // the last chunks may be shorter (or even empty if rounding over-covers)
-            uint32_t used_chunks = (uint32_t)ceil_div(len, (int)chunk_len);
-            sr.nchunks = used_chunks;
-            for (uint32_t c = 0; c < used_chunks; ++c) {
-                const int clen = std::min<int>((int)chunk_len, len - (int)(c * chunk_len));
-                proto.push_back({(uint32_t)p, (uint16_t)ceil_div(clen, 64), 5, 1,
-                                 (int32_t)out.splits.size(), c, chunk_len});
-            }
-            out.num_partials += used_chunks;
-            out.splits.push_back(sr);
-            ++p;
-            continue;
+        const int k = ceil_div(len, 64 * chunk_steps);
+        const int clen = 64 * ceil_div(ceil_div(len, k), 64);  // balanced, whole warp-steps
+        for (int e0 = 0; e0 < len; e0 += clen) {
+            const int e1 = std::min(len, e0 + clen);
+            chunks.push_back({(uint32_t)p, (uint16_t)ceil_div(e1 - e0, 64), 5, 1, p, (uint32_t)e0, (uint32_t)e1});
         }
+        out.splits.push_back({(uint32_t)p, 0u, 0u, 0u});
+    }
+
+    // ---- 1b. regular rows: tiles of 32/L consecutive rows of one class -----------------------
+    std::vector<ProtoTile> regular;
+    for (int p = nsplit_rows; p < nrows;) {
+        const int r = order[p];
+        const RowClass rc = classify(ptr[r + 1] - ptr[r], bp);
         const int rows_per_tile = 32 >> rc.logL;
         int q = p + 1;
         while (q < nrows && q - p < rows_per_tile) {
@@ -129,73 +202,118 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
             if (rc2.nchunks != 1 || rc2.logL != rc.logL || rc2.nsteps != rc.nsteps) break;
             ++q;
         }
-        proto.push_back({(uint32_t)p, (uint16_t)rc.nsteps, (uint8_t)rc.logL, (uint8_t)(q - p),
-                         -1, 0, 0});
+        regular.push_back({(uint32_t)p, (uint16_t)rc.nsteps, (uint8_t)rc.logL, (uint8_t)(q - p), -1, 0, 0});
         p = q;
     }
 
-    // ---- 2. deal tiles to CTAs, heavy first, snake order --------------------------------
-    const int G = std::max(1, bp.num_ctas);
-    std::vector<uint32_t> by_cost(proto.size());
+    // ---- 2. deal to CTAs: chunks in contiguous runs, regular tiles to the least loaded CTA -----
+    std::vector<std::vector<ProtoTile>> per_cta((size_t)G);
+    std::vector<int64_t> load((size_t)G, 0);
+    // chunks go to CTAs in row order; a row that fits in one CTA's quota is never cut across CTAs
+    // (then the CTA finishes it alone), larger rows fill consecutive CTAs
+    const size_t C = chunks.size();
+    {
+        const size_t quota = C ? (C + (size_t)G - 1) / (size_t)G : 0;
+        size_t g = 0, used = 0;
+        for (size_t q = 0; q < C;) {
+            size_t q2 = q;
+            while (q2 < C && chunks[q2].split == chunks[q].split) ++q2;
+            const size_t k = q2 - q;
+            if (k <= quota && used + k > quota && g + 1 < (size_t)G) { ++g; used = 0; }
+            for (; q < q2; ++q) {
+                if (used >= quota && g + 1 < (size_t)G) { ++g; used = 0; }
+                per_cta[g].push_back(chunks[q]);
+                load[g] += chunks[q].nsteps + 2;
+                ++used;
+            }
+        }
+    }
+    out.cta_nsplit.assign((size_t)G, 0);
+    out.cta_lsplit_begin.assign((size_t)G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        out.cta_nsplit[g] = (uint32_t)per_cta[g].size();
+        out.cta_lsplit_begin[g] = (uint32_t)out.lsplits.size();
+        for (size_t k = 0; k < per_cta[g].size();) {
+            size_t k2 = k;
+            while (k2 < per_cta[g].size() && per_cta[g][k2].split == per_cta[g][k].split) ++k2;
+            SplitRow& sr = out.splits[per_cta[g][k].split];
+            out.lsplits.push_back({(uint32_t)per_cta[g][k].split, sr.nparts /* rank, fixed below */, (uint16_t)k,
+                                   (uint16_t)(k2 - k), 0u});
+            sr.nparts++;
+            k = k2;
+        }
+    }
+    out.cta_lsplit_begin[G] = (uint32_t)out.lsplits.size();
+    for (SplitRow& sr : out.splits) {
+        sr.first_slot = out.num_partials;
+        out.num_partials += sr.nparts;
+    }
+    for (LocalSplit& ls : out.lsplits) ls.gslot += out.splits[ls.split_id].first_slot;
+
+    std::vector<uint32_t> by_cost(regular.size());
     std::iota(by_cost.begin(), by_cost.end(), 0u);
-    std::stable_sort(by_cost.begin(), by_cost.end(), [&](uint32_t a, uint32_t b) {
-        const int sa = proto[a].split >= 0, sb = proto[b].split >= 0;
-        if (sa != sb) return sa > sb;  // split chunks first: their join is the critical path
-        return proto[a].nsteps > proto[b].nsteps;
-    });
-    std::vector<std::vector<uint32_t>> per_cta((size_t)G);
-    for (size_t i = 0; i < by_cost.size(); ++i) {
-        const size_t pass = i / (size_t)G, k = i % (size_t)G;
-        const size_t cta = (pass & 1) ? (size_t)G - 1 - k : k;
-        per_cta[cta].push_back(by_cost[i]);
+    std::stable_sort(by_cost.begin(), by_cost.end(),
+                     [&](uint32_t a, uint32_t b) { return regular[a].nsteps > regular[b].nsteps; });
+    {
+        // min-heap of (load, cta)
+        std::vector<std::pair<int64_t, int>> heap;
+        for (int g = 0; g < G; ++g) heap.emplace_back(load[g], g);
+        auto cmp = [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a > b; };
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        for (uint32_t ti : by_cost) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            auto& top = heap.back();
+            per_cta[top.second].push_back(regular[ti]);
+            top.first += regular[ti].nsteps + 2;
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
     }
 
     // ---- 3. emit CTA-major storage ---------------------------------------------------------
     uint64_t total_steps = 0;
-    for (const ProtoTile& t : proto) total_steps += t.nsteps;
+    size_t total_tiles = 0;
+    for (int g = 0; g < G; ++g) {
+        total_tiles += per_cta[g].size();
+        for (const ProtoTile& t : per_cta[g]) total_steps += t.nsteps;
+    }
     out.total_steps = total_steps;
     out.vals.assign((size_t)total_steps * 64, 0.0);
     out.idx.assign((size_t)total_steps * 64, 0);
-    out.tiles.reserve(proto.size());
+    out.tiles.reserve(total_tiles);
     out.cta_begin.assign((size_t)G + 1, 0);
     out.cta_step_begin.assign((size_t)G + 1, 0);
 
     std::vector<std::pair<int32_t, double>> row_buf;
-    std::vector<std::vector<std::pair<int32_t, double>>> split_rows(out.splits.size());
+    int cached_split = -1;  // chunks of one row are emitted back to back: sort it once
     uint64_t step_cursor = 0;
     for (int g = 0; g < G; ++g) {
         out.cta_begin[g] = (uint32_t)out.tiles.size();
         out.cta_step_begin[g] = (uint32_t)step_cursor;
-        for (uint32_t ti : per_cta[g]) {
-            const ProtoTile& t = proto[ti];
+        for (size_t k = 0; k < per_cta[g].size(); ++k) {
+            const ProtoTile& t = per_cta[g][k];
             const int L = 1 << t.logL;
             Tile tile;
             tile.off = (uint32_t)step_cursor;
-            tile.row_base = t.split >= 0 ? t.chunk : t.row_base;
+            tile.row_base = t.row_base;
             tile.nsteps = t.nsteps;
             tile.logL = t.logL;
             tile.nrows = t.nrows;
-            tile.split = t.split;
+            tile.split = t.split >= 0 ? (int32_t)k : -1;  // split chunks lead the list: slot = position
             out.tiles.push_back(tile);
             for (int rr = 0; rr < t.nrows; ++rr) {
                 const int r = order[t.row_base + rr];
                 const int len = ptr[r + 1] - ptr[r];
-                if (t.split >= 0 && !split_rows[t.split].empty()) {
-                    row_buf = split_rows[t.split];  // sorted once per split row
-                } else {
+                if (t.split < 0 || t.split != cached_split) {
                     row_buf.clear();
-                    for (int32_t k = ptr[r]; k < ptr[r + 1]; ++k)
-                        row_buf.emplace_back(colpos[ind[k]], val[k]);
+                    for (int32_t q = ptr[r]; q < ptr[r + 1]; ++q) row_buf.emplace_back(colpos[ind[q]], val[q]);
                     std::sort(row_buf.begin(), row_buf.end(),
-                              [](const std::pair<int32_t, double>& a,
-                                 const std::pair<int32_t, double>& b) { return a.first < b.first; });
-                    if (t.split >= 0) split_rows[t.split] = row_buf;
+                              [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) {
+                                  return a.first < b.first;
+                              });
+                    cached_split = t.split;
                 }
-                int e0 = 0, e1 = len;
-                if (t.split >= 0) {
-                    e0 = (int)(t.chunk * t.chunk_len);
-                    e1 = std::min(len, e0 + (int)t.chunk_len);
-                }
+                const int e0 = t.split >= 0 ? (int)t.e0 : 0;
+                const int e1 = t.split >= 0 ? (int)t.e1 : len;
                 const int32_t pad_idx = len > 0 ? row_buf[e0 < len ? e0 : 0].first : 0;
                 const int slots = t.nsteps * 2 * L;
                 for (int e = 0; e < slots; ++e) {
@@ -243,8 +361,7 @@ extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const in
     std::vector<double> tval;
     csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);
     std::vector<int32_t> orderY, posY, orderX, posX;
-    plan_row_order(m, indptr, bp, orderY, posY);
-    plan_row_order(n, tptr.data(), bp, orderX, posX);
+    plan_orders(m, n, indptr, indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
     HostMat H[2];
     build_host_mat(m, n, indptr, indices, values, orderY, posX, bp, H[0]);
     build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, H[1]);
@@ -262,47 +379,62 @@ extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const in
         std::vector<double> v_user((size_t)nc), v_int((size_t)nc), out_int((size_t)nr, NAN), partial(M.num_partials, 0.0);
         for (int j = 0; j < nc; ++j) v_user[j] = 0.25 + (double)((j * 2654435761u) % 1000u) / 997.0;
         for (int k = 0; k < nc; ++k) v_int[k] = v_user[colorder[k]];
-        std::vector<uint32_t> arrived(M.splits.size(), 0);
         if (M.cta_begin.size() != (size_t)bp.num_ctas + 1 || M.cta_begin.back() != M.tiles.size()) return 2;
-        for (const Tile& t : M.tiles) {
-            const int L = 1 << t.logL;
-            double lane_sum[32];
-            for (int lane = 0; lane < 32; ++lane) {
-                double s = 0.0;
-                for (int st = 0; st < t.nsteps; ++st) {
-                    const size_t at = ((size_t)(t.off + st) * 32 + lane) * 2;
-                    if (M.idx[at] < 0 || M.idx[at] >= nc || M.idx[at + 1] < 0 || M.idx[at + 1] >= nc) return 3;
-                    s = std::fma(M.vals[at], v_int[M.idx[at]], s);
-                    s = std::fma(M.vals[at + 1], v_int[M.idx[at + 1]], s);
-                }
-                lane_sum[lane] = s;
-            }
+        auto butterfly = [](double* ls, int L) {
             for (int o = L >> 1; o > 0; o >>= 1) {
                 double nxt[32];
-                for (int lane = 0; lane < 32; ++lane) nxt[lane] = lane_sum[lane] + lane_sum[lane ^ o];
-                for (int lane = 0; lane < 32; ++lane) lane_sum[lane] = nxt[lane];
+                for (int lane = 0; lane < 32; ++lane) nxt[lane] = ls[lane] + ls[lane ^ o];
+                for (int lane = 0; lane < 32; ++lane) ls[lane] = nxt[lane];
             }
-            if (t.split < 0) {
-                if (t.nrows < 1 || t.nrows > (32 >> t.logL)) return 4;
-                for (int rr = 0; rr < t.nrows; ++rr) {
-                    const uint32_t r = t.row_base + rr;
-                    if (r >= (uint32_t)nr || !std::isnan(out_int[r])) return 5;  // each row exactly once
-                    out_int[r] = lane_sum[rr * L];
-                }
-            } else {
-                const SplitRow& sr = M.splits[t.split];
-                if (t.row_base >= sr.nchunks) return 6;
-                partial[sr.first_slot + t.row_base] = lane_sum[0];
-                if (++arrived[t.split] == sr.nchunks) {
-                    double ls[32] = {0};
-                    for (uint32_t k = 0; k < sr.nchunks; ++k) ls[k % 32] += partial[sr.first_slot + k];
-                    for (int o = 16; o > 0; o >>= 1) {
-                        double nxt[32];
-                        for (int lane = 0; lane < 32; ++lane) nxt[lane] = ls[lane] + ls[lane ^ o];
-                        for (int lane = 0; lane < 32; ++lane) ls[lane] = nxt[lane];
+        };
+        std::vector<uint32_t> arrived(M.splits.size(), 0);
+        for (int g = 0; g < bp.num_ctas; ++g) {
+            double spart[SPLIT_SLOTS];
+            if (M.cta_nsplit[g] > (uint32_t)SPLIT_SLOTS) return 10;
+            for (uint32_t ti = M.cta_begin[g]; ti < M.cta_begin[g + 1]; ++ti) {
+                const Tile& t = M.tiles[ti];
+                const uint32_t local = ti - M.cta_begin[g];
+                if ((t.split >= 0) != (local < M.cta_nsplit[g])) return 11;  // split chunks lead the list
+                const int L = 1 << t.logL;
+                double lane_sum[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    double s = 0.0;
+                    for (int st = 0; st < t.nsteps; ++st) {
+                        const size_t at = ((size_t)(t.off + st) * 32 + lane) * 2;
+                        if (M.idx[at] < 0 || M.idx[at] >= nc || M.idx[at + 1] < 0 || M.idx[at + 1] >= nc) return 3;
+                        s = std::fma(M.vals[at], v_int[M.idx[at]], s);
+                        s = std::fma(M.vals[at + 1], v_int[M.idx[at + 1]], s);
                     }
+                    lane_sum[lane] = s;
+                }
+                butterfly(lane_sum, L);
+                if (t.split < 0) {
+                    if (t.nrows < 1 || t.nrows > (32 >> t.logL)) return 4;
+                    for (int rr = 0; rr < t.nrows; ++rr) {
+                        const uint32_t r = t.row_base + rr;
+                        if (r >= (uint32_t)nr || !std::isnan(out_int[r])) return 5;  // each row exactly once
+                        out_int[r] = lane_sum[rr * L];
+                    }
+                } else {
+                    if ((uint32_t)t.split != local) return 6;
+                    spart[t.split] = lane_sum[0];
+                }
+            }
+            // publish: one partial per (CTA, split row), slots summed in order
+            for (uint32_t li = M.cta_lsplit_begin[g]; li < M.cta_lsplit_begin[g + 1]; ++li) {
+                const LocalSplit& ls = M.lsplits[li];
+                const SplitRow& sr = M.splits[ls.split_id];
+                if (ls.gslot < sr.first_slot || ls.gslot >= sr.first_slot + sr.nparts) return 12;
+                double pl[32] = {0};
+                for (int k = 0; k < ls.count; ++k) pl[k % 32] += spart[ls.first + k];
+                butterfly(pl, 32);
+                partial[ls.gslot] = pl[0];
+                if (++arrived[ls.split_id] == sr.nparts) {
+                    double ls32[32] = {0};   // per lane: k = k0 + 32u + lane, u ascending, k0 in steps of 256
+                    for (uint32_t k = 0; k < sr.nparts; ++k) ls32[k % 32] += partial[sr.first_slot + k];
+                    butterfly(ls32, 32);
                     if (sr.row >= (uint32_t)nr || !std::isnan(out_int[sr.row])) return 7;
-                    out_int[sr.row] = ls[0];
+                    out_int[sr.row] = ls32[0];
                 }
             }
         }
@@ -328,4 +460,54 @@ extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const in
     out8[6] = (double)H[0].max_cta_steps;
     out8[7] = (double)H[1].max_cta_steps;
     return rows_seen == (int64_t)m + n ? 0 : 9;
+}
+
+// Host-only statistic of the built format: how many distinct 128 B lines the warp-wide gather
+// instructions touch (the L1 tag stage serves about one line per cycle per SM, so this is the
+// gather cost model).  out6: [0]/[1] total lines for A / A', [2]/[3] the largest per-CTA sum,
+// [4]/[5] total gather instructions (2 per warp-step).
+extern "C" int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr,
+                                        const int32_t* indices, const double* values, int32_t num_ctas,
+                                        int32_t pref_steps, int32_t max_steps, int32_t cluster, double* out6)
+{
+    using namespace mllp;
+    if (m < 0 || n < 0 || !indptr || !out6 || (int64_t)indptr[m] != nnz) return 1001;
+    BuildParams bp;
+    bp.num_ctas = num_ctas;
+    bp.pref_steps = pref_steps;
+    bp.max_steps = max_steps < pref_steps ? pref_steps : max_steps;
+    bp.cluster = cluster != 0;
+    std::vector<int32_t> tptr, tind;
+    std::vector<double> tval;
+    csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);
+    std::vector<int32_t> orderY, posY, orderX, posX;
+    plan_orders(m, n, indptr, indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
+    HostMat H[2];
+    build_host_mat(m, n, indptr, indices, values, orderY, posX, bp, H[0]);
+    build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, H[1]);
+    for (int w = 0; w < 2; ++w) {
+        const HostMat& M = H[w];
+        double total = 0, worst = 0;
+        for (int g = 0; g < bp.num_ctas; ++g) {
+            double here = 0;
+            for (uint32_t st = M.cta_step_begin[g]; st < M.cta_step_begin[g + 1]; ++st)
+                for (int half = 0; half < 2; ++half) {
+                    int32_t lines[32];
+                    int cnt = 0;
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int32_t ln = M.idx[((size_t)st * 32 + lane) * 2 + half] >> 4;
+                        bool seen = false;
+                        for (int q = 0; q < cnt; ++q) seen |= (lines[q] == ln);
+                        if (!seen) lines[cnt++] = ln;
+                    }
+                    here += cnt;
+                }
+            total += here;
+            worst = std::max(worst, here);
+        }
+        out6[w] = total;
+        out6[2 + w] = worst;
+        out6[4 + w] = 2.0 * (double)M.total_steps;
+    }
+    return 0;
 }

@@ -8,8 +8,10 @@
 // (32 x double2, 128-bit loads) and a 256 B run of indices (32 x int2); within a step the
 // entries are arranged so that ONE gather instruction covers L consecutive entries of a row
 // (entry e of a step sits in lane e % L, half e / L).  Rows longer than 64*max_steps entries
-// are split into chunks (one tile each, L = 32) whose partial dot products meet in a
-// scratch array; the last chunk to arrive sums them in a fixed order, so results are
+// are split into chunks (one tile each, L = 32).  The chunks of all split rows form one
+// sequence that is dealt to the CTAs in contiguous runs; a CTA first adds up its own chunks of
+// a row in shared memory (fixed order), publishes ONE partial per (CTA, row) to a scratch
+// array, and the last CTA to arrive sums the row's partials in a fixed order.  Results are
 // deterministic and no fp64 atomics are used.
 //
 // Tiles are dealt to the CTAs of the persistent grid at build time (cost-balanced) and the
@@ -27,21 +29,32 @@ struct Tile {            // 16 bytes, loaded as one int4
     uint16_t nsteps;     // steps of 2 entries per lane
     uint8_t logL;        // log2(lanes per row)
     uint8_t nrows;       // valid rows in this tile (1 .. 32 >> logL)
-    int32_t split;       // -1, or index into the split-row table
+    int32_t split;       // -1, or (chunk of a split row) the CTA-local partial slot it fills
 };
 static_assert(sizeof(Tile) == 16, "Tile must be 16 bytes");
 
 struct SplitRow {        // 16 bytes
     uint32_t row;        // internal row id
-    uint32_t first_slot; // first partial slot of this row
-    uint32_t nchunks;
+    uint32_t first_slot; // first global partial slot of this row
+    uint32_t nparts;     // number of CTAs that contribute a partial
     uint32_t pad;
 };
+
+struct LocalSplit {      // 16 bytes: one split row as seen by one CTA
+    uint32_t split_id;   // index into the split-row table
+    uint32_t gslot;      // global partial slot this CTA publishes to
+    uint16_t first;      // first CTA-local slot
+    uint16_t count;      // number of CTA-local slots (chunks of this row in this CTA)
+    uint32_t pad;
+};
+
+constexpr int SPLIT_SLOTS = 256;  // max split chunks per CTA (shared-memory partial slots)
 
 struct BuildParams {
     int num_ctas = 148;      // CTAs of the persistent grid
     int pref_steps = 4;      // choose L so a row needs at most this many steps
     int max_steps = 4;       // rows longer than 64*max_steps entries are split
+    bool cluster = true;     // cluster rows inside a length class by the entries they touch
 };
 
 // Host-side image of one matrix in the tiled format.
@@ -54,6 +67,9 @@ struct HostMat {
     std::vector<uint32_t> cta_begin;   // num_ctas + 1 (tile index)
     std::vector<uint32_t> cta_step_begin; // num_ctas + 1 (warp-step index)
     std::vector<SplitRow> splits;
+    std::vector<LocalSplit> lsplits;       // CTA-major
+    std::vector<uint32_t> cta_lsplit_begin;// num_ctas + 1
+    std::vector<uint32_t> cta_nsplit;      // num_ctas: leading split-chunk tiles of each CTA
     uint32_t num_partials = 0;
     uint64_t total_steps = 0;
     int max_cta_steps = 0;             // largest per-CTA warp-step count
@@ -64,6 +80,14 @@ struct HostMat {
 // order[k] = original row at internal position k; pos[r] = internal position of row r.
 void plan_row_order(int nrows, const int32_t* ptr, const BuildParams& bp,
                     std::vector<int32_t>& order, std::vector<int32_t>& pos);
+
+// Both orderings of an LP: rows of A (= y order) and rows of A' (= x order).  Inside a length
+// class the rows are clustered lexicographically by the (internal) ids of the entries they
+// touch, so that neighbouring rows gather from neighbouring addresses: one warp-wide gather
+// then touches few 128 B lines (the L1 tag stage serves about one line per cycle per SM).
+void plan_orders(int m, int n, const int32_t* ptr, const int32_t* ind, const int32_t* tptr, const int32_t* tind,
+                 const BuildParams& bp, std::vector<int32_t>& orderY, std::vector<int32_t>& posY,
+                 std::vector<int32_t>& orderX, std::vector<int32_t>& posX);
 
 // Emit the tiled image of a CSR matrix whose rows follow `order`/`pos` and whose column
 // ids are renamed through `colpos` (the other matrix's pos[]).

@@ -16,9 +16,10 @@ int launch_spmv(const DevMat& M, const double* in, double* out, int G, int threa
 int launch_primal(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
 int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
 int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s);
-int persistent_max_blocks_per_sm(int threads, bool bounds);
-int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, double tau, double sigma, int iters,
-                           cudaStream_t s);
-int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, double eta, double w0, int max_iters,
-                            int check_every, double tol, double* out, cudaStream_t s);
+int persistent_set_smem(bool bounds, size_t dyn_smem);
+int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem);
+int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double tau, double sigma,
+                           int iters, cudaStream_t s);
+int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
+                            int max_iters, int check_every, double tol, double* out, cudaStream_t s);
 }  // namespace mllp

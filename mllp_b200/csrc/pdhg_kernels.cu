@@ -53,33 +53,36 @@ __global__ void __launch_bounds__(1024, 1) k_spmv(DevMat M, const double* in, do
 {
     SpmvOp op{in, out};
     double acc[NRED];
-    run_phase(M, op, acc, M.vals, M.idx, 0u);
+    run_phase(M, global_view(M), op, acc);
 }
 
 template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1) k_primal(DevLP lp)
 {
     PrimalOp<BOUNDS> op{lp, __ldcg(lp.ctrl + CTRL_TAU)};
+    const MatView VAT = global_view(lp.AT);
     double acc[NRED];
-    run_phase(lp.AT, op, acc, lp.AT.vals, lp.AT.idx, 0u);
+    run_phase(lp.AT, VAT, op, acc);
 }
 template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1) k_dual(DevLP lp)
 {
     DualOp<BOUNDS> op{lp, __ldcg(lp.ctrl + CTRL_SIGMA)};
+    const MatView VA = global_view(lp.A);
     double acc[NRED];
-    run_phase(lp.A, op, acc, lp.A.vals, lp.A.idx, 0u);
+    run_phase(lp.A, VA, op, acc);
 }
 
 template <bool BOUNDS>
-__device__ __forceinline__ void eval_phases(const DevLP& lp, double* red_p, double* red_d, double* smem)
+__device__ __forceinline__ void eval_phases(const DevLP& lp, const MatView& VA, const MatView& VAT, double* red_p,
+                                            double* red_d, double* smem)
 {
     {
         EvalPrimalOp<BOUNDS> op{lp};
         double acc[NRED];
 #pragma unroll
         for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-        run_phase(lp.AT, op, acc, lp.AT.vals, lp.AT.idx, 0u);
+        run_phase(lp.AT, VAT, op, acc);
         cta_reduce_store<6>(acc, red_p + (size_t)blockIdx.x * NRED, smem);
     }
     {
@@ -87,7 +90,7 @@ __device__ __forceinline__ void eval_phases(const DevLP& lp, double* red_p, doub
         double acc[NRED];
 #pragma unroll
         for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-        run_phase(lp.A, op, acc, lp.A.vals, lp.A.idx, 0u);
+        run_phase(lp.A, VA, op, acc);
         cta_reduce_store<5>(acc, red_d + (size_t)blockIdx.x * NRED, smem);
     }
 }
@@ -96,7 +99,8 @@ template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1) k_eval(DevLP lp, int G)
 {
     __shared__ double smem[32 * NRED];
-    eval_phases<BOUNDS>(lp, lp.red + (size_t)RED_EVALP * G * NRED, lp.red + (size_t)RED_EVALD * G * NRED, smem);
+    eval_phases<BOUNDS>(lp, global_view(lp.A), global_view(lp.AT), lp.red + (size_t)RED_EVALP * G * NRED,
+                        lp.red + (size_t)RED_EVALD * G * NRED, smem);
 }
 
 // Turn the summed eval partials into the public scalars (calling warp, all lanes).
@@ -134,18 +138,47 @@ __global__ void k_eval_finalize(DevLP lp, int G, double* out, double iters)
 // ---------------------------------------------------------------------------------------
 // persistent cooperative kernel, parity mode: `iters` full iterations in one launch,
 // two grid barriers per iteration, no host involvement.
+// Shared-memory layout of the persistent kernels (dynamic part):
+//   [ A: tile descriptors, resident vals, resident idx | A': same ]
+struct PersistentSmem {
+    MatView VA, VAT;
+};
+__device__ __forceinline__ void persistent_setup(const DevLP& lp, unsigned char* dsm, PersistentSmem& P)
+{
+    unsigned char* base = dsm;
+    const uint32_t used = resident_view(lp.A, lp.res_steps_A, base, P.VA);
+    resident_view(lp.AT, lp.res_steps_AT, base + used, P.VAT);
+    __syncthreads();
+}
+
+// A' phase (gathers y) and A phase (gathers xbar).
+template <class Op>
+__device__ __forceinline__ void phase_AT(const DevLP& lp, const PersistentSmem& P, const Op& op, double* acc)
+{
+    run_phase(lp.AT, P.VAT, op, acc);
+}
+template <class Op>
+__device__ __forceinline__ void phase_A(const DevLP& lp, const PersistentSmem& P, const Op& op, double* acc)
+{
+    run_phase(lp.A, P.VA, op, acc);
+}
+
 template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double tau, double sigma, int iters)
 {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    PersistentSmem P;
+    persistent_setup(lp, dsm, P);
     unsigned target = 0;
     PrimalOp<BOUNDS> pop{lp, tau};
     DualOp<BOUNDS> dop{lp, sigma};
     double acc[NRED];
     for (int it = 0; it < iters; ++it) {
-        run_phase(lp.AT, pop, acc, lp.AT.vals, lp.AT.idx, 0u);
-        grid_barrier(lp.barrier, target);
-        run_phase(lp.A, dop, acc, lp.A.vals, lp.A.idx, 0u);
-        grid_barrier(lp.barrier, target);
+        unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 4 : nullptr;
+        phase_AT(lp, P, pop, acc);
+        grid_barrier(lp.barrier, target, tr);
+        phase_A(lp, P, dop, acc);
+        grid_barrier(lp.barrier, target, tr ? tr + 2 : nullptr);
     }
 }
 
@@ -158,6 +191,11 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
 {
     __shared__ double smem[32 * NRED];
     __shared__ double bc[16];
+    extern __shared__ __align__(16) unsigned char dsm[];
+    PersistentSmem P;
+    persistent_setup(lp, dsm, P);
+    const MatView& VA = P.VA;
+    const MatView& VAT = P.VAT;
     unsigned target = 0;
     const size_t RS = (size_t)G * NRED;  // one reduction buffer
     // x0 = x, y0 = y
@@ -181,7 +219,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
             PrimalHalpernOp<BOUNDS> op{lp, tau, lam};
             double acc[NRED];
             acc[0] = 0.0;
-            run_phase(lp.AT, op, acc, lp.AT.vals, lp.AT.idx, 0u);
+            phase_AT(lp, P, op, acc);
             if (need_fpe) cta_reduce_store<1>(acc, redp + (size_t)blockIdx.x * NRED, smem);
         }
         grid_barrier(lp.barrier, target);
@@ -189,13 +227,13 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
             DualHalpernOp<BOUNDS> op{lp, sigma, lam};
             double acc[NRED];
             acc[0] = 0.0;
-            run_phase(lp.A, op, acc, lp.A.vals, lp.A.idx, 0u);
+            phase_A(lp, P, op, acc);
             if (need_fpe) cta_reduce_store<1>(acc, redd + (size_t)blockIdx.x * NRED, smem);
         }
         if (check) {
             // KKT at the new iterate needs the complete x and y
             grid_barrier(lp.barrier, target);
-            eval_phases<BOUNDS>(lp, lp.red + (size_t)((it & 1) * 4 + RED_EVALP) * RS,
+            eval_phases<BOUNDS>(lp, VA, VAT, lp.red + (size_t)((it & 1) * 4 + RED_EVALP) * RS,
                                 lp.red + (size_t)((it & 1) * 4 + RED_EVALD) * RS, smem);
         }
         grid_barrier(lp.barrier, target);
@@ -314,38 +352,50 @@ int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, d
     return (int)cudaGetLastError();
 }
 
-int persistent_max_blocks_per_sm(int threads, bool bounds)
+static const void* persistent_fn(bool solve, bool bounds)
 {
-    int nb = 0;
-    cudaError_t e = bounds ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pdhg_persistent<true>, threads, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pdhg_persistent<false>, threads, 0);
-    if (e != cudaSuccess) return -(int)e;
-    int nb2 = 0;
-    e = bounds ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_solve_persistent<true>, threads, 0)
-               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_solve_persistent<false>, threads, 0);
-    if (e != cudaSuccess) return -(int)e;
-    return nb < nb2 ? nb : nb2;
+    if (solve) return bounds ? (const void*)k_solve_persistent<true> : (const void*)k_solve_persistent<false>;
+    return bounds ? (const void*)k_pdhg_persistent<true> : (const void*)k_pdhg_persistent<false>;
 }
 
-int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, double tau, double sigma, int iters,
-                           cudaStream_t s)
+int persistent_set_smem(bool bounds, size_t dyn_smem)
+{
+    for (int solve = 0; solve < 2; ++solve) {
+        cudaError_t e = cudaFuncSetAttribute(persistent_fn(solve, bounds), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem)
+{
+    int best = 1 << 30;
+    for (int solve = 0; solve < 2; ++solve) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, persistent_fn(solve, bounds), threads, dyn_smem);
+        if (e != cudaSuccess) return -(int)e;
+        if (nb < best) best = nb;
+    }
+    return best;
+}
+
+int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double tau, double sigma,
+                           int iters, cudaStream_t s)
 {
     CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
     DevLP lpv = lp;
     void* args[] = {&lpv, &tau, &sigma, &iters};
-    const void* fn = bounds ? (const void*)k_pdhg_persistent<true> : (const void*)k_pdhg_persistent<false>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, 0, s));
+    CK(cudaLaunchCooperativeKernel(persistent_fn(false, bounds), dim3(G), dim3(threads), args, dyn_smem, s));
     return 0;
 }
 
-int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, double eta, double w0, int max_iters,
-                            int check_every, double tol, double* out, cudaStream_t s)
+int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
+                            int max_iters, int check_every, double tol, double* out, cudaStream_t s)
 {
     CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
     DevLP lpv = lp;
     void* args[] = {&lpv, &G, &eta, &w0, &max_iters, &check_every, &tol, &out};
-    const void* fn = bounds ? (const void*)k_solve_persistent<true> : (const void*)k_solve_persistent<false>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, 0, s));
+    CK(cudaLaunchCooperativeKernel(persistent_fn(true, bounds), dim3(G), dim3(threads), args, dyn_smem, s));
     return 0;
 }
 

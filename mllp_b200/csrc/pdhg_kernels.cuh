@@ -29,8 +29,11 @@ struct DevMat {
     const uint32_t* cta_begin;     // [G+1]
     const uint32_t* cta_step_begin;// [G+1]
     const SplitRow* splits;
-    double* partials;
-    unsigned* counters;
+    const LocalSplit* lsplits;     // CTA-major
+    const uint32_t* cta_lsplit_begin; // [G+1]
+    const uint32_t* cta_nsplit;    // [G] leading split-chunk tiles of each CTA
+    double* partials;              // one slot per (CTA, split row)
+    unsigned* counters;            // one per split row
     int nrows, ncols;
 };
 
@@ -51,7 +54,10 @@ struct DevLP {
     double* y0;
     double* red;        // [2 parity][4 kinds][G][NRED] per-CTA partial sums (RED_* below)
     unsigned* barrier;  // grid barrier counter
-    double* ctrl;       // solve-mode control block (device): see SolveCtrl
+    uint32_t res_steps_A;   // per-CTA cap of shared-memory resident warp-steps of A / A'
+    uint32_t res_steps_AT;
+    double* ctrl;       // control block (device doubles): CTRL_* slots
+    unsigned long long* trace;  // dev tool: [iter][cta][4] barrier timestamps, or null
 };
 
 __device__ __forceinline__ double ld_mut(const double* p) { return __ldcg(p); }   // L2-coherent
@@ -60,16 +66,27 @@ __device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }   
 // ---------------------------------------------------------------------------------------
 // Grid barrier for the persistent cooperative kernel: monotonic counter, one arrival per
 // CTA (release), acquire-poll.  `target` lives in thread 0's register.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target)
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// `trace` (dev tool, may be null): thread 0 stores the time at which the whole CTA had arrived
+// and the time at which the barrier released it.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned long long* trace = nullptr)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (trace) trace[0] = global_ns();
         target += gridDim.x;
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         } while ((int)(v - target) < 0);
+        if (trace) trace[1] = global_ns();
     }
     __syncthreads();
 }
@@ -232,97 +249,222 @@ struct SpmvOp {
 };
 
 // ---------------------------------------------------------------------------------------
-// The tile walker.  Every warp of the CTA takes tiles warp, warp+nwarps, ... of the CTA's
-// range.  `vals`/`idx` may point to global memory or to the CTA's shared-memory copy; in
-// both cases they are indexed by (step - step_base).
-template <class Op>
-__device__ __forceinline__ void run_phase(const DevMat& M, const Op& op, double* acc,
-                                          const double2* __restrict__ vals,
-                                          const int2* __restrict__ idx, uint32_t step_base)
+// Per-CTA view of a matrix.  The CTA's tile descriptors and a prefix of its tiles' data can
+// live in shared memory for the whole persistent kernel (the matrix never changes), the rest
+// is streamed from global memory / L2.
+struct MatView {
+    const Tile* desc;        // this CTA's tiles, index 0 .. ntiles-1 (shared or global memory)
+    const double2* rvals;    // resident copy of the first res_steps warp-steps (shared), or null
+    const int2* ridx;
+    const double2* gvals;    // global arrays, indexed by absolute warp-step
+    const int2* gidx;
+    uint32_t ntiles, res_steps, step0;   // step0 = first absolute warp-step of this CTA
+    uint32_t nsplit;         // leading split-chunk tiles
+    uint32_t ls0, nls;       // this CTA's LocalSplit range
+};
+
+__device__ __forceinline__ void view_common(const DevMat& M, MatView& V)
 {
+    V.nsplit = __ldg(M.cta_nsplit + blockIdx.x);
+    V.ls0 = __ldg(M.cta_lsplit_begin + blockIdx.x);
+    V.nls = __ldg(M.cta_lsplit_begin + blockIdx.x + 1) - V.ls0;
+}
+
+__device__ __forceinline__ MatView global_view(const DevMat& M)
+{
+    const uint32_t t0 = __ldg(M.cta_begin + blockIdx.x), t1 = __ldg(M.cta_begin + blockIdx.x + 1);
+    MatView V;
+    V.desc = M.tiles + t0;
+    V.rvals = nullptr; V.ridx = nullptr;
+    V.gvals = M.vals; V.gidx = M.idx;
+    V.ntiles = t1 - t0; V.res_steps = 0;
+    V.step0 = __ldg(M.cta_step_begin + blockIdx.x);
+    view_common(M, V);
+    return V;
+}
+
+// Copy this CTA's descriptors and its first `res_steps` warp-steps into shared memory.
+// Layout at `base` (16 B aligned): desc[ntiles] | vals[res_steps*32] (double2) | idx[res_steps*32] (int2).
+// Returns the number of bytes used (multiple of 16).
+__device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_steps_cap, unsigned char* base,
+                                                  MatView& V)
+{
+    const uint32_t t0 = __ldg(M.cta_begin + blockIdx.x), t1 = __ldg(M.cta_begin + blockIdx.x + 1);
+    const uint32_t s0 = __ldg(M.cta_step_begin + blockIdx.x), s1 = __ldg(M.cta_step_begin + blockIdx.x + 1);
+    const uint32_t nt = t1 - t0;
+    const uint32_t rs = min(res_steps_cap, s1 - s0);
+    int4* d_desc = reinterpret_cast<int4*>(base);
+    int4* d_vals = d_desc + nt;
+    int4* d_idx = d_vals + (size_t)rs * 32;
+    const int4* g_desc = reinterpret_cast<const int4*>(M.tiles + t0);
+    const int4* g_vals = reinterpret_cast<const int4*>(M.vals + (size_t)s0 * 32);
+    const int4* g_idx = reinterpret_cast<const int4*>(M.idx + (size_t)s0 * 32);
+    for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) d_desc[k] = __ldg(g_desc + k);
+    for (uint32_t k = threadIdx.x; k < rs * 32; k += blockDim.x) d_vals[k] = __ldg(g_vals + k);
+    for (uint32_t k = threadIdx.x; k < rs * 16; k += blockDim.x) d_idx[k] = __ldg(g_idx + k);
+    V.desc = reinterpret_cast<const Tile*>(d_desc);
+    V.rvals = reinterpret_cast<const double2*>(d_vals);
+    V.ridx = reinterpret_cast<const int2*>(d_idx);
+    V.gvals = M.vals; V.gidx = M.idx;
+    V.ntiles = nt; V.res_steps = rs; V.step0 = s0;
+    view_common(M, V);
+    return nt * 16u + rs * 768u;
+}
+
+// ---------------------------------------------------------------------------------------
+// The tile walker.
+//
+// One tile: steps are consumed in groups of 4 (8 gathers per lane in flight) with the next
+// group's gathers issued before the current group is folded in.
+__device__ __forceinline__ double tile_dot(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps,
+                                           int lane)
+{
+    // whole tiles are resident or not (the resident region is a prefix of the CTA's steps)
+    const uint32_t loc = off - V.step0;
+    const bool res = loc + (uint32_t)nsteps <= V.res_steps;
+    const double2* vp = res ? V.rvals + (size_t)loc * 32 + lane : V.gvals + (size_t)off * 32 + lane;
+    const int2* ip = res ? V.ridx + (size_t)loc * 32 + lane : V.gidx + (size_t)off * 32 + lane;
+    // L1-cached gather: the grid barrier's acquire invalidated this SM's L1, and the gathered
+    // vector is not written during the phase, so lines fetched now stay valid until the next barrier
+    auto gather = [&](int j) -> double { return __ldca(vec + j); };
+
+    double dot = 0.0;
+    double g[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (u < nsteps) {
+            const int2 j = ip[u * 32];
+            g[2 * u] = gather(j.x);
+            g[2 * u + 1] = gather(j.y);
+        } else {
+            g[2 * u] = 0.0;
+            g[2 * u + 1] = 0.0;
+        }
+    }
+    for (int s0 = 0; s0 < nsteps; s0 += 4) {
+        double gn[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (s0 + 4 + u < nsteps) {
+                const int2 j = ip[(s0 + 4 + u) * 32];
+                gn[2 * u] = gather(j.x);
+                gn[2 * u + 1] = gather(j.y);
+            } else {
+                gn[2 * u] = 0.0;
+                gn[2 * u + 1] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (s0 + u < nsteps) {
+                const double2 v = vp[(s0 + u) * 32];
+                dot = fma(v.x, g[2 * u], dot);
+                dot = fma(v.y, g[2 * u + 1], dot);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[u] = gn[u];
+    }
+    return dot;
+}
+
+// One phase of one CTA.  Split-row chunks come first: each warp parks its chunk's partial in
+// shared memory; after a CTA barrier warp 0 adds the CTA's chunks per row (fixed order),
+// publishes one partial per (CTA, row), and the last CTA to arrive for a row sums the row's
+// partials (fixed order) and applies the row update.  The other warps go straight on to the
+// regular tiles (warp 0 takes the last tile of every round).
+__device__ __forceinline__ double* split_scratch()
+{
+    __shared__ double s_part[SPLIT_SLOTS];  // one instance per kernel (not per instantiation of run_phase)
+    return s_part;
+}
+
+template <class Op>
+__device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, const Op& op, double* acc)
+{
+    const double* __restrict__ vec = op.vec();
+    double* s_part = split_scratch();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const uint32_t t0 = __ldg(M.cta_begin + blockIdx.x);
-    const uint32_t t1 = __ldg(M.cta_begin + blockIdx.x + 1);
-    const double* __restrict__ vec = op.vec();
 
-    for (uint32_t t = t0 + warp; t < t1; t += nwarps) {
-        const int4 raw = __ldg(reinterpret_cast<const int4*>(M.tiles + t));
-        const uint32_t off = (uint32_t)raw.x - step_base;
-        const uint32_t row_base = (uint32_t)raw.y;
-        const int nsteps = raw.z & 0xffff;
-        const int logL = (raw.z >> 16) & 0xff;
-        const int nrows = (raw.z >> 24) & 0xff;
-        const int split = raw.w;
-        const int L = 1 << logL;
-        const int rr = lane >> logL;
-        const bool owner = ((lane & (L - 1)) == 0) && (rr < nrows) && (split < 0);
-        const int r = (int)row_base + rr;
-
-        typename Op::Pre pre{};
-        if (owner) pre = op.prefetch(r);
-
-        const double2* vp = vals + (size_t)off * 32 + lane;
-        const int2* ip = idx + (size_t)off * 32 + lane;
-        double dot = 0.0;
-        for (int s0 = 0; s0 < nsteps; s0 += 4) {
-            double2 v[4];
-            int2 j[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (s0 + u < nsteps) {
-                    v[u] = vp[(s0 + u) * 32];
-                    j[u] = ip[(s0 + u) * 32];
-                } else {
-                    v[u] = make_double2(0.0, 0.0);
-                    j[u] = make_int2(0, 0);
-                }
-            }
-            double g[8];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (s0 + u < nsteps) {
-                    g[2 * u] = ld_mut(vec + j[u].x);
-                    g[2 * u + 1] = ld_mut(vec + j[u].y);
-                } else {
-                    g[2 * u] = 0.0;
-                    g[2 * u + 1] = 0.0;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                dot = fma(v[u].x, g[2 * u], dot);
-                dot = fma(v[u].y, g[2 * u + 1], dot);
-            }
+    if (V.nsplit > 0) {
+        for (uint32_t t = warp; t < V.nsplit; t += nwarps) {
+            const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
+            double dot = tile_dot(V, vec, (uint32_t)raw.x, raw.z & 0xffff, lane);
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+            if (lane == 0) s_part[raw.w] = dot;
         }
-        for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-
-        if (split < 0) {
-            if (owner) op.row(r, dot, pre, acc);
+        // every warp signals that its chunks are parked; only the publishing warps wait
+        const uint32_t npub = min(V.nls, (uint32_t)nwarps);
+        if ((uint32_t)warp < npub) {
+            asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory");
         } else {
-            // chunk of a split row: park the partial, last arrival sums them in index order
-            const int4 sraw = __ldg(reinterpret_cast<const int4*>(M.splits + split));
-            const uint32_t srow = (uint32_t)sraw.x, first = (uint32_t)sraw.y, nch = (uint32_t)sraw.z;
+            asm volatile("bar.arrive 1, %0;" ::"r"(blockDim.x) : "memory");
+        }
+        // local split row w is published by warp w (round robin if there are more rows than warps)
+        for (uint32_t li = warp; li < V.nls; li += nwarps) {
+            const int4 ls = __ldg(reinterpret_cast<const int4*>(M.lsplits + V.ls0 + li));
+            const int4 sr = __ldg(reinterpret_cast<const int4*>(M.splits + ls.x));
+            const int first = ls.z & 0xffff, count = (ls.z >> 16) & 0xffff;
+            // the CTA's chunks of this row, summed in a fixed order (lane-strided, then butterfly)
+            double p = 0.0;
+            for (int k = lane; k < count; k += 32) p += s_part[first + k];
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+            if (sr.z == 1) {   // the whole row lives in this CTA: no global join
+                if (lane == 0) op.row(sr.x, p, op.prefetch(sr.x), acc);
+                continue;
+            }
             unsigned last = 0;
             if (lane == 0) {
-                __stcg(M.partials + first + row_base, dot);
+                __stcg(M.partials + ls.y, p);
                 __threadfence();
-                const unsigned old = atomicAdd(M.counters + split, 1u);
-                last = (old == nch - 1);
+                const unsigned old = atomicAdd(M.counters + ls.x, 1u);
+                last = (old == (unsigned)sr.z - 1u);
             }
             last = __shfl_sync(FULL, last, 0);
             if (last) {
                 __threadfence();
+                const uint32_t np = (uint32_t)sr.z;
+                const double* pp = M.partials + (uint32_t)sr.y;
                 double s = 0.0;
-                for (uint32_t k = lane; k < nch; k += 32) s += __ldcg(M.partials + first + k);
+                for (uint32_t k0 = 0; k0 < np; k0 += 128) {   // 4 loads per lane in flight
+                    double q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t k = k0 + u * 32 + lane;
+                        q[u] = k < np ? __ldcg(pp + k) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) s += q[u];
+                }
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0) {
-                    M.counters[split] = 0;
-                    op.row((int)srow, s, op.prefetch((int)srow), acc);
+                    M.counters[ls.x] = 0;
+                    op.row(sr.x, s, op.prefetch(sr.x), acc);
                 }
             }
         }
+    }
+
+    // regular tiles; the warps that published split rows are served last in every round
+    const uint32_t busy = min(V.nls, (uint32_t)nwarps);
+    const uint32_t wslot = ((uint32_t)warp + (uint32_t)nwarps - busy) % (uint32_t)nwarps;
+    for (uint32_t t = V.nsplit + wslot; t < V.ntiles; t += nwarps) {
+        const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
+        const uint32_t row_base = (uint32_t)raw.y;
+        const int nsteps = raw.z & 0xffff;
+        const int logL = (raw.z >> 16) & 0xff;
+        const int nrows = (raw.z >> 24) & 0xff;
+        const int L = 1 << logL;
+        const int rr = lane >> logL;
+        const bool owner = ((lane & (L - 1)) == 0) && (rr < nrows);
+        const int r = (int)row_base + rr;
+        typename Op::Pre pre{};
+        if (owner) pre = op.prefetch(r);
+        double dot = tile_dot(V, vec, (uint32_t)raw.x, nsteps, lane);
+        for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+        if (owner) op.row(r, dot, pre, acc);
     }
 }
 

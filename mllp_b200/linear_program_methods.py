@@ -126,8 +126,8 @@ class DeviceLP:
         out = (ctypes.c_int64 * 16)()
         _cabi.check(_cabi.lib().mllp_lp_info(self.handle, out), "mllp_lp_info")
         keys = ("m", "n", "nnz", "tiles_A", "tiles_AT", "padded_A", "padded_AT", "split_rows_A", "split_rows_AT",
-                "grid_ctas", "threads", "smem_resident_bytes", "bytes_per_iter", "max_cta_steps_A",
-                "max_cta_steps_AT", "ctas_per_sm")
+                "grid_ctas", "threads", "dyn_smem_bytes", "bytes_per_iter", "res_steps_A", "res_steps_AT",
+                "ctas_per_sm")
         return dict(zip(keys, (int(v) for v in out)))
 
     def sigma_max(self, iters=50, stream=None):
