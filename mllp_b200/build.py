@@ -57,6 +57,7 @@ def build(force=False, verbose=False):
         common += ["-ccbin", cxx]
     if verbose:
         common += ["-Xptxas", "-v"]
+    common += os.environ.get("MLLP_NVCC_FLAGS", "").split()
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")

@@ -17,6 +17,9 @@ namespace mllp {
 
 constexpr int NRED = 8;            // reduction slots per phase
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef MLLP_BARRIER_BACKOFF
+#define MLLP_BARRIER_BACKOFF 40
+#endif
 // kinds of per-CTA reduction buffers
 constexpr int RED_STEPP = 0, RED_STEPD = 1, RED_EVALP = 2, RED_EVALD = 3, RED_BUFFERS = 8;
 // control block slots (device doubles)
@@ -83,9 +86,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
         target += gridDim.x;
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
         unsigned v;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while ((int)(v - target) < 0);
+            if ((int)(v - target) >= 0) break;
+            __nanosleep(MLLP_BARRIER_BACKOFF);  // keeps the pollers from crowding out the arrivals
+        }
         if (trace) trace[1] = global_ns();
     }
     __syncthreads();
@@ -314,8 +319,33 @@ __device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_
 // ---------------------------------------------------------------------------------------
 // The tile walker.
 //
-// One tile: steps are consumed in groups of 4 (8 gathers per lane in flight) with the next
-// group's gathers issued before the current group is folded in.
+// One tile = `nsteps` warp-steps.  The common step counts (1..4) run as straight-line code
+// with all gathers of the tile in flight at once; longer tiles (chunks of split rows) run in
+// groups of 4 steps.  Gathers are L1-cached loads: the grid barrier's acquire invalidated this
+// SM's L1 and the gathered vector is not written during the phase, so lines fetched now stay
+// valid until the next barrier (hot entries -- the long rows' y -- are then served by L1).
+template <int NS>
+__device__ __forceinline__ double steps_dot(const double2* __restrict__ vp, const int2* __restrict__ ip,
+                                            const double* __restrict__ vec, double dot)
+{
+    int2 j[NS];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) j[u] = ip[u * 32];
+    double g[2 * NS];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+        g[2 * u] = __ldca(vec + j[u].x);
+        g[2 * u + 1] = __ldca(vec + j[u].y);
+    }
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+        const double2 v = vp[u * 32];
+        dot = fma(v.x, g[2 * u], dot);
+        dot = fma(v.y, g[2 * u + 1], dot);
+    }
+    return dot;
+}
+
 __device__ __forceinline__ double tile_dot(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps,
                                            int lane)
 {
@@ -324,46 +354,14 @@ __device__ __forceinline__ double tile_dot(const MatView& V, const double* __res
     const bool res = loc + (uint32_t)nsteps <= V.res_steps;
     const double2* vp = res ? V.rvals + (size_t)loc * 32 + lane : V.gvals + (size_t)off * 32 + lane;
     const int2* ip = res ? V.ridx + (size_t)loc * 32 + lane : V.gidx + (size_t)off * 32 + lane;
-    // L1-cached gather: the grid barrier's acquire invalidated this SM's L1, and the gathered
-    // vector is not written during the phase, so lines fetched now stay valid until the next barrier
-    auto gather = [&](int j) -> double { return __ldca(vec + j); };
-
     double dot = 0.0;
-    double g[8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (u < nsteps) {
-            const int2 j = ip[u * 32];
-            g[2 * u] = gather(j.x);
-            g[2 * u + 1] = gather(j.y);
-        } else {
-            g[2 * u] = 0.0;
-            g[2 * u + 1] = 0.0;
-        }
-    }
-    for (int s0 = 0; s0 < nsteps; s0 += 4) {
-        double gn[8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (s0 + 4 + u < nsteps) {
-                const int2 j = ip[(s0 + 4 + u) * 32];
-                gn[2 * u] = gather(j.x);
-                gn[2 * u + 1] = gather(j.y);
-            } else {
-                gn[2 * u] = 0.0;
-                gn[2 * u + 1] = 0.0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (s0 + u < nsteps) {
-                const double2 v = vp[(s0 + u) * 32];
-                dot = fma(v.x, g[2 * u], dot);
-                dot = fma(v.y, g[2 * u + 1], dot);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) g[u] = gn[u];
+    for (; nsteps > 4; nsteps -= 4, vp += 128, ip += 128) dot = steps_dot<4>(vp, ip, vec, dot);
+    switch (nsteps) {
+        case 4: dot = steps_dot<4>(vp, ip, vec, dot); break;
+        case 3: dot = steps_dot<3>(vp, ip, vec, dot); break;
+        case 2: dot = steps_dot<2>(vp, ip, vec, dot); break;
+        case 1: dot = steps_dot<1>(vp, ip, vec, dot); break;
+        default: break;
     }
     return dot;
 }
