@@ -152,6 +152,9 @@ int mllp_batch_destroy(mllp_batch_t bt);
  * [5]=threads per CTA, [6]=dynamic smem bytes per CTA, [7]=algorithmic bytes per batch iteration,
  * [8]=instances per CTA, [9..15] reserved. */
 int mllp_batch_info(mllp_batch_t bt, int64_t *out16);
+/* sigma_max(A_k) of every instance by power iteration (as mllp_estimate_norm) into the device
+ * array d_sigma_max[count]; asynchronous on `stream`. */
+int mllp_batch_estimate_norm(mllp_batch_t bt, int32_t iters, double *d_sigma_max, void *stream);
 /* per-instance tau[k], sigma[k] (device arrays of `count`); scalars: count*MLLP_NUM_SCALARS */
 int mllp_batch_run(mllp_batch_t bt, double *d_x, double *d_y, const double *d_b,
                    const double *d_c, const double *d_tau, const double *d_sigma,

@@ -37,6 +37,7 @@ SIGNATURES = {
                                          ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "mllp_batch_destroy": (ctypes.c_int, [_vp]),
     "mllp_batch_info": (ctypes.c_int, [_vp, _vp]),
+    "mllp_batch_estimate_norm": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
     "mllp_batch_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mllp_batch_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _dbl, _vp, _vp]),
 }

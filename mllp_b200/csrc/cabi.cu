@@ -36,6 +36,10 @@ int env_int(const char* name, int dflt)
 }
 }  // namespace
 
+namespace mllp {
+void set_last_error(const std::string& msg) { g_err = msg; }  // used by batch_kernels.cu
+}
+
 #define CUDA_OK(call)                                           \
     do {                                                        \
         cudaError_t e_ = (call);                                \

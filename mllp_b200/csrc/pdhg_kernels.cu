@@ -51,7 +51,7 @@ __global__ void k_scale_by_invnorm(double* __restrict__ dst, const double* __res
 // to CTA assignment is fixed at build time.
 __global__ void __launch_bounds__(1024, 1) k_spmv(DevMat M, const double* in, double* out)
 {
-    SpmvOp op{in, out};
+    SpmvOp<> op{in, out};
     double acc[NRED];
     run_phase(M, global_view(M), op, acc);
 }

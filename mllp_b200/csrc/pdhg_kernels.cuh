@@ -63,8 +63,19 @@ struct DevLP {
     unsigned long long* trace;  // dev tool: [iter][cta][4] barrier timestamps, or null
 };
 
-__device__ __forceinline__ double ld_mut(const double* p) { return __ldcg(p); }   // L2-coherent
-__device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }     // read-only path
+// Memory policies of the row ops.  GlobalMem: vectors live in global memory and are shared by
+// all CTAs (single-instance path).  SmemMem: vectors are the CTA's own shared-memory copies
+// (batched path: one LP per CTA), reached through generic pointers.
+struct GlobalMem {
+    static __device__ __forceinline__ double ld_mut(const double* p) { return __ldcg(p); }  // L2-coherent
+    static __device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }    // read-only path
+    static __device__ __forceinline__ double gather(const double* p) { return __ldca(p); }  // L1, see tile_dot
+};
+struct SmemMem {
+    static __device__ __forceinline__ double ld_mut(const double* p) { return *p; }
+    static __device__ __forceinline__ double ld_ro(const double* p) { return *p; }
+    static __device__ __forceinline__ double gather(const double* p) { return *p; }
+};
 
 // ---------------------------------------------------------------------------------------
 // Grid barrier for the persistent cooperative kernel: monotonic counter, one arrival per
@@ -104,19 +115,20 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
 //   void row_late(int r, double dot)        same, without prefetch (split rows)
 // Each op may accumulate into acc[NRED] (thread-local), reduced per CTA at the phase end.
 
-template <bool BOUNDS>
+template <bool BOUNDS, class MEM = GlobalMem>
 struct PrimalOp {
+    using Mem = MEM;
     const DevLP& lp;
     double tau;
     struct Pre { double c, x; };
     __device__ __forceinline__ const double* vec() const { return lp.y; }
-    __device__ __forceinline__ Pre prefetch(int r) const { return {ld_ro(lp.c + r), ld_mut(lp.x + r)}; }
+    __device__ __forceinline__ Pre prefetch(int r) const { return {MEM::ld_ro(lp.c + r), MEM::ld_mut(lp.x + r)}; }
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double*) const
     {
         const double g = p.c - dot;
         double xn = p.x - tau * g;
         if (BOUNDS) {
-            xn = fmin(fmax(xn, ld_ro(lp.lb + r)), ld_ro(lp.ub + r));
+            xn = fmin(fmax(xn, MEM::ld_ro(lp.lb + r)), MEM::ld_ro(lp.ub + r));
         } else {
             xn = fmax(xn, 0.0);
         }
@@ -125,38 +137,40 @@ struct PrimalOp {
     }
 };
 
-template <bool BOUNDS>
+template <bool BOUNDS, class MEM = GlobalMem>
 struct DualOp {
+    using Mem = MEM;
     const DevLP& lp;
     double sigma;
     struct Pre { double b, y; };
     __device__ __forceinline__ const double* vec() const { return lp.xbar; }
-    __device__ __forceinline__ Pre prefetch(int r) const { return {ld_ro(lp.b + r), ld_mut(lp.y + r)}; }
+    __device__ __forceinline__ Pre prefetch(int r) const { return {MEM::ld_ro(lp.b + r), MEM::ld_mut(lp.y + r)}; }
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double*) const
     {
         double yn = p.y + sigma * (p.b - dot);
-        if (BOUNDS) yn = fmin(fmax(yn, ld_ro(lp.ylo + r)), ld_ro(lp.yhi + r));
+        if (BOUNDS) yn = fmin(fmax(yn, MEM::ld_ro(lp.ylo + r)), MEM::ld_ro(lp.yhi + r));
         lp.y[r] = yn;
     }
 };
 
 // Solve mode (reflected Halpern).  acc[0] accumulates ||x' - x||^2 (resp. y).
-template <bool BOUNDS>
+template <bool BOUNDS, class MEM = GlobalMem>
 struct PrimalHalpernOp {
+    using Mem = MEM;
     const DevLP& lp;
     double tau, lam;
     struct Pre { double c, x, x0; };
     __device__ __forceinline__ const double* vec() const { return lp.y; }
     __device__ __forceinline__ Pre prefetch(int r) const
     {
-        return {ld_ro(lp.c + r), ld_mut(lp.x + r), ld_mut(lp.x0 + r)};
+        return {MEM::ld_ro(lp.c + r), MEM::ld_mut(lp.x + r), MEM::ld_mut(lp.x0 + r)};
     }
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double* acc) const
     {
         const double g = p.c - dot;
         double xn = p.x - tau * g;
         if (BOUNDS) {
-            xn = fmin(fmax(xn, ld_ro(lp.lb + r)), ld_ro(lp.ub + r));
+            xn = fmin(fmax(xn, MEM::ld_ro(lp.lb + r)), MEM::ld_ro(lp.ub + r));
         } else {
             xn = fmax(xn, 0.0);
         }
@@ -168,20 +182,21 @@ struct PrimalHalpernOp {
     }
 };
 
-template <bool BOUNDS>
+template <bool BOUNDS, class MEM = GlobalMem>
 struct DualHalpernOp {
+    using Mem = MEM;
     const DevLP& lp;
     double sigma, lam;
     struct Pre { double b, y, y0; };
     __device__ __forceinline__ const double* vec() const { return lp.xbar; }
     __device__ __forceinline__ Pre prefetch(int r) const
     {
-        return {ld_ro(lp.b + r), ld_mut(lp.y + r), ld_mut(lp.y0 + r)};
+        return {MEM::ld_ro(lp.b + r), MEM::ld_mut(lp.y + r), MEM::ld_mut(lp.y0 + r)};
     }
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double* acc) const
     {
         double yn = p.y + sigma * (p.b - dot);
-        if (BOUNDS) yn = fmin(fmax(yn, ld_ro(lp.ylo + r)), ld_ro(lp.yhi + r));
+        if (BOUNDS) yn = fmin(fmax(yn, MEM::ld_ro(lp.ylo + r)), MEM::ld_ro(lp.yhi + r));
         const double d = yn - p.y;
         acc[0] += d * d;
         lp.y[r] = lam * (2.0 * yn - p.y) + (1.0 - lam) * p.y0;
@@ -190,21 +205,22 @@ struct DualHalpernOp {
 
 // KKT scalars, A' side: r = c - A'y.
 // acc: 0 pobj, 1 dobj bound terms, 2 dual residual^2, 3 ||c||^2, 4 ||x||^2, 5 ||x - x0||^2
-template <bool BOUNDS>
+template <bool BOUNDS, class MEM = GlobalMem>
 struct EvalPrimalOp {
+    using Mem = MEM;
     const DevLP& lp;
     struct Pre { double c, x, x0; };
     __device__ __forceinline__ const double* vec() const { return lp.y; }
     __device__ __forceinline__ Pre prefetch(int r) const
     {
-        return {ld_ro(lp.c + r), ld_mut(lp.x + r), ld_mut(lp.x0 + r)};
+        return {MEM::ld_ro(lp.c + r), MEM::ld_mut(lp.x + r), MEM::ld_mut(lp.x0 + r)};
     }
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double* acc) const
     {
         const double rc = p.c - dot;
         const double rp = rc > 0.0 ? rc : 0.0, rn = rc < 0.0 ? rc : 0.0;
         double lo = 0.0, hi = INFINITY;
-        if (BOUNDS) { lo = ld_ro(lp.lb + r); hi = ld_ro(lp.ub + r); }
+        if (BOUNDS) { lo = MEM::ld_ro(lp.lb + r); hi = MEM::ld_ro(lp.ub + r); }
         double viol = 0.0, dob = 0.0;
         if (isinf(hi)) viol += rn * rn; else dob += hi * rn;
         if (isinf(lo)) viol += rp * rp; else dob += lo * rp;
@@ -219,20 +235,21 @@ struct EvalPrimalOp {
 
 // KKT scalars, A side: res = Ax - b.
 // acc: 0 b'y, 1 primal residual^2, 2 ||b||^2, 3 ||y||^2, 4 ||y - y0||^2
-template <bool BOUNDS>
+template <bool BOUNDS, class MEM = GlobalMem>
 struct EvalDualOp {
+    using Mem = MEM;
     const DevLP& lp;
     struct Pre { double b, y, y0; };
     __device__ __forceinline__ const double* vec() const { return lp.x; }
     __device__ __forceinline__ Pre prefetch(int r) const
     {
-        return {ld_ro(lp.b + r), ld_mut(lp.y + r), ld_mut(lp.y0 + r)};
+        return {MEM::ld_ro(lp.b + r), MEM::ld_mut(lp.y + r), MEM::ld_mut(lp.y0 + r)};
     }
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double* acc) const
     {
         double res = dot - p.b;
         if (BOUNDS) {
-            const double lo = ld_ro(lp.ylo + r), hi = ld_ro(lp.yhi + r);
+            const double lo = MEM::ld_ro(lp.ylo + r), hi = MEM::ld_ro(lp.yhi + r);
             if (res > 0.0 && isinf(hi) && lo == 0.0) res = 0.0;
             if (res < 0.0 && isinf(lo) && hi == 0.0) res = 0.0;
         }
@@ -244,7 +261,9 @@ struct EvalDualOp {
     }
 };
 
+template <class MEM = GlobalMem>
 struct SpmvOp {
+    using Mem = MEM;
     const double* in;
     double* out;
     struct Pre {};
@@ -268,25 +287,28 @@ struct MatView {
     uint32_t ls0, nls;       // this CTA's LocalSplit range
 };
 
-__device__ __forceinline__ void view_common(const DevMat& M, MatView& V)
+__device__ __forceinline__ void view_common(const DevMat& M, MatView& V, uint32_t cta)
 {
-    V.nsplit = __ldg(M.cta_nsplit + blockIdx.x);
-    V.ls0 = __ldg(M.cta_lsplit_begin + blockIdx.x);
-    V.nls = __ldg(M.cta_lsplit_begin + blockIdx.x + 1) - V.ls0;
+    V.nsplit = __ldg(M.cta_nsplit + cta);
+    V.ls0 = __ldg(M.cta_lsplit_begin + cta);
+    V.nls = __ldg(M.cta_lsplit_begin + cta + 1) - V.ls0;
 }
 
-__device__ __forceinline__ MatView global_view(const DevMat& M)
+// `cta` = which CTA's share of the format to walk (the batched path builds formats for a
+// one-CTA grid and always walks share 0).
+__device__ __forceinline__ MatView global_view(const DevMat& M, uint32_t cta)
 {
-    const uint32_t t0 = __ldg(M.cta_begin + blockIdx.x), t1 = __ldg(M.cta_begin + blockIdx.x + 1);
+    const uint32_t t0 = __ldg(M.cta_begin + cta), t1 = __ldg(M.cta_begin + cta + 1);
     MatView V;
     V.desc = M.tiles + t0;
     V.rvals = nullptr; V.ridx = nullptr;
     V.gvals = M.vals; V.gidx = M.idx;
     V.ntiles = t1 - t0; V.res_steps = 0;
-    V.step0 = __ldg(M.cta_step_begin + blockIdx.x);
-    view_common(M, V);
+    V.step0 = __ldg(M.cta_step_begin + cta);
+    view_common(M, V, cta);
     return V;
 }
+__device__ __forceinline__ MatView global_view(const DevMat& M) { return global_view(M, blockIdx.x); }
 
 // Copy this CTA's descriptors and its first `res_steps` warp-steps into shared memory.
 // Layout at `base` (16 B aligned): desc[ntiles] | vals[res_steps*32] (double2) | idx[res_steps*32] (int2).
@@ -312,7 +334,7 @@ __device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_
     V.ridx = reinterpret_cast<const int2*>(d_idx);
     V.gvals = M.vals; V.gidx = M.idx;
     V.ntiles = nt; V.res_steps = rs; V.step0 = s0;
-    view_common(M, V);
+    view_common(M, V, blockIdx.x);
     return nt * 16u + rs * 768u;
 }
 
@@ -324,7 +346,7 @@ __device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_
 // groups of 4 steps.  Gathers are L1-cached loads: the grid barrier's acquire invalidated this
 // SM's L1 and the gathered vector is not written during the phase, so lines fetched now stay
 // valid until the next barrier (hot entries -- the long rows' y -- are then served by L1).
-template <int NS>
+template <class MEM, int NS>
 __device__ __forceinline__ double steps_dot(const double2* __restrict__ vp, const int2* __restrict__ ip,
                                             const double* __restrict__ vec, double dot)
 {
@@ -334,8 +356,8 @@ __device__ __forceinline__ double steps_dot(const double2* __restrict__ vp, cons
     double g[2 * NS];
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
-        g[2 * u] = __ldca(vec + j[u].x);
-        g[2 * u + 1] = __ldca(vec + j[u].y);
+        g[2 * u] = MEM::gather(vec + j[u].x);
+        g[2 * u + 1] = MEM::gather(vec + j[u].y);
     }
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
@@ -346,6 +368,7 @@ __device__ __forceinline__ double steps_dot(const double2* __restrict__ vp, cons
     return dot;
 }
 
+template <class MEM>
 __device__ __forceinline__ double tile_dot(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps,
                                            int lane)
 {
@@ -355,12 +378,12 @@ __device__ __forceinline__ double tile_dot(const MatView& V, const double* __res
     const double2* vp = res ? V.rvals + (size_t)loc * 32 + lane : V.gvals + (size_t)off * 32 + lane;
     const int2* ip = res ? V.ridx + (size_t)loc * 32 + lane : V.gidx + (size_t)off * 32 + lane;
     double dot = 0.0;
-    for (; nsteps > 4; nsteps -= 4, vp += 128, ip += 128) dot = steps_dot<4>(vp, ip, vec, dot);
+    for (; nsteps > 4; nsteps -= 4, vp += 128, ip += 128) dot = steps_dot<MEM, 4>(vp, ip, vec, dot);
     switch (nsteps) {
-        case 4: dot = steps_dot<4>(vp, ip, vec, dot); break;
-        case 3: dot = steps_dot<3>(vp, ip, vec, dot); break;
-        case 2: dot = steps_dot<2>(vp, ip, vec, dot); break;
-        case 1: dot = steps_dot<1>(vp, ip, vec, dot); break;
+        case 4: dot = steps_dot<MEM, 4>(vp, ip, vec, dot); break;
+        case 3: dot = steps_dot<MEM, 3>(vp, ip, vec, dot); break;
+        case 2: dot = steps_dot<MEM, 2>(vp, ip, vec, dot); break;
+        case 1: dot = steps_dot<MEM, 1>(vp, ip, vec, dot); break;
         default: break;
     }
     return dot;
@@ -389,7 +412,7 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
     if (V.nsplit > 0) {
         for (uint32_t t = warp; t < V.nsplit; t += nwarps) {
             const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
-            double dot = tile_dot(V, vec, (uint32_t)raw.x, raw.z & 0xffff, lane);
+            double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, raw.z & 0xffff, lane);
             for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
             if (lane == 0) s_part[raw.w] = dot;
         }
@@ -460,7 +483,7 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
         const int r = (int)row_base + rr;
         typename Op::Pre pre{};
         if (owner) pre = op.prefetch(r);
-        double dot = tile_dot(V, vec, (uint32_t)raw.x, nsteps, lane);
+        double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
         for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
         if (owner) op.row(r, dot, pre, acc);
     }

@@ -25,7 +25,7 @@ from . import _cabi
 
 __all__ = [
     "DeviceLP", "device_lp", "pdhg_linear_program", "solve_linear_program", "estimate_step_size",
-    "csr_from_constrs", "SCALAR_NAMES",
+    "csr_from_constrs", "SCALAR_NAMES", "BatchLP", "pdhg_linear_program_batch", "solve_linear_program_batch",
 ]
 
 SCALAR_NAMES = ("pobj", "dobj", "primal_res", "dual_res", "norm_b", "norm_c", "norm_x", "norm_y",
@@ -289,3 +289,153 @@ def solve_linear_program(constrs, constr_weights, rhs, coefs, *, tol=1e-6, max_i
         print("solve: %d iters, %d restarts, converged=%s, pobj %.9g, rel_kkt %.3e"
               % (info["iters"], info["restarts"], info["converged"], s[0], s[8]))
     return float(s[0]), x.cpu().numpy(), y.cpu().numpy(), info
+
+
+# ---------------------------------------------------------------------------------------------
+# batched multi-instance mode: many LPs in one launch
+
+
+class BatchLP:
+    """Device formats of a batch of LP instances (``mllp_batch_t``).
+
+    ``instances``: list of ``(constrs, constr_weights, rhs, coefs)`` in the loader's
+    representation (the per-instance tuple of linear_program_experiment.py:123 without name and
+    labels), or -- ``shared=True`` -- ONE such matrix used by ``count`` instances that differ
+    only in b and c (BASELINE.json configs[4])."""
+
+    def __init__(self, instances, shared=False, count=None, device=0):
+        L = _cabi.lib()
+        self.device = _device_index(device)
+        self.shared = bool(shared)
+        mats = [instances[0]] if self.shared else list(instances)
+        self.count = int(count if self.shared else len(mats))
+        if self.count < 1:
+            raise ValueError("empty batch")
+        ms, ns, ips, iis, vvs = [], [], [], [], []
+        for constrs, weights, rhs, coefs in mats:
+            m, n = len(rhs) if np.ndim(rhs) == 1 else np.shape(rhs)[-1], len(coefs) if np.ndim(coefs) == 1 else np.shape(coefs)[-1]
+            ip, ii, vv = csr_from_constrs(constrs, weights, n)
+            if ip.shape[0] != m + 1:
+                raise ValueError("constrs has %d rows, rhs has %d" % (ip.shape[0] - 1, m))
+            ms.append(m); ns.append(n); ips.append(ip); iis.append(ii); vvs.append(vv)
+        self.m = np.array(ms * (self.count if self.shared else 1), dtype=np.int64)
+        self.n = np.array(ns * (self.count if self.shared else 1), dtype=np.int64)
+        h_m, h_n = np.array(ms, dtype=np.int32), np.array(ns, dtype=np.int32)
+        ip_off = np.concatenate([[0], np.cumsum([a.shape[0] for a in ips])[:-1]]).astype(np.int64)
+        nz_off = np.concatenate([[0], np.cumsum([a.shape[0] for a in iis])[:-1]]).astype(np.int64)
+        ip_all = np.ascontiguousarray(np.concatenate(ips), dtype=np.int32)
+        ii_all = np.ascontiguousarray(np.concatenate(iis), dtype=np.int32) if sum(a.shape[0] for a in iis) else np.zeros(1, np.int32)
+        vv_all = np.ascontiguousarray(np.concatenate(vvs), dtype=np.float64) if sum(a.shape[0] for a in vvs) else np.zeros(1)
+        h = ctypes.c_void_p()
+        rc = L.mllp_batch_create(self.count, int(self.shared), _ptr(h_m), _ptr(h_n), _ptr(ip_off), _ptr(nz_off),
+                                 _ptr(ip_all), _ptr(ii_all), _ptr(vv_all), self.device, 0, ctypes.byref(h))
+        _cabi.check(rc, "mllp_batch_create")
+        self._h = h
+        self._finalizer = weakref.finalize(self, L.mllp_batch_destroy, h)
+        self.x_off = np.concatenate([[0], np.cumsum(self.n)])
+        self.y_off = np.concatenate([[0], np.cumsum(self.m)])
+        self._sigma = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        self._finalizer()
+        self._h = None
+
+    def info(self):
+        out = (ctypes.c_int64 * 16)()
+        _cabi.check(_cabi.lib().mllp_batch_info(self.handle, out), "mllp_batch_info")
+        keys = ("count", "sum_m", "sum_n", "sum_nnz", "grid_ctas", "threads", "dyn_smem_bytes", "bytes_per_iter",
+                "instances_per_cta")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def sigma_max(self, iters=50):
+        """per-instance ||A_k||_2 estimates (device tensor, cached)."""
+        import torch
+        if self._sigma is None:
+            dev = torch.device("cuda", self.device)
+            s = torch.zeros(self.count, dtype=torch.float64, device=dev)
+            _cabi.check(_cabi.lib().mllp_batch_estimate_norm(self.handle, int(iters), s.data_ptr(), _torch_stream(dev)),
+                        "mllp_batch_estimate_norm")
+            self._sigma = s
+        return self._sigma
+
+    # device-tensor level entries (concatenated vectors, caller's stream, no host sync)
+    def run(self, x, y, b, c, tau, sigma, num_iters, scalars=None):
+        _cabi.check(_cabi.lib().mllp_batch_run(self.handle, x.data_ptr(), y.data_ptr(), b.data_ptr(), c.data_ptr(),
+                                               tau.data_ptr(), sigma.data_ptr(), int(num_iters),
+                                               None if scalars is None else scalars.data_ptr(),
+                                               _torch_stream(x.device)), "mllp_batch_run")
+
+    def solve(self, x, y, b, c, eta, scalars, w0=1.0, max_iters=200000, check_every=64, tol=1e-6):
+        _cabi.check(_cabi.lib().mllp_batch_solve(self.handle, x.data_ptr(), y.data_ptr(), b.data_ptr(), c.data_ptr(),
+                                                 eta.data_ptr(), float(w0), int(max_iters), int(check_every), float(tol),
+                                                 scalars.data_ptr(), _torch_stream(x.device)), "mllp_batch_solve")
+
+
+def _batch_vectors(bt, instances, rhs_batch, coefs_batch, x0, y0):
+    import torch
+    dev = torch.device("cuda", bt.device)
+    if bt.shared:
+        b = np.ascontiguousarray(rhs_batch, dtype=np.float64).reshape(bt.count, -1)
+        c = np.ascontiguousarray(coefs_batch, dtype=np.float64).reshape(bt.count, -1)
+        if b.shape[1] != bt.m[0] or c.shape[1] != bt.n[0]:
+            raise ValueError("rhs/coefs batches must be (count, m) and (count, n)")
+        b, c = b.reshape(-1), c.reshape(-1)
+    else:
+        b = np.concatenate([_np_f64(i[2], int(m), "rhs") for i, m in zip(instances, bt.m)])
+        c = np.concatenate([_np_f64(i[3], int(n), "coefs") for i, n in zip(instances, bt.n)])
+    nx, ny = int(bt.x_off[-1]), int(bt.y_off[-1])
+    x = np.zeros(nx) if x0 is None else np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in x0])
+    y = np.zeros(ny) if y0 is None else np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in y0])
+    if x.shape[0] != nx or y.shape[0] != ny:
+        raise ValueError("x0 / y0 sizes do not match the batch")
+    t = lambda a: torch.as_tensor(a, device=dev)
+    return t(b), t(c), t(x), t(y), dev
+
+
+def _batch_results(bt, x, y, scal, extra):
+    xs, ys, sc = x.cpu().numpy(), y.cpu().numpy(), scal.cpu().numpy().reshape(bt.count, _cabi.NUM_SCALARS)
+    out = []
+    for k in range(bt.count):
+        info = _info_dict(sc[k])
+        info.update({key: float(val[k]) for key, val in extra.items()})
+        out.append((float(sc[k, 0]), xs[bt.x_off[k]:bt.x_off[k + 1]], ys[bt.y_off[k]:bt.y_off[k + 1]], info))
+    return out
+
+
+def pdhg_linear_program_batch(instances, *, num_iters, x0=None, y0=None, tau=None, sigma=None, device=0, handle=None,
+                              shared=False, rhs_batch=None, coefs_batch=None):
+    """Parity mode on a whole batch in ONE launch (one CTA per LP).  ``instances`` = list of
+    ``(constrs, constr_weights, rhs, coefs)``; with ``shared=True`` one matrix
+    ``instances[0]`` and ``rhs_batch`` (B, m) / ``coefs_batch`` (B, n).  ``tau`` / ``sigma``:
+    scalars, per-instance arrays, or None (0.9 / sigma_max(A_k) computed on the device).
+    Returns a list of ``(objective, x, y, info)`` per instance."""
+    import torch
+    bt = handle if handle is not None else BatchLP(instances, shared=shared,
+                                                   count=None if not shared else len(rhs_batch), device=device)
+    b, c, x, y, dev = _batch_vectors(bt, instances, rhs_batch, coefs_batch, x0, y0)
+    if tau is None or sigma is None:
+        eta = 0.9 / bt.sigma_max()
+    as_arr = lambda v: eta.clone() if v is None else torch.as_tensor(np.broadcast_to(np.asarray(v, dtype=np.float64), (bt.count,)).copy(), device=dev)
+    tau_t, sigma_t = as_arr(tau), as_arr(sigma)
+    scal = torch.zeros(bt.count * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
+    bt.run(x, y, b, c, tau_t, sigma_t, num_iters, scal)
+    return _batch_results(bt, x, y, scal, {"tau": tau_t.cpu().numpy(), "sigma": sigma_t.cpu().numpy()})
+
+
+def solve_linear_program_batch(instances, *, tol=1e-6, max_iters=200000, check_every=64, x0=None, y0=None, eta=None,
+                               primal_weight=1.0, device=0, handle=None, shared=False, rhs_batch=None, coefs_batch=None):
+    """Solve mode on a whole batch in one launch; every instance restarts and terminates on
+    its own.  Returns a list of ``(objective, x, y, info)``."""
+    import torch
+    bt = handle if handle is not None else BatchLP(instances, shared=shared,
+                                                   count=None if not shared else len(rhs_batch), device=device)
+    b, c, x, y, dev = _batch_vectors(bt, instances, rhs_batch, coefs_batch, x0, y0)
+    eta_t = 0.99 / bt.sigma_max() if eta is None else torch.as_tensor(
+        np.broadcast_to(np.asarray(eta, dtype=np.float64), (bt.count,)).copy(), device=dev)
+    scal = torch.zeros(bt.count * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
+    bt.solve(x, y, b, c, eta_t, scal, primal_weight, max_iters, check_every, tol)
+    return _batch_results(bt, x, y, scal, {"eta": eta_t.cpu().numpy()})

@@ -1,0 +1,116 @@
+"""GPU parity tests of the batched multi-instance mode (BASELINE.json configs[1] and [4])."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import mllp_b200 as M
+import mllp_b200.linear_program_data as D
+from oracle import pdhg_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HIGHS = json.load(open(os.path.join(GOLD, "highs_objectives.json")))
+SMALL = ["sc50a", "sc105", "adlittle", "blend", "share2b", "kb2"]
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def load_batch(names):
+    insts, mats = [], []
+    for nm in names:
+        A, b, c = D.load_csr(nm)
+        constrs = np.split(A.indices, A.indptr)[1:-1]   # loader representation
+        insts.append((constrs, A.data, b, c))
+        mats.append((A, b, c))
+    return insts, mats
+
+
+def test_small_netlib_batch_parity_one_launch():
+    """configs[1]: sc50a, sc105, adlittle, blend, share2b, kb2 packed into one launch, fp64."""
+    insts, mats = load_batch(SMALL)
+    bt = M.BatchLP(insts)
+    info = bt.info()
+    assert info["count"] == 6 and info["sum_m"] == 424 and info["sum_n"] == 723 and info["sum_nnz"] == 2536
+    sig = bt.sigma_max().cpu().numpy()
+    K = 1000
+    res = M.pdhg_linear_program_batch(insts, num_iters=K, handle=bt)
+    for (A, b, c), (obj, x, y, inf), s in zip(mats, res, sig):
+        assert abs(s - O.power_iteration(A, 50)) <= 1e-10 * s
+        eta = 0.9 / s
+        xo, yo = O.pdhg_run(A, b, c, np.zeros(A.shape[1]), np.zeros(A.shape[0]), eta, eta, K)
+        assert rel(x, xo) < 1e-9 and rel(y, yo) < 1e-9
+        kk = O.kkt(A, b, c, xo, yo)
+        assert abs(obj - kk[0]) <= 1e-6 * (1 + abs(kk[0])) and abs(inf["rel_kkt"] - kk[8]) <= 1e-6 * (1 + kk[8])
+
+
+def test_batch_warm_start_and_per_instance_steps():
+    insts, mats = load_batch(["afiro", "blend", "sc50a"])
+    rng = np.random.default_rng(4)
+    x0 = [np.abs(rng.standard_normal(A.shape[1])) for A, _, _ in mats]
+    y0 = [rng.standard_normal(A.shape[0]) for A, _, _ in mats]
+    tau, sigma = np.array([0.05, 0.1, 0.2]), np.array([0.3, 0.2, 0.1])
+    res = M.pdhg_linear_program_batch(insts, num_iters=150, x0=x0, y0=y0, tau=tau, sigma=sigma)
+    for k, ((A, b, c), (obj, x, y, inf)) in enumerate(zip(mats, res)):
+        xo, yo = O.pdhg_run(A, b, c, x0[k], y0[k], tau[k], sigma[k], 150)
+        assert rel(x, xo) < 1e-9 and rel(y, yo) < 1e-9
+    res0 = M.pdhg_linear_program_batch(insts, num_iters=0, x0=x0, y0=y0, tau=0.1, sigma=0.1)
+    for k in range(3):
+        assert np.array_equal(res0[k][1], x0[k]) and np.array_equal(res0[k][2], y0[k])
+
+
+def test_batch_solve_mode_matches_highs_and_single_instance_path():
+    names = ["sc50a", "sc105", "adlittle", "blend", "share2b"]   # kb2 is unbounded without its MPS bounds
+    insts, mats = load_batch(names)
+    res = M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000)
+    for nm, (A, b, c), (obj, x, y, inf) in zip(names, mats, res):
+        assert inf["converged"] and inf["rel_kkt"] <= 1e-6
+        assert abs(obj - HIGHS[nm]) <= 1e-4 * (1 + abs(HIGHS[nm]))
+        kk = O.kkt(A, b, c, x, y)
+        assert abs(kk[0] - obj) <= 1e-6 * (1 + abs(obj))
+    # same algorithm as the grid-wide solver: identical iteration counts on a well-conditioned case
+    A, b, c = mats[0]
+    _, _, _, single = M.solve_linear_program(A, A.data, b, c, tol=1e-6)
+    assert single["iters"] == res[0][3]["iters"] and single["restarts"] == res[0][3]["restarts"]
+
+
+def test_shared_matrix_batch_of_perturbed_instances():
+    """configs[4] (scaled down): random b/c perturbations of a fixed Netlib A (25fv47)."""
+    A, b, c = D.load_csr("25fv47")
+    m, n = A.shape
+    B = 300   # more instances than CTAs: exercises the grid-stride loop
+    cb = np.empty((B, n))
+    bb = np.empty((B, m))
+    for i in range(B):
+        g = np.random.default_rng(1234 + i)
+        cb[i] = c * (1 + 0.1 * g.uniform(-1, 1, n))
+        bb[i] = b * (1 + 0.1 * g.uniform(0, 1, m))
+    bt = M.BatchLP([(A, A.data, b, c)], shared=True, count=B)
+    assert bt.info()["sum_nnz"] == A.nnz and bt.info()["count"] == B
+    res = M.pdhg_linear_program_batch([(A, A.data, b, c)], num_iters=200, handle=bt, shared=True, rhs_batch=bb,
+                                      coefs_batch=cb)
+    eta = 0.9 / O.power_iteration(A, 50)
+    for k in (0, 1, 147, 148, 149, B - 1):
+        xo, yo = O.pdhg_run(A, bb[k], cb[k], np.zeros(n), np.zeros(m), eta, eta, 200)
+        assert rel(res[k][1], xo) < 1e-9 and rel(res[k][2], yo) < 1e-9
+    # linearity in (b, c) of the unprojected part is not available (projection), but instances are
+    # independent: permuting the batch permutes the results
+    perm = np.random.default_rng(0).permutation(B)
+    res2 = M.pdhg_linear_program_batch([(A, A.data, b, c)], num_iters=200, handle=bt, shared=True,
+                                       rhs_batch=bb[perm], coefs_batch=cb[perm])
+    for k in (0, 5, B - 1):
+        assert np.array_equal(res2[k][1], res[perm[k]][1]) and np.array_equal(res2[k][2], res[perm[k]][2])
+
+
+def test_batch_errors():
+    A, b, c = D.load_csr("afiro")
+    with pytest.raises(ValueError):
+        M.BatchLP([])
+    big_n = 40000   # 8(4n+3m) exceeds shared memory
+    import scipy.sparse as sp
+    Abig = sp.random(10, big_n, density=1e-3, format="csr", random_state=1)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        M.BatchLP([(Abig, Abig.data, np.zeros(10), np.zeros(big_n))])
