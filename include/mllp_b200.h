@@ -71,6 +71,14 @@ int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indp
                           const int32_t *indices, const double *values, int32_t num_ctas,
                           int32_t pref_steps, int32_t max_steps, double *out8);
 
+/* Host-only self check of the row-partitioned build: emulates all `nranks` ranks on the CPU
+ * (tile walk + all-gather of the slices) against the plain CSR products.  out4: [0] worst
+ * relative row error, [1]/[2] padded internal lengths of y / x, [3] largest nonzeros per rank
+ * over the mean. */
+int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr,
+                           const int32_t *indices, const double *values, int32_t num_ctas,
+                           int32_t nranks, double *out4);
+
 /* Host-only statistic of the built format: distinct 128-byte lines touched by the warp-wide
  * gather instructions (the gather cost model).  out6: [0]/[1] total lines A / A', [2]/[3] the
  * largest per-CTA sum, [4]/[5] gather instructions.  `cluster` = cluster rows inside length
@@ -133,6 +141,25 @@ int mllp_pdhg_run_host(mllp_lp_t lp, double *h_x, double *h_y, const double *h_b
 int mllp_pdhg_solve(mllp_lp_t lp, double *d_x, double *d_y, const double *d_b,
                     const double *d_c, double eta, double w0, int32_t max_iters,
                     int32_t check_every, double tol, double *d_scalars, void *stream);
+
+/*
+ * Row partition of ONE large LP over `nranks` GPUs (one process per GPU; BASELINE.json
+ * configs[3]: ken-18, osa-60, pds-20).  Every rank passes the whole matrix; rank p keeps the
+ * rows of A (entries of y) and the rows of A' (entries of x) assigned to it (balanced by nonzeros)
+ * and the ranks exchange their slices of xbar and y with two NCCL all-gathers per iteration on
+ * the caller's stream.  mllp_nccl_unique_id() is called on rank 0 and its 128 bytes are sent to
+ * the other ranks by the host (e.g. torch.distributed.broadcast) before the collective
+ * mllp_lp_create_rowpart().  mllp_pdhg_run() on such a handle is a collective call: all ranks
+ * pass the same full-length x, y, b, c (caller order) and all receive the full result.
+ * mllp_pdhg_solve / mllp_spmv / mllp_estimate_norm are not available on these handles.
+ */
+#define MLLP_NCCL_UNIQUE_ID_BYTES 128
+int mllp_nccl_unique_id(unsigned char *out128);
+int mllp_lp_create_rowpart(int32_t m, int32_t n, int64_t nnz, const int32_t *h_indptr,
+                           const int32_t *h_indices, const double *h_values, const double *h_lb,
+                           const double *h_ub, const double *h_ylo, const double *h_yhi, int device,
+                           uint32_t flags, int32_t rank, int32_t nranks,
+                           const unsigned char *uid128, mllp_lp_t *out);
 
 /*
  * Batched mode: `count` independent LPs in one launch (one CTA per LP, the whole LP held

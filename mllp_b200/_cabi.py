@@ -22,10 +22,14 @@ SIGNATURES = {
     "mllp_last_error": (ctypes.c_char_p, []),
     "mllp_version": (ctypes.c_int, []),
     "mllp_format_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "mllp_rowpart_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mllp_format_gather_lines": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mllp_device_info": (ctypes.c_int, [ctypes.c_int, _vp]),
     "mllp_lp_create": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                       ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "mllp_nccl_unique_id": (ctypes.c_int, [_vp]),
+    "mllp_lp_create_rowpart": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
+                                              ctypes.c_uint32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),
     "mllp_lp_destroy": (ctypes.c_int, [_vp]),
     "mllp_lp_info": (ctypes.c_int, [_vp, _vp]),
     "mllp_spmv": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),

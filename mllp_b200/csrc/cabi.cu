@@ -1,5 +1,6 @@
 // cabi.cu -- the C ABI of include/mllp_b200.h for the single-instance path.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -85,6 +86,13 @@ struct mllp_lp {
     double* d_norm2 = nullptr;
     int64_t info[16] = {0};
     cudaGraphExec_t graph = nullptr;  // graph mode: GRAPH_UNROLL iterations
+    // row partition over GPUs (nranks > 1): this rank owns a slice of the rows of A (y) and of the
+    // rows of A' (x); internal vectors have nranks * Ly (Lx) entries, slices are exchanged with
+    // NCCL all-gathers between the half-iterations
+    int rank = 0, nranks = 1;
+    int mi = 0, ni = 0;               // internal (padded) vector lengths
+    int Ly = 0, Lx = 0;               // slice lengths
+    void* comm = nullptr;             // ncclComm_t
 };
 constexpr int GRAPH_UNROLL = 32;
 
@@ -172,6 +180,62 @@ int build_graph(mllp_lp* lp)
     return 0;
 }
 
+// ---- NCCL, bound at run time (the library is usually already loaded by torch.distributed) ----
+struct NcclId { char internal[128]; };   // ncclUniqueId
+typedef int (*nccl_get_unique_id_t)(NcclId*);
+typedef int (*nccl_comm_init_rank_t)(void**, int, NcclId, int);
+typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_comm_destroy_t)(void*);
+typedef const char* (*nccl_get_error_string_t)(int);
+struct NcclApi {
+    void* lib = nullptr;
+    nccl_get_unique_id_t get_unique_id = nullptr;
+    nccl_comm_init_rank_t comm_init_rank = nullptr;
+    nccl_all_gather_t all_gather = nullptr;
+    nccl_all_reduce_t all_reduce = nullptr;
+    nccl_comm_destroy_t comm_destroy = nullptr;
+    nccl_get_error_string_t get_error_string = nullptr;
+};
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {getenv("MLLP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (api.lib) {
+            api.get_unique_id = (nccl_get_unique_id_t)dlsym(api.lib, "ncclGetUniqueId");
+            api.comm_init_rank = (nccl_comm_init_rank_t)dlsym(api.lib, "ncclCommInitRank");
+            api.all_gather = (nccl_all_gather_t)dlsym(api.lib, "ncclAllGather");
+            api.all_reduce = (nccl_all_reduce_t)dlsym(api.lib, "ncclAllReduce");
+            api.comm_destroy = (nccl_comm_destroy_t)dlsym(api.lib, "ncclCommDestroy");
+            api.get_error_string = (nccl_get_error_string_t)dlsym(api.lib, "ncclGetErrorString");
+        }
+    }
+    if (!api.lib || !api.get_unique_id || !api.comm_init_rank || !api.all_gather || !api.all_reduce || !api.comm_destroy)
+        return nullptr;
+    return &api;
+}
+int nccl_fail(int rc, const char* what)
+{
+    NcclApi* a = nccl_api();
+    g_err = std::string(what) + ": NCCL error " + std::to_string(rc) + (a && a->get_error_string ? std::string(" (") + a->get_error_string(rc) + ")" : "");
+    return 2000 + rc;
+}
+#define NCCL_OK(call)                                     \
+    do {                                                  \
+        int r_ = (call);                                  \
+        if (r_ != 0) return nccl_fail(r_, #call);         \
+    } while (0)
+
 }  // namespace
 
 extern "C" {
@@ -190,9 +254,10 @@ int mllp_device_info(int device, int64_t* out3)
     return 0;
 }
 
-int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, const int32_t* h_indices,
-                   const double* h_values, const double* h_lb, const double* h_ub, const double* h_ylo,
-                   const double* h_yhi, int device, uint32_t flags, mllp_lp_t* out)
+static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, const int32_t* h_indices,
+                       const double* h_values, const double* h_lb, const double* h_ub, const double* h_ylo,
+                       const double* h_yhi, int device, uint32_t flags, int rank, int nranks, const unsigned char* uid,
+                       mllp_lp_t* out)
 {
     if (!out) return fail(MLLP_E_INVALID, "mllp_lp_create: null output handle");
     *out = nullptr;
@@ -218,8 +283,11 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
     mllp_lp* lp = new (std::nothrow) mllp_lp();
     if (!lp) return fail(MLLP_E_NOMEM, "mllp_lp_create: out of host memory");
     lp->device = device;
-    lp->m = m; lp->n = n; lp->nnz = nnz; lp->flags = flags;
+    lp->m = m; lp->n = n; lp->nnz = nnz;
     lp->bounds = (h_lb != nullptr) || (h_ylo != nullptr);
+    lp->rank = rank; lp->nranks = nranks;
+    if (nranks > 1) flags |= MLLP_F_GRAPH_MODE;   // half-iterations are separate launches around the all-gathers
+    lp->flags = flags;
 
     // launch geometry of the persistent grid.  Resident mode (default): one 1024-thread CTA per
     // SM whose share of A and A' lives in shared memory; streaming mode: 2 x 512.
@@ -249,23 +317,51 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
         std::vector<int32_t> orderY, posY, orderX, posX;
         plan_orders(m, n, h_indptr, h_indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
         HostMat HA, HAT;
-        build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, HA);
-        build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
+        int mi = m, ni = n;
+        if (nranks == 1) {
+            build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, HA);
+            build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
+        } else {
+            // Row partition: rank p owns the rows of A (entries of y) and the rows of A' (entries of x)
+            // that LPT-by-nnz gives it.  The global internal order is [rank 0's rows | rank 1's | ...],
+            // each slice padded to the same even length so one in-place all-gather moves it.
+            const BuildParams bpA = effective_params(m, h_indptr, bp), bpAT = effective_params(n, tptr.data(), bp);
+            RowPartition PY, PX;
+            partition_rows(m, h_indptr, orderY, nranks, PY);
+            partition_rows(n, tptr.data(), orderX, nranks, PX);
+            lp->Ly = PY.L; lp->Lx = PX.L;
+            posY = PY.pos; posX = PX.pos;
+            const std::vector<int32_t>& mineY = PY.lists[rank];
+            const std::vector<int32_t>& mineX = PX.lists[rank];
+            std::vector<int32_t> oY = PY.order_pad, oX = PX.order_pad;
+            mi = lp->Ly * nranks; ni = lp->Lx * nranks;
+            build_host_mat((int)mineY.size(), ni, h_indptr, h_indices, h_values, mineY, posX, bpA, HA, (uint32_t)(rank * lp->Ly));
+            build_host_mat((int)mineX.size(), mi, tptr.data(), tind.data(), tval.data(), mineX, posY, bpAT, HAT,
+                           (uint32_t)(rank * lp->Lx));
+            orderY.swap(oY);
+            orderX.swap(oX);
+        }
+        lp->mi = mi; lp->ni = ni;
+        auto permuted_pad = [](const double* src, const std::vector<int32_t>& order, double fill) {
+            std::vector<double> outv(order.size());
+            for (size_t k = 0; k < order.size(); ++k) outv[k] = order[k] >= 0 ? src[order[k]] : fill;
+            return outv;
+        };
 
         auto body = [&]() -> int {
             RC_OK(upload_mat(lp, HA, lp->d.A));
             RC_OK(upload_mat(lp, HAT, lp->d.AT));
             RC_OK(dev_upload(lp, &lp->d_orderX, orderX.data(), orderX.size()));
             RC_OK(dev_upload(lp, &lp->d_orderY, orderY.data(), orderY.size()));
-            lp->d.m = m; lp->d.n = n;
-            RC_OK(dev_zeros(lp, &lp->d_b, (size_t)m));
-            RC_OK(dev_zeros(lp, &lp->d_c, (size_t)n));
+            lp->d.m = mi; lp->d.n = ni;
+            RC_OK(dev_zeros(lp, &lp->d_b, (size_t)mi));
+            RC_OK(dev_zeros(lp, &lp->d_c, (size_t)ni));
             lp->d.b = lp->d_b; lp->d.c = lp->d_c;
             if (lp->bounds) {
                 // general form: every box array is materialised (missing ones get +-inf / 0)
-                std::vector<double> lb((size_t)n, 0.0), ub((size_t)n, INFINITY), ylo((size_t)m, -INFINITY), yhi((size_t)m, INFINITY);
-                if (h_lb) { lb = permuted(h_lb, orderX); ub = permuted(h_ub, orderX); }
-                if (h_ylo) { ylo = permuted(h_ylo, orderY); yhi = permuted(h_yhi, orderY); }
+                std::vector<double> lb((size_t)ni, 0.0), ub((size_t)ni, INFINITY), ylo((size_t)mi, -INFINITY), yhi((size_t)mi, INFINITY);
+                if (h_lb) { lb = permuted_pad(h_lb, orderX, 0.0); ub = permuted_pad(h_ub, orderX, 0.0); }
+                if (h_ylo) { ylo = permuted_pad(h_ylo, orderY, 0.0); yhi = permuted_pad(h_yhi, orderY, 0.0); }
                 double *p1, *p2, *p3, *p4;
                 RC_OK(dev_upload(lp, &p1, lb.data(), lb.size()));
                 RC_OK(dev_upload(lp, &p2, ub.data(), ub.size()));
@@ -273,17 +369,17 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
                 RC_OK(dev_upload(lp, &p4, yhi.data(), yhi.size()));
                 lp->d.lb = p1; lp->d.ub = p2; lp->d.ylo = p3; lp->d.yhi = p4;
             }
-            RC_OK(dev_zeros(lp, &lp->d.x, (size_t)n + 1));
-            RC_OK(dev_zeros(lp, &lp->d.y, (size_t)m + 1));
-            RC_OK(dev_zeros(lp, &lp->d.xbar, (size_t)n + 1));
-            RC_OK(dev_zeros(lp, &lp->d.x0, (size_t)n));
-            RC_OK(dev_zeros(lp, &lp->d.y0, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->d.x, (size_t)ni + 2));
+            RC_OK(dev_zeros(lp, &lp->d.y, (size_t)mi + 2));
+            RC_OK(dev_zeros(lp, &lp->d.xbar, (size_t)ni + 2));
+            RC_OK(dev_zeros(lp, &lp->d.x0, (size_t)ni));
+            RC_OK(dev_zeros(lp, &lp->d.y0, (size_t)mi));
             RC_OK(dev_zeros(lp, &lp->d.red, (size_t)RED_BUFFERS * lp->G * NRED));
             RC_OK(dev_zeros(lp, &lp->d.barrier, 4));
             RC_OK(dev_zeros(lp, &lp->d.ctrl, CTRL_SIZE));
-            RC_OK(dev_zeros(lp, &lp->tmp_n, (size_t)n));
-            RC_OK(dev_zeros(lp, &lp->tmp_n2, (size_t)n));
-            RC_OK(dev_zeros(lp, &lp->tmp_m, (size_t)m));
+            RC_OK(dev_zeros(lp, &lp->tmp_n, (size_t)ni));
+            RC_OK(dev_zeros(lp, &lp->tmp_n2, (size_t)ni));
+            RC_OK(dev_zeros(lp, &lp->tmp_m, (size_t)mi));
             RC_OK(dev_zeros(lp, &lp->u_x, (size_t)n));
             RC_OK(dev_zeros(lp, &lp->u_y, (size_t)m));
             RC_OK(dev_zeros(lp, &lp->u_b, (size_t)m));
@@ -291,6 +387,13 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
             RC_OK(dev_zeros(lp, &lp->d_scal, MLLP_NUM_SCALARS));
             RC_OK(dev_zeros(lp, &lp->d_norm2, 2));
             if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
+            if (nranks > 1) {
+                NcclApi* api = nccl_api();
+                if (!api) return fail(MLLP_E_STATE, "mllp_lp_create_rowpart: libnccl.so.2 could not be loaded");
+                NcclId id;
+                memcpy(id.internal, uid, sizeof(id.internal));
+                NCCL_OK(api->comm_init_rank(&lp->comm, nranks, id, rank));
+            }
             // shared-memory residency of the matrix slices
             const size_t desc_bytes = 16 * ((size_t)HA.max_cta_tiles + (size_t)HAT.max_cta_tiles);
             lp->dyn_smem = desc_bytes;
@@ -323,7 +426,7 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
         rc = body();
 
         int64_t* I = lp->info;
-        I[0] = m; I[1] = n; I[2] = nnz;
+        I[0] = m; I[1] = n; I[2] = nranks > 1 ? HA.nnz_emitted : nnz;
         I[3] = (int64_t)HA.tiles.size(); I[4] = (int64_t)HAT.tiles.size();
         I[5] = (int64_t)HA.total_steps * 64; I[6] = (int64_t)HAT.total_steps * 64;
         I[7] = (int64_t)HA.splits.size(); I[8] = (int64_t)HAT.splits.size();
@@ -343,10 +446,40 @@ int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, c
     return 0;
 }
 
+int mllp_lp_create(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, const int32_t* h_indices,
+                   const double* h_values, const double* h_lb, const double* h_ub, const double* h_ylo,
+                   const double* h_yhi, int device, uint32_t flags, mllp_lp_t* out)
+{
+    return create_impl(m, n, nnz, h_indptr, h_indices, h_values, h_lb, h_ub, h_ylo, h_yhi, device, flags, 0, 1, nullptr, out);
+}
+
+int mllp_nccl_unique_id(unsigned char* out128)
+{
+    if (!out128) return fail(MLLP_E_INVALID, "mllp_nccl_unique_id: null output");
+    NcclApi* api = nccl_api();
+    if (!api) return fail(MLLP_E_STATE, "mllp_nccl_unique_id: libnccl.so.2 could not be loaded");
+    NcclId id;
+    NCCL_OK(api->get_unique_id(&id));
+    memcpy(out128, id.internal, sizeof(id.internal));
+    return 0;
+}
+
+int mllp_lp_create_rowpart(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, const int32_t* h_indices,
+                           const double* h_values, const double* h_lb, const double* h_ub, const double* h_ylo,
+                           const double* h_yhi, int device, uint32_t flags, int32_t rank, int32_t nranks,
+                           const unsigned char* uid128, mllp_lp_t* out)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !uid128))
+        return fail(MLLP_E_INVALID, "mllp_lp_create_rowpart: bad rank / nranks / unique id");
+    return create_impl(m, n, nnz, h_indptr, h_indices, h_values, h_lb, h_ub, h_ylo, h_yhi, device, flags, rank, nranks,
+                       uid128, out);
+}
+
 int mllp_lp_destroy(mllp_lp_t lp)
 {
     if (!lp) return 0;
     DeviceGuard guard(lp->device);
+    if (lp->comm) { NcclApi* api = nccl_api(); if (api) api->comm_destroy(lp->comm); }
     if (lp->graph) cudaGraphExecDestroy(lp->graph);
     for (void* p : lp->allocs) cudaFree(p);
     delete lp;
@@ -363,6 +496,7 @@ int mllp_lp_info(mllp_lp_t lp, int64_t* out16)
 int mllp_spmv(mllp_lp_t lp, int trans, const double* d_in, double* d_out, void* stream)
 {
     if (!lp || !d_in || !d_out) return fail(MLLP_E_INVALID, "mllp_spmv: null argument");
+    if (lp->nranks > 1) return fail(MLLP_E_STATE, "mllp_spmv: not available on a row-partitioned handle");
     DeviceGuard guard(lp->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (!trans) {
@@ -380,6 +514,7 @@ int mllp_spmv(mllp_lp_t lp, int trans, const double* d_in, double* d_out, void* 
 int mllp_estimate_norm(mllp_lp_t lp, int iters, double* h_sigma_max, void* stream)
 {
     if (!lp || !h_sigma_max || iters < 1) return fail(MLLP_E_INVALID, "mllp_estimate_norm: bad argument");
+    if (lp->nranks > 1) return fail(MLLP_E_STATE, "mllp_estimate_norm: not available on a row-partitioned handle");
     DeviceGuard guard(lp->device);
     cudaStream_t s = (cudaStream_t)stream;
     // v (tmp_n) = 1/sqrt(n); order does not matter for a constant vector
@@ -400,16 +535,16 @@ int mllp_estimate_norm(mllp_lp_t lp, int iters, double* h_sigma_max, void* strea
 static int load_problem(mllp_lp* lp, const double* d_x, const double* d_y, const double* d_b, const double* d_c,
                         cudaStream_t s)
 {
-    RC_OK(launch_gather(lp->d.x, d_x, lp->d_orderX, lp->n, s));
-    RC_OK(launch_gather(lp->d.y, d_y, lp->d_orderY, lp->m, s));
-    RC_OK(launch_gather(lp->d_b, d_b, lp->d_orderY, lp->m, s));
-    RC_OK(launch_gather(lp->d_c, d_c, lp->d_orderX, lp->n, s));
+    RC_OK(launch_gather(lp->d.x, d_x, lp->d_orderX, lp->ni, s));
+    RC_OK(launch_gather(lp->d.y, d_y, lp->d_orderY, lp->mi, s));
+    RC_OK(launch_gather(lp->d_b, d_b, lp->d_orderY, lp->mi, s));
+    RC_OK(launch_gather(lp->d_c, d_c, lp->d_orderX, lp->ni, s));
     return 0;
 }
 static int store_solution(mllp_lp* lp, double* d_x, double* d_y, cudaStream_t s)
 {
-    RC_OK(launch_scatter(d_x, lp->d.x, lp->d_orderX, lp->n, s));
-    RC_OK(launch_scatter(d_y, lp->d.y, lp->d_orderY, lp->m, s));
+    RC_OK(launch_scatter(d_x, lp->d.x, lp->d_orderX, lp->ni, s));
+    RC_OK(launch_scatter(d_y, lp->d.y, lp->d_orderY, lp->mi, s));
     return 0;
 }
 
@@ -421,6 +556,28 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
     DeviceGuard guard(lp->device);
     cudaStream_t s = (cudaStream_t)stream;
     RC_OK(load_problem(lp, d_x, d_y, d_b, d_c, s));
+    if (lp->nranks > 1) {
+        // row partition: x-slice update | all-gather xbar | y-slice update | all-gather y, all on `s`
+        NcclApi* api = nccl_api();
+        const double ts[2] = {tau, sigma};
+        CUDA_OK(cudaMemcpyAsync(lp->d.ctrl, ts, sizeof(ts), cudaMemcpyHostToDevice, s));
+        for (int it = 0; it < num_iters; ++it) {
+            RC_OK(launch_primal(lp->d, lp->bounds, lp->G, lp->threads, s));
+            NCCL_OK(api->all_gather(lp->d.xbar + (size_t)lp->rank * lp->Lx, lp->d.xbar, (size_t)lp->Lx, NCCL_FLOAT64, lp->comm, s));
+            RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));
+            NCCL_OK(api->all_gather(lp->d.y + (size_t)lp->rank * lp->Ly, lp->d.y, (size_t)lp->Ly, NCCL_FLOAT64, lp->comm, s));
+        }
+        if (num_iters > 0)
+            NCCL_OK(api->all_gather(lp->d.x + (size_t)lp->rank * lp->Lx, lp->d.x, (size_t)lp->Lx, NCCL_FLOAT64, lp->comm, s));
+        if (d_scalars) {
+            RC_OK(launch_eval_partial(lp->d, lp->bounds, lp->G, lp->threads, s));
+            double* red = lp->d.red + (size_t)RED_EVALP * lp->G * NRED;   // EVALP and EVALD buffers are adjacent
+            NCCL_OK(api->all_reduce(red, red, (size_t)2 * lp->G * NRED, NCCL_FLOAT64, NCCL_SUM, lp->comm, s));
+            RC_OK(launch_eval_finalize(lp->d, lp->G, d_scalars, (double)num_iters, s));
+        }
+        RC_OK(store_solution(lp, d_x, d_y, s));
+        return 0;
+    }
     if (lp->flags & MLLP_F_GRAPH_MODE) {
         const double ts[2] = {tau, sigma};
         CUDA_OK(cudaMemcpyAsync(lp->d.ctrl, ts, sizeof(ts), cudaMemcpyHostToDevice, s));
@@ -485,6 +642,7 @@ int mllp_pdhg_solve(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, c
     if (!lp || !d_x || !d_y || !d_b || !d_c || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 > 0.0) ||
         !(eta > 0.0))
         return fail(MLLP_E_INVALID, "mllp_pdhg_solve: bad argument");
+    if (lp->nranks > 1) return fail(MLLP_E_STATE, "mllp_pdhg_solve: not available on a row-partitioned handle");
     if (lp->flags & MLLP_F_GRAPH_MODE) return fail(MLLP_E_STATE, "mllp_pdhg_solve: needs the persistent kernel (handle was created with MLLP_F_GRAPH_MODE)");
     DeviceGuard guard(lp->device);
     cudaStream_t s = (cudaStream_t)stream;

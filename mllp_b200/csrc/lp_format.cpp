@@ -36,11 +36,14 @@ RowClass classify(int len, const BuildParams& bp)
     return rc;
 }
 
+}  // namespace
+
 // Raise max_steps (the split threshold and chunk length) until no CTA gets more than
 // SPLIT_SLOTS split chunks.  Deterministic in (row lengths, bp), so the row-order planner and
 // the emitter agree.
 BuildParams effective_params(int nrows, const int32_t* ptr, BuildParams bp)
 {
+    if (bp.final_params) return bp;
     const int G = std::max(1, bp.num_ctas);
     if (bp.pref_steps < 1) bp.pref_steps = 1;
     if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
@@ -51,11 +54,13 @@ BuildParams effective_params(int nrows, const int32_t* ptr, BuildParams bp)
             const int64_t len = ptr[r + 1] - ptr[r];
             if (len > cap) chunks += (len + cap - 1) / cap;
         }
-        if ((chunks + G - 1) / G <= SPLIT_SLOTS || bp.max_steps >= 16384) return bp;
+        if ((chunks + G - 1) / G <= SPLIT_SLOTS || bp.max_steps >= 16384) {
+            bp.final_params = true;
+            return bp;
+        }
     }
 }
 
-}  // namespace
 
 void csr_transpose(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
                    const double* val, std::vector<int32_t>& tptr, std::vector<int32_t>& tind,
@@ -149,15 +154,52 @@ void plan_orders(int m, int n, const int32_t* ptr, const int32_t* ind, const int
     }
 }
 
+void partition_rows(int nrows, const int32_t* ptr, const std::vector<int32_t>& global_order, int nranks,
+                    RowPartition& out)
+{
+    nranks = std::max(1, nranks);
+    std::vector<int> owner((size_t)nrows, 0);
+    if (nranks > 1) {
+        std::vector<int32_t> by((size_t)nrows);
+        std::iota(by.begin(), by.end(), 0);
+        std::stable_sort(by.begin(), by.end(),
+                         [&](int32_t a, int32_t b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
+        std::vector<int64_t> load((size_t)nranks, 0), cnt((size_t)nranks, 0);
+        for (int32_t r : by) {
+            int best = 0;
+            for (int p = 1; p < nranks; ++p)
+                if (load[p] < load[best] || (load[p] == load[best] && cnt[p] < cnt[best])) best = p;
+            owner[r] = best;
+            load[best] += (ptr[r + 1] - ptr[r]) + 1;  // +1: every row also costs a vector update
+            cnt[best]++;
+        }
+    }
+    out.lists.assign((size_t)nranks, {});
+    for (int32_t r : global_order) out.lists[owner[r]].push_back(r);  // stable: class order kept inside a rank
+    size_t mx = 0;
+    for (auto& l : out.lists) mx = std::max(mx, l.size());
+    out.L = (int)((mx + 1) & ~(size_t)1);
+    out.order_pad.assign((size_t)out.L * nranks, -1);
+    out.pos.assign((size_t)nrows, 0);
+    for (int p = 0; p < nranks; ++p)
+        for (size_t k = 0; k < out.lists[p].size(); ++k) {
+            out.order_pad[(size_t)p * out.L + k] = out.lists[p][k];
+            out.pos[out.lists[p][k]] = (int32_t)((size_t)p * out.L + k);
+        }
+}
+
 void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
                     const double* val, const std::vector<int32_t>& order,
-                    const std::vector<int32_t>& colpos, const BuildParams& bp_in, HostMat& out)
+                    const std::vector<int32_t>& colpos, const BuildParams& bp_in, HostMat& out,
+                    uint32_t row_offset)
 {
     const BuildParams bp = effective_params(nrows, ptr, bp_in);
     out = HostMat();
     out.nrows = nrows;
     out.ncols = ncols;
-    out.nnz = ptr[nrows];
+    out.nnz = 0;
+    for (int p = 0; p < nrows; ++p) out.nnz += ptr[order[p] + 1] - ptr[order[p]];
+    out.nnz_emitted = out.nnz;
     const int G = std::max(1, bp.num_ctas);
 
     struct ProtoTile {
@@ -186,7 +228,7 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
             const int e1 = std::min(len, e0 + clen);
             chunks.push_back({(uint32_t)p, (uint16_t)ceil_div(e1 - e0, 64), 5, 1, p, (uint32_t)e0, (uint32_t)e1});
         }
-        out.splits.push_back({(uint32_t)p, 0u, 0u, 0u});
+        out.splits.push_back({(uint32_t)p + row_offset, 0u, 0u, 0u});
     }
 
     // ---- 1b. regular rows: tiles of 32/L consecutive rows of one class -----------------------
@@ -294,7 +336,7 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
             const int L = 1 << t.logL;
             Tile tile;
             tile.off = (uint32_t)step_cursor;
-            tile.row_base = t.row_base;
+            tile.row_base = t.row_base + row_offset;
             tile.nsteps = t.nsteps;
             tile.logL = t.logL;
             tile.nrows = t.nrows;
@@ -509,5 +551,118 @@ extern "C" int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const
         out6[2 + w] = worst;
         out6[4 + w] = 2.0 * (double)M.total_steps;
     }
+    return 0;
+}
+
+// Host-only self check of the ROW-PARTITIONED build: emulates all `nranks` ranks on the CPU --
+// each rank's tiles produce its slice of A v and A' w, slices are "all-gathered" by writing
+// into the shared padded vector -- and compares with the plain CSR products.  out4: [0] worst
+// relative row error, [1] padded y length, [2] padded x length, [3] largest / mean nonzeros per rank.
+extern "C" int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr,
+                                      const int32_t* indices, const double* values, int32_t num_ctas,
+                                      int32_t nranks, double* out4)
+{
+    using namespace mllp;
+    if (m < 0 || n < 0 || !indptr || !out4 || nranks < 1 || (int64_t)indptr[m] != nnz) return 1001;
+    BuildParams bp;
+    bp.num_ctas = num_ctas;
+    bp.pref_steps = 4;
+    bp.max_steps = 8;
+    std::vector<int32_t> tptr, tind;
+    std::vector<double> tval;
+    csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);
+    std::vector<int32_t> orderY, posY, orderX, posX;
+    plan_orders(m, n, indptr, indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
+    const BuildParams bpA = effective_params(m, indptr, bp), bpAT = effective_params(n, tptr.data(), bp);
+    RowPartition PY, PX;
+    partition_rows(m, indptr, orderY, nranks, PY);
+    partition_rows(n, tptr.data(), orderX, nranks, PX);
+    const int mi = PY.L * nranks, ni = PX.L * nranks;
+    double worst = 0.0, max_nnz = 0.0;
+    for (int which = 0; which < 2; ++which) {
+        const int nr = which ? n : m, nc = which ? m : n, nci = which ? mi : ni, nri = which ? ni : mi;
+        const int32_t* ptr = which ? tptr.data() : indptr;
+        const int32_t* ind = which ? tind.data() : indices;
+        const double* val = which ? tval.data() : values;
+        const RowPartition& PR = which ? PX : PY;
+        const RowPartition& PC = which ? PY : PX;
+        std::vector<double> v_user((size_t)nc), v_int((size_t)nci, 0.0), out_int((size_t)nri, NAN);
+        for (int j = 0; j < nc; ++j) v_user[j] = 0.25 + (double)((j * 2654435761u) % 1000u) / 997.0;
+        for (int k = 0; k < nci; ++k) if (PC.order_pad[k] >= 0) v_int[k] = v_user[PC.order_pad[k]];
+        for (int rank = 0; rank < nranks; ++rank) {
+            HostMat M;
+            build_host_mat((int)PR.lists[rank].size(), nci, ptr, ind, val, PR.lists[rank], PC.pos, which ? bpAT : bpA, M,
+                           (uint32_t)(rank * PR.L));
+            max_nnz = std::max(max_nnz, (double)M.nnz_emitted);
+            std::vector<double> partial(M.num_partials, 0.0);
+            std::vector<uint32_t> arrived(M.splits.size(), 0);
+            auto butterfly = [](double* ls, int L) {
+                for (int o = L >> 1; o > 0; o >>= 1) {
+                    double nxt[32];
+                    for (int lane = 0; lane < 32; ++lane) nxt[lane] = ls[lane] + ls[lane ^ o];
+                    for (int lane = 0; lane < 32; ++lane) ls[lane] = nxt[lane];
+                }
+            };
+            for (int g = 0; g < bp.num_ctas; ++g) {
+                double spart[SPLIT_SLOTS];
+                for (uint32_t ti = M.cta_begin[g]; ti < M.cta_begin[g + 1]; ++ti) {
+                    const Tile& t = M.tiles[ti];
+                    const int L = 1 << t.logL;
+                    double lane_sum[32];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        double s = 0.0;
+                        for (int st = 0; st < t.nsteps; ++st) {
+                            const size_t at = ((size_t)(t.off + st) * 32 + lane) * 2;
+                            if (M.idx[at] < 0 || M.idx[at] >= nci || M.idx[at + 1] < 0 || M.idx[at + 1] >= nci) return 3;
+                            s = std::fma(M.vals[at], v_int[M.idx[at]], s);
+                            s = std::fma(M.vals[at + 1], v_int[M.idx[at + 1]], s);
+                        }
+                        lane_sum[lane] = s;
+                    }
+                    butterfly(lane_sum, L);
+                    if (t.split < 0) {
+                        for (int rr = 0; rr < t.nrows; ++rr) {
+                            const uint32_t r = t.row_base + rr;
+                            if (r < (uint32_t)(rank * PR.L) || r >= (uint32_t)((rank + 1) * PR.L) || !std::isnan(out_int[r])) return 5;
+                            out_int[r] = lane_sum[rr * L];
+                        }
+                    } else {
+                        spart[t.split] = lane_sum[0];
+                    }
+                }
+                for (uint32_t li = M.cta_lsplit_begin[g]; li < M.cta_lsplit_begin[g + 1]; ++li) {
+                    const LocalSplit& ls = M.lsplits[li];
+                    const SplitRow& sr = M.splits[ls.split_id];
+                    double pl[32] = {0};
+                    for (int k = 0; k < ls.count; ++k) pl[k % 32] += spart[ls.first + k];
+                    butterfly(pl, 32);
+                    partial[ls.gslot] = pl[0];
+                    if (++arrived[ls.split_id] == sr.nparts) {
+                        double ls32[32] = {0};
+                        for (uint32_t k = 0; k < sr.nparts; ++k) ls32[k % 32] += partial[sr.first_slot + k];
+                        butterfly(ls32, 32);
+                        if (sr.row >= (uint32_t)nri || !std::isnan(out_int[sr.row])) return 7;
+                        out_int[sr.row] = ls32[0];
+                    }
+                }
+            }
+        }
+        for (int r = 0; r < nr; ++r) {
+            const double got = out_int[PR.pos[r]];
+            if (std::isnan(got)) return 8;
+            double ref = 0.0, mag = 0.0;
+            for (int32_t q = ptr[r]; q < ptr[r + 1]; ++q) {
+                ref += val[q] * v_user[ind[q]];
+                mag += std::fabs(val[q] * v_user[ind[q]]);
+            }
+            worst = std::max(worst, std::fabs(ref - got) / (mag > 0.0 ? mag : 1.0));
+        }
+        for (int k = 0; k < nri; ++k)
+            if (PR.order_pad[k] < 0 && !std::isnan(out_int[k])) return 9;  // padding must stay untouched
+    }
+    out4[0] = worst;
+    out4[1] = mi;
+    out4[2] = ni;
+    out4[3] = nnz > 0 ? max_nnz / ((double)nnz / nranks) : 1.0;
     return 0;
 }

@@ -55,12 +55,17 @@ struct BuildParams {
     int pref_steps = 4;      // choose L so a row needs at most this many steps
     int max_steps = 4;       // rows longer than 64*max_steps entries are split
     bool cluster = true;     // cluster rows inside a length class by the entries they touch
+    bool final_params = false; // max_steps already adjusted (effective_params is then the identity)
 };
+
+// max_steps raised until no CTA gets more than SPLIT_SLOTS split chunks (idempotent).
+BuildParams effective_params(int nrows, const int32_t* ptr, BuildParams bp);
 
 // Host-side image of one matrix in the tiled format.
 struct HostMat {
     int nrows = 0, ncols = 0;
     int64_t nnz = 0;
+    int64_t nnz_emitted = 0;           // nonzeros of the rows actually emitted (row partition)
     std::vector<double> vals;          // 64 * total_steps
     std::vector<int32_t> idx;          // 64 * total_steps (internal column ids)
     std::vector<Tile> tiles;           // CTA-major
@@ -91,9 +96,25 @@ void plan_orders(int m, int n, const int32_t* ptr, const int32_t* ind, const int
 
 // Emit the tiled image of a CSR matrix whose rows follow `order`/`pos` and whose column
 // ids are renamed through `colpos` (the other matrix's pos[]).
+// `order` may list a subset of the rows (row partition over GPUs): tile k then covers the
+// internal rows row_offset + k..., `ptr/ind/val` stay the full matrix.
 void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
                     const double* val, const std::vector<int32_t>& order,
-                    const std::vector<int32_t>& colpos, const BuildParams& bp, HostMat& out);
+                    const std::vector<int32_t>& colpos, const BuildParams& bp, HostMat& out,
+                    uint32_t row_offset = 0);
+
+// Row partition over `nranks` GPUs: rows go to ranks by longest-processing-time on their
+// nonzero counts; inside a rank the global (class, cluster) order is kept.  The global internal
+// order is [rank 0's rows | rank 1's rows | ...], every slice padded to the same even length L
+// (order_pad = -1 on padding), so one in-place all-gather exchanges the slices.
+struct RowPartition {
+    int L = 0;
+    std::vector<int32_t> order_pad;               // nranks * L
+    std::vector<int32_t> pos;                     // nrows: padded internal position of every row
+    std::vector<std::vector<int32_t>> lists;      // per rank: its rows (original ids) in order
+};
+void partition_rows(int nrows, const int32_t* ptr, const std::vector<int32_t>& global_order, int nranks,
+                    RowPartition& out);
 
 // CSR transpose (counting sort); outputs sized by the callee.
 void csr_transpose(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,

@@ -15,6 +15,8 @@ int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2,
 int launch_spmv(const DevMat& M, const double* in, double* out, int G, int threads, cudaStream_t s);
 int launch_primal(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
 int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
+int launch_eval_partial(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
+int launch_eval_finalize(const DevLP& lp, int G, double* out, double iters, cudaStream_t s);
 int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s);
 int persistent_set_smem(bool bounds, size_t dyn_smem);
 int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem);

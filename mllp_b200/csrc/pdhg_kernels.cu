@@ -10,13 +10,13 @@ __global__ void k_gather(double* __restrict__ dst, const double* __restrict__ sr
                          const int32_t* __restrict__ order, int n)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-        dst[k] = src[order[k]];
+        dst[k] = order[k] >= 0 ? src[order[k]] : 0.0;   // -1: padding of a row-partitioned slice
 }
 __global__ void k_scatter(double* __restrict__ dst, const double* __restrict__ src,
                           const int32_t* __restrict__ order, int n)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-        dst[order[k]] = src[k];
+        if (order[k] >= 0) dst[order[k]] = src[k];
 }
 __global__ void k_fill(double* dst, double v, int n)
 {
@@ -341,6 +341,17 @@ int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s
 {
     if (bounds) k_dual<true><<<G, threads, 0, s>>>(lp);
     else k_dual<false><<<G, threads, 0, s>>>(lp);
+    return (int)cudaGetLastError();
+}
+int launch_eval_partial(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s)
+{
+    if (bounds) k_eval<true><<<G, threads, 0, s>>>(lp, G);
+    else k_eval<false><<<G, threads, 0, s>>>(lp, G);
+    return (int)cudaGetLastError();
+}
+int launch_eval_finalize(const DevLP& lp, int G, double* out, double iters, cudaStream_t s)
+{
+    k_eval_finalize<<<1, 32, 0, s>>>(lp, G, out, iters);
     return (int)cudaGetLastError();
 }
 int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s)
