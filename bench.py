@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="osa-60")
@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -116,9 +116,10 @@ def cpu_oracle_rate(A, b, c, eta, seconds, min_iters=5):
     from oracle import pdhg_oracle as O
     csr = O.CSR(A)
     m, n = A.shape
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, min_iters)  # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, min_iters)  # warm-up + estimate
-    per_it = max((time.perf_counter() - t0) / min_iters, 1e-7)
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, 4 * min_iters)
+    per_it = max((time.perf_counter() - t0) / (4 * min_iters), 1e-7)
     iters = int(max(min_iters, min(20000, seconds / per_it)))
     t0 = time.perf_counter()
     O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, iters)
