@@ -111,20 +111,29 @@ def perturbed(b, c, rank):
     return b * (1.0 + 0.1 * rng.random(b.shape[0])), c * (1.0 + 0.1 * rng.uniform(-1, 1, c.shape[0]))
 
 
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(A, b, c, eta, seconds, min_iters=5):
     """iterations/s of the CPU oracle (all host threads) on a bounded sample."""
     from oracle import pdhg_oracle as O
     csr = O.CSR(A)
     m, n = A.shape
-    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, min_iters)  # warm-up (thread pool, page faults)
+    nt = host_threads()
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, min_iters, nthreads=nt)  # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, 4 * min_iters)
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, 4 * min_iters, nthreads=nt)
     per_it = max((time.perf_counter() - t0) / (4 * min_iters), 1e-7)
     iters = int(max(min_iters, min(20000, seconds / per_it)))
     t0 = time.perf_counter()
-    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, iters)
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, iters, nthreads=nt)
     dt = time.perf_counter() - t0
-    return iters / dt, iters, dt, O.num_threads()
+    return iters / dt, iters, dt, nt
 
 
 def run_reference(args, rank, world):
@@ -136,19 +145,21 @@ def run_reference(args, rank, world):
     A, b, c = D.load_csr(args.workload)
     m, n = A.shape
     csr = O.CSR(A)
-    eta = 0.9 / O.power_iteration(csr, 50)
+    nt = host_threads()
+    eta = 0.9 / O.power_iteration(csr, 50, nthreads=nt)
     # bounded sample per step, sized so steps+warmup end within a few minutes
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, 5, nthreads=nt)
     t0 = time.perf_counter()
-    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, 5)
-    per_it = (time.perf_counter() - t0) / 5
+    O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, 10, nthreads=nt)
+    per_it = (time.perf_counter() - t0) / 10
     budget = 120.0 / max(1, args.steps + args.warmup)
     iters = int(max(5, min(args.iters_per_step, budget / per_it)))
     x, y = np.zeros(n), np.zeros(m)
     for _ in range(args.warmup):
-        O.pdhg_run(csr, b, c, x, y, eta, eta, iters)
+        x, y = O.pdhg_run(csr, b, c, x, y, eta, eta, iters, nthreads=nt)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.pdhg_run(csr, b, c, x, y, eta, eta, iters)
+        x, y = O.pdhg_run(csr, b, c, x, y, eta, eta, iters, nthreads=nt)
     dt = time.perf_counter() - t0
     val = args.steps * iters / dt
     info_bytes = 24 * A.nnz + 36 * m + 44 * n + 8
@@ -158,7 +169,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "netlib " + args.workload + " (_norm arrays)",
         "config": {"workload": args.workload, "m": m, "n": n, "nnz": int(A.nnz), "mode": "parity (fixed step PDHG)",
                    "iters_per_step": iters, "bytes_per_iter": info_bytes},
-        "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": O.num_threads(), "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": nt, "kind": "port",
                          "sample": "%d steps x %d iterations of %s on the CPU oracle (OpenMP, all threads)" % (args.steps, iters, args.workload)},
         "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no implementation of this path (SURVEY.md section 0); this arm times the repo's CPU oracle",

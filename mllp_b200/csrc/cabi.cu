@@ -303,7 +303,7 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
     BuildParams bp;
     bp.num_ctas = lp->G;
     bp.pref_steps = env_int("MLLP_PREF_STEPS", 4);
-    bp.max_steps = env_int("MLLP_MAX_STEPS", 8);
+    bp.max_steps = env_int("MLLP_MAX_STEPS", 4);
     if (bp.pref_steps < 1) bp.pref_steps = 1;
     if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
     if (bp.max_steps > 1024) bp.max_steps = 1024;
@@ -405,7 +405,7 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
                 budget -= std::min<size_t>(budget, desc_bytes);
                 // The gathered vectors are read through L1 (the grid barrier invalidates it), so part of
                 // the SM's 228 KB stays L1: cap the shared-memory share of the matrix.
-                budget = std::min<size_t>(budget, (size_t)env_int("MLLP_RES_KB", 96) * 1024);
+                budget = std::min<size_t>(budget, (size_t)env_int("MLLP_RES_KB", 140) * 1024);
                 // what is left keeps (a prefix of) each CTA's share of A' and A resident
                 const size_t cap = budget / 768;
                 size_t a = (size_t)HA.max_cta_steps, at = (size_t)HAT.max_cta_steps;

@@ -255,15 +255,21 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
     // (then the CTA finishes it alone), larger rows fill consecutive CTAs
     const size_t C = chunks.size();
     {
-        const size_t quota = C ? (C + (size_t)G - 1) / (size_t)G : 0;
+        // quota of the current CTA = what is left, spread over the CTAs that are left
         size_t g = 0, used = 0;
+        auto quota_of = [&](size_t q_done, size_t g_now) {
+            const size_t left = C - q_done, ctas = (size_t)G - g_now;
+            return (left + ctas - 1) / ctas;
+        };
+        size_t quota = quota_of(0, 0);
         for (size_t q = 0; q < C;) {
             size_t q2 = q;
             while (q2 < C && chunks[q2].split == chunks[q].split) ++q2;
             const size_t k = q2 - q;
-            if (k <= quota && used + k > quota && g + 1 < (size_t)G) { ++g; used = 0; }
+            // a row that would fit in a fresh CTA but not in the rest of this one starts a new CTA
+            if (k <= quota && used > 0 && used + k > quota && g + 1 < (size_t)G) { ++g; used = 0; quota = quota_of(q, g); }
             for (; q < q2; ++q) {
-                if (used >= quota && g + 1 < (size_t)G) { ++g; used = 0; }
+                if (used >= quota && g + 1 < (size_t)G) { ++g; used = 0; quota = quota_of(q, g); }
                 per_cta[g].push_back(chunks[q]);
                 load[g] += chunks[q].nsteps + 2;
                 ++used;
@@ -567,7 +573,7 @@ extern "C" int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const i
     BuildParams bp;
     bp.num_ctas = num_ctas;
     bp.pref_steps = 4;
-    bp.max_steps = 8;
+    bp.max_steps = 4;
     std::vector<int32_t> tptr, tind;
     std::vector<double> tval;
     csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);

@@ -368,6 +368,41 @@ __device__ __forceinline__ double steps_dot(const double2* __restrict__ vp, cons
     return dot;
 }
 
+// Two tiles of the same small step count at once: both tiles' gathers are in flight together, so a
+// warp that owns two tiles of a phase pays one memory round trip instead of two.
+template <class MEM, int NS>
+__device__ __forceinline__ void pair_dot(const double2* __restrict__ vpa, const int2* __restrict__ ipa,
+                                         const double2* __restrict__ vpb, const int2* __restrict__ ipb,
+                                         const double* __restrict__ vec, double& da, double& db)
+{
+    int2 ja[NS], jb[NS];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) { ja[u] = ipa[u * 32]; jb[u] = ipb[u * 32]; }
+    double ga[2 * NS], gb[2 * NS];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+        ga[2 * u] = MEM::gather(vec + ja[u].x); ga[2 * u + 1] = MEM::gather(vec + ja[u].y);
+        gb[2 * u] = MEM::gather(vec + jb[u].x); gb[2 * u + 1] = MEM::gather(vec + jb[u].y);
+    }
+    da = 0.0; db = 0.0;
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+        const double2 va = vpa[u * 32], vb = vpb[u * 32];
+        da = fma(va.x, ga[2 * u], da); da = fma(va.y, ga[2 * u + 1], da);
+        db = fma(vb.x, gb[2 * u], db); db = fma(vb.y, gb[2 * u + 1], db);
+    }
+}
+
+// pointers to a tile's values / indices for this lane (resident copy or global)
+__device__ __forceinline__ void tile_ptrs(const MatView& V, uint32_t off, int nsteps, int lane, const double2*& vp,
+                                          const int2*& ip)
+{
+    const uint32_t loc = off - V.step0;
+    const bool res = loc + (uint32_t)nsteps <= V.res_steps;
+    vp = res ? V.rvals + (size_t)loc * 32 + lane : V.gvals + (size_t)off * 32 + lane;
+    ip = res ? V.ridx + (size_t)loc * 32 + lane : V.gidx + (size_t)off * 32 + lane;
+}
+
 template <class MEM>
 __device__ __forceinline__ double tile_dot(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps,
                                            int lane)
@@ -471,21 +506,51 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
     // regular tiles; the warps that published split rows are served last in every round
     const uint32_t busy = min(V.nls, (uint32_t)nwarps);
     const uint32_t wslot = ((uint32_t)warp + (uint32_t)nwarps - busy) % (uint32_t)nwarps;
-    for (uint32_t t = V.nsplit + wslot; t < V.ntiles; t += nwarps) {
+    for (uint32_t t = V.nsplit + wslot; t < V.ntiles; t += 2 * nwarps) {
+        const uint32_t t2 = t + nwarps;
         const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
-        const uint32_t row_base = (uint32_t)raw.y;
         const int nsteps = raw.z & 0xffff;
         const int logL = (raw.z >> 16) & 0xff;
         const int nrows = (raw.z >> 24) & 0xff;
         const int L = 1 << logL;
         const int rr = lane >> logL;
         const bool owner = ((lane & (L - 1)) == 0) && (rr < nrows);
-        const int r = (int)row_base + rr;
+        const int r = raw.y + rr;
         typename Op::Pre pre{};
         if (owner) pre = op.prefetch(r);
-        double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
-        for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-        if (owner) op.row(r, dot, pre, acc);
+        if (t2 < V.ntiles) {
+            const int4 raw2 = *reinterpret_cast<const int4*>(V.desc + t2);
+            const int nsteps2 = raw2.z & 0xffff;
+            const int logL2 = (raw2.z >> 16) & 0xff;
+            const int nrows2 = (raw2.z >> 24) & 0xff;
+            const int L2 = 1 << logL2;
+            const int rr2 = lane >> logL2;
+            const bool owner2 = ((lane & (L2 - 1)) == 0) && (rr2 < nrows2);
+            const int r2 = raw2.y + rr2;
+            typename Op::Pre pre2{};
+            if (owner2) pre2 = op.prefetch(r2);
+            double dot, dot2;
+            if (nsteps == nsteps2 && nsteps >= 1 && nsteps <= 3) {
+                const double2 *vpa, *vpb;
+                const int2 *ipa, *ipb;
+                tile_ptrs(V, (uint32_t)raw.x, nsteps, lane, vpa, ipa);
+                tile_ptrs(V, (uint32_t)raw2.x, nsteps2, lane, vpb, ipb);
+                if (nsteps == 1) pair_dot<typename Op::Mem, 1>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                else if (nsteps == 2) pair_dot<typename Op::Mem, 2>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                else pair_dot<typename Op::Mem, 3>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+            } else {
+                dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
+                dot2 = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw2.x, nsteps2, lane);
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+            for (int o = L2 >> 1; o > 0; o >>= 1) dot2 += __shfl_xor_sync(FULL, dot2, o);
+            if (owner) op.row(r, dot, pre, acc);
+            if (owner2) op.row(r2, dot2, pre2, acc);
+        } else {
+            double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
+            for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+            if (owner) op.row(r, dot, pre, acc);
+        }
     }
 }
 
