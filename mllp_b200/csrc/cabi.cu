@@ -303,7 +303,17 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
     BuildParams bp;
     bp.num_ctas = lp->G;
     bp.pref_steps = env_int("MLLP_PREF_STEPS", 4);
-    bp.max_steps = env_int("MLLP_MAX_STEPS", 4);
+    // chunk length of split rows: 8 steps (512 entries) unless there is enough long-row work to give
+    // every warp of the grid its own 4-step chunk (then the chunk round is one gather group deep)
+    {
+        int64_t heavy = 0;
+        for (int i = 0; i < m; ++i) {
+            const int64_t len = h_indptr[i + 1] - h_indptr[i];
+            if (len > 512) heavy += len;
+        }
+        const int64_t one_round = (int64_t)lp->G * (lp->threads / 32) * 256;
+        bp.max_steps = env_int("MLLP_MAX_STEPS", 2 * heavy >= one_round ? 4 : 8);
+    }
     if (bp.pref_steps < 1) bp.pref_steps = 1;
     if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
     if (bp.max_steps > 1024) bp.max_steps = 1024;

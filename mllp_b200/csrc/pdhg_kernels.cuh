@@ -467,8 +467,12 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
             double p = 0.0;
             for (int k = lane; k < count; k += 32) p += s_part[first + k];
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+            // the row's own vector entries are needed by whoever finishes the row: fetch them now,
+            // off the critical path of the join
+            typename Op::Pre spre{};
+            if (lane == 0) spre = op.prefetch(sr.x);
             if (sr.z == 1) {   // the whole row lives in this CTA: no global join
-                if (lane == 0) op.row(sr.x, p, op.prefetch(sr.x), acc);
+                if (lane == 0) op.row(sr.x, p, spre, acc);
                 continue;
             }
             unsigned last = 0;
@@ -497,7 +501,7 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0) {
                     M.counters[ls.x] = 0;
-                    op.row(sr.x, s, op.prefetch(sr.x), acc);
+                    op.row(sr.x, s, spre, acc);
                 }
             }
         }
