@@ -161,6 +161,18 @@ int mllp_lp_create_rowpart(int32_t m, int32_t n, int64_t nnz, const int32_t *h_i
                            uint32_t flags, int32_t rank, int32_t nranks,
                            const unsigned char *uid128, mllp_lp_t *out);
 
+/* In-kernel exchange for a row-partitioned handle: export this rank's three CUDA IPC handles
+ * (xbar, y, flags; 3 x 64 bytes), let the host all-gather them (nranks x 192 bytes, rank order)
+ * and import.  Afterwards mllp_pdhg_run() runs ALL iterations in one cooperative launch per rank:
+ * each rank stores its slice of xbar / y straight into every peer's vector over NVLink as part of the
+ * row update, and the two exchanges per iteration are cross-GPU flag barriers in peer memory (no NCCL
+ * call, no kernel launch inside the loop).  Waits time out (status via mllp_rowpart_error) instead of
+ * hanging.  Without import the handle uses two NCCL all-gathers per iteration. */
+int mllp_rowpart_ipc_export(mllp_lp_t lp, unsigned char *out192);
+int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char *all_ranks);
+/* 0 = no exchange wait has timed out on this rank (synchronises the device). */
+int mllp_rowpart_error(mllp_lp_t lp, int32_t *out_flag);
+
 /*
  * Batched mode: `count` independent LPs in one launch (one CTA per LP, the whole LP held
  * in shared memory).  Instance k has shape m[k] x n[k]; its CSR arrays are the slices

@@ -30,6 +30,9 @@ SIGNATURES = {
     "mllp_nccl_unique_id": (ctypes.c_int, [_vp]),
     "mllp_lp_create_rowpart": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                               ctypes.c_uint32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),
+    "mllp_rowpart_ipc_export": (ctypes.c_int, [_vp, _vp]),
+    "mllp_rowpart_ipc_import": (ctypes.c_int, [_vp, _vp]),
+    "mllp_rowpart_error": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     "mllp_lp_destroy": (ctypes.c_int, [_vp]),
     "mllp_lp_info": (ctypes.c_int, [_vp, _vp]),
     "mllp_spmv": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),

@@ -93,6 +93,13 @@ struct mllp_lp {
     int mi = 0, ni = 0;               // internal (padded) vector lengths
     int Ly = 0, Lx = 0;               // slice lengths
     void* comm = nullptr;             // ncclComm_t
+    // in-kernel exchange over NVLink peer memory (mllp_rowpart_ipc_export / _import)
+    PeerInfo peers{};
+    unsigned* d_flags = nullptr;      // [MAX_RANKS] flags written by the peers
+    unsigned* d_err = nullptr;
+    bool p2p_ready = false;
+    unsigned epoch = 0;               // flag value of the last completed exchange
+    std::vector<void*> ipc_opened;
 };
 constexpr int GRAPH_UNROLL = 32;
 
@@ -398,6 +405,8 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             RC_OK(dev_zeros(lp, &lp->d_norm2, 2));
             if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
             if (nranks > 1) {
+                RC_OK(dev_zeros(lp, &lp->d_flags, (size_t)MAX_RANKS));
+                RC_OK(dev_zeros(lp, &lp->d_err, 4));
                 NcclApi* api = nccl_api();
                 if (!api) return fail(MLLP_E_STATE, "mllp_lp_create_rowpart: libnccl.so.2 could not be loaded");
                 NcclId id;
@@ -485,10 +494,62 @@ int mllp_lp_create_rowpart(int32_t m, int32_t n, int64_t nnz, const int32_t* h_i
                        uid128, out);
 }
 
+int mllp_rowpart_ipc_export(mllp_lp_t lp, unsigned char* out192)
+{
+    if (!lp || !out192 || lp->nranks < 2) return fail(MLLP_E_INVALID, "mllp_rowpart_ipc_export: not a row-partitioned handle");
+    DeviceGuard guard(lp->device);
+    cudaIpcMemHandle_t h[3];
+    CUDA_OK(cudaIpcGetMemHandle(&h[0], lp->d.xbar));
+    CUDA_OK(cudaIpcGetMemHandle(&h[1], lp->d.y));
+    CUDA_OK(cudaIpcGetMemHandle(&h[2], lp->d_flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out192, h, sizeof(h));
+    return 0;
+}
+
+int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char* all)
+{
+    if (!lp || !all || lp->nranks < 2) return fail(MLLP_E_INVALID, "mllp_rowpart_ipc_import: not a row-partitioned handle");
+    if (lp->nranks > MAX_RANKS) return fail(MLLP_E_STATE, "mllp_rowpart_ipc_import: at most 8 ranks");
+    DeviceGuard guard(lp->device);
+    PeerInfo& P = lp->peers;
+    P.rank = lp->rank; P.nranks = lp->nranks; P.err = lp->d_err;
+    for (int q = 0; q < lp->nranks; ++q) {
+        if (q == lp->rank) {
+            P.xbar[q] = lp->d.xbar; P.y[q] = lp->d.y; P.flags[q] = lp->d_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, all + (size_t)q * 192, sizeof(h));
+        void* ptr[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; ++k) {
+            CUDA_OK(cudaIpcOpenMemHandle(&ptr[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+            lp->ipc_opened.push_back(ptr[k]);
+        }
+        P.xbar[q] = (double*)ptr[0]; P.y[q] = (double*)ptr[1]; P.flags[q] = (unsigned*)ptr[2];
+    }
+    if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(xchg_set_smem(lp->bounds, lp->dyn_smem));
+    lp->p2p_ready = true;
+    return 0;
+}
+
+int mllp_rowpart_error(mllp_lp_t lp, int32_t* out_flag)
+{
+    if (!lp || !out_flag) return fail(MLLP_E_INVALID, "mllp_rowpart_error: null argument");
+    *out_flag = 0;
+    if (!lp->d_err) return 0;
+    DeviceGuard guard(lp->device);
+    unsigned v = 0;
+    CUDA_OK(cudaMemcpy(&v, lp->d_err, sizeof(v), cudaMemcpyDeviceToHost));
+    *out_flag = (int32_t)v;
+    return 0;
+}
+
 int mllp_lp_destroy(mllp_lp_t lp)
 {
     if (!lp) return 0;
     DeviceGuard guard(lp->device);
+    for (void* p : lp->ipc_opened) cudaIpcCloseMemHandle(p);
     if (lp->comm) { NcclApi* api = nccl_api(); if (api) api->comm_destroy(lp->comm); }
     if (lp->graph) cudaGraphExecDestroy(lp->graph);
     for (void* p : lp->allocs) cudaFree(p);
@@ -571,7 +632,14 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
         NcclApi* api = nccl_api();
         const double ts[2] = {tau, sigma};
         CUDA_OK(cudaMemcpyAsync(lp->d.ctrl, ts, sizeof(ts), cudaMemcpyHostToDevice, s));
-        for (int it = 0; it < num_iters; ++it) {
+        const bool p2p = lp->p2p_ready && env_int("MLLP_ROWPART_NCCL", 0) == 0;
+        if (p2p && num_iters > 0) {
+            // all iterations in ONE cooperative launch per rank; exchange = peer stores + flag barriers
+            RC_OK(launch_pdhg_persistent_xchg(lp->d, lp->peers, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma,
+                                              num_iters, lp->epoch, s));
+            lp->epoch += 2u * (unsigned)num_iters;
+        }
+        for (int it = 0; it < (p2p ? 0 : num_iters); ++it) {
             RC_OK(launch_primal(lp->d, lp->bounds, lp->G, lp->threads, s));
             NCCL_OK(api->all_gather(lp->d.xbar + (size_t)lp->rank * lp->Lx, lp->d.xbar, (size_t)lp->Lx, NCCL_FLOAT64, lp->comm, s));
             RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));

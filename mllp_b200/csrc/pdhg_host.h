@@ -6,6 +6,7 @@
 namespace mllp {
 struct DevMat;
 struct DevLP;
+struct PeerInfo;
 
 int launch_gather(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
 int launch_scatter(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
@@ -22,6 +23,9 @@ int persistent_set_smem(bool bounds, size_t dyn_smem);
 int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem);
 int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double tau, double sigma,
                            int iters, cudaStream_t s);
+int xchg_set_smem(bool bounds, size_t dyn_smem);
+int launch_pdhg_persistent_xchg(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
+                                double tau, double sigma, int iters, unsigned epoch, cudaStream_t s);
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
                             int max_iters, int check_every, double tol, double* out, cudaStream_t s);
 }  // namespace mllp

@@ -182,6 +182,27 @@ __global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double ta
     }
 }
 
+// Row-partitioned persistent kernel: the same loop, but the row updates also store into the peers'
+// vectors and the grid barriers are cross-GPU barriers (see PeerInfo / xchg_barrier).
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1)
+k_pdhg_persistent_xchg(DevLP lp, PeerInfo pi, double tau, double sigma, int iters, unsigned epoch)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    PersistentSmem P;
+    persistent_setup(lp, dsm, P);
+    unsigned target = 0;
+    PrimalXchgOp<BOUNDS> pop{lp, pi, tau};
+    DualXchgOp<BOUNDS> dop{lp, pi, sigma};
+    double acc[NRED];
+    for (int it = 0; it < iters; ++it) {
+        phase_AT(lp, P, pop, acc);
+        if (!xchg_barrier(lp.barrier, target, epoch + 2u * (unsigned)it + 1u, pi)) return;
+        phase_A(lp, P, dop, acc);
+        if (!xchg_barrier(lp.barrier, target, epoch + 2u * (unsigned)it + 2u, pi)) return;
+    }
+}
+
 // persistent cooperative kernel, solve mode (reflected restarted Halpern PDHG).
 // Control state is replicated: every CTA derives it from the same global partial sums with
 // the same arithmetic, so all CTAs take identical branches.
@@ -397,6 +418,24 @@ int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, siz
     DevLP lpv = lp;
     void* args[] = {&lpv, &tau, &sigma, &iters};
     CK(cudaLaunchCooperativeKernel(persistent_fn(false, bounds), dim3(G), dim3(threads), args, dyn_smem, s));
+    return 0;
+}
+
+int xchg_set_smem(bool bounds, size_t dyn_smem)
+{
+    const void* fn = bounds ? (const void*)k_pdhg_persistent_xchg<true> : (const void*)k_pdhg_persistent_xchg<false>;
+    return (int)cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+}
+
+int launch_pdhg_persistent_xchg(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
+                                double tau, double sigma, int iters, unsigned epoch, cudaStream_t s)
+{
+    CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
+    DevLP lpv = lp;
+    PeerInfo piv = pi;
+    void* args[] = {&lpv, &piv, &tau, &sigma, &iters, &epoch};
+    const void* fn = bounds ? (const void*)k_pdhg_persistent_xchg<true> : (const void*)k_pdhg_persistent_xchg<false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, dyn_smem, s));
     return 0;
 }
 

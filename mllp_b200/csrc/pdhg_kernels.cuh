@@ -273,6 +273,105 @@ struct SpmvOp {
 };
 
 // ---------------------------------------------------------------------------------------
+// Row partition over GPUs with the exchange INSIDE the persistent kernel: every rank writes its
+// slice of xbar (resp. y) straight into all peers' vectors with NVLink peer stores as part of the
+// row update, and the two all-gathers per iteration become two cross-GPU barriers on flags in
+// peer memory.  No NCCL call and no kernel launch inside the iteration loop.
+constexpr int MAX_RANKS = 8;
+struct PeerInfo {
+    double* xbar[MAX_RANKS];      // every rank's xbar vector (own entry = local pointer)
+    double* y[MAX_RANKS];
+    unsigned* flags[MAX_RANKS];   // every rank's flag array [MAX_RANKS]: slot q is written by rank q
+    unsigned* err;                // local: set to 1 when a wait timed out
+    int rank, nranks;
+};
+
+template <bool BOUNDS>
+struct PrimalXchgOp {
+    using Mem = GlobalMem;
+    const DevLP& lp;
+    const PeerInfo& pi;
+    double tau;
+    struct Pre { double c, x; };
+    __device__ __forceinline__ const double* vec() const { return lp.y; }
+    __device__ __forceinline__ Pre prefetch(int r) const { return {Mem::ld_ro(lp.c + r), Mem::ld_mut(lp.x + r)}; }
+    __device__ __forceinline__ void row(int r, double dot, const Pre& p, double*) const
+    {
+        const double g = p.c - dot;
+        double xn = p.x - tau * g;
+        if (BOUNDS) xn = fmin(fmax(xn, Mem::ld_ro(lp.lb + r)), Mem::ld_ro(lp.ub + r));
+        else xn = fmax(xn, 0.0);
+        const double xb = 2.0 * xn - p.x;
+        lp.x[r] = xn;
+#pragma unroll
+        for (int q = 0; q < MAX_RANKS; ++q)
+            if (q < pi.nranks) pi.xbar[q][r] = xb;   // own copy and every peer's, over NVLink
+    }
+};
+
+template <bool BOUNDS>
+struct DualXchgOp {
+    using Mem = GlobalMem;
+    const DevLP& lp;
+    const PeerInfo& pi;
+    double sigma;
+    struct Pre { double b, y; };
+    __device__ __forceinline__ const double* vec() const { return lp.xbar; }
+    __device__ __forceinline__ Pre prefetch(int r) const { return {Mem::ld_ro(lp.b + r), Mem::ld_mut(lp.y + r)}; }
+    __device__ __forceinline__ void row(int r, double dot, const Pre& p, double*) const
+    {
+        double yn = p.y + sigma * (p.b - dot);
+        if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
+#pragma unroll
+        for (int q = 0; q < MAX_RANKS; ++q)
+            if (q < pi.nranks) pi.y[q][r] = yn;
+    }
+};
+
+// Cross-GPU barrier: local arrivals on the grid counter (system-scope release, because the phase's
+// peer stores must be visible on the other GPUs); the CTA that completes the local count raises this
+// rank's flag on every GPU; every CTA then waits until all ranks' flags on ITS OWN GPU carry `tag`.
+// Waits time out (~2 s) and raise pi.err instead of hanging the GPU.  Returns false on error.
+__device__ __forceinline__ bool xchg_barrier(unsigned* counter, unsigned& target, unsigned tag, const PeerInfo& pi)
+{
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        __threadfence_system();        // this CTA's peer stores are performed (acknowledged) before it arrives
+        target += gridDim.x;
+        const unsigned old = atomicAdd(counter, 1u);
+        if (old + 1u == target) {
+            // every CTA of this GPU fenced at system scope before its arrival, so all of this rank's
+            // peer stores are performed: raise the flag everywhere (own GPU included)
+            __threadfence();
+            for (int q = 0; q < pi.nranks; ++q) {
+                volatile unsigned* f = pi.flags[q] + pi.rank;
+                *f = tag;
+            }
+        }
+        const long long t0 = clock64();
+        for (int q = 0; q < pi.nranks && ok; ++q) {
+            const volatile unsigned* f = pi.flags[pi.rank] + q;
+            for (;;) {
+                const unsigned v = *f;
+                if ((int)(v - tag) >= 0) break;
+                if (*(volatile unsigned*)pi.err != 0u || clock64() - t0 > 4000000000LL) {
+                    atomicExch(pi.err, 1u);
+                    ok = 0;
+                    break;
+                }
+                __nanosleep(MLLP_BARRIER_BACKOFF);
+            }
+        }
+        __threadfence();               // acquire: invalidates this SM's L1 before the next phase gathers
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Per-CTA view of a matrix.  The CTA's tile descriptors and a prefix of its tiles' data can
 // live in shared memory for the whole persistent kernel (the matrix never changes), the rest
 // is streamed from global memory / L2.

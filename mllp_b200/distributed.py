@@ -85,7 +85,7 @@ class RowPartLP(DeviceLP):
     """Row-partitioned handle of one large LP; collective constructor (all ranks call it)."""
 
     def __init__(self, constrs, constr_weights, num_rows, num_cols, lb=None, ub=None, ylo=None, yhi=None, device=None,
-                 flags=_cabi.F_DEFAULT):
+                 flags=_cabi.F_DEFAULT, p2p=True):
         import weakref
         dist = _dist()
         L = _cabi.lib()
@@ -108,6 +108,22 @@ class RowPartLP(DeviceLP):
         self._h = h
         self._finalizer = weakref.finalize(self, L.mllp_lp_destroy, h)
         self._sigma_max = None
+        self.p2p = False
+        if p2p and 1 < self.world <= 8:
+            # in-kernel exchange over NVLink peer memory: swap CUDA IPC handles of xbar / y / flags
+            mine = np.zeros(192, dtype=np.uint8)
+            _cabi.check(L.mllp_rowpart_ipc_export(h, mine.ctypes.data), "mllp_rowpart_ipc_export")
+            parts = [None] * self.world
+            dist.all_gather_object(parts, (self.rank, mine.tobytes()))
+            blob = np.frombuffer(b"".join(b for _, b in sorted(parts)), dtype=np.uint8).copy()
+            _cabi.check(L.mllp_rowpart_ipc_import(h, blob.ctypes.data), "mllp_rowpart_ipc_import")
+            dist.barrier()
+            self.p2p = True
+
+    def exchange_error(self):
+        f = ctypes.c_int32(0)
+        _cabi.check(_cabi.lib().mllp_rowpart_error(self.handle, ctypes.byref(f)), "mllp_rowpart_error")
+        return int(f.value)
 
 
 def pdhg_linear_program_rowpart(lp, rhs, coefs, *, num_iters, tau, sigma, x0=None, y0=None):
@@ -124,6 +140,8 @@ def pdhg_linear_program_rowpart(lp, rhs, coefs, *, num_iters, tau, sigma, x0=Non
                                           float(sigma), int(num_iters), scal.data_ptr(), _torch_stream(dev)),
                 "mllp_pdhg_run (row-partitioned)")
     s = scal.cpu().numpy()
+    if lp.exchange_error():
+        raise RuntimeError("mllp_b200: a cross-GPU exchange wait timed out on rank %d" % lp.rank)
     info = _info_dict(s)
-    info.update(tau=float(tau), sigma=float(sigma))
+    info.update(tau=float(tau), sigma=float(sigma), p2p=lp.p2p)
     return float(s[0]), x.cpu().numpy(), y.cpu().numpy(), info

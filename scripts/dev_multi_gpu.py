@@ -13,7 +13,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 def p0(*a):
     if rank == 0: print(*a, flush=True)
 
-for name, K in (("pilot87", 200), ("osa-60", 100), ("ken-18", 100), ("pds-20", 100)):
+for name, K in (("afiro", 200), ("pilot87", 200), ("osa-60", 100), ("ken-18", 100), ("pds-20", 100)):
     A, b, c = M.load_csr(name); m, n = A.shape
     eta = 0.9 / O.power_iteration(A, 50)
     lp = RowPartLP(A, A.data, m, n, device=local)

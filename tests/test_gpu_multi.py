@@ -26,7 +26,7 @@ def test_row_partition_two_gpus_matches_oracle():
         pytest.skip("needs 2 GPUs")
     r = _torchrun(["scripts/dev_multi_gpu.py"], 29541)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("rowpart parity") == 8   # 4 instances x 2 ranks, each asserted < 1e-9 inside
+    assert r.stdout.count("rowpart parity") == 10   # 5 instances x 2 ranks, each asserted < 1e-9 inside
 
 
 def test_bench_two_gpus_prints_one_json_line():
