@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (ken-18, batches)")
     return ap.parse_args()
 
 
@@ -134,6 +135,87 @@ def cpu_oracle_rate(A, b, c, eta, seconds, min_iters=5):
     O.pdhg_run(csr, b, c, np.zeros(n), np.zeros(m), eta, eta, iters, nthreads=nt)
     dt = time.perf_counter() - t0
     return iters / dt, iters, dt, nt
+
+
+def measure_extras(M, torch, dev, local, rank, world, dist):
+    """Secondary numbers of BASELINE.json's metric, outside the headline's timed region:
+    ken-18 iterations/s, batched LP-iterations/s (4096 perturbed instances of one Netlib matrix per
+    rank) and LPs solved/s (solve mode to 1e-6 on perturbed small Netlib instances).  Whole-job sums."""
+    from mllp_b200 import _cabi
+    L = _cabi.lib()
+    out = {}
+
+    def timed(fn, reps=3):
+        fn(); torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        t = torch.tensor([best], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) * 1e-3
+
+    # (1) ken-18, parity mode, 1000 fused iterations
+    A, b, c = M.load_csr("ken-18")
+    m, n = A.shape
+    lp = M.DeviceLP(A, A.data, m, n, device=local)
+    eta = 0.9 / lp.sigma_max()
+    bt, ct = torch.tensor(b, device=dev), torch.tensor(c, device=dev)
+    xt, yt = torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(m, dtype=torch.float64, device=dev)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    sec = timed(lambda: _cabi.check(L.mllp_pdhg_run(lp.handle, xt.data_ptr(), yt.data_ptr(), bt.data_ptr(), ct.data_ptr(),
+                                                    eta, eta, 1000, None, sp), "run"))
+    hbm, _ = peaks()
+    bpi = lp.info()["bytes_per_iter"]
+    out["ken-18"] = {"iterations_per_sec": world * 1000 / sec, "us_per_iteration": sec * 1e3,
+                     "roofline_frac_of_measured_hbm": bpi * 1000 / sec / 1e9 / hbm, "bytes_per_iter": bpi}
+    lp.close()
+
+    # (2) shared-matrix batch: 4096 perturbed (b, c) instances of 25fv47 per rank, parity mode
+    A, b, c = M.load_csr("25fv47")
+    m, n = A.shape
+    B = 4096
+    bs = M.BatchLP([(A, A.data, b, c)], shared=True, count=B, device=local)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    cb = torch.tensor(c).repeat(B, 1) * (1 + 0.1 * (2 * torch.rand(B, n, generator=g, dtype=torch.float64) - 1))
+    bb = torch.tensor(b).repeat(B, 1) * (1 + 0.1 * torch.rand(B, m, generator=g, dtype=torch.float64))
+    cb, bb = cb.reshape(-1).to(dev), bb.reshape(-1).to(dev)
+    xb, yb = torch.zeros(B * n, dtype=torch.float64, device=dev), torch.zeros(B * m, dtype=torch.float64, device=dev)
+    etab = (0.9 / bs.sigma_max()).contiguous()
+    K = 200
+    sec = timed(lambda: bs.run(xb, yb, bb, cb, etab, etab, K), reps=2)
+    out["batch_4096x25fv47"] = {"lp_iterations_per_sec": world * B * K / sec, "instances_per_rank": B,
+                                "us_per_batch_iteration": sec / K * 1e6, "algorithmic_GBps_per_gpu": bs.info()["bytes_per_iter"] * K / sec / 1e9}
+    bs.close()
+    del cb, bb, xb, yb
+
+    # (3) LPs solved per second: 1024 perturbed copies each of sc50a / sc105 / blend per rank, solve mode to 1e-6
+    insts = []
+    for nm in ("sc50a", "sc105", "blend"):
+        A, b, c = M.load_csr(nm)
+        for i in range(1024):
+            rg = np.random.default_rng(99991 * rank + i)
+            insts.append((A, A.data, b, c * (1 + 0.05 * rg.uniform(-1, 1, c.shape[0]))))
+    bsol = M.BatchLP(insts, device=local)
+    bvec = torch.tensor(np.concatenate([i[2] for i in insts]), device=dev)
+    cvec = torch.tensor(np.concatenate([i[3] for i in insts]), device=dev)
+    nx, ny = int(bsol.x_off[-1]), int(bsol.y_off[-1])
+    etas = (0.99 / bsol.sigma_max()).contiguous()
+    scal = torch.zeros(len(insts) * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
+
+    def solve_all():
+        xs, ys = torch.zeros(nx, dtype=torch.float64, device=dev), torch.zeros(ny, dtype=torch.float64, device=dev)
+        bsol.solve(xs, ys, bvec, cvec, etas, scal, 1.0, 400000, 64, 1e-6)
+
+    sec = timed(solve_all, reps=2)
+    sc = scal.cpu().numpy().reshape(len(insts), _cabi.NUM_SCALARS)
+    out["solve_3072_small_netlib"] = {"lps_solved_per_sec": world * len(insts) / sec, "instances_per_rank": len(insts),
+                                      "converged_fraction": float(sc[:, 12].mean()), "mean_iterations": float(sc[:, 10].mean()),
+                                      "tol": 1e-6, "seconds": sec}
+    bsol.close()
+    return out
 
 
 def run_reference(args, rank, world):
@@ -279,6 +361,10 @@ def main():
                "call": "mllp_b200.pdhg_linear_program(constrs, constr_weights, rhs, coefs, num_iters=%d) with numpy (pinned) arrays; device formats cached by the loader" % KI}
         assert abs(inf["pobj"] - final_scal[0]) <= 1e-9 * (1 + abs(final_scal[0])) or rank != 0 or True
 
+    extras = None
+    if not args.no_extras:
+        extras = measure_extras(M, torch, dev, local, rank, world, dist)
+
     if rank == 0:
         peak, peak_src = peaks()
         bytes_iter = info["bytes_per_iter"]
@@ -302,6 +388,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if extras is not None:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pdhg_oracle as O  # the checker, used here only as the timed CPU baseline
             rate, its, dt, cores = cpu_oracle_rate(A, b, c, eta, args.cpu_baseline_seconds)

@@ -184,10 +184,18 @@ k_batch_run(const BatchInst* __restrict__ insts, int count, int shared, double* 
 __global__ void __launch_bounds__(1024, 1)
 k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, double* x, double* y, const double* b,
               const double* c, const double* eta_arr, double w0, int max_iters, int check_every, double tol,
-              double* scalars)
+              double* scalars, int* next_inst)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
-    for (int inst = blockIdx.x; inst < count; inst += gridDim.x) {
+    __shared__ int s_inst;
+    // instances converge after very different iteration counts: CTAs pull the next instance from a
+    // device counter instead of a static stride
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_inst = atomicAdd(next_inst, 1);
+        __syncthreads();
+        const int inst = s_inst;
+        if (inst >= count) break;
         BatchInst I = insts[shared ? 0 : inst];
         if (shared) { I.x_off = (long long)inst * I.n; I.y_off = (long long)inst * I.m; }
         const BatchSmem S = carve(dsm, I.m, I.n, true);
@@ -313,6 +321,7 @@ struct mllp_batch {
     int max_m = 0, max_n = 0;
     BatchInst* d_insts = nullptr;
     std::vector<void*> allocs;
+    int* d_next = nullptr;            // work counter of k_batch_solve
     int64_t info[16] = {0};
 };
 
@@ -451,6 +460,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             ck(up(bt, &d_order, P.order), "upload orders");
             ck(up(bt, &d_dummy_partials, std::vector<double>(P.splits.size() + 1, 0.0)), "alloc partials");
             ck(up(bt, &d_dummy_counters, std::vector<unsigned>(P.splits.size() + 1, 0u)), "alloc counters");
+            ck(up(bt, &bt->d_next, std::vector<int>(4, 0)), "alloc work counter");
             if (rc == 0) {
                 auto dev_mat = [&](const MatOff& o) {
                     DevMat D{};
@@ -565,9 +575,11 @@ int mllp_batch_solve(mllp_batch_t bt, double* d_x, double* d_y, const double* d_
     if (!bt || !d_x || !d_y || !d_b || !d_c || !d_eta || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 > 0.0))
         return bfail(MLLP_E_INVALID, "mllp_batch_solve: bad argument");
     DevGuard guard(bt->device);
+    cudaError_t e0 = cudaMemsetAsync(bt->d_next, 0, sizeof(int), (cudaStream_t)stream);
+    if (e0 != cudaSuccess) return bfail((int)e0, std::string("mllp_batch_solve: ") + cudaGetErrorString(e0));
     k_batch_solve<<<bt->grid, bt->threads, bt->dyn_smem, (cudaStream_t)stream>>>(bt->d_insts, bt->count, bt->shared, d_x, d_y, d_b,
                                                                                 d_c, d_eta, w0, max_iters, check_every, tol,
-                                                                                d_scalars);
+                                                                                d_scalars, bt->d_next);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bfail((int)e, std::string("mllp_batch_solve: ") + cudaGetErrorString(e));
     return 0;
