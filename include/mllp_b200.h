@@ -143,6 +143,15 @@ int mllp_pdhg_solve(mllp_lp_t lp, double *d_x, double *d_y, const double *d_b,
                     int32_t check_every, double tol, double *d_scalars, void *stream);
 
 /*
+ * LP -> bipartite graph edges on the device, replacing the Python double loop of
+ * build_graph_from_weights_sets (linear_program_methods.py:93-96): from DEVICE CSR arrays
+ * (m rows) fills edge_index [2][nnz] int64 (row 0 = variable/column id, row 1 = constraint/row id,
+ * CSR nonzero order) and edge_attr [nnz] float32 = a_ij.
+ */
+int mllp_graph_edges(int32_t m, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                     const double *d_values, int64_t *d_edge_index, float *d_edge_attr, void *stream);
+
+/*
  * Row partition of ONE large LP over `nranks` GPUs (one process per GPU; BASELINE.json
  * configs[3]: ken-18, osa-60, pds-20).  Every rank passes the whole matrix; rank p keeps the
  * rows of A (entries of y) and the rows of A' (entries of x) assigned to it (balanced by nonzeros)

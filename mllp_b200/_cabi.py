@@ -27,6 +27,7 @@ SIGNATURES = {
     "mllp_device_info": (ctypes.c_int, [ctypes.c_int, _vp]),
     "mllp_lp_create": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                       ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "mllp_graph_edges": (ctypes.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mllp_nccl_unique_id": (ctypes.c_int, [_vp]),
     "mllp_lp_create_rowpart": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                               ctypes.c_uint32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),

@@ -533,6 +533,15 @@ int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char* all)
     return 0;
 }
 
+int mllp_graph_edges(int32_t m, int64_t nnz, const int32_t* d_indptr, const int32_t* d_indices, const double* d_values,
+                     int64_t* d_edge_index, float* d_edge_attr, void* stream)
+{
+    if (m < 0 || nnz < 0 || !d_indptr || (nnz > 0 && (!d_indices || !d_values || !d_edge_index || !d_edge_attr)))
+        return fail(MLLP_E_INVALID, "mllp_graph_edges: bad argument");
+    RC_OK(launch_graph_edges(m, nnz, d_indptr, d_indices, d_values, (long long*)d_edge_index, d_edge_attr, (cudaStream_t)stream));
+    return 0;
+}
+
 int mllp_rowpart_error(mllp_lp_t lp, int32_t* out_flag)
 {
     if (!lp || !out_flag) return fail(MLLP_E_INVALID, "mllp_rowpart_error: null argument");

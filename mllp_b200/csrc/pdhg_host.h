@@ -13,6 +13,8 @@ int launch_scatter(double* dst, const double* src, const int32_t* order, int n, 
 int launch_fill(double* dst, double v, int n, cudaStream_t s);
 int launch_sumsq(const double* v, int n, double* out, cudaStream_t s);
 int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2, int n, cudaStream_t s);
+int launch_graph_edges(int m, long long nnz, const int32_t* indptr, const int32_t* indices, const double* values,
+                       long long* edge_index, float* edge_attr, cudaStream_t s);
 int launch_spmv(const DevMat& M, const double* in, double* out, int G, int threads, cudaStream_t s);
 int launch_primal(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);
 int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s);

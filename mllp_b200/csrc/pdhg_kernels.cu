@@ -46,6 +46,34 @@ __global__ void k_scale_by_invnorm(double* __restrict__ dst, const double* __res
         dst[k] = nz > 0.0 ? src[k] / nz : src[k];
 }
 
+// CSR -> COO edge list of the LP's bipartite graph: one warp per row, lanes stride the row.
+// edge_index is [2][nnz] int64 (row 0: variable = column id, row 1: constraint = row id), edge_attr
+// float32, in CSR nonzero order (the order the reference's Python loop produces).
+__global__ void k_graph_edges(int m, long long nnz, const int32_t* __restrict__ indptr,
+                              const int32_t* __restrict__ indices, const double* __restrict__ values,
+                              long long* __restrict__ edge_index, float* __restrict__ edge_attr)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < m; row += warps) {
+        const int32_t a = indptr[row], b = indptr[row + 1];
+        for (int32_t k = a + lane; k < b; k += 32) {
+            edge_index[k] = (long long)indices[k];
+            edge_index[nnz + k] = (long long)row;
+            edge_attr[k] = (float)values[k];
+        }
+    }
+}
+
+int launch_graph_edges(int m, long long nnz, const int32_t* indptr, const int32_t* indices, const double* values,
+                       long long* edge_index, float* edge_attr, cudaStream_t s)
+{
+    if (m <= 0 || nnz <= 0) return 0;
+    const int blocks = (m + 7) / 8 > 2368 ? 2368 : (m + 7) / 8;
+    k_graph_edges<<<blocks, 256, 0, s>>>(m, nnz, indptr, indices, values, edge_index, edge_attr);
+    return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------
 // phase kernels (graph mode, evaluation, unit SpMV).  Grid = the persistent grid G: the tile
 // to CTA assignment is fixed at build time.

@@ -83,9 +83,9 @@ def full():
     open(os.path.join(OUT, tag + "_persistent_ncu_full.md"), "w").write("\n".join(lines) + "\n")
 
 launches(); full()
-for f in ("bench_r1c.json", "bench_r1c_ken18.json", "bench_r1c_ref.json"):
+for f in ("bench_r1d.json", "bench_r1d_ken18.json", "bench_r1d_ref.json", "bench_r1d_n2.json"):
     p = os.path.join(GO, f)
     if os.path.exists(p):
         txt = [l for l in open(p).read().splitlines() if l.startswith("{")]
-        if txt: open(os.path.join(OUT, tag + "_" + f.replace("_r1c", "")), "w").write(txt[-1] + "\n")
+        if txt: open(os.path.join(OUT, tag + "_" + f.replace("_r1d", "")), "w").write(txt[-1] + "\n")
 print("ok")

@@ -203,3 +203,24 @@ def test_random_skewed_matrix_with_empty_rows():
     obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=200, tau=eta, sigma=eta)
     xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, 200)
     assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+
+
+def test_device_graph_builder_matches_reference_loop(torch_cuda):
+    """same tensors as the reference's build_graph_from_weights_sets
+    (linear_program_methods.py:89-103), restated here as the reference's Python loop."""
+    torch = torch_cuda
+    from mllp_b200.graph import build_graph_from_weights_sets
+    for name in ("afiro", "25fv47"):
+        A, b, c = D.load_csr(name)
+        constrs = np.split(A.indices, A.indptr)[1:-1]
+        g = build_graph_from_weights_sets(constrs, A.data, b, c, device=0)
+        index_1, index_2 = [], []
+        for constr_idx, vars_ in enumerate(constrs):       # the reference's loop
+            for var_index in vars_:
+                index_1.append(var_index)
+                index_2.append(constr_idx)
+        ref_edge = torch.tensor([index_1, index_2])
+        assert torch.equal(g["edge_index"].cpu(), ref_edge)
+        assert torch.equal(g["edge_attr"].cpu(), torch.tensor(A.data, dtype=torch.float).unsqueeze(-1))
+        assert torch.equal(g["x_src"].cpu(), torch.tensor(c, dtype=torch.float).unsqueeze(-1))
+        assert torch.equal(g["x_tgt"].cpu(), torch.tensor(b, dtype=torch.float).unsqueeze(-1))
