@@ -470,7 +470,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                     D.cta_begin = d_u32 + o.cb; D.cta_step_begin = d_u32 + o.csb;
                     D.cta_lsplit_begin = d_u32 + o.clb; D.cta_nsplit = d_u32 + o.cns;
                     D.splits = d_splits + o.splits; D.lsplits = d_ls + o.lsplits;
-                    D.partials = d_dummy_partials + o.splits; D.counters = d_dummy_counters + o.splits;
+                    D.partials = d_dummy_partials + o.splits; D.slots = nullptr; D.counters = d_dummy_counters + o.splits;
                     D.nrows = o.nrows; D.ncols = o.ncols;
                     return D;
                 };

@@ -97,6 +97,7 @@ struct mllp_lp {
     PeerInfo peers{};
     unsigned* d_flags = nullptr;      // [MAX_RANKS] flags written by the peers
     unsigned* d_err = nullptr;
+    unsigned long long join_epoch = 0;   // last tag used by the polled split-row join
     bool p2p_ready = false;
     unsigned epoch = 0;               // flag value of the last completed exchange
     std::vector<void*> ipc_opened;
@@ -144,7 +145,8 @@ int upload_mat(mllp_lp* lp, const HostMat& H, DevMat& D)
     RC_OK(dev_upload(lp, &clb, H.cta_lsplit_begin.data(), H.cta_lsplit_begin.size()));
     RC_OK(dev_upload(lp, &cns, H.cta_nsplit.data(), H.cta_nsplit.size()));
     D.lsplits = lsp; D.cta_lsplit_begin = clb; D.cta_nsplit = cns;
-    RC_OK(dev_zeros(lp, &D.partials, (size_t)H.num_partials));
+    RC_OK(dev_zeros(lp, &D.partials, (size_t)H.num_partials + 1));
+    RC_OK(dev_zeros(lp, &D.slots, 2 * (size_t)H.num_partials + 2));
     RC_OK(dev_zeros(lp, &D.counters, H.splits.size()));
     D.vals = reinterpret_cast<const double2*>(vals);
     D.idx = reinterpret_cast<const int2*>(idx);
@@ -644,6 +646,8 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
         const bool p2p = lp->p2p_ready && env_int("MLLP_ROWPART_NCCL", 0) == 0;
         if (p2p && num_iters > 0) {
             // all iterations in ONE cooperative launch per rank; exchange = peer stores + flag barriers
+            lp->d.join_base = lp->join_epoch;
+            lp->join_epoch += 2ull * (unsigned long long)num_iters + 2ull;
             RC_OK(launch_pdhg_persistent_xchg(lp->d, lp->peers, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma,
                                               num_iters, lp->epoch, s));
             lp->epoch += 2u * (unsigned)num_iters;
@@ -675,6 +679,8 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
             RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));
         }
     } else if (num_iters > 0) {
+        lp->d.join_base = lp->join_epoch;
+        lp->join_epoch += 2ull * (unsigned long long)num_iters + 2ull;
         RC_OK(launch_pdhg_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, num_iters, s));
     }
     if (d_scalars) RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, (double)num_iters, s));
@@ -693,6 +699,8 @@ int mllp_debug_trace(mllp_lp_t lp, double tau, double sigma, int32_t iters, unsi
     const size_t cnt = (size_t)iters * lp->G * 4;
     CUDA_OK(cudaMalloc(&d_tr, cnt * sizeof(unsigned long long)));
     CUDA_OK(cudaMemset(d_tr, 0, cnt * sizeof(unsigned long long)));
+    lp->d.join_base = lp->join_epoch;
+    lp->join_epoch += 2ull * (unsigned long long)iters + 2ull;
     DevLP d = lp->d;
     d.trace = d_tr;
     int rc = launch_pdhg_persistent(d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, iters, 0);
@@ -736,6 +744,8 @@ int mllp_pdhg_solve(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, c
     RC_OK(load_problem(lp, d_x, d_y, d_b, d_c, s));
     // scalars of the starting point (also what is returned when max_iters == 0)
     RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, 0.0, s));
+    lp->d.join_base = lp->join_epoch;
+    lp->join_epoch += 2ull * (unsigned long long)max_iters + 2ull;
     if (max_iters > 0)
         RC_OK(launch_solve_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, eta, w0, max_iters, check_every, tol,
                                       d_scalars, s));

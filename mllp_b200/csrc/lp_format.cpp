@@ -296,7 +296,11 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
         sr.first_slot = out.num_partials;
         out.num_partials += sr.nparts;
     }
-    for (LocalSplit& ls : out.lsplits) ls.gslot += out.splits[ls.split_id].first_slot;
+    for (LocalSplit& ls : out.lsplits) {
+        // the rank was stored in gslot: the highest rank of a row is its finisher
+        ls.finisher = (ls.gslot + 1 == out.splits[ls.split_id].nparts) ? 1u : 0u;
+        ls.gslot += out.splits[ls.split_id].first_slot;
+    }
 
     std::vector<uint32_t> by_cost(regular.size());
     std::iota(by_cost.begin(), by_cost.end(), 0u);

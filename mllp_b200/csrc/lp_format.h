@@ -45,7 +45,8 @@ struct LocalSplit {      // 16 bytes: one split row as seen by one CTA
     uint32_t gslot;      // global partial slot this CTA publishes to
     uint16_t first;      // first CTA-local slot
     uint16_t count;      // number of CTA-local slots (chunks of this row in this CTA)
-    uint32_t pad;
+    uint32_t finisher;   // 1 on the CTA that holds the row's last chunk (it finishes the row in the
+                         // cooperative kernels' polled join), else 0
 };
 
 constexpr int SPLIT_SLOTS = 256;  // max split chunks per CTA (shared-memory partial slots)

@@ -170,10 +170,12 @@ __global__ void k_eval_finalize(DevLP lp, int G, double* out, double iters)
 //   [ A: tile descriptors, resident vals, resident idx | A': same ]
 struct PersistentSmem {
     MatView VA, VAT;
+    unsigned long long tag;   // tag of the last polled split-row join (one per phase call)
 };
 __device__ __forceinline__ void persistent_setup(const DevLP& lp, unsigned char* dsm, PersistentSmem& P)
 {
     unsigned char* base = dsm;
+    P.tag = lp.join_base;
     const uint32_t used = resident_view(lp.A, lp.res_steps_A, base, P.VA);
     resident_view(lp.AT, lp.res_steps_AT, base + used, P.VAT);
     __syncthreads();
@@ -181,14 +183,14 @@ __device__ __forceinline__ void persistent_setup(const DevLP& lp, unsigned char*
 
 // A' phase (gathers y) and A phase (gathers xbar).
 template <class Op>
-__device__ __forceinline__ void phase_AT(const DevLP& lp, const PersistentSmem& P, const Op& op, double* acc)
+__device__ __forceinline__ void phase_AT(const DevLP& lp, PersistentSmem& P, const Op& op, double* acc)
 {
-    run_phase(lp.AT, P.VAT, op, acc);
+    run_phase<true>(lp.AT, P.VAT, op, acc, ++P.tag);
 }
 template <class Op>
-__device__ __forceinline__ void phase_A(const DevLP& lp, const PersistentSmem& P, const Op& op, double* acc)
+__device__ __forceinline__ void phase_A(const DevLP& lp, PersistentSmem& P, const Op& op, double* acc)
 {
-    run_phase(lp.A, P.VA, op, acc);
+    run_phase<true>(lp.A, P.VA, op, acc, ++P.tag);
 }
 
 template <bool BOUNDS>

@@ -23,7 +23,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // kinds of per-CTA reduction buffers
 constexpr int RED_STEPP = 0, RED_STEPD = 1, RED_EVALP = 2, RED_EVALD = 3, RED_BUFFERS = 8;
 // control block slots (device doubles)
-constexpr int CTRL_TAU = 0, CTRL_SIGMA = 1, CTRL_SIZE = 16;
+constexpr int CTRL_TAU = 0, CTRL_SIGMA = 1, CTRL_ERR = 15, CTRL_SIZE = 16;
 
 struct DevMat {
     const double2* vals;           // [total_steps][32]
@@ -36,6 +36,7 @@ struct DevMat {
     const uint32_t* cta_lsplit_begin; // [G+1]
     const uint32_t* cta_nsplit;    // [G] leading split-chunk tiles of each CTA
     double* partials;              // one slot per (CTA, split row)
+    double* slots;                 // 16 B per (CTA, split row): {partial, partial ^ tag} of the polled join
     unsigned* counters;            // one per split row
     int nrows, ncols;
 };
@@ -60,6 +61,7 @@ struct DevLP {
     uint32_t res_steps_A;   // per-CTA cap of shared-memory resident warp-steps of A / A'
     uint32_t res_steps_AT;
     double* ctrl;       // control block (device doubles): CTRL_* slots
+    unsigned long long join_base;  // tags of the polled split-row join start above this value
     unsigned long long* trace;  // dev tool: [iter][cta][4] barrier timestamps, or null
 };
 
@@ -534,8 +536,14 @@ __device__ __forceinline__ double* split_scratch()
     return s_part;
 }
 
-template <class Op>
-__device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, const Op& op, double* acc)
+// COOP (cooperative persistent kernels only: all CTAs are co-resident): rows that span several CTAs
+// are joined WITHOUT fences or atomics -- every CTA stores {partial, partial ^ tag} as one 16 B word
+// (value and validity travel together; a torn or stale word fails the xor test) and the row's
+// finisher CTA polls the row's words until all carry this phase's `tag`, then sums them in the same
+// fixed order as the atomic join.  Other kernels use the last-arrival join (fence + atomic counter).
+template <bool COOP = false, class Op>
+__device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, const Op& op, double* acc,
+                                          unsigned long long tag = 0ull)
 {
     const double* __restrict__ vec = op.vec();
     double* s_part = split_scratch();
@@ -574,6 +582,40 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
                 if (lane == 0) op.row(sr.x, p, spre, acc);
                 continue;
             }
+            if (COOP) {
+                if (lane == 0) {
+                    const unsigned long long a = (unsigned long long)__double_as_longlong(p);
+                    unsigned long long* w = reinterpret_cast<unsigned long long*>(M.slots) + 2 * (size_t)ls.y;
+                    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(a), "l"(a ^ tag) : "memory");
+                }
+                if (ls.w == 0) continue;               // not the finisher of this row
+                const uint32_t np = (uint32_t)sr.z;
+                const unsigned long long* w0 = reinterpret_cast<const unsigned long long*>(M.slots) + 2 * (size_t)(uint32_t)sr.y;
+                double s = 0.0;
+                const long long t0 = clock64();
+                for (uint32_t k0 = 0; k0 < np; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    double v = 0.0;
+                    for (;;) {
+                        bool ok = true;
+                        if (k < np) {
+                            unsigned long long qa, qb;
+                            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(qa), "=l"(qb) : "l"(w0 + 2 * (size_t)k) : "memory");
+                            ok = (qa ^ qb) == tag;
+                            v = __longlong_as_double((long long)qa);
+                        }
+                        if (__all_sync(FULL, ok)) break;
+                        if (clock64() - t0 > 4000000000LL) {   // never hang: flag the error and move on
+                            if (lane == 0) M.partials[0] = NAN, *reinterpret_cast<volatile double*>(M.slots) = NAN;
+                            break;
+                        }
+                    }
+                    s += v;
+                }
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                if (lane == 0) op.row(sr.x, s, spre, acc);
+                continue;
+            }
             unsigned last = 0;
             if (lane == 0) {
                 __stcg(M.partials + ls.y, p);
@@ -587,15 +629,9 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
                 const uint32_t np = (uint32_t)sr.z;
                 const double* pp = M.partials + (uint32_t)sr.y;
                 double s = 0.0;
-                for (uint32_t k0 = 0; k0 < np; k0 += 128) {   // 4 loads per lane in flight
-                    double q[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t k = k0 + u * 32 + lane;
-                        q[u] = k < np ? __ldcg(pp + k) : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) s += q[u];
+                for (uint32_t k0 = 0; k0 < np; k0 += 32) {   // lane-strided, ascending: the order of the polled join
+                    const uint32_t k = k0 + lane;
+                    s += k < np ? __ldcg(pp + k) : 0.0;
                 }
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0) {
