@@ -552,6 +552,15 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
     const int nwarps = blockDim.x >> 5;
 
     if (V.nsplit > 0) {
+        // a publishing warp fetches its first row's descriptors and the row's own vector entries NOW, so the
+        // two dependent L2 round trips overlap the chunk tiles instead of following the CTA barrier
+        int4 ls_first = make_int4(0, 0, 0, 0), sr_first = make_int4(0, 0, 0, 0);
+        typename Op::Pre spre_first{};
+        if ((uint32_t)warp < V.nls) {
+            ls_first = __ldg(reinterpret_cast<const int4*>(M.lsplits + V.ls0 + warp));
+            sr_first = __ldg(reinterpret_cast<const int4*>(M.splits + ls_first.x));
+            if (lane == 0) spre_first = op.prefetch(sr_first.x);
+        }
         for (uint32_t t = warp; t < V.nsplit; t += nwarps) {
             const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
             double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, raw.z & 0xffff, lane);
@@ -567,8 +576,9 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
         }
         // local split row w is published by warp w (round robin if there are more rows than warps)
         for (uint32_t li = warp; li < V.nls; li += nwarps) {
-            const int4 ls = __ldg(reinterpret_cast<const int4*>(M.lsplits + V.ls0 + li));
-            const int4 sr = __ldg(reinterpret_cast<const int4*>(M.splits + ls.x));
+            const bool firstrow = (li == (uint32_t)warp);
+            const int4 ls = firstrow ? ls_first : __ldg(reinterpret_cast<const int4*>(M.lsplits + V.ls0 + li));
+            const int4 sr = firstrow ? sr_first : __ldg(reinterpret_cast<const int4*>(M.splits + ls.x));
             const int first = ls.z & 0xffff, count = (ls.z >> 16) & 0xffff;
             // the CTA's chunks of this row, summed in a fixed order (lane-strided, then butterfly)
             double p = 0.0;
@@ -576,8 +586,8 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
             // the row's own vector entries are needed by whoever finishes the row: fetch them now,
             // off the critical path of the join
-            typename Op::Pre spre{};
-            if (lane == 0) spre = op.prefetch(sr.x);
+            typename Op::Pre spre = spre_first;
+            if (lane == 0 && !firstrow) spre = op.prefetch(sr.x);
             if (sr.z == 1) {   // the whole row lives in this CTA: no global join
                 if (lane == 0) op.row(sr.x, p, spre, acc);
                 continue;
