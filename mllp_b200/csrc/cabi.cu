@@ -159,13 +159,6 @@ int upload_mat(mllp_lp* lp, const HostMat& H, DevMat& D)
     return 0;
 }
 
-std::vector<double> permuted(const double* src, const std::vector<int32_t>& order)
-{
-    std::vector<double> out(order.size());
-    for (size_t k = 0; k < order.size(); ++k) out[k] = src[order[k]];
-    return out;
-}
-
 int build_graph(mllp_lp* lp)
 {
     cudaStream_t cs;

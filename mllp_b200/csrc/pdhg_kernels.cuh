@@ -495,24 +495,29 @@ __device__ __forceinline__ void pair_dot(const double2* __restrict__ vpa, const 
 }
 
 // pointers to a tile's values / indices for this lane (resident copy or global)
-__device__ __forceinline__ void tile_ptrs(const MatView& V, uint32_t off, int nsteps, int lane, const double2*& vp,
+__device__ __forceinline__ bool tile_ptrs(const MatView& V, uint32_t off, int nsteps, int lane, const double2*& vp,
                                           const int2*& ip)
 {
     const uint32_t loc = off - V.step0;
     const bool res = loc + (uint32_t)nsteps <= V.res_steps;
     vp = res ? V.rvals + (size_t)loc * 32 + lane : V.gvals + (size_t)off * 32 + lane;
     ip = res ? V.ridx + (size_t)loc * 32 + lane : V.gidx + (size_t)off * 32 + lane;
+    return res;
 }
 
-template <class MEM>
-__device__ __forceinline__ double tile_dot(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps,
-                                           int lane)
+// `RES`: the tile's values / indices are the CTA's shared-memory copy (tell the compiler, so the
+// loads are LDS with immediate offsets instead of generic loads); otherwise global memory.
+template <class MEM, bool RES>
+__device__ __forceinline__ double tile_dot_at(const double2* __restrict__ vp, const int2* __restrict__ ip,
+                                              const double* __restrict__ vec, int nsteps)
 {
-    // whole tiles are resident or not (the resident region is a prefix of the CTA's steps)
-    const uint32_t loc = off - V.step0;
-    const bool res = loc + (uint32_t)nsteps <= V.res_steps;
-    const double2* vp = res ? V.rvals + (size_t)loc * 32 + lane : V.gvals + (size_t)off * 32 + lane;
-    const int2* ip = res ? V.ridx + (size_t)loc * 32 + lane : V.gidx + (size_t)off * 32 + lane;
+    if (RES) {
+        __builtin_assume(__isShared(vp));
+        __builtin_assume(__isShared(ip));
+    } else {
+        __builtin_assume(__isGlobal(vp));
+        __builtin_assume(__isGlobal(ip));
+    }
     double dot = 0.0;
     for (; nsteps > 4; nsteps -= 4, vp += 128, ip += 128) dot = steps_dot<MEM, 4>(vp, ip, vec, dot);
     switch (nsteps) {
@@ -523,6 +528,17 @@ __device__ __forceinline__ double tile_dot(const MatView& V, const double* __res
         default: break;
     }
     return dot;
+}
+
+template <class MEM>
+__device__ __forceinline__ double tile_dot(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps,
+                                           int lane)
+{
+    // whole tiles are resident or not (the resident region is a prefix of the CTA's steps)
+    const uint32_t loc = off - V.step0;
+    if (loc + (uint32_t)nsteps <= V.res_steps)
+        return tile_dot_at<MEM, true>(V.rvals + (size_t)loc * 32 + lane, V.ridx + (size_t)loc * 32 + lane, vec, nsteps);
+    return tile_dot_at<MEM, false>(V.gvals + (size_t)off * 32 + lane, V.gidx + (size_t)off * 32 + lane, vec, nsteps);
 }
 
 // One phase of one CTA.  Split-row chunks come first: each warp parks its chunk's partial in
@@ -682,11 +698,19 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
             if (nsteps == nsteps2 && nsteps >= 1 && nsteps <= 3) {
                 const double2 *vpa, *vpb;
                 const int2 *ipa, *ipb;
-                tile_ptrs(V, (uint32_t)raw.x, nsteps, lane, vpa, ipa);
-                tile_ptrs(V, (uint32_t)raw2.x, nsteps2, lane, vpb, ipb);
-                if (nsteps == 1) pair_dot<typename Op::Mem, 1>(vpa, ipa, vpb, ipb, vec, dot, dot2);
-                else if (nsteps == 2) pair_dot<typename Op::Mem, 2>(vpa, ipa, vpb, ipb, vec, dot, dot2);
-                else pair_dot<typename Op::Mem, 3>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                const bool ra = tile_ptrs(V, (uint32_t)raw.x, nsteps, lane, vpa, ipa);
+                const bool rb = tile_ptrs(V, (uint32_t)raw2.x, nsteps2, lane, vpb, ipb);
+                if (ra && rb) {   // both in shared memory: LDS with immediate offsets
+                    __builtin_assume(__isShared(vpa)); __builtin_assume(__isShared(ipa));
+                    __builtin_assume(__isShared(vpb)); __builtin_assume(__isShared(ipb));
+                    if (nsteps == 1) pair_dot<typename Op::Mem, 1>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                    else if (nsteps == 2) pair_dot<typename Op::Mem, 2>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                    else pair_dot<typename Op::Mem, 3>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                } else {
+                    if (nsteps == 1) pair_dot<typename Op::Mem, 1>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                    else if (nsteps == 2) pair_dot<typename Op::Mem, 2>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                    else pair_dot<typename Op::Mem, 3>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                }
             } else {
                 dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
                 dot2 = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw2.x, nsteps2, lane);
