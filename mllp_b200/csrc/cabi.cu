@@ -305,14 +305,18 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
     BuildParams bp;
     bp.num_ctas = lp->G;
     bp.pref_steps = env_int("MLLP_PREF_STEPS", 4);
-    // chunk length of split rows: 8 steps (512 entries) unless there is enough long-row work to give
-    // every warp of the grid its own 4-step chunk (then the chunk round is one gather group deep)
+    // Two decisions from the share of the nonzeros that sits in very long rows (> 512 entries) of A:
+    //  * chunk length of split rows: 8 steps (512 entries) unless there is enough long-row work to give
+    //    every warp of the grid its own 4-step chunk (then the chunk round is one gather group deep);
+    //  * dealing of the regular tiles: contiguous runs per CTA (neighbouring rows share gathered sectors,
+    //    which one SM's L1 then serves: ken-18 -8 %, pds-20 -1 %, pilot87 -2 %) unless the long rows
+    //    dominate (osa-60: 83 % of nnz), where the least-loaded dealing balances better (+6 % otherwise).
+    int64_t heavy = 0;
+    for (int i = 0; i < m; ++i) {
+        const int64_t len = h_indptr[i + 1] - h_indptr[i];
+        if (len > 512) heavy += len;
+    }
     {
-        int64_t heavy = 0;
-        for (int i = 0; i < m; ++i) {
-            const int64_t len = h_indptr[i + 1] - h_indptr[i];
-            if (len > 512) heavy += len;
-        }
         const int64_t one_round = (int64_t)lp->G * (lp->threads / 32) * 256;
         bp.max_steps = env_int("MLLP_MAX_STEPS", 2 * heavy >= one_round ? 4 : 8);
     }
@@ -320,6 +324,7 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
     if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
     if (bp.max_steps > 1024) bp.max_steps = 1024;
     bp.cluster = env_int("MLLP_CLUSTER", 1) != 0;
+    bp.contiguous = env_int("MLLP_CONTIGUOUS", 2 * heavy < nnz ? 1 : 0) != 0;
 
     int rc = 0;
     try {

@@ -302,11 +302,31 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
         ls.gslot += out.splits[ls.split_id].first_slot;
     }
 
-    std::vector<uint32_t> by_cost(regular.size());
-    std::iota(by_cost.begin(), by_cost.end(), 0u);
-    std::stable_sort(by_cost.begin(), by_cost.end(),
-                     [&](uint32_t a, uint32_t b) { return regular[a].nsteps > regular[b].nsteps; });
-    {
+    if (bp.contiguous) {
+        // Contiguous runs of the (class, cluster)-ordered tile list per CTA, cut by a cost prefix sum:
+        // neighbouring rows gather from neighbouring addresses, so keeping them on ONE SM lets its L1
+        // serve the sectors they share (the least-loaded dealing below scatters them over all SMs).
+        int64_t total = 0;
+        for (int g = 0; g < G; ++g) total += load[g];
+        for (const ProtoTile& t : regular) total += t.nsteps + 2;
+        int g = 0;
+        int64_t acc_cost = 0;   // cost handed to CTAs 0..g (split chunks included)
+        int64_t mine = load[0];
+        for (const ProtoTile& t : regular) {
+            // move on when this CTA has reached its share of the total
+            while (g + 1 < G && (acc_cost + mine) * G >= total * (int64_t)(g + 1)) {
+                acc_cost += mine;
+                ++g;
+                mine = load[g];
+            }
+            per_cta[g].push_back(t);
+            mine += t.nsteps + 2;
+        }
+    } else {
+        std::vector<uint32_t> by_cost(regular.size());
+        std::iota(by_cost.begin(), by_cost.end(), 0u);
+        std::stable_sort(by_cost.begin(), by_cost.end(),
+                         [&](uint32_t a, uint32_t b) { return regular[a].nsteps > regular[b].nsteps; });
         // min-heap of (load, cta)
         std::vector<std::pair<int64_t, int>> heap;
         for (int g = 0; g < G; ++g) heap.emplace_back(load[g], g);
@@ -399,9 +419,9 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
 // kernel does (per-lane sequential sums, then the butterfly over L lanes, then the fixed
 // order join of split rows) on a deterministic test vector and compares every row with
 // the plain CSR dot product.  Used by the CPU test-suite to validate the format logic.
-extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr,
-                                     const int32_t* indices, const double* values, int32_t num_ctas,
-                                     int32_t pref_steps, int32_t max_steps, double* out8)
+static int format_selfcheck_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr,
+                                 const int32_t* indices, const double* values, int32_t num_ctas,
+                                 int32_t pref_steps, int32_t max_steps, bool contiguous, double* out8)
 {
     using namespace mllp;
     if (m < 0 || n < 0 || !indptr || !out8 || (int64_t)indptr[m] != nnz) return 1001;
@@ -409,6 +429,7 @@ extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const in
     bp.num_ctas = num_ctas;
     bp.pref_steps = pref_steps;
     bp.max_steps = max_steps < pref_steps ? pref_steps : max_steps;
+    bp.contiguous = contiguous;
     std::vector<int32_t> tptr, tind;
     std::vector<double> tval;
     csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);
@@ -514,6 +535,21 @@ extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const in
     return rows_seen == (int64_t)m + n ? 0 : 9;
 }
 
+
+// Both dealings of the regular tiles (least-loaded and contiguous runs) are checked; the statistics
+// returned are those of the least-loaded build.
+extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr,
+                                     const int32_t* indices, const double* values, int32_t num_ctas,
+                                     int32_t pref_steps, int32_t max_steps, double* out8)
+{
+    if (!out8) return 1001;
+    double tmp[8];
+    const int rc = format_selfcheck_impl(m, n, nnz, indptr, indices, values, num_ctas, pref_steps, max_steps, true, tmp);
+    if (rc != 0) return 100 + rc;
+    if (!(tmp[0] < 1e-9)) return 199;
+    return format_selfcheck_impl(m, n, nnz, indptr, indices, values, num_ctas, pref_steps, max_steps, false, out8);
+}
+
 // Host-only statistic of the built format: how many distinct 128 B lines the warp-wide gather
 // instructions touch (the L1 tag stage serves about one line per cycle per SM, so this is the
 // gather cost model).  out6: [0]/[1] total lines for A / A', [2]/[3] the largest per-CTA sum,
@@ -528,7 +564,8 @@ extern "C" int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const
     bp.num_ctas = num_ctas;
     bp.pref_steps = pref_steps;
     bp.max_steps = max_steps < pref_steps ? pref_steps : max_steps;
-    bp.cluster = cluster != 0;
+    bp.cluster = (cluster & 1) != 0;
+    bp.contiguous = (cluster & 2) != 0;
     std::vector<int32_t> tptr, tind;
     std::vector<double> tval;
     csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);
@@ -560,6 +597,21 @@ extern "C" int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const
         out6[w] = total;
         out6[2 + w] = worst;
         out6[4 + w] = 2.0 * (double)M.total_steps;
+        if (cluster & 4) {   // report instead: distinct 32 B sectors per CTA (what L2 serves if L1 captures all reuse)
+            double tot_s = 0, worst_s = 0;
+            std::vector<int32_t> secs;
+            for (int g = 0; g < bp.num_ctas; ++g) {
+                secs.clear();
+                for (uint32_t st = M.cta_step_begin[g]; st < M.cta_step_begin[g + 1]; ++st)
+                    for (int q = 0; q < 64; ++q) secs.push_back(M.idx[(size_t)st * 64 + q] >> 2);
+                std::sort(secs.begin(), secs.end());
+                const double d = (double)(std::unique(secs.begin(), secs.end()) - secs.begin());
+                tot_s += d;
+                worst_s = std::max(worst_s, d);
+            }
+            out6[w] = tot_s;
+            out6[2 + w] = worst_s;
+        }
     }
     return 0;
 }
