@@ -324,6 +324,7 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
     if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
     if (bp.max_steps > 1024) bp.max_steps = 1024;
     bp.cluster = env_int("MLLP_CLUSTER", 1) != 0;
+    bp.cluster_rounds = env_int("MLLP_CLUSTER_ROUNDS", 3);
     bp.contiguous = env_int("MLLP_CONTIGUOUS", 2 * heavy < nnz ? 1 : 0) != 0;
 
     int rc = 0;

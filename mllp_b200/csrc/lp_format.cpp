@@ -149,8 +149,10 @@ void plan_orders(int m, int n, const int32_t* ptr, const int32_t* ind, const int
     plan_row_order(m, ptr, bp, orderY, posY);
     plan_row_order(n, tptr, bp, orderX, posX);
     if (bp.cluster) {
-        cluster_within_classes(n, tptr, tind, bp, posY, orderX, posX);   // columns by the rows they touch
-        cluster_within_classes(m, ptr, ind, bp, posX, orderY, posY);     // rows by the columns they touch
+        for (int round = 0; round < std::max(1, bp.cluster_rounds); ++round) {
+            cluster_within_classes(n, tptr, tind, bp, posY, orderX, posX);   // columns by the rows they touch
+            cluster_within_classes(m, ptr, ind, bp, posX, orderY, posY);     // rows by the columns they touch
+        }
     }
 }
 
@@ -233,6 +235,7 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
 
     // ---- 1b. regular rows: tiles of 32/L consecutive rows of one class -----------------------
     std::vector<ProtoTile> regular;
+    std::vector<int32_t> sector_buf;
     for (int p = nsplit_rows; p < nrows;) {
         const int r = order[p];
         const RowClass rc = classify(ptr[r + 1] - ptr[r], bp);
@@ -244,7 +247,19 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
             if (rc2.nchunks != 1 || rc2.logL != rc.logL || rc2.nsteps != rc.nsteps) break;
             ++q;
         }
-        regular.push_back({(uint32_t)p, (uint16_t)rc.nsteps, (uint8_t)rc.logL, (uint8_t)(q - p), -1, 0, 0});
+        ProtoTile t{(uint32_t)p, (uint16_t)rc.nsteps, (uint8_t)rc.logL, (uint8_t)(q - p), -1, 0, 0};
+        if (bp.contiguous) {
+            // e1 doubles as the tile's cost for the contiguous dealing: steps + the distinct 32 B sectors
+            // its gathers touch (what the SM has to fetch)
+            sector_buf.clear();
+            for (int pp = p; pp < q; ++pp) {
+                const int rr = order[pp];
+                for (int32_t k = ptr[rr]; k < ptr[rr + 1]; ++k) sector_buf.push_back(colpos[ind[k]] >> 2);
+            }
+            std::sort(sector_buf.begin(), sector_buf.end());
+            t.e1 = (uint32_t)(std::unique(sector_buf.begin(), sector_buf.end()) - sector_buf.begin());
+        }
+        regular.push_back(t);
         p = q;
     }
 
@@ -306,21 +321,25 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
         // Contiguous runs of the (class, cluster)-ordered tile list per CTA, cut by a cost prefix sum:
         // neighbouring rows gather from neighbouring addresses, so keeping them on ONE SM lets its L1
         // serve the sectors they share (the least-loaded dealing below scatters them over all SMs).
+        auto cost = [](const ProtoTile& t) { return (int64_t)t.e1 + 2 * (int64_t)t.nsteps + 4; };
+        std::vector<int64_t> cl((size_t)G);
+        for (int g = 0; g < G; ++g) cl[g] = 3 * load[g];   // split chunks: ~3 units per step (dense gathers)
+        const size_t nheavy = 0;   // (spreading the whole-warp rows least-loaded-first was measured slower: ken-18 +4 %)
         int64_t total = 0;
-        for (int g = 0; g < G; ++g) total += load[g];
-        for (const ProtoTile& t : regular) total += t.nsteps + 2;
+        for (int g = 0; g < G; ++g) total += cl[g];
+        for (size_t k = nheavy; k < regular.size(); ++k) total += cost(regular[k]);
         int g = 0;
-        int64_t acc_cost = 0;   // cost handed to CTAs 0..g (split chunks included)
-        int64_t mine = load[0];
-        for (const ProtoTile& t : regular) {
+        int64_t acc_cost = 0;   // cost handed to CTAs 0..g
+        int64_t mine = cl[0];
+        for (size_t k = nheavy; k < regular.size(); ++k) {
             // move on when this CTA has reached its share of the total
             while (g + 1 < G && (acc_cost + mine) * G >= total * (int64_t)(g + 1)) {
                 acc_cost += mine;
                 ++g;
-                mine = load[g];
+                mine = cl[g];
             }
-            per_cta[g].push_back(t);
-            mine += t.nsteps + 2;
+            per_cta[g].push_back(regular[k]);
+            mine += cost(regular[k]);
         }
     } else {
         std::vector<uint32_t> by_cost(regular.size());
@@ -566,6 +585,7 @@ extern "C" int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const
     bp.max_steps = max_steps < pref_steps ? pref_steps : max_steps;
     bp.cluster = (cluster & 1) != 0;
     bp.contiguous = (cluster & 2) != 0;
+    bp.cluster_rounds = ((cluster >> 4) & 7) ? 1 + ((cluster >> 4) & 7) : bp.cluster_rounds;
     std::vector<int32_t> tptr, tind;
     std::vector<double> tval;
     csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);

@@ -56,6 +56,7 @@ struct BuildParams {
     int pref_steps = 4;      // choose L so a row needs at most this many steps
     int max_steps = 4;       // rows longer than 64*max_steps entries are split
     bool cluster = true;     // cluster rows inside a length class by the entries they touch
+    int cluster_rounds = 3;  // alternate column / row clustering this many times
     bool contiguous = false; // deal regular tiles to CTAs in contiguous runs (L1 reuse) instead of least-loaded first
     bool final_params = false; // max_steps already adjusted (effective_params is then the identity)
 };
