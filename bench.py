@@ -53,6 +53,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload, iters_per_step):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json), if it was taken on this workload / launch size; else None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d["workload"] == workload and int(d["iters_per_step"]) == int(iters_per_step):
+            return int(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -381,7 +394,8 @@ def main():
                        "grid_ctas": info["grid_ctas"], "threads": info["threads"], "final_pobj": float(final_scal[0]),
                        "final_rel_kkt": float(final_scal[8])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_pdhg_persistent (one launch = %d iterations)" % KI,
+                         "traffic": measured_traffic(args.workload, KI), "algorithmic_bytes_per_launch": bytes_iter * KI,
+                         "kernel": "k_pdhg_persistent (one launch = %d iterations)" % KI,
                          "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
                          "note": "achieved = (24 nnz + 36 m + 44 n + 8) B x iterations / CUDA-event time of the step; the working set is L2-resident so DRAM traffic is far below the algorithmic bytes"},
             "clocks": clocks, "gpu_launches": 9 * args.steps, "wall_ms_per_step": wall_ms / args.steps,

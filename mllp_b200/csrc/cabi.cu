@@ -403,7 +403,7 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             RC_OK(dev_zeros(lp, &lp->u_b, (size_t)m));
             RC_OK(dev_zeros(lp, &lp->u_c, (size_t)n));
             RC_OK(dev_zeros(lp, &lp->d_scal, MLLP_NUM_SCALARS));
-            RC_OK(dev_zeros(lp, &lp->d_norm2, 2));
+            RC_OK(dev_zeros(lp, &lp->d_norm2, 2 + 256));
             if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
             if (nranks > 1) {
                 RC_OK(dev_zeros(lp, &lp->d_flags, (size_t)MAX_RANKS));
@@ -603,7 +603,7 @@ int mllp_estimate_norm(mllp_lp_t lp, int iters, double* h_sigma_max, void* strea
     for (int it = 0; it < iters; ++it) {
         RC_OK(launch_spmv(lp->d.A, lp->tmp_n, lp->tmp_m, lp->G, lp->threads, s));
         RC_OK(launch_spmv(lp->d.AT, lp->tmp_m, lp->tmp_n2, lp->G, lp->threads, s));
-        RC_OK(launch_sumsq(lp->tmp_n2, lp->n, lp->d_norm2, s));
+        RC_OK(launch_sumsq(lp->tmp_n2, lp->n, lp->d_norm2, lp->d_norm2 + 2, s));
         RC_OK(launch_scale_by_invnorm(lp->tmp_n, lp->tmp_n2, lp->d_norm2, lp->n, s));
     }
     double nz2 = 0.0;

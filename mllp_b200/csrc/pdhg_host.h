@@ -11,7 +11,7 @@ struct PeerInfo;
 int launch_gather(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
 int launch_scatter(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
 int launch_fill(double* dst, double v, int n, cudaStream_t s);
-int launch_sumsq(const double* v, int n, double* out, cudaStream_t s);
+int launch_sumsq(const double* v, int n, double* out, double* scratch, cudaStream_t s);
 int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2, int n, cudaStream_t s);
 int launch_graph_edges(int m, long long nnz, const int32_t* indptr, const int32_t* indices, const double* values,
                        long long* edge_index, float* edge_attr, cudaStream_t s);

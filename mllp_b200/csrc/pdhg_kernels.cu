@@ -22,20 +22,34 @@ __global__ void k_fill(double* dst, double v, int n)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[k] = v;
 }
-// single block: out[0] = sum v^2 (fixed order)
-__global__ void k_sumsq(const double* __restrict__ v, int n, double* out)
+// out[0] = sum v^2 in a fixed order: 148 block partials (grid-stride, block tree), then one block.
+constexpr int SUMSQ_BLOCKS = 148;
+__device__ __forceinline__ double block_sum(double s, double* sm)
 {
-    __shared__ double sm[32];
-    double s = 0.0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) s += v[k] * v[k];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
     __syncthreads();
+    s = 0.0;
     if (threadIdx.x < 32) {
         s = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-        if (threadIdx.x == 0) out[0] = s;
     }
+    return s;   // valid in thread 0
+}
+__global__ void k_sumsq_partial(const double* __restrict__ v, int n, double* __restrict__ part)
+{
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) s += v[k] * v[k];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void k_sumsq_final(const double* __restrict__ part, int nparts, double* out)
+{
+    __shared__ double sm[32];
+    double s = threadIdx.x < nparts ? part[threadIdx.x] : 0.0;
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) out[0] = s;
 }
 // dst = src / sqrt(sqrt-free norm2[0])   (dst = src * rsqrt(norm2))
 __global__ void k_scale_by_invnorm(double* __restrict__ dst, const double* __restrict__ src,
@@ -364,9 +378,10 @@ int launch_fill(double* dst, double v, int n, cudaStream_t s)
     k_fill<<<blocks_for(n), 256, 0, s>>>(dst, v, n);
     return (int)cudaGetLastError();
 }
-int launch_sumsq(const double* v, int n, double* out, cudaStream_t s)
+int launch_sumsq(const double* v, int n, double* out, double* scratch /* >= SUMSQ_BLOCKS doubles */, cudaStream_t s)
 {
-    k_sumsq<<<1, 1024, 0, s>>>(v, n, out);
+    k_sumsq_partial<<<SUMSQ_BLOCKS, 256, 0, s>>>(v, n, scratch);
+    k_sumsq_final<<<1, 256, 0, s>>>(scratch, SUMSQ_BLOCKS, out);
     return (int)cudaGetLastError();
 }
 int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2, int n, cudaStream_t s)

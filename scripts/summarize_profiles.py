@@ -40,8 +40,8 @@ def full():
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
             "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
             "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-    lines = ["# %s -- `ncu --set full` of `k_pdhg_persistent` (osa-60, 50 fused iterations in the launch)" % tag, "",
-             "Command: `ncu --set full --clock-control none --import-source on -k regex:k_pdhg_persistent -s 3 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --iters-per-step 50`", "",
+    lines = ["# %s -- `ncu --set full` of `k_pdhg_persistent` (osa-60, 1000 fused iterations in the launch = the bench configuration)" % tag, "",
+             "Command: `ncu --set full --clock-control none --import-source on -k regex:k_pdhg_persistent -s 3 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras --iters-per-step 1000`", "",
              "| metric | unit | value |", "|---|---|---:|"]
     d = {}
     for h, u, v in zip(hdr, unit, val):
@@ -50,8 +50,8 @@ def full():
     try:
         dur = float(d["gpu__time_duration.sum"].replace(",", ""))
         rd = float(d["dram__bytes_read.sum"].replace(",", "")); wr = float(d["dram__bytes_write.sum"].replace(",", ""))
-        lines += ["", "Per launch (50 iterations): DRAM traffic = %s + %s (units above); algorithmic bytes = 50 x 44 866 664 B = 2.24 GB." % (d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]),
-                  "DRAM traffic is ~60x BELOW the algorithmic bytes: after the first iteration the matrix is served from L2 and shared memory.",
+        lines += ["", "Per launch (1000 iterations): DRAM traffic = %s + %s (units above); algorithmic bytes = 1000 x 44 866 664 B = 44.9 GB." % (d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]),
+                  "DRAM traffic is ~1000x BELOW the algorithmic bytes: after the first iteration the matrix is served from L2 and shared memory.",
                   "The per-launch time under ncu is cold-cache/serialised; the bench number (CUDA events) is the one to quote."]
     except Exception as e:
         lines.append("(derived numbers unavailable: %s)" % e)
@@ -83,9 +83,9 @@ def full():
     open(os.path.join(OUT, tag + "_persistent_ncu_full.md"), "w").write("\n".join(lines) + "\n")
 
 launches(); full()
-for f in ("bench_r1d.json", "bench_r1d_ken18.json", "bench_r1d_ref.json", "bench_r1d_n2.json"):
+for f in ("bench_r1e.json", "bench_r1e_ken18.json", "bench_r1e_ref.json", "bench_r1e_n2.json"):
     p = os.path.join(GO, f)
     if os.path.exists(p):
         txt = [l for l in open(p).read().splitlines() if l.startswith("{")]
-        if txt: open(os.path.join(OUT, tag + "_" + f.replace("_r1d", "")), "w").write(txt[-1] + "\n")
+        if txt: open(os.path.join(OUT, tag + "_" + f.replace("_r1e", "")), "w").write(txt[-1] + "\n")
 print("ok")
