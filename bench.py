@@ -215,7 +215,7 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
     bvec = torch.tensor(np.concatenate([i[2] for i in insts]), device=dev)
     cvec = torch.tensor(np.concatenate([i[3] for i in insts]), device=dev)
     nx, ny = int(bsol.x_off[-1]), int(bsol.y_off[-1])
-    etas = (0.99 / bsol.sigma_max()).contiguous()
+    etas = (0.99 / bsol.sigma_max_robust()).contiguous()
     scal = torch.zeros(len(insts) * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
 
     def solve_all():

@@ -58,6 +58,8 @@ typedef struct mllp_batch *mllp_batch_t;
 #define MLLP_F_NO_SMEM_RESIDENT 1u /* stream the matrix from L2/HBM even if it fits on-chip */
 #define MLLP_F_GRAPH_MODE 2u       /* one kernel launch per half-iteration (CUDA graph) instead
                                       of the persistent cooperative kernel */
+#define MLLP_F_NO_TUNE 4u          /* skip the tuning rounds of mllp_lp_create (measured re-dealing of the
+                                      tiles to the CTAs; results never depend on it, only speed) */
 
 const char *mllp_last_error(void);
 int mllp_version(void);
@@ -109,6 +111,11 @@ int mllp_lp_destroy(mllp_lp_t lp);
  * +16 m with row senses), [13]/[14]=per-CTA cap of shared-memory resident warp-steps of A/A',
  * [15]=CTAs per SM. */
 int mllp_lp_info(mllp_lp_t lp, int64_t *out16);
+
+/* Tuning rounds of mllp_lp_create (single GPU, persistent kernel): a few traced iterations give every
+ * CTA's time per phase, which is fed back into the dealing of the tiles; the fastest build is kept.
+ * out4: [0] ns / iteration of the first build, [1] of the build kept, [2] rounds run, [3] reserved. */
+int mllp_lp_tune_info(mllp_lp_t lp, double *out4);
 
 /* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */
 int mllp_spmv(mllp_lp_t lp, int trans, const double *d_in, double *d_out, void *stream);

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libmllp_b200.so")
 
 NUM_SCALARS = 16
-F_DEFAULT, F_NO_SMEM_RESIDENT, F_GRAPH_MODE = 0, 1, 2
+F_DEFAULT, F_NO_SMEM_RESIDENT, F_GRAPH_MODE, F_NO_TUNE = 0, 1, 2, 4
 
 _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32
@@ -36,6 +36,7 @@ SIGNATURES = {
     "mllp_rowpart_error": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     "mllp_lp_destroy": (ctypes.c_int, [_vp]),
     "mllp_lp_info": (ctypes.c_int, [_vp, _vp]),
+    "mllp_lp_tune_info": (ctypes.c_int, [_vp, _vp]),
     "mllp_spmv": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
     "mllp_estimate_norm": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_dbl), _vp]),
     "mllp_pdhg_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),

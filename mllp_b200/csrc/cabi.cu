@@ -71,6 +71,10 @@ struct mllp_lp {
     size_t dyn_smem = 0;          // dynamic shared memory of the persistent kernels
     DevLP d{};
     std::vector<void*> allocs;
+    std::vector<void*> mat_allocs;    // device arrays of the two tiled matrices (replaced by the tuning rounds)
+    std::vector<void*>* sink = &allocs;
+    double tune_ns[2] = {0.0, 0.0};   // measured ns / iteration before and after the tuning rounds
+    int tune_rounds = 0;
     int32_t* d_orderX = nullptr;  // internal position k holds original column order[k]
     int32_t* d_orderY = nullptr;
     double* tmp_n = nullptr;
@@ -112,7 +116,7 @@ int dev_alloc(mllp_lp* lp, T** out, size_t count)
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    lp->allocs.push_back(p);
+    lp->sink->push_back(p);
     *out = (T*)p;
     return 0;
 }
@@ -131,8 +135,15 @@ int dev_zeros(mllp_lp* lp, T** out, size_t count)
     return 0;
 }
 
+struct SinkGuard {   // route the allocations of a scope into lp->mat_allocs
+    mllp_lp* lp;
+    explicit SinkGuard(mllp_lp* l) : lp(l) { lp->sink = &lp->mat_allocs; }
+    ~SinkGuard() { lp->sink = &lp->allocs; }
+};
+
 int upload_mat(mllp_lp* lp, const HostMat& H, DevMat& D)
 {
+    SinkGuard sg(lp);
     double* vals; int32_t* idx; Tile* tiles; uint32_t* cb; uint32_t* csb; SplitRow* sp;
     LocalSplit* lsp; uint32_t* clb; uint32_t* cns;
     RC_OK(dev_upload(lp, &vals, H.vals.data(), H.vals.size()));
@@ -237,6 +248,142 @@ int nccl_fail(int rc, const char* what)
         int r_ = (call);                                  \
         if (r_ != 0) return nccl_fail(r_, #call);         \
     } while (0)
+
+
+// Shared-memory residency of the matrix slices (persistent kernels): sizes lp->dyn_smem and the per-CTA
+// caps of resident warp-steps from the built images.
+static int configure_residency(mllp_lp* lp, const HostMat& HA, const HostMat& HAT, const cudaDeviceProp& prop, int bpsm,
+                               bool resident)
+{
+    const size_t desc_bytes = 16 * ((size_t)HA.max_cta_tiles + (size_t)HAT.max_cta_tiles);
+    // Own entries of the CTA's rows (y, b / x, c) resident in shared memory (parity kernel): only when (nearly) the whole
+    // matrix share stays resident next to them (measured: ken-18 -2 %; on osa-60, where they would push matrix steps
+    // out of shared memory, +2 %).
+    bool own = env_int("MLLP_OWN", 1) != 0 && resident && lp->nranks == 1 && !(lp->flags & MLLP_F_GRAPH_MODE);
+    size_t own_bytes = 16 * ((size_t)((HA.max_cta_rows + 1) & ~1) + (size_t)((HAT.max_cta_rows + 1) & ~1));
+    {
+        const size_t res_cap = (size_t)env_int("MLLP_RES_KB", 140) * 1024;
+        const size_t all = 768 * ((size_t)HA.max_cta_steps + (size_t)HAT.max_cta_steps);
+        if (env_int("MLLP_OWN", 1) < 2 && all + own_bytes > res_cap + res_cap / 7) own = false;   // MLLP_OWN=2 forces it (dev knob)
+    }
+    if (!own) own_bytes = 0;
+    lp->d.own_rows_A = own ? (uint32_t)((HA.max_cta_rows + 1) & ~1) : 0u;
+    lp->d.own_rows_AT = own ? (uint32_t)((HAT.max_cta_rows + 1) & ~1) : 0u;
+    lp->dyn_smem = desc_bytes + own_bytes;
+    lp->d.res_steps_A = 0; lp->d.res_steps_AT = 0;
+    if (resident) {
+        const size_t per_cta = (size_t)prop.sharedMemPerMultiprocessor / (size_t)bpsm;
+        size_t budget = std::min<size_t>(per_cta - 1024, (size_t)prop.sharedMemPerBlockOptin);
+        budget -= std::min<size_t>(budget, 6144);  // static shared memory of the kernels + slack
+        budget -= std::min<size_t>(budget, desc_bytes + own_bytes);
+        // The gathered vectors are read through L1 (the grid barrier invalidates it), so part of
+        // the SM's 228 KB stays L1: cap the shared-memory share of the matrix.
+        const size_t res_cap = (size_t)env_int("MLLP_RES_KB", 140) * 1024;
+        budget = std::min<size_t>(budget, res_cap > own_bytes ? res_cap - own_bytes : 0);
+        // what is left keeps (a prefix of) each CTA's share of A' and A resident
+        const size_t cap = budget / 768;
+        size_t a = (size_t)HA.max_cta_steps, at = (size_t)HAT.max_cta_steps;
+        if (a + at > cap) {   // A' first: its tiles are the short, latency-dominated ones
+            at = std::min(at, cap);
+            a = std::min(a, cap - at);
+        }
+        const int lim = env_int("MLLP_RES_STEPS", -1);  // dev knob: cap the resident steps
+        if (lim >= 0) { a = std::min<size_t>(a, (size_t)lim); at = std::min<size_t>(at, (size_t)lim); }
+        lp->d.res_steps_A = (uint32_t)a; lp->d.res_steps_AT = (uint32_t)at;
+        lp->dyn_smem = desc_bytes + own_bytes + 768 * (a + at);
+    }
+    if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(persistent_set_smem(lp->bounds, lp->dyn_smem));
+    if (persistent_max_blocks_per_sm(lp->threads, lp->bounds, lp->dyn_smem) < bpsm)
+        return fail(MLLP_E_STATE, "mllp_lp_create: persistent grid does not fit with the chosen shared memory");
+    return 0;
+}
+
+static void free_mats(mllp_lp* lp)
+{
+    for (void* p : lp->mat_allocs) cudaFree(p);
+    lp->mat_allocs.clear();
+}
+
+// `iters` traced parity iterations on the current internal state: per CTA and iteration
+// [A' phase done, barrier released, A phase done, barrier released] (globaltimer ns).
+static int run_trace(mllp_lp* lp, double tau, double sigma, int iters, std::vector<unsigned long long>& out)
+{
+    unsigned long long* d_tr = nullptr;
+    const size_t cnt = (size_t)iters * lp->G * 4;
+    out.assign(cnt, 0ull);
+    CUDA_OK(cudaMalloc(&d_tr, cnt * sizeof(unsigned long long)));
+    int rc = (int)cudaMemset(d_tr, 0, cnt * sizeof(unsigned long long));
+    lp->d.join_base = lp->join_epoch;
+    lp->join_epoch += 2ull * (unsigned long long)iters + 2ull;
+    DevLP d = lp->d;
+    d.trace = d_tr;
+    if (rc == 0) rc = launch_pdhg_persistent(d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, iters, 0);
+    if (rc == 0) rc = (int)cudaDeviceSynchronize();
+    if (rc == 0) rc = (int)cudaMemcpy(out.data(), d_tr, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_tr);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "traced persistent run");
+    return 0;
+}
+
+// Mean work time of every CTA in the A' phase and in the A phase (ns) and the mean iteration time.
+struct PhaseTimes {
+    std::vector<double> at, a;
+    double iter_ns = 0.0;
+};
+static int measure_phases(mllp_lp* lp, PhaseTimes& T)
+{
+    const int iters = 48, skip = 8, G = lp->G;
+    std::vector<unsigned long long> tr;
+    RC_OK(run_trace(lp, 1.0, 1.0, iters, tr));
+    T.at.assign((size_t)G, 0.0);
+    T.a.assign((size_t)G, 0.0);
+    auto at = [&](int it, int g, int k) { return tr[((size_t)it * G + g) * 4 + k]; };
+    for (int g = 0; g < G; ++g) {
+        double sa = 0, sat = 0;
+        for (int it = skip; it < iters; ++it) {
+            sat += (double)(long long)(at(it, g, 0) - at(it - 1, g, 3));
+            sa += (double)(long long)(at(it, g, 2) - at(it, g, 1));
+        }
+        T.at[g] = sat / (iters - skip);
+        T.a[g] = sa / (iters - skip);
+    }
+    unsigned long long t0 = 0, t1 = 0;
+    for (int g = 0; g < G; ++g) {
+        t0 = std::max(t0, at(skip - 1, g, 3));
+        t1 = std::max(t1, at(iters - 1, g, 3));
+    }
+    T.iter_ns = (double)(long long)(t1 - t0) / (iters - skip);
+    return 0;
+}
+
+// One feedback step of the dealing from measured per-CTA phase times (see DealFeedback).
+static void update_feedback(const HostMat& H, const std::vector<double>& t, bool contiguous, DealFeedback& fb)
+{
+    const size_t G = t.size();
+    double mean = 0;
+    for (double v : t) mean += v;
+    mean /= (double)G;
+    if (!(mean > 0)) return;
+    // fixed cost of a phase (start-up after the barrier, first round trip): half of the fastest CTA's time
+    double t0 = mean;
+    for (double v : t) t0 = std::min(t0, v);
+    t0 *= 0.5;
+    if (contiguous) {
+        if (fb.tile_w.size() != H.reg_cta.size()) fb.tile_w.assign(H.reg_cta.size(), 1.0);
+        if (fb.cta_f.size() != G) fb.cta_f.assign(G, 1.0);
+        std::vector<double> f(G);
+        for (size_t g = 0; g < G; ++g) f[g] = std::min(2.0, std::max(0.5, (t[g] - t0) / (mean - t0)));
+        for (size_t k = 0; k < H.reg_cta.size(); ++k) fb.tile_w[k] *= f[H.reg_cta[k]];
+        for (size_t g = 0; g < G; ++g) fb.cta_f[g] *= f[g];
+    } else {
+        if (fb.cta_bias.size() != G) fb.cta_bias.assign(G, 0.0);
+        double load = 0;
+        for (double v : H.cta_load) load += v;
+        if (!(load > 0)) return;
+        const double unit_ns = (mean - t0) * (double)G / load;   // ns per load unit
+        for (size_t g = 0; g < G; ++g) fb.cta_bias[g] += 0.8 * (t[g] - mean) / unit_ns;
+    }
+}
 
 }  // namespace
 
@@ -414,36 +561,60 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
                 memcpy(id.internal, uid, sizeof(id.internal));
                 NCCL_OK(api->comm_init_rank(&lp->comm, nranks, id, rank));
             }
-            // shared-memory residency of the matrix slices
-            const size_t desc_bytes = 16 * ((size_t)HA.max_cta_tiles + (size_t)HAT.max_cta_tiles);
-            lp->dyn_smem = desc_bytes;
-            lp->d.res_steps_A = 0; lp->d.res_steps_AT = 0;
-            if (resident) {
-                const size_t per_cta = (size_t)prop.sharedMemPerMultiprocessor / (size_t)bpsm;
-                size_t budget = std::min<size_t>(per_cta - 1024, (size_t)prop.sharedMemPerBlockOptin);
-                budget -= std::min<size_t>(budget, 6144);  // static shared memory of the kernels + slack
-                budget -= std::min<size_t>(budget, desc_bytes);
-                // The gathered vectors are read through L1 (the grid barrier invalidates it), so part of
-                // the SM's 228 KB stays L1: cap the shared-memory share of the matrix.
-                budget = std::min<size_t>(budget, (size_t)env_int("MLLP_RES_KB", 140) * 1024);
-                // what is left keeps (a prefix of) each CTA's share of A' and A resident
-                const size_t cap = budget / 768;
-                size_t a = (size_t)HA.max_cta_steps, at = (size_t)HAT.max_cta_steps;
-                if (a + at > cap) {   // A' first: its tiles are the short, latency-dominated ones
-                    at = std::min(at, cap);
-                    a = std::min(a, cap - at);
-                }
-                const int lim = env_int("MLLP_RES_STEPS", -1);  // dev knob: cap the resident steps
-                if (lim >= 0) { a = std::min<size_t>(a, (size_t)lim); at = std::min<size_t>(at, (size_t)lim); }
-                lp->d.res_steps_A = (uint32_t)a; lp->d.res_steps_AT = (uint32_t)at;
-                lp->dyn_smem = desc_bytes + 768 * (a + at);
-            }
-            if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(persistent_set_smem(lp->bounds, lp->dyn_smem));
-            if (persistent_max_blocks_per_sm(lp->threads, lp->bounds, lp->dyn_smem) < bpsm)
-                return fail(MLLP_E_STATE, "mllp_lp_create: persistent grid does not fit with the chosen shared memory");
+            RC_OK(configure_residency(lp, HA, HAT, prop, bpsm, resident));
             return 0;
         };
         rc = body();
+
+        // Tuning rounds (single GPU, persistent kernel): trace a few iterations on the zero state, feed the
+        // per-CTA phase times back into the dealing of the regular tiles, rebuild, keep the fastest build.
+        // The dealing does not change the summation order inside a row, so results are unaffected.
+        const int tune = env_int("MLLP_TUNE", (flags & MLLP_F_NO_TUNE) ? 0 : 8);
+        const bool worth = (int64_t)HA.tiles.size() + (int64_t)HAT.tiles.size() >= 8 * (int64_t)lp->G;
+        if (rc == 0 && tune > 0 && nranks == 1 && !(flags & MLLP_F_GRAPH_MODE) && worth) {
+            auto tuning = [&]() -> int {
+                PhaseTimes T;
+                RC_OK(measure_phases(lp, T));
+                lp->tune_ns[0] = lp->tune_ns[1] = T.iter_ns;
+                DealFeedback fbA, fbAT;
+                HostMat bestA, bestAT, curA, curAT;   // best = fastest build so far (if not the first), cur = uploaded
+                bool have_best = false, cur_is_first = true, uploaded_is_best = true;
+                int stale = 0;   // rounds since the last improvement: stop after 3
+                for (int r = 0; r < tune && stale < 3; ++r) {
+                    update_feedback(cur_is_first ? HA : curA, T.a, bp.contiguous, fbA);
+                    update_feedback(cur_is_first ? HAT : curAT, T.at, bp.contiguous, fbAT);
+                    HostMat nA, nAT;
+                    build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, nA, 0, &fbA);
+                    build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, nAT, 0, &fbAT);
+                    free_mats(lp);
+                    RC_OK(upload_mat(lp, nA, lp->d.A));
+                    RC_OK(upload_mat(lp, nAT, lp->d.AT));
+                    RC_OK(configure_residency(lp, nA, nAT, prop, bpsm, resident));
+                    RC_OK(measure_phases(lp, T));
+                    ++lp->tune_rounds;
+                    curA = std::move(nA); curAT = std::move(nAT);
+                    cur_is_first = false;
+                    if (T.iter_ns < 0.995 * lp->tune_ns[1]) {
+                        lp->tune_ns[1] = T.iter_ns;
+                        bestA = curA; bestAT = curAT;
+                        have_best = true; uploaded_is_best = true;
+                        stale = 0;
+                    } else {
+                        uploaded_is_best = false;
+                        ++stale;
+                    }
+                }
+                if (have_best) { HA = std::move(bestA); HAT = std::move(bestAT); }
+                if (!uploaded_is_best) {
+                    free_mats(lp);
+                    RC_OK(upload_mat(lp, HA, lp->d.A));
+                    RC_OK(upload_mat(lp, HAT, lp->d.AT));
+                    RC_OK(configure_residency(lp, HA, HAT, prop, bpsm, resident));
+                }
+                return 0;
+            };
+            rc = tuning();
+        }
 
         int64_t* I = lp->info;
         I[0] = m; I[1] = n; I[2] = nranks > 1 ? HA.nnz_emitted : nnz;
@@ -563,6 +734,7 @@ int mllp_lp_destroy(mllp_lp_t lp)
     if (lp->comm) { NcclApi* api = nccl_api(); if (api) api->comm_destroy(lp->comm); }
     if (lp->graph) cudaGraphExecDestroy(lp->graph);
     for (void* p : lp->allocs) cudaFree(p);
+    for (void* p : lp->mat_allocs) cudaFree(p);
     delete lp;
     return 0;
 }
@@ -571,6 +743,13 @@ int mllp_lp_info(mllp_lp_t lp, int64_t* out16)
 {
     if (!lp || !out16) return fail(MLLP_E_INVALID, "mllp_lp_info: null argument");
     memcpy(out16, lp->info, sizeof(lp->info));
+    return 0;
+}
+
+int mllp_lp_tune_info(mllp_lp_t lp, double* out4)
+{
+    if (!lp || !out4) return fail(MLLP_E_INVALID, "mllp_lp_tune_info: null argument");
+    out4[0] = lp->tune_ns[0]; out4[1] = lp->tune_ns[1]; out4[2] = (double)lp->tune_rounds; out4[3] = 0.0;
     return 0;
 }
 
@@ -694,20 +873,12 @@ int mllp_debug_trace(mllp_lp_t lp, double tau, double sigma, int32_t iters, unsi
 {
     if (!lp || !h_out || iters < 1) return fail(MLLP_E_INVALID, "mllp_debug_trace: bad argument");
     DeviceGuard guard(lp->device);
-    unsigned long long* d_tr = nullptr;
-    const size_t cnt = (size_t)iters * lp->G * 4;
-    CUDA_OK(cudaMalloc(&d_tr, cnt * sizeof(unsigned long long)));
-    CUDA_OK(cudaMemset(d_tr, 0, cnt * sizeof(unsigned long long)));
-    lp->d.join_base = lp->join_epoch;
-    lp->join_epoch += 2ull * (unsigned long long)iters + 2ull;
-    DevLP d = lp->d;
-    d.trace = d_tr;
-    int rc = launch_pdhg_persistent(d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, iters, 0);
-    if (rc == 0) rc = (int)cudaDeviceSynchronize();
-    if (rc == 0) rc = (int)cudaMemcpy(h_out, d_tr, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaFree(d_tr);
-    if (rc != 0) return cuda_fail((cudaError_t)rc, "mllp_debug_trace");
-    return 0;
+    {
+        std::vector<unsigned long long> tr;
+        RC_OK(run_trace(lp, tau, sigma, iters, tr));
+        memcpy(h_out, tr.data(), tr.size() * sizeof(unsigned long long));
+        return 0;
+    }
 }
 
 int mllp_pdhg_run_host(mllp_lp_t lp, double* h_x, double* h_y, const double* h_b, const double* h_c, double tau,

@@ -193,7 +193,7 @@ void partition_rows(int nrows, const int32_t* ptr, const std::vector<int32_t>& g
 void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
                     const double* val, const std::vector<int32_t>& order,
                     const std::vector<int32_t>& colpos, const BuildParams& bp_in, HostMat& out,
-                    uint32_t row_offset)
+                    uint32_t row_offset, const DealFeedback* fb)
 {
     const BuildParams bp = effective_params(nrows, ptr, bp_in);
     out = HostMat();
@@ -317,45 +317,60 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
         ls.gslot += out.splits[ls.split_id].first_slot;
     }
 
+    out.reg_cta.assign(regular.size(), 0u);
+    out.cta_load.assign((size_t)G, 0.0);
     if (bp.contiguous) {
         // Contiguous runs of the (class, cluster)-ordered tile list per CTA, cut by a cost prefix sum:
         // neighbouring rows gather from neighbouring addresses, so keeping them on ONE SM lets its L1
         // serve the sectors they share (the least-loaded dealing below scatters them over all SMs).
-        auto cost = [](const ProtoTile& t) { return (int64_t)t.e1 + 2 * (int64_t)t.nsteps + 4; };
-        std::vector<int64_t> cl((size_t)G);
-        for (int g = 0; g < G; ++g) cl[g] = 3 * load[g];   // split chunks: ~3 units per step (dense gathers)
-        const size_t nheavy = 0;   // (spreading the whole-warp rows least-loaded-first was measured slower: ken-18 +4 %)
-        int64_t total = 0;
+        // Model cost of a tile: steps + distinct gathered sectors; a tuning round scales it by what was measured.
+        const bool have_w = fb && fb->tile_w.size() == regular.size();
+        const bool have_f = fb && fb->cta_f.size() == (size_t)G;
+        auto cost = [&](size_t k) {
+            const ProtoTile& t = regular[k];
+            return (double)((int64_t)t.e1 + 2 * (int64_t)t.nsteps + 4) * (have_w ? fb->tile_w[k] : 1.0);
+        };
+        std::vector<double> cl((size_t)G);
+        for (int g = 0; g < G; ++g) cl[g] = 3.0 * (double)load[g] * (have_f ? fb->cta_f[g] : 1.0);   // split chunks: ~3 units per step
+        double total = 0;
         for (int g = 0; g < G; ++g) total += cl[g];
-        for (size_t k = nheavy; k < regular.size(); ++k) total += cost(regular[k]);
+        for (size_t k = 0; k < regular.size(); ++k) total += cost(k);
         int g = 0;
-        int64_t acc_cost = 0;   // cost handed to CTAs 0..g
-        int64_t mine = cl[0];
-        for (size_t k = nheavy; k < regular.size(); ++k) {
+        double acc_cost = 0;   // cost handed to CTAs 0..g-1
+        double mine = cl[0];
+        for (size_t k = 0; k < regular.size(); ++k) {
             // move on when this CTA has reached its share of the total
-            while (g + 1 < G && (acc_cost + mine) * G >= total * (int64_t)(g + 1)) {
+            while (g + 1 < G && (acc_cost + mine) * G >= total * (double)(g + 1)) {
                 acc_cost += mine;
+                out.cta_load[g] = mine;
                 ++g;
                 mine = cl[g];
             }
             per_cta[g].push_back(regular[k]);
-            mine += cost(regular[k]);
+            out.reg_cta[k] = (uint32_t)g;
+            mine += cost(k);
         }
+        out.cta_load[g] = mine;
+        for (int h = g + 1; h < G; ++h) out.cta_load[h] = cl[h];
     } else {
         std::vector<uint32_t> by_cost(regular.size());
         std::iota(by_cost.begin(), by_cost.end(), 0u);
         std::stable_sort(by_cost.begin(), by_cost.end(),
                          [&](uint32_t a, uint32_t b) { return regular[a].nsteps > regular[b].nsteps; });
-        // min-heap of (load, cta)
-        std::vector<std::pair<int64_t, int>> heap;
-        for (int g = 0; g < G; ++g) heap.emplace_back(load[g], g);
-        auto cmp = [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a > b; };
+        // min-heap of (load, cta); a tuning round biases the starting loads by what was measured
+        const bool have_b = fb && fb->cta_bias.size() == (size_t)G;
+        std::vector<std::pair<double, int>> heap;
+        for (int g = 0; g < G; ++g) heap.emplace_back((double)load[g] + (have_b ? fb->cta_bias[g] : 0.0), g);
+        auto cmp = [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a > b; };
         std::make_heap(heap.begin(), heap.end(), cmp);
+        for (int g = 0; g < G; ++g) out.cta_load[g] = (double)load[g];
         for (uint32_t ti : by_cost) {
             std::pop_heap(heap.begin(), heap.end(), cmp);
             auto& top = heap.back();
             per_cta[top.second].push_back(regular[ti]);
+            out.reg_cta[ti] = (uint32_t)top.second;
             top.first += regular[ti].nsteps + 2;
+            out.cta_load[top.second] += regular[ti].nsteps + 2;
             std::push_heap(heap.begin(), heap.end(), cmp);
         }
     }
@@ -426,6 +441,9 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
         const int steps_here = (int)(step_cursor - out.cta_step_begin[g]);
         out.max_cta_steps = std::max(out.max_cta_steps, steps_here);
         out.max_cta_tiles = std::max<int>(out.max_cta_tiles, (int)per_cta[g].size());
+        int rows_here = 0;
+        for (const ProtoTile& t : per_cta[g]) rows_here += t.split < 0 ? t.nrows : 0;
+        out.max_cta_rows = std::max(out.max_cta_rows, rows_here);
     }
     out.cta_begin[G] = (uint32_t)out.tiles.size();
     out.cta_step_begin[G] = (uint32_t)step_cursor;

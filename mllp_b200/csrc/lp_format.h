@@ -61,6 +61,15 @@ struct BuildParams {
     bool final_params = false; // max_steps already adjusted (effective_params is then the identity)
 };
 
+// Measured correction of the dealing of the regular tiles (the tuning rounds of mllp_lp_create: per-CTA
+// phase times of a traced run feed the next build).  The summation order inside every row is untouched by
+// the dealing, so results do not depend on it.
+struct DealFeedback {
+    std::vector<double> tile_w;    // contiguous dealing: factor on the cost of each regular tile (build order)
+    std::vector<double> cta_f;     // contiguous dealing: factor on each CTA's split-chunk cost
+    std::vector<double> cta_bias;  // least-loaded dealing: initial load of each CTA (load units)
+};
+
 // max_steps raised until no CTA gets more than SPLIT_SLOTS split chunks (idempotent).
 BuildParams effective_params(int nrows, const int32_t* ptr, BuildParams bp);
 
@@ -82,6 +91,10 @@ struct HostMat {
     uint64_t total_steps = 0;
     int max_cta_steps = 0;             // largest per-CTA warp-step count
     int max_cta_tiles = 0;
+    int max_cta_rows = 0;              // largest per-CTA count of rows in regular tiles
+    // host-only bookkeeping for the tuning rounds
+    std::vector<uint32_t> reg_cta;     // CTA of every regular tile, in build order
+    std::vector<double> cta_load;      // modelled load of every CTA (units of the dealing that was used)
 };
 
 // Internal ordering of the rows of a CSR matrix, derived from row lengths only.
@@ -104,7 +117,7 @@ void plan_orders(int m, int n, const int32_t* ptr, const int32_t* ind, const int
 void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind,
                     const double* val, const std::vector<int32_t>& order,
                     const std::vector<int32_t>& colpos, const BuildParams& bp, HostMat& out,
-                    uint32_t row_offset = 0);
+                    uint32_t row_offset = 0, const DealFeedback* fb = nullptr);
 
 // Row partition over `nranks` GPUs: rows go to ranks by longest-processing-time on their
 // nonzero counts; inside a rank the global (class, cluster) order is kept.  The global internal

@@ -185,14 +185,57 @@ __global__ void k_eval_finalize(DevLP lp, int G, double* out, double iters)
 struct PersistentSmem {
     MatView VA, VAT;
     unsigned long long tag;   // tag of the last polled split-row join (one per phase call)
+    double *ys, *bs, *xs, *cs; // own entries of the CTA's regular rows (parity kernel), or null
 };
-__device__ __forceinline__ void persistent_setup(const DevLP& lp, unsigned char* dsm, PersistentSmem& P)
+
+// CTA-local row slots of the regular tiles: written into the .split field of the shared-memory copy of
+// the descriptors (it is -1 there for regular tiles); one thread, once per launch.
+__device__ __forceinline__ void assign_row_slots(const MatView& V)
+{
+    Tile* d = const_cast<Tile*>(V.desc);
+    int run = 0;
+    for (uint32_t t = V.nsplit; t < V.ntiles; ++t) {
+        d[t].split = run;
+        run += d[t].nrows;
+    }
+}
+// own[slot] <-> vec[row] for all regular rows of this CTA
+template <bool TO_SMEM>
+__device__ __forceinline__ void copy_own(const MatView& V, double* vec, double* own)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t t = V.nsplit + warp; t < V.ntiles; t += nwarps) {
+        const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
+        const int nrows = (raw.z >> 24) & 0xff;
+        if (lane < nrows) {
+            if (TO_SMEM) own[raw.w + lane] = __ldcg(vec + raw.y + lane);
+            else vec[raw.y + lane] = own[raw.w + lane];
+        }
+    }
+}
+
+__device__ __forceinline__ void persistent_setup(const DevLP& lp, unsigned char* dsm, PersistentSmem& P, bool own = false)
 {
     unsigned char* base = dsm;
     P.tag = lp.join_base;
     const uint32_t used = resident_view(lp.A, lp.res_steps_A, base, P.VA);
-    resident_view(lp.AT, lp.res_steps_AT, base + used, P.VAT);
+    const uint32_t used2 = resident_view(lp.AT, lp.res_steps_AT, base + used, P.VAT);
+    P.ys = P.bs = P.xs = P.cs = nullptr;
     __syncthreads();
+    if (own && lp.own_rows_A + lp.own_rows_AT > 0) {
+        P.ys = reinterpret_cast<double*>(base + used + used2);
+        P.bs = P.ys + lp.own_rows_A;
+        P.xs = P.bs + lp.own_rows_A;
+        P.cs = P.xs + lp.own_rows_AT;
+        if (threadIdx.x == 0) assign_row_slots(P.VA);
+        if (threadIdx.x == 32) assign_row_slots(P.VAT);
+        __syncthreads();
+        copy_own<true>(P.VA, lp.y, P.ys);
+        copy_own<true>(P.VA, const_cast<double*>(lp.b), P.bs);
+        copy_own<true>(P.VAT, lp.x, P.xs);
+        copy_own<true>(P.VAT, const_cast<double*>(lp.c), P.cs);
+        __syncthreads();
+    }
 }
 
 // A' phase (gathers y) and A phase (gathers xbar).
@@ -212,11 +255,25 @@ __global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double ta
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     PersistentSmem P;
-    persistent_setup(lp, dsm, P);
+    persistent_setup(lp, dsm, P, true);
     unsigned target = 0;
+    double acc[NRED];
+    if (P.xs) {
+        // own entries (x, c / y, b) of the CTA's rows stay in shared memory across the iterations
+        PrimalResOp<BOUNDS> pop{lp, tau, P.xs, P.cs};
+        DualResOp<BOUNDS> dop{lp, sigma, P.ys, P.bs};
+        for (int it = 0; it < iters; ++it) {
+            unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 4 : nullptr;
+            phase_AT(lp, P, pop, acc);
+            grid_barrier(lp.barrier, target, tr);
+            phase_A(lp, P, dop, acc);
+            grid_barrier(lp.barrier, target, tr ? tr + 2 : nullptr);
+        }
+        copy_own<false>(P.VAT, lp.x, P.xs);   // y was published every iteration
+        return;
+    }
     PrimalOp<BOUNDS> pop{lp, tau};
     DualOp<BOUNDS> dop{lp, sigma};
-    double acc[NRED];
     for (int it = 0; it < iters; ++it) {
         unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 4 : nullptr;
         phase_AT(lp, P, pop, acc);

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 
 #include "lp_format.h"
 
@@ -60,6 +61,8 @@ struct DevLP {
     unsigned* barrier;  // grid barrier counter
     uint32_t res_steps_A;   // per-CTA cap of shared-memory resident warp-steps of A / A'
     uint32_t res_steps_AT;
+    uint32_t own_rows_A;    // parity kernel: per-CTA capacity of shared-memory resident own entries (y, b / x, c);
+    uint32_t own_rows_AT;   // both 0 = own entries stay in global memory
     double* ctrl;       // control block (device doubles): CTRL_* slots
     unsigned long long join_base;  // tags of the polled split-row join start above this value
     unsigned long long* trace;  // dev tool: [iter][cta][4] barrier timestamps, or null
@@ -154,6 +157,81 @@ struct DualOp {
         lp.y[r] = yn;
     }
 };
+
+// Ops whose rows' OWN vector entries (x, c / y, b) live in the CTA's shared memory for the whole persistent
+// kernel (`slot` = CTA-local row slot, -1 for the rows of split chunks, which stay in global memory).  The
+// tile -> CTA assignment is fixed, so x and c are read from L2 once per launch instead of once per iteration and
+// x is written back once at the end; only the gathered vectors (xbar, y) go to global memory every iteration.
+template <class T, class = void>
+struct op_slots : std::false_type {};
+template <class T>
+struct op_slots<T, std::void_t<decltype(T::kSlots)>> : std::bool_constant<T::kSlots> {};
+
+template <bool BOUNDS>
+struct PrimalResOp {
+    using Mem = GlobalMem;
+    static constexpr bool kSlots = true;
+    const DevLP& lp;
+    double tau;
+    double* xs;          // shared: own x
+    const double* cs;    // shared: own c
+    struct Pre { double c, x; };
+    __device__ __forceinline__ const double* vec() const { return lp.y; }
+    __device__ __forceinline__ Pre prefetch(int r, int slot) const
+    {
+        if (slot >= 0) return {cs[slot], xs[slot]};
+        return {Mem::ld_ro(lp.c + r), Mem::ld_mut(lp.x + r)};
+    }
+    __device__ __forceinline__ void row(int r, int slot, double dot, const Pre& p, double*) const
+    {
+        const double g = p.c - dot;
+        double xn = p.x - tau * g;
+        if (BOUNDS) {
+            xn = fmin(fmax(xn, Mem::ld_ro(lp.lb + r)), Mem::ld_ro(lp.ub + r));
+        } else {
+            xn = fmax(xn, 0.0);
+        }
+        lp.xbar[r] = 2.0 * xn - p.x;
+        if (slot >= 0) xs[slot] = xn; else lp.x[r] = xn;
+    }
+};
+
+template <bool BOUNDS>
+struct DualResOp {
+    using Mem = GlobalMem;
+    static constexpr bool kSlots = true;
+    const DevLP& lp;
+    double sigma;
+    double* ys;          // shared: own y
+    const double* bs;    // shared: own b
+    struct Pre { double b, y; };
+    __device__ __forceinline__ const double* vec() const { return lp.xbar; }
+    __device__ __forceinline__ Pre prefetch(int r, int slot) const
+    {
+        if (slot >= 0) return {bs[slot], ys[slot]};
+        return {Mem::ld_ro(lp.b + r), Mem::ld_mut(lp.y + r)};
+    }
+    __device__ __forceinline__ void row(int r, int slot, double dot, const Pre& p, double*) const
+    {
+        double yn = p.y + sigma * (p.b - dot);
+        if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
+        lp.y[r] = yn;    // y is the gather vector of the A' phase: always published
+        if (slot >= 0) ys[slot] = yn;
+    }
+};
+
+template <class Op>
+__device__ __forceinline__ typename Op::Pre op_prefetch(const Op& op, int r, int slot)
+{
+    if constexpr (op_slots<Op>::value) return op.prefetch(r, slot);
+    else return op.prefetch(r);
+}
+template <class Op>
+__device__ __forceinline__ void op_row(const Op& op, int r, int slot, double dot, const typename Op::Pre& p, double* acc)
+{
+    if constexpr (op_slots<Op>::value) op.row(r, slot, dot, p, acc);
+    else op.row(r, dot, p, acc);
+}
 
 // Solve mode (reflected Halpern).  acc[0] accumulates ||x' - x||^2 (resp. y).
 template <bool BOUNDS, class MEM = GlobalMem>
@@ -575,7 +653,7 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
         if ((uint32_t)warp < V.nls) {
             ls_first = __ldg(reinterpret_cast<const int4*>(M.lsplits + V.ls0 + warp));
             sr_first = __ldg(reinterpret_cast<const int4*>(M.splits + ls_first.x));
-            if (lane == 0) spre_first = op.prefetch(sr_first.x);
+            if (lane == 0) spre_first = op_prefetch(op, sr_first.x, -1);
         }
         for (uint32_t t = warp; t < V.nsplit; t += nwarps) {
             const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
@@ -603,9 +681,9 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
             // the row's own vector entries are needed by whoever finishes the row: fetch them now,
             // off the critical path of the join
             typename Op::Pre spre = spre_first;
-            if (lane == 0 && !firstrow) spre = op.prefetch(sr.x);
+            if (lane == 0 && !firstrow) spre = op_prefetch(op, sr.x, -1);
             if (sr.z == 1) {   // the whole row lives in this CTA: no global join
-                if (lane == 0) op.row(sr.x, p, spre, acc);
+                if (lane == 0) op_row(op, sr.x, -1, p, spre, acc);
                 continue;
             }
             if (COOP) {
@@ -639,7 +717,7 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
                     s += v;
                 }
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-                if (lane == 0) op.row(sr.x, s, spre, acc);
+                if (lane == 0) op_row(op, sr.x, -1, s, spre, acc);
                 continue;
             }
             unsigned last = 0;
@@ -662,7 +740,7 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0) {
                     M.counters[ls.x] = 0;
-                    op.row(sr.x, s, spre, acc);
+                    op_row(op, sr.x, -1, s, spre, acc);
                 }
             }
         }
@@ -681,8 +759,9 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
         const int rr = lane >> logL;
         const bool owner = ((lane & (L - 1)) == 0) && (rr < nrows);
         const int r = raw.y + rr;
+        const int slot = op_slots<Op>::value ? raw.w + rr : -1;   // resident views hold the CTA-local row slot in .split
         typename Op::Pre pre{};
-        if (owner) pre = op.prefetch(r);
+        if (owner) pre = op_prefetch(op, r, slot);
         if (t2 < V.ntiles) {
             const int4 raw2 = *reinterpret_cast<const int4*>(V.desc + t2);
             const int nsteps2 = raw2.z & 0xffff;
@@ -692,8 +771,9 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
             const int rr2 = lane >> logL2;
             const bool owner2 = ((lane & (L2 - 1)) == 0) && (rr2 < nrows2);
             const int r2 = raw2.y + rr2;
+            const int slot2 = op_slots<Op>::value ? raw2.w + rr2 : -1;
             typename Op::Pre pre2{};
-            if (owner2) pre2 = op.prefetch(r2);
+            if (owner2) pre2 = op_prefetch(op, r2, slot2);
             double dot, dot2;
             if (nsteps == nsteps2 && nsteps >= 1 && nsteps <= 3) {
                 const double2 *vpa, *vpb;
@@ -717,12 +797,12 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
             }
             for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
             for (int o = L2 >> 1; o > 0; o >>= 1) dot2 += __shfl_xor_sync(FULL, dot2, o);
-            if (owner) op.row(r, dot, pre, acc);
-            if (owner2) op.row(r2, dot2, pre2, acc);
+            if (owner) op_row(op, r, slot, dot, pre, acc);
+            if (owner2) op_row(op, r2, slot2, dot2, pre2, acc);
         } else {
             double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
             for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-            if (owner) op.row(r, dot, pre, acc);
+            if (owner) op_row(op, r, slot, dot, pre, acc);
         }
     }
 }

@@ -111,6 +111,16 @@ class DeviceLP:
         self._h = h
         self._finalizer = weakref.finalize(self, L.mllp_lp_destroy, h)
         self._sigma_max = None
+        self._sigma_robust = None
+        # sqrt(||A||_1 ||A||_inf) >= ||A||_2: the guaranteed side of the step-size estimate
+        absv = np.abs(values)
+        row_sum = 0.0
+        if self.nnz:
+            row_sum = np.bincount(np.repeat(np.arange(self.m), np.diff(indptr)), weights=absv, minlength=self.m).max()
+            col_sum = np.bincount(indices, weights=absv, minlength=self.n).max()
+        else:
+            col_sum = 0.0
+        self.norm_upper = float(np.sqrt(row_sum * col_sum))
 
     def close(self):
         self._finalizer()
@@ -130,6 +140,12 @@ class DeviceLP:
                 "ctas_per_sm")
         return dict(zip(keys, (int(v) for v in out)))
 
+    def tune_info(self):
+        """ns / iteration measured by mllp_lp_create before and after its tuning rounds."""
+        out = (ctypes.c_double * 4)()
+        _cabi.check(_cabi.lib().mllp_lp_tune_info(self.handle, out), "mllp_lp_tune_info")
+        return {"ns_per_iter_first": out[0], "ns_per_iter_kept": out[1], "rounds": int(out[2])}
+
     def sigma_max(self, iters=50, stream=None):
         """||A||_2 estimate by power iteration on the device (cached)."""
         if self._sigma_max is None:
@@ -138,6 +154,24 @@ class DeviceLP:
                         "mllp_estimate_norm")
             self._sigma_max = s.value
         return self._sigma_max
+
+    def sigma_max_robust(self, rel_change=1e-4, max_iters=3200, stream=None):
+        """||A||_2 for solve mode, where an underestimate makes the iteration diverge (50 steps
+        are 2 % low on sc50b / ken-11): power iteration with doubling step counts until the estimate
+        moves by less than ``rel_change``, inflated by 2 % and capped by sqrt(||A||_1 ||A||_inf)."""
+        if self._sigma_robust is None:
+            prev, iters = 0.0, 100
+            while True:
+                s = ctypes.c_double(0.0)
+                _cabi.check(_cabi.lib().mllp_estimate_norm(self.handle, int(iters), ctypes.byref(s), stream),
+                            "mllp_estimate_norm")
+                cur = s.value
+                if abs(cur - prev) <= rel_change * cur or iters >= max_iters:
+                    break
+                prev, iters = cur, iters * 2
+            est = 1.02 * cur
+            self._sigma_robust = min(est, self.norm_upper) if self.norm_upper > 0 else est
+        return self._sigma_robust
 
     # -- torch-tensor level helpers (device pointers, caller's stream) --------------------------
     def spmv(self, v, trans=False):
@@ -266,7 +300,8 @@ def solve_linear_program(constrs, constr_weights, rhs, coefs, *, tol=1e-6, max_i
     lp = handle if handle is not None else device_lp(constrs, constr_weights, rhs, coefs, lb, ub, ylo, yhi,
                                                      device, flags)
     if eta is None:
-        eta = estimate_step_size(lp, safety=0.99)
+        sm = lp.sigma_max_robust()
+        eta = 0.99 / sm if sm > 0 else 1.0
     dev = torch.device("cuda", lp.device)
     as_t = lambda a, n, name: torch.as_tensor(_np_f64(a, n, name), device=dev)
     tensors_in = _is_tensor(rhs)
@@ -352,15 +387,21 @@ class BatchLP:
         return dict(zip(keys, (int(v) for v in out)))
 
     def sigma_max(self, iters=50):
-        """per-instance ||A_k||_2 estimates (device tensor, cached)."""
+        """per-instance ||A_k||_2 estimates (device tensor, cached per step count)."""
         import torch
         if self._sigma is None:
+            self._sigma = {}
+        if iters not in self._sigma:
             dev = torch.device("cuda", self.device)
             s = torch.zeros(self.count, dtype=torch.float64, device=dev)
             _cabi.check(_cabi.lib().mllp_batch_estimate_norm(self.handle, int(iters), s.data_ptr(), _torch_stream(dev)),
                         "mllp_batch_estimate_norm")
-            self._sigma = s
-        return self._sigma
+            self._sigma[iters] = s
+        return self._sigma[iters]
+
+    def sigma_max_robust(self):
+        """solve mode: 400 power-iteration steps, inflated by 2 % (see DeviceLP.sigma_max_robust)."""
+        return 1.02 * self.sigma_max(400)
 
     # device-tensor level entries (concatenated vectors, caller's stream, no host sync)
     def run(self, x, y, b, c, tau, sigma, num_iters, scalars=None):
@@ -434,7 +475,7 @@ def solve_linear_program_batch(instances, *, tol=1e-6, max_iters=200000, check_e
     bt = handle if handle is not None else BatchLP(instances, shared=shared,
                                                    count=None if not shared else len(rhs_batch), device=device)
     b, c, x, y, dev = _batch_vectors(bt, instances, rhs_batch, coefs_batch, x0, y0)
-    eta_t = 0.99 / bt.sigma_max() if eta is None else torch.as_tensor(
+    eta_t = 0.99 / bt.sigma_max_robust() if eta is None else torch.as_tensor(
         np.broadcast_to(np.asarray(eta, dtype=np.float64), (bt.count,)).copy(), device=dev)
     scal = torch.zeros(bt.count * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
     bt.solve(x, y, b, c, eta_t, scal, primal_weight, max_iters, check_every, tol)

@@ -13,6 +13,8 @@ Dialect handled: fixed/free format with whitespace-separated f
 comments, OBJSENSE (MAX is turned into MIN of -c), objective-row RHS = -offset, bound types
 UP / LO / FX / FR / MI / PL / BV, negative UP with untouched lower bound -> lower = -inf.
 """
+import gzip
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -29,7 +31,8 @@ def read_mps(path):
     touched_lb = set()
     offset, maximize = 0.0, False
     section = None
-    with open(path, "r") as fh:
+    opener = (lambda p: gzip.open(p, "rt")) if str(path).endswith(".gz") else (lambda p: open(p, "r"))
+    with opener(path) as fh:
         for raw in fh:
             if not raw.strip() or raw[0] == "*":
                 continue
@@ -137,6 +140,7 @@ def read_mps(path):
         b[i] = 0.0; ylo[i] = -INF; yhi[i] = INF
     n2 = n + len(extra_cols)
     A = sp.csr_matrix((vv, (ri, ci)), shape=(m, n2))
+    A.eliminate_zeros()   # explicit zeros in the file (standgub has one) are not entries; HiGHS drops them too
     A.sum_duplicates(); A.sort_indices()
     if extra_cols:
         c = np.concatenate([c, np.zeros(len(extra_cols))])

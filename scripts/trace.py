@@ -26,6 +26,7 @@ def trace(name, iters=40, **env):
     it_time = (t[1:, :, 3] - t[:-1, :, 3]).mean()
     f = lambda x: 'mean %.0f min %.0f p50 %.0f max %.0f' % (x.mean(), x.min(axis=1).mean(), np.median(x, axis=1).mean(), x.max(axis=1).mean())
     print('%s %s: iteration %.0f ns  %s' % (name, env, it_time, {k: lp.info()[k] for k in ('dyn_smem_bytes', 'res_steps_A', 'res_steps_AT', 'tiles_A', 'tiles_AT')}))
+    print('   tune: %s' % (lp.tune_info(),))
     print('   A\' work  (ns): ' + f(at_work)); print('   barrier1 wait: ' + f(at_wait))
     print('   A  work  (ns): ' + f(a_work)); print('   barrier2 wait: ' + f(a_wait))
     # barrier latency proper: last arrival -> mean release

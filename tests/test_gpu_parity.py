@@ -137,7 +137,11 @@ def test_graph_mode_is_bitwise_identical_to_persistent(name):
     _, x1, y1, i1 = M.pdhg_linear_program(A, A.data, b, c, num_iters=K, tau=eta, sigma=eta)
     lpg = M.DeviceLP(A, A.data, m, n, flags=_cabi.F_GRAPH_MODE)
     _, x2, y2, i2 = M.pdhg_linear_program(A, A.data, b, c, num_iters=K, tau=eta, sigma=eta, handle=lpg)
-    assert np.array_equal(x1, x2) and np.array_equal(y1, y2) and i1["pobj"] == i2["pobj"]
+    # iterates are bitwise equal (the summation order inside a row never depends on the kernel or on the
+    # dealing of the tiles to CTAs); the KKT scalars are sums of per-CTA partials, so they can differ in the
+    # last bits between two dealings (the persistent handle is tuned, the graph-mode one is not)
+    assert np.array_equal(x1, x2) and np.array_equal(y1, y2)
+    assert abs(i1["pobj"] - i2["pobj"]) <= 1e-13 * (1 + abs(i2["pobj"]))
 
 
 def test_torch_tensor_interface_no_host_sync(torch_cuda):
