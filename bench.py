@@ -200,9 +200,33 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
     K = 200
     sec = timed(lambda: bs.run(xb, yb, bb, cb, etab, etab, K), reps=2)
     out["batch_4096x25fv47"] = {"lp_iterations_per_sec": world * B * K / sec, "instances_per_rank": B,
-                                "us_per_batch_iteration": sec / K * 1e6, "algorithmic_GBps_per_gpu": bs.info()["bytes_per_iter"] * K / sec / 1e9}
+                                "us_per_batch_iteration": sec / K * 1e6, "algorithmic_GBps_per_gpu": bs.info()["bytes_per_iter"] * K / sec / 1e9,
+                                "instances_per_cta": bs.info()["instances_per_cta"]}
     bs.close()
     del cb, bb, xb, yb
+
+    # (2b) shared-matrix batch solved to 1e-6: 4096 cost-perturbed instances of sc105 per rank (two instances per CTA
+    # share every matrix step; a slot that converges pulls the next instance at once)
+    A, b, c = M.load_csr("sc105")
+    m, n = A.shape
+    bs = M.BatchLP([(A, A.data, b, c)], shared=True, count=B, device=local)
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    cb = (torch.tensor(c).repeat(B, 1) * (1 + 0.05 * (2 * torch.rand(B, n, generator=g, dtype=torch.float64) - 1))).reshape(-1).to(dev)
+    bb = torch.tensor(b).repeat(B).to(dev)
+    etas = (0.99 / bs.sigma_max_robust()).contiguous()
+    scal = torch.zeros(B * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
+
+    def solve_shared():
+        xs, ys = torch.zeros(B * n, dtype=torch.float64, device=dev), torch.zeros(B * m, dtype=torch.float64, device=dev)
+        bs.solve(xs, ys, bb, cb, etas, scal, 1.0, 200000, 64, 1e-6)
+
+    sec = timed(solve_shared, reps=2)
+    sc = scal.cpu().numpy().reshape(B, _cabi.NUM_SCALARS)
+    out["solve_4096x_sc105_shared"] = {"lps_solved_per_sec": world * B / sec, "instances_per_rank": B,
+                                       "converged_fraction": float(sc[:, 12].mean()), "mean_iterations": float(sc[:, 10].mean()),
+                                       "instances_per_cta": bs.info()["instances_per_cta_solve"], "tol": 1e-6, "seconds": sec}
+    bs.close()
+    del cb, bb
 
     # (3) LPs solved per second: 1024 perturbed copies each of sc50a / sc105 / blend per rank, solve mode to 1e-6
     insts = []

@@ -205,7 +205,9 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t *h_m,
 int mllp_batch_destroy(mllp_batch_t bt);
 /* out[0]=count, [1]=sum m, [2]=sum n, [3]=sum nnz (shared: nnz of the one matrix), [4]=CTAs,
  * [5]=threads per CTA, [6]=dynamic smem bytes per CTA, [7]=algorithmic bytes per batch iteration,
- * [8]=instances per CTA, [9..15] reserved. */
+ * [8]=instances per CTA of the parity kernel (shared matrix: R instances share every matrix step),
+ * [9]=same for the solve kernel, [10]/[11]=shared-memory resident warp-steps of A / A' (parity kernel),
+ * [12]/[13]=same (solve kernel), [14]=dynamic smem of the solve kernel, [15]=CTAs of the solve kernel. */
 int mllp_batch_info(mllp_batch_t bt, int64_t *out16);
 /* sigma_max(A_k) of every instance by power iteration (as mllp_estimate_norm) into the device
  * array d_sigma_max[count]; asynchronous on `stream`. */

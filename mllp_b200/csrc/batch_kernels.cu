@@ -64,6 +64,28 @@ __device__ __forceinline__ DevLP smem_lp(const BatchInst& I, const BatchSmem& S)
     return lp;
 }
 
+// Where the matrix lives for the CTA: with `use_res` the tile descriptors and a prefix of the warp-steps of
+// A' and A are copied into shared memory behind the vectors (byte offset mat_off) -- once per CTA for a shared
+// matrix, once per instance otherwise -- and the rest streams through L1 / L2; without it everything streams.
+struct BatchGeom {
+    uint32_t mat_off;
+    uint32_t res_A, res_AT;
+    int use_res;
+};
+__device__ __forceinline__ void batch_views(const BatchInst& I, const BatchGeom& g, unsigned char* dsm, MatView& VA, MatView& VAT)
+{
+    if (g.use_res) {
+        __syncthreads();   // the previous instance's tiles are no longer read
+        unsigned char* mb = dsm + g.mat_off;
+        const uint32_t used = resident_view(I.AT, g.res_AT, mb, VAT, 0u);
+        resident_view(I.A, g.res_A, mb + used, VA, 0u);
+        __syncthreads();
+    } else {
+        VA = global_view(I.A, 0u);
+        VAT = global_view(I.AT, 0u);
+    }
+}
+
 // Sum acc[0..N) over the CTA (fixed order); result in every thread.
 template <int N>
 __device__ __forceinline__ void cta_allreduce(double* acc, const BatchSmem& S)
@@ -143,10 +165,12 @@ __device__ __forceinline__ void batch_kkt(const DevLP& lp, const MatView& VA, co
 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
-k_batch_run(const BatchInst* __restrict__ insts, int count, int shared, double* x, double* y, const double* b,
+k_batch_run(const BatchInst* __restrict__ insts, int count, int shared, BatchGeom geom, double* x, double* y, const double* b,
             const double* c, const double* tau, const double* sigma, int iters, double* scalars)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
+    MatView VA, VAT;
+    bool have_views = false;
     for (int inst = blockIdx.x; inst < count; inst += gridDim.x) {
         BatchInst I = insts[shared ? 0 : inst];
         if (shared) { I.x_off = (long long)inst * I.n; I.y_off = (long long)inst * I.m; }
@@ -155,7 +179,7 @@ k_batch_run(const BatchInst* __restrict__ insts, int count, int shared, double* 
         for (int k = threadIdx.x; k < I.n; k += blockDim.x) S.x0[k] = 0.0;   // anchors unused here; keep eval finite
         for (int k = threadIdx.x; k < I.m; k += blockDim.x) S.y0[k] = 0.0;
         const DevLP lp = smem_lp(I, S);
-        const MatView VA = global_view(I.A, 0u), VAT = global_view(I.AT, 0u);
+        if (!have_views || !shared) { batch_views(I, geom, dsm, VA, VAT); have_views = true; }
         PrimalOp<false, SmemMem> pop{lp, __ldg(tau + inst)};
         DualOp<false, SmemMem> dop{lp, __ldg(sigma + inst)};
         double acc[NRED];
@@ -182,12 +206,15 @@ k_batch_run(const BatchInst* __restrict__ insts, int count, int shared, double* 
 // Solve mode per CTA: same control flow as k_solve_persistent / oracle_pdhg_solve, with
 // __syncthreads() in place of the grid barrier.
 __global__ void __launch_bounds__(1024, 1)
-k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, double* x, double* y, const double* b,
-              const double* c, const double* eta_arr, double w0, int max_iters, int check_every, double tol,
+k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, BatchGeom geom, double* x, double* y,
+              const double* b, const double* c, const double* eta_arr, double w0, int max_iters, int check_every, double tol,
               double* scalars, int* next_inst)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ int s_inst;
+    __shared__ double s_par[2][3];   // [buffer][tau, sigma, lam]: computed by one thread, one iteration ahead (see k_batch_solve_r)
+    MatView VA, VAT;
+    bool have_views = false;
     // instances converge after very different iteration counts: CTAs pull the next instance from a
     // device counter instead of a static stride
     for (;;) {
@@ -202,17 +229,22 @@ k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, double
         load_instance(I, S, x, y, b, c);
         for (int k = threadIdx.x; k < I.n; k += blockDim.x) S.x0[k] = S.x[k];
         for (int k = threadIdx.x; k < I.m; k += blockDim.x) S.y0[k] = S.y[k];
+        const double eta = __ldg(eta_arr + inst);
+        int pb = 0;
+        if (threadIdx.x == 0) { s_par[0][0] = eta / w0; s_par[0][1] = eta * w0; s_par[0][2] = 0.5; }
         __syncthreads();
         const DevLP lp = smem_lp(I, S);
-        const MatView VA = global_view(I.A, 0u), VAT = global_view(I.AT, 0u);
-        const double eta = __ldg(eta_arr + inst);
+        if (!have_views || !shared) { batch_views(I, geom, dsm, VA, VAT); have_views = true; }
         double w = w0, fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
         int k = 0, it = 0, restarts = 0, converged = 0;
         double kk[10], dd[2];
         batch_kkt(lp, VA, VAT, S, kk, dd);
         while (it < max_iters) {
-            const double tau = eta / w, sigma = eta * w;
-            const double lam = (double)(k + 1) / (double)(k + 2);
+            const double tau = s_par[pb][0], sigma = s_par[pb][1], lam = s_par[pb][2];
+            if (threadIdx.x == 0) {   // the next iteration's parameters if nothing restarts
+                s_par[pb ^ 1][0] = tau; s_par[pb ^ 1][1] = sigma;
+                s_par[pb ^ 1][2] = (double)(k + 2) / (double)(k + 3);
+            }
             const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iters);
             const bool need_fpe = check || fpe_restart < 0.0;
             double a2[2];
@@ -233,6 +265,7 @@ k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, double
             }
             __syncthreads();
             ++it; ++k;
+            pb ^= 1;
             if (need_fpe) {
                 cta_allreduce<2>(a2, S);
                 fpe = sqrt(w * a2[0] + a2[1] / w);
@@ -247,6 +280,7 @@ k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, double
                 if (do_restart) {
                     const double ddx = sqrt(dd[0]), ddy = sqrt(dd[1]);
                     if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
+                    if (threadIdx.x == 0) { s_par[pb][0] = eta / w; s_par[pb][1] = eta * w; s_par[pb][2] = 0.5; }
                     for (int q = threadIdx.x; q < I.n; q += blockDim.x) S.x0[q] = S.x[q];
                     for (int q = threadIdx.x; q < I.m; q += blockDim.x) S.y0[q] = S.y[q];
                     __syncthreads();
@@ -261,6 +295,579 @@ k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, double
             o[10] = (double)it; o[11] = (double)restarts; o[12] = (double)converged; o[13] = w; o[14] = fpe; o[15] = 0.0;
         }
         store_instance(I, S, x, y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared matrix, R instances per CTA ("multi-RHS"): the R instances' vectors are interleaved in shared memory
+// (entry k of instance r at [k * R + r]), every matrix step (values + indices) is fetched ONCE and applied to all
+// R instances, so the matrix stream from L2 / shared memory, the descriptor decoding and the address arithmetic
+// are paid once per R instance-iterations.  Per instance the summation order is exactly that of the one-instance
+// walker (run_phase), so the iterates are bitwise the same for every R.
+template <int R>
+struct SmemR {
+    double *x, *xbar, *c, *y, *b, *x0, *y0;
+    double* red;    // 32 * NRED
+    double* bc;     // 16 * R
+    double* spart;  // SPLIT_SLOTS * R
+};
+template <int R>
+__device__ __forceinline__ SmemR<R> carve_r(unsigned char* dsm, int m, int n, bool anchors)
+{
+    SmemR<R> S;
+    double* p = reinterpret_cast<double*>(dsm);
+    S.red = p; p += 32 * NRED;
+    S.bc = p; p += 16 * R;
+    S.spart = p; p += SPLIT_SLOTS * R;
+    S.x = p; p += (size_t)n * R; S.xbar = p; p += (size_t)n * R; S.c = p; p += (size_t)n * R;
+    S.y = p; p += (size_t)m * R; S.b = p; p += (size_t)m * R;
+    S.x0 = anchors ? p : nullptr; if (anchors) p += (size_t)n * R;
+    S.y0 = anchors ? p : nullptr;
+    return S;
+}
+
+template <int R>
+__device__ __forceinline__ void ld_r(const double* __restrict__ p, double* g)
+{
+    if (R % 2 == 0) {
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + r);
+            g[r] = t.x; g[r + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) g[r] = p[r];
+    }
+}
+
+template <int R, bool RES>
+__device__ __forceinline__ void tile_dot_r_at(const double2* __restrict__ vp, const int2* __restrict__ ip,
+                                              const double* __restrict__ vec, int nsteps, double* dot)
+{
+    if (RES) {
+        __builtin_assume(__isShared(vp));
+        __builtin_assume(__isShared(ip));
+    } else {
+        __builtin_assume(__isGlobal(vp));
+        __builtin_assume(__isGlobal(ip));
+    }
+    __builtin_assume(__isShared(vec));
+#pragma unroll 2
+    for (int s = 0; s < nsteps; ++s) {
+        const int2 j = ip[s * 32];
+        const double2 v = vp[s * 32];
+        double g0[R], g1[R];
+        ld_r<R>(vec + (size_t)j.x * R, g0);
+        ld_r<R>(vec + (size_t)j.y * R, g1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            dot[r] = fma(v.x, g0[r], dot[r]);
+            dot[r] = fma(v.y, g1[r], dot[r]);
+        }
+    }
+}
+template <int R>
+__device__ __forceinline__ void tile_dot_r(const MatView& V, const double* __restrict__ vec, uint32_t off, int nsteps, int lane,
+                                           double* dot)
+{
+    const double2* vp;
+    const int2* ip;
+    if (tile_ptrs(V, off, nsteps, lane, vp, ip)) tile_dot_r_at<R, true>(vp, ip, vec, nsteps, dot);
+    else tile_dot_r_at<R, false>(vp, ip, vec, nsteps, dot);
+}
+
+// Walker for a one-CTA grid (every split row is joined inside the CTA).  Op: vec(), row(i, dot[R], acc).
+template <int R, class Op>
+__device__ __forceinline__ void run_phase_r(const DevMat& M, const MatView& V, const Op& op, double* spart, double* acc)
+{
+    const double* __restrict__ vec = op.vec();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (V.nsplit > 0) {
+        for (uint32_t t = warp; t < V.nsplit; t += nwarps) {
+            const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
+            double dot[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) dot[r] = 0.0;
+            tile_dot_r<R>(V, vec, (uint32_t)raw.x, raw.z & 0xffff, lane, dot);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                for (int o = 16; o > 0; o >>= 1) dot[r] += __shfl_xor_sync(FULL, dot[r], o);
+                if (lane == 0) spart[raw.w * R + r] = dot[r];
+            }
+        }
+        __syncthreads();
+        for (uint32_t li = warp; li < V.nls; li += nwarps) {
+            const int4 ls = __ldg(reinterpret_cast<const int4*>(M.lsplits + V.ls0 + li));
+            const int4 sr = __ldg(reinterpret_cast<const int4*>(M.splits + ls.x));
+            const int first = ls.z & 0xffff, count = (ls.z >> 16) & 0xffff;
+            double p[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                p[r] = 0.0;
+                for (int k = lane; k < count; k += 32) p[r] += spart[(first + k) * R + r];
+                for (int o = 16; o > 0; o >>= 1) p[r] += __shfl_xor_sync(FULL, p[r], o);
+            }
+            if (lane == 0) op.row(sr.x, p, acc);
+        }
+    }
+    for (uint32_t t = V.nsplit + warp; t < V.ntiles; t += nwarps) {
+        const int4 raw = *reinterpret_cast<const int4*>(V.desc + t);
+        const int nsteps = raw.z & 0xffff;
+        const int logL = (raw.z >> 16) & 0xff;
+        const int nrows = (raw.z >> 24) & 0xff;
+        const int L = 1 << logL;
+        const int rr = lane >> logL;
+        const bool owner = ((lane & (L - 1)) == 0) && (rr < nrows);
+        double dot[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) dot[r] = 0.0;
+        tile_dot_r<R>(V, vec, (uint32_t)raw.x, nsteps, lane, dot);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            for (int o = L >> 1; o > 0; o >>= 1) dot[r] += __shfl_xor_sync(FULL, dot[r], o);
+        if (owner) op.row(raw.y + rr, dot, acc);
+    }
+}
+
+// R-wide row updates (same arithmetic as PrimalOp / DualOp / *HalpernOp / Eval*Op, instance r at [i * R + r])
+template <int R>
+struct PrimalR {
+    const SmemR<R>& S;
+    const double* tau;      // [R]
+    __device__ __forceinline__ const double* vec() const { return S.y; }
+    __device__ __forceinline__ void row(int i, const double* dot, double*) const
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double xx = S.x[(size_t)i * R + r];
+            const double g = S.c[(size_t)i * R + r] - dot[r];
+            const double xn = fmax(xx - tau[r] * g, 0.0);
+            S.xbar[(size_t)i * R + r] = 2.0 * xn - xx;
+            S.x[(size_t)i * R + r] = xn;
+        }
+    }
+};
+template <int R>
+struct DualR {
+    const SmemR<R>& S;
+    const double* sigma;
+    __device__ __forceinline__ const double* vec() const { return S.xbar; }
+    __device__ __forceinline__ void row(int i, const double* dot, double*) const
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double yy = S.y[(size_t)i * R + r];
+            S.y[(size_t)i * R + r] = yy + sigma[r] * (S.b[(size_t)i * R + r] - dot[r]);
+        }
+    }
+};
+// solve mode; `active[r]` = 0 freezes instance r (it has converged; the group runs on for the others)
+template <int R>
+struct PrimalHalpernR {
+    const SmemR<R>& S;
+    const double *tau, *lam;
+    const int* active;
+    __device__ __forceinline__ const double* vec() const { return S.y; }
+    __device__ __forceinline__ void row(int i, const double* dot, double* acc) const
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!active[r]) continue;
+            const double xx = S.x[(size_t)i * R + r];
+            const double g = S.c[(size_t)i * R + r] - dot[r];
+            const double xn = fmax(xx - tau[r] * g, 0.0);
+            const double d = xn - xx;
+            acc[r] += d * d;
+            const double xb = 2.0 * xn - xx;
+            S.xbar[(size_t)i * R + r] = xb;
+            S.x[(size_t)i * R + r] = lam[r] * xb + (1.0 - lam[r]) * S.x0[(size_t)i * R + r];
+        }
+    }
+};
+template <int R>
+struct DualHalpernR {
+    const SmemR<R>& S;
+    const double *sigma, *lam;
+    const int* active;
+    __device__ __forceinline__ const double* vec() const { return S.xbar; }
+    __device__ __forceinline__ void row(int i, const double* dot, double* acc) const
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!active[r]) continue;
+            const double yy = S.y[(size_t)i * R + r];
+            const double yn = yy + sigma[r] * (S.b[(size_t)i * R + r] - dot[r]);
+            const double d = yn - yy;
+            acc[r] += d * d;
+            S.y[(size_t)i * R + r] = lam[r] * (2.0 * yn - yy) + (1.0 - lam[r]) * S.y0[(size_t)i * R + r];
+        }
+    }
+};
+// acc[r * 6 + k]: 0 pobj, 1 dobj bound terms (0 here: l = 0, u = inf), 2 dual residual^2, 3 ||c||^2, 4 ||x||^2, 5 ||x-x0||^2
+template <int R>
+struct EvalPrimalR {
+    const SmemR<R>& S;
+    __device__ __forceinline__ const double* vec() const { return S.y; }
+    __device__ __forceinline__ void row(int i, const double* dot, double* acc) const
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double cc = S.c[(size_t)i * R + r], xx = S.x[(size_t)i * R + r], x0 = S.x0 ? S.x0[(size_t)i * R + r] : 0.0;
+            const double rc = cc - dot[r];
+            const double rn = rc < 0.0 ? rc : 0.0;
+            acc[r * 6 + 0] += cc * xx;
+            acc[r * 6 + 2] += rn * rn;
+            acc[r * 6 + 3] += cc * cc;
+            acc[r * 6 + 4] += xx * xx;
+            acc[r * 6 + 5] += (xx - x0) * (xx - x0);
+        }
+    }
+};
+// acc[r * 6 + k]: 0 b'y, 1 primal residual^2, 2 ||b||^2, 3 ||y||^2, 4 ||y-y0||^2
+template <int R>
+struct EvalDualR {
+    const SmemR<R>& S;
+    __device__ __forceinline__ const double* vec() const { return S.x; }
+    __device__ __forceinline__ void row(int i, const double* dot, double* acc) const
+    {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double bb = S.b[(size_t)i * R + r], yy = S.y[(size_t)i * R + r], y0 = S.y0 ? S.y0[(size_t)i * R + r] : 0.0;
+            const double res = dot[r] - bb;
+            acc[r * 6 + 0] += bb * yy;
+            acc[r * 6 + 1] += res * res;
+            acc[r * 6 + 2] += bb * bb;
+            acc[r * 6 + 3] += yy * yy;
+            acc[r * 6 + 4] += (yy - y0) * (yy - y0);
+        }
+    }
+};
+
+// CTA-wide sums of acc[0..N) (fixed order), result in every thread; N may exceed NRED (done in slices)
+template <int N, int R>
+__device__ __forceinline__ void cta_allreduce_r(double* acc, const SmemR<R>& S)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k0 = 0; k0 < N; k0 += NRED) {
+        const int kn = N - k0 < NRED ? N - k0 : NRED;
+        for (int k = 0; k < kn; ++k) {
+            double v = acc[k0 + k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            if (lane == 0) S.red[warp * NRED + k] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int k = 0; k < kn; ++k) {
+                double v = lane < nwarps ? S.red[lane * NRED + k] : 0.0;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                if (lane == 0) S.bc[k] = v;
+            }
+        }
+        __syncthreads();
+        for (int k = 0; k < kn; ++k) acc[k0 + k] = S.bc[k];
+        __syncthreads();
+    }
+}
+
+// KKT scalars of the R instances: s[r * 10 + q], dd[r * 2 + q]
+template <int R>
+__device__ __forceinline__ void batch_kkt_r(const BatchInst& I, const MatView& VA, const MatView& VAT, const SmemR<R>& S,
+                                            double* s, double* dd)
+{
+    double ap[R * 6], ad[R * 6];
+#pragma unroll
+    for (int k = 0; k < R * 6; ++k) { ap[k] = 0.0; ad[k] = 0.0; }
+    { EvalPrimalR<R> op{S}; run_phase_r<R>(I.AT, VAT, op, S.spart, ap); }
+    __syncthreads();
+    { EvalDualR<R> op{S}; run_phase_r<R>(I.A, VA, op, S.spart, ad); }
+    cta_allreduce_r<R * 6, R>(ap, S);
+    cta_allreduce_r<R * 6, R>(ad, S);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double* p = ap + r * 6;
+        const double* d = ad + r * 6;
+        double* o = s + r * 10;
+        const double pobj = p[0], dobj = d[0] + p[1];
+        o[0] = pobj; o[1] = dobj; o[2] = sqrt(d[1]); o[3] = sqrt(p[2]);
+        o[4] = sqrt(d[2]); o[5] = sqrt(p[3]); o[6] = sqrt(p[4]); o[7] = sqrt(d[3]);
+        const double gap = fabs(pobj - dobj);
+        double e = o[2] / (1.0 + o[4]);
+        e = fmax(e, o[3] / (1.0 + o[5]));
+        e = fmax(e, gap / (1.0 + fabs(pobj) + fabs(dobj)));
+        o[8] = e; o[9] = gap;
+        dd[r * 2 + 0] = p[5]; dd[r * 2 + 1] = d[4];
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void load_group(const BatchInst& I, const SmemR<R>& S, int inst0, int count, const double* x,
+                                           const double* y, const double* b, const double* c)
+{
+    for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
+        const int j = __ldg(I.orderX + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool ok = inst0 + r < count;
+            const size_t at = (size_t)(inst0 + r) * I.n + j;
+            S.x[(size_t)k * R + r] = ok ? x[at] : 0.0;
+            S.c[(size_t)k * R + r] = ok ? c[at] : 0.0;
+            S.xbar[(size_t)k * R + r] = 0.0;
+        }
+    }
+    for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
+        const int i = __ldg(I.orderY + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool ok = inst0 + r < count;
+            const size_t at = (size_t)(inst0 + r) * I.m + i;
+            S.y[(size_t)k * R + r] = ok ? y[at] : 0.0;
+            S.b[(size_t)k * R + r] = ok ? b[at] : 0.0;
+        }
+    }
+    __syncthreads();
+}
+template <int R>
+__device__ __forceinline__ void store_group(const BatchInst& I, const SmemR<R>& S, int inst0, int count, double* x, double* y)
+{
+    for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
+        const int j = __ldg(I.orderX + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (inst0 + r < count) x[(size_t)(inst0 + r) * I.n + j] = S.x[(size_t)k * R + r];
+    }
+    for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
+        const int i = __ldg(I.orderY + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (inst0 + r < count) y[(size_t)(inst0 + r) * I.m + i] = S.y[(size_t)k * R + r];
+    }
+    __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024, 1)
+k_batch_run_r(const BatchInst* __restrict__ insts, int count, BatchGeom geom, double* x, double* y, const double* b,
+              const double* c, const double* tau, const double* sigma, int iters, double* scalars)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const BatchInst I = insts[0];
+    const SmemR<R> S = carve_r<R>(dsm, I.m, I.n, false);
+    MatView VA, VAT;
+    batch_views(I, geom, dsm, VA, VAT);
+    const int ngroups = (count + R - 1) / R;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int inst0 = grp * R;
+        load_group<R>(I, S, inst0, count, x, y, b, c);
+        double ta[R], si[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            ta[r] = inst0 + r < count ? __ldg(tau + inst0 + r) : 0.0;
+            si[r] = inst0 + r < count ? __ldg(sigma + inst0 + r) : 0.0;
+        }
+        PrimalR<R> pop{S, ta};
+        DualR<R> dop{S, si};
+        for (int it = 0; it < iters; ++it) {
+            run_phase_r<R>(I.AT, VAT, pop, S.spart, nullptr);
+            __syncthreads();
+            run_phase_r<R>(I.A, VA, dop, S.spart, nullptr);
+            __syncthreads();
+        }
+        if (scalars) {
+            double s[R * 10], dd[R * 2];
+            batch_kkt_r<R>(I, VA, VAT, S, s, dd);
+            if (threadIdx.x == 0) {
+                for (int r = 0; r < R; ++r) {
+                    if (inst0 + r >= count) break;
+                    double* o = scalars + (size_t)(inst0 + r) * MLLP_NUM_SCALARS;
+                    for (int k = 0; k < 10; ++k) o[k] = s[r * 10 + k];
+                    o[10] = (double)iters; o[11] = 0.0; o[12] = 0.0; o[13] = 1.0; o[14] = 0.0; o[15] = 0.0;
+                }
+            }
+        }
+        store_group<R>(I, S, inst0, count, x, y);
+    }
+}
+
+// one slot of the interleaved vectors <-> one instance of the batch (anchors = the loaded point)
+template <int R>
+__device__ __forceinline__ void load_slot(const BatchInst& I, const SmemR<R>& S, int r, int inst, const double* x,
+                                          const double* y, const double* b, const double* c)
+{
+    for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
+        const size_t at = (size_t)inst * I.n + __ldg(I.orderX + k);
+        const double xv = x[at];
+        S.x[(size_t)k * R + r] = xv; S.x0[(size_t)k * R + r] = xv;
+        S.c[(size_t)k * R + r] = c[at];
+        S.xbar[(size_t)k * R + r] = 0.0;
+    }
+    for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
+        const size_t at = (size_t)inst * I.m + __ldg(I.orderY + k);
+        const double yv = y[at];
+        S.y[(size_t)k * R + r] = yv; S.y0[(size_t)k * R + r] = yv;
+        S.b[(size_t)k * R + r] = b[at];
+    }
+}
+template <int R>
+__device__ __forceinline__ void store_slot(const BatchInst& I, const SmemR<R>& S, int r, int inst, double* x, double* y)
+{
+    for (int k = threadIdx.x; k < I.n; k += blockDim.x) x[(size_t)inst * I.n + __ldg(I.orderX + k)] = S.x[(size_t)k * R + r];
+    for (int k = threadIdx.x; k < I.m; k += blockDim.x) y[(size_t)inst * I.m + __ldg(I.orderY + k)] = S.y[(size_t)k * R + r];
+}
+
+// Solve mode for a shared matrix, R instances per CTA: every slot runs its own instance with its own primal
+// weight, Halpern counter, restart state, iteration count and termination (the rules of k_batch_solve /
+// oracle_pdhg_solve); the matrix steps are shared by the R slots.  A slot whose instance has finished stores it
+// and pulls the next instance from the device counter at once, so slow instances do not hold the others back.
+template <int R>
+__global__ void __launch_bounds__(1024, 1)
+k_batch_solve_r(const BatchInst* __restrict__ insts, int count, BatchGeom geom, double* x, double* y, const double* b,
+                const double* c, const double* eta_arr, double w0, int max_iters, int check_every, double tol,
+                double* scalars, int* next_inst)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ int s_next[R];
+    // step parameters of the slots, double buffered by iteration parity: [buffer][tau, sigma, lam][slot].  The two
+    // fp64 divisions per slot and iteration (eta / w, (k+1)/(k+2)) are done by R threads one iteration ahead instead
+    // of by every thread (they cost more than a small LP's share of the SpMV per thread).
+    __shared__ double s_par[2][3][R];
+    __shared__ int s_act[R];
+    const BatchInst I = insts[0];
+    const SmemR<R> S = carve_r<R>(dsm, I.m, I.n, true);
+    MatView VA, VAT;
+    batch_views(I, geom, dsm, VA, VAT);
+
+    double eta[R], w[R], fpe_restart[R], fpe_prev[R], fpe[R];
+    int k[R], it[R], restarts[R], active[R], inst[R];
+    int pb = 0;   // buffer of s_par the next iteration reads
+    // (re)fill the slots flagged in `want`: uniform control flow, the state is replicated in every thread
+    auto fill = [&](const bool* want) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int r = 0; r < R; ++r) s_next[r] = want[r] ? atomicAdd(next_inst, 1) : -1;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!want[r]) continue;
+            const int nx = s_next[r];
+            active[r] = nx < count;
+            inst[r] = nx;
+            eta[r] = 1.0; w[r] = w0; fpe_restart[r] = -1.0; fpe_prev[r] = INFINITY; fpe[r] = 0.0;
+            k[r] = 0; it[r] = 0; restarts[r] = 0;
+            if (threadIdx.x == 0) s_act[r] = active[r];
+            if (active[r]) {
+                eta[r] = __ldg(eta_arr + nx);
+                if (threadIdx.x == 0) { s_par[pb][0][r] = eta[r] / w0; s_par[pb][1][r] = eta[r] * w0; s_par[pb][2][r] = 0.5; }
+                load_slot<R>(I, S, r, nx, x, y, b, c);
+            } else {
+                // idle slot: zero vectors keep its (masked) lanes finite
+                for (int q = threadIdx.x; q < I.n; q += blockDim.x) {
+                    S.x[(size_t)q * R + r] = 0.0; S.xbar[(size_t)q * R + r] = 0.0; S.c[(size_t)q * R + r] = 0.0; S.x0[(size_t)q * R + r] = 0.0;
+                }
+                for (int q = threadIdx.x; q < I.m; q += blockDim.x) {
+                    S.y[(size_t)q * R + r] = 0.0; S.b[(size_t)q * R + r] = 0.0; S.y0[(size_t)q * R + r] = 0.0;
+                }
+            }
+        }
+        __syncthreads();
+    };
+    {
+        bool all[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { all[r] = true; active[r] = 0; }
+        fill(all);
+    }
+    for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) any |= (active[r] != 0);
+        if (!any) break;
+        const double* tau = &s_par[pb][0][0];
+        const double* sigma = &s_par[pb][1][0];
+        const double* lam = &s_par[pb][2][0];
+        bool check[R];
+        bool need = false, any_check = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            check[r] = active[r] && (((it[r] + 1) % check_every == 0) || (it[r] + 1 >= max_iters));
+            any_check |= check[r];
+            need |= check[r] || (active[r] && fpe_restart[r] < 0.0);
+            if (threadIdx.x == r) {   // the next iteration's parameters if nothing restarts (rewritten below if it does)
+                const int kn = k[r] + active[r];
+                s_par[pb ^ 1][0][r] = tau[r]; s_par[pb ^ 1][1][r] = sigma[r];
+                s_par[pb ^ 1][2][r] = (double)(kn + 1) / (double)(kn + 2);
+            }
+        }
+        double a2[2 * R];
+#pragma unroll
+        for (int q = 0; q < 2 * R; ++q) a2[q] = 0.0;
+        { PrimalHalpernR<R> op{S, tau, lam, s_act}; run_phase_r<R>(I.AT, VAT, op, S.spart, a2); }
+        __syncthreads();
+        { DualHalpernR<R> op{S, sigma, lam, s_act}; run_phase_r<R>(I.A, VA, op, S.spart, a2 + R); }
+        __syncthreads();
+        pb ^= 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { it[r] += active[r]; k[r] += active[r]; }
+        if (need) {
+            cta_allreduce_r<2 * R, R>(a2, S);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (active[r] && (check[r] || fpe_restart[r] < 0.0)) {
+                    fpe[r] = sqrt(w[r] * a2[r] + a2[R + r] / w[r]);
+                    if (fpe_restart[r] < 0.0) fpe_restart[r] = fpe[r];
+                }
+        }
+        if (any_check) {
+            double kk[R * 10], dd[R * 2];
+            batch_kkt_r<R>(I, VA, VAT, S, kk, dd);
+            bool rs[R], done[R];
+            bool any_rs = false, any_done = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                rs[r] = false; done[r] = false;
+                if (!check[r]) continue;
+                const bool conv = kk[r * 10 + 8] <= tol;
+                if (conv || it[r] >= max_iters) {
+                    done[r] = true; any_done = true;
+                    if (threadIdx.x == 0) {
+                        double* o = scalars + (size_t)inst[r] * MLLP_NUM_SCALARS;
+                        for (int q = 0; q < 10; ++q) o[q] = kk[r * 10 + q];
+                        o[10] = (double)it[r]; o[11] = (double)restarts[r]; o[12] = conv ? 1.0 : 0.0; o[13] = w[r];
+                        o[14] = fpe[r]; o[15] = 0.0;
+                    }
+                    continue;
+                }
+                const bool do_restart = (fpe[r] <= 0.2 * fpe_restart[r]) ||
+                                        (fpe[r] <= 0.8 * fpe_restart[r] && fpe[r] > fpe_prev[r]) ||
+                                        ((double)k[r] >= 0.36 * (double)it[r]);
+                fpe_prev[r] = fpe[r];
+                if (do_restart) {
+                    const double ddx = sqrt(dd[r * 2]), ddy = sqrt(dd[r * 2 + 1]);
+                    if (ddx > 1e-10 && ddy > 1e-10) w[r] = exp(0.5 * log(ddy / ddx) + 0.5 * log(w[r]));
+                    rs[r] = true; any_rs = true;
+                    k[r] = 0; fpe_restart[r] = -1.0; fpe_prev[r] = INFINITY;
+                    ++restarts[r];
+                    if (threadIdx.x == 0) { s_par[pb][0][r] = eta[r] / w[r]; s_par[pb][1][r] = eta[r] * w[r]; s_par[pb][2][r] = 0.5; }
+                }
+            }
+            if (any_rs) {
+                for (int q = threadIdx.x; q < I.n; q += blockDim.x)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (rs[r]) S.x0[(size_t)q * R + r] = S.x[(size_t)q * R + r];
+                for (int q = threadIdx.x; q < I.m; q += blockDim.x)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (rs[r]) S.y0[(size_t)q * R + r] = S.y[(size_t)q * R + r];
+                __syncthreads();
+            }
+            if (any_done) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (done[r]) store_slot<R>(I, S, r, inst[r], x, y);
+                fill(done);
+            }
+        }
     }
 }
 
@@ -323,6 +930,11 @@ struct mllp_batch {
     std::vector<void*> allocs;
     int* d_next = nullptr;            // work counter of k_batch_solve
     int64_t info[16] = {0};
+    // shared matrix: instances per CTA (multi-RHS) and launch geometry of the parity / solve kernels
+    int R_run = 1, R_solve = 1;
+    int grid_run = 0, grid_solve = 0;
+    size_t smem_run = 0, smem_solve = 0;
+    BatchGeom g_run{}, g_solve{};
 };
 
 namespace {
@@ -415,7 +1027,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
         Pools P;
         std::vector<MatOff> offA((size_t)nmat), offAT((size_t)nmat);
         std::vector<size_t> offOX((size_t)nmat), offOY((size_t)nmat);
-        int max_tiles = 0;
+        int max_tiles = 0, max_tiles_A = 0, max_tiles_AT = 0, max_steps_A = 0, max_steps_AT = 0;
         for (int k = 0; k < nmat && rc == 0; ++k) {
             const int m = h_m[k], n = h_n[k];
             const int32_t* ip = h_indptr + h_indptr_off[k];
@@ -440,6 +1052,10 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             offOX[k] = P.order.size(); P.order.insert(P.order.end(), orderX.begin(), orderX.end());
             offOY[k] = P.order.size(); P.order.insert(P.order.end(), orderY.begin(), orderY.end());
             max_tiles = std::max<int>(max_tiles, (int)std::max(HA.tiles.size(), HAT.tiles.size()));
+            max_tiles_A = std::max<int>(max_tiles_A, (int)HA.tiles.size());
+            max_tiles_AT = std::max<int>(max_tiles_AT, (int)HAT.tiles.size());
+            max_steps_A = std::max<int>(max_steps_A, (int)HA.total_steps);
+            max_steps_AT = std::max<int>(max_steps_AT, (int)HAT.total_steps);
             bt->max_m = std::max(bt->max_m, m); bt->max_n = std::max(bt->max_n, n);
             bt->sum_nnz += nnz;
         }
@@ -497,26 +1113,85 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             const char* tv = getenv("MLLP_BATCH_THREADS");
             if (tv && *tv) threads = std::max(32, std::min(1024, atoi(tv) & ~31));
             bt->threads = threads;
-            if (rc == 0) {
-                const void* fns[3] = {(const void*)k_batch_run, (const void*)k_batch_solve, (const void*)k_batch_norm};
-                int nb = 1 << 30;
-                for (const void* fn : fns) {
-                    if (bt->dyn_smem > 40 * 1024)
-                        ck(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->dyn_smem), "cudaFuncSetAttribute");
-                    int b = 0;
-                    ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, threads, bt->dyn_smem), "occupancy");
-                    nb = std::min(nb, b);
+
+            // Shared matrix: R instances per CTA with interleaved vectors (multi-RHS), as many as fit in shared memory
+            // while every SM still gets a group.  What is left of the shared memory keeps the tile descriptors and a
+            // prefix of the matrix steps resident (A' first); also used for one big matrix per instance.
+            auto bytes_r = [&](int R, bool anchors) {
+                const size_t per = anchors ? 4 * (size_t)bt->max_n + 3 * (size_t)bt->max_m : 3 * (size_t)bt->max_n + 2 * (size_t)bt->max_m;
+                return (8 * ((size_t)32 * NRED + 16 * (size_t)R + (size_t)SPLIT_SLOTS * R + per * R) + 15) & ~(size_t)15;
+            };
+            const size_t desc_bytes = 16 * ((size_t)max_tiles_A + (size_t)max_tiles_AT);
+            const size_t mat_bytes = desc_bytes + 768 * ((size_t)max_steps_A + (size_t)max_steps_AT);
+            auto pick_R = [&](bool anchors) {
+                int R = 1;
+                if (bt->shared) {
+                    // measured (scripts/batch_bench.py): R = 2 brings 1.5x (25fv47) to 2.1x (sc105) in LP-iterations/s,
+                    // R = 3, 4 add nothing (the interleaved gathers are bound by shared-memory bank conflicts)
+                    for (int cand : {2})
+                        if (bytes_r(cand, anchors) + desc_bytes <= smem_cap && (int64_t)count >= (int64_t)cand * prop.multiProcessorCount) R = cand;
+                    const char* rv = getenv("MLLP_BATCH_R");
+                    if (rv && *rv) {
+                        const int want = atoi(rv);
+                        if (want >= 1 && want <= 4 && (want == 1 || bytes_r(want, anchors) + desc_bytes <= smem_cap)) R = want;
+                    }
                 }
-                if (rc == 0 && nb < 1) rc = bfail(MLLP_E_STATE, "mllp_batch_create: kernel does not fit on an SM");
-                if (rc == 0) bt->grid = std::min<int64_t>(count, (int64_t)prop.multiProcessorCount * nb);
+                return R;
+            };
+            auto geometry = [&](int R, bool anchors, size_t& smem, BatchGeom& g) {
+                const size_t vec = R == 1 ? bt->dyn_smem : bytes_r(R, anchors);
+                smem = vec;
+                g = BatchGeom{0u, 0u, 0u, 0};
+                const char* rv = getenv("MLLP_BATCH_RES");
+                // default: resident only if the WHOLE matrix fits behind the vectors (a partly resident matrix leaves too
+                // little L1 for the streamed rest: 25fv47, R = 1: -10 %)
+                const bool forced = rv && *rv && atoi(rv) != 0;
+                const bool want_res = rv && *rv ? forced : (bt->shared && vec + mat_bytes <= smem_cap);
+                if (want_res && vec + desc_bytes <= smem_cap) {
+                    size_t steps = (smem_cap - vec - desc_bytes) / 768;
+                    g.use_res = 1;
+                    g.mat_off = (uint32_t)vec;
+                    g.res_AT = (uint32_t)std::min<size_t>(steps, (size_t)max_steps_AT);
+                    steps -= g.res_AT;
+                    g.res_A = (uint32_t)std::min<size_t>(steps, (size_t)max_steps_A);
+                    smem = vec + desc_bytes + 768 * ((size_t)g.res_A + g.res_AT);
+                }
+            };
+            if (rc == 0) {
+                bt->R_run = pick_R(false);
+                bt->R_solve = pick_R(true);
+                geometry(bt->R_run, false, bt->smem_run, bt->g_run);
+                geometry(bt->R_solve, true, bt->smem_solve, bt->g_solve);
+                auto run_fn = [](int R) -> const void* {
+                    return R == 4 ? (const void*)k_batch_run_r<4> : R == 3 ? (const void*)k_batch_run_r<3> : R == 2 ? (const void*)k_batch_run_r<2> : (const void*)k_batch_run;
+                };
+                auto solve_fn = [](int R) -> const void* {
+                    return R == 4 ? (const void*)k_batch_solve_r<4> : R == 3 ? (const void*)k_batch_solve_r<3> : R == 2 ? (const void*)k_batch_solve_r<2> : (const void*)k_batch_solve;
+                };
+                auto prepare = [&](const void* fn, size_t smem, int64_t units, int& grid) {
+                    if (smem > 40 * 1024)
+                        ck(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+                    int b = 0;
+                    ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, threads, smem), "occupancy");
+                    if (rc == 0 && b < 1) rc = bfail(MLLP_E_STATE, "mllp_batch_create: kernel does not fit on an SM");
+                    grid = (int)std::min<int64_t>(units, (int64_t)prop.multiProcessorCount * std::max(b, 1));
+                };
+                prepare(run_fn(bt->R_run), bt->smem_run, (count + bt->R_run - 1) / bt->R_run, bt->grid_run);
+                prepare(solve_fn(bt->R_solve), bt->smem_solve, (count + bt->R_solve - 1) / bt->R_solve, bt->grid_solve);
+                if (bt->R_solve > 1 && bt->smem_solve > 40 * 1024)   // max_iters == 0 runs the one-instance kernel with this geometry
+                    ck(cudaFuncSetAttribute((const void*)k_batch_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_solve), "cudaFuncSetAttribute");
+                int gn = 0;
+                prepare((const void*)k_batch_norm, bt->dyn_smem, count, gn);
+                bt->grid = gn;
             }
             int64_t* I = bt->info;
-            I[0] = count; I[1] = bt->sum_m; I[2] = bt->sum_n; I[3] = bt->sum_nnz; I[4] = bt->grid; I[5] = bt->threads;
-            I[6] = (int64_t)bt->dyn_smem;
+            I[0] = count; I[1] = bt->sum_m; I[2] = bt->sum_n; I[3] = bt->sum_nnz; I[4] = bt->grid_run; I[5] = bt->threads;
+            I[6] = (int64_t)bt->smem_run;
             // algorithmic bytes per batch iteration: per instance 36 m + 44 n, plus the matrix (24 nnz) once per
             // instance (separate matrices) or once per batch (shared matrix)
             I[7] = 36 * bt->sum_m + 44 * bt->sum_n + 24 * bt->sum_nnz;
-            I[8] = 1;
+            I[8] = bt->R_run; I[9] = bt->R_solve; I[10] = bt->g_run.res_A; I[11] = bt->g_run.res_AT;
+            I[12] = bt->g_solve.res_A; I[13] = bt->g_solve.res_AT; I[14] = (int64_t)bt->smem_solve; I[15] = bt->grid_solve;
         }
     } catch (const std::bad_alloc&) {
         rc = bfail(MLLP_E_NOMEM, "mllp_batch_create: out of host memory");
@@ -562,8 +1237,17 @@ int mllp_batch_run(mllp_batch_t bt, double* d_x, double* d_y, const double* d_b,
     if (!bt || !d_x || !d_y || !d_b || !d_c || !d_tau || !d_sigma || num_iters < 0)
         return bfail(MLLP_E_INVALID, "mllp_batch_run: null argument or negative iteration count");
     DevGuard guard(bt->device);
-    k_batch_run<<<bt->grid, bt->threads, bt->dyn_smem, (cudaStream_t)stream>>>(bt->d_insts, bt->count, bt->shared, d_x, d_y, d_b,
-                                                                              d_c, d_tau, d_sigma, num_iters, d_scalars);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MLLP_RUN_R(RR) k_batch_run_r<RR><<<bt->grid_run, bt->threads, bt->smem_run, st>>>(bt->d_insts, bt->count, bt->g_run, d_x, d_y, d_b, d_c, d_tau, d_sigma, num_iters, d_scalars)
+    switch (bt->R_run) {
+        case 4: MLLP_RUN_R(4); break;
+        case 3: MLLP_RUN_R(3); break;
+        case 2: MLLP_RUN_R(2); break;
+        default:
+            k_batch_run<<<bt->grid_run, bt->threads, bt->smem_run, st>>>(bt->d_insts, bt->count, bt->shared, bt->g_run, d_x, d_y, d_b,
+                                                                       d_c, d_tau, d_sigma, num_iters, d_scalars);
+    }
+#undef MLLP_RUN_R
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bfail((int)e, std::string("mllp_batch_run: ") + cudaGetErrorString(e));
     return 0;
@@ -577,9 +1261,18 @@ int mllp_batch_solve(mllp_batch_t bt, double* d_x, double* d_y, const double* d_
     DevGuard guard(bt->device);
     cudaError_t e0 = cudaMemsetAsync(bt->d_next, 0, sizeof(int), (cudaStream_t)stream);
     if (e0 != cudaSuccess) return bfail((int)e0, std::string("mllp_batch_solve: ") + cudaGetErrorString(e0));
-    k_batch_solve<<<bt->grid, bt->threads, bt->dyn_smem, (cudaStream_t)stream>>>(bt->d_insts, bt->count, bt->shared, d_x, d_y, d_b,
-                                                                                d_c, d_eta, w0, max_iters, check_every, tol,
-                                                                                d_scalars, bt->d_next);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MLLP_SOLVE_R(RR) k_batch_solve_r<RR><<<bt->grid_solve, bt->threads, bt->smem_solve, st>>>(bt->d_insts, bt->count, bt->g_solve, d_x, d_y, d_b, d_c, d_eta, w0, max_iters, check_every, tol, d_scalars, bt->d_next)
+    switch (max_iters > 0 ? bt->R_solve : 1) {   // max_iters == 0 (scalars of the starting point): one-instance kernel
+        case 4: MLLP_SOLVE_R(4); break;
+        case 3: MLLP_SOLVE_R(3); break;
+        case 2: MLLP_SOLVE_R(2); break;
+        default:
+            k_batch_solve<<<bt->grid_solve, bt->threads, bt->smem_solve, st>>>(bt->d_insts, bt->count, bt->shared, bt->g_solve, d_x, d_y,
+                                                                             d_b, d_c, d_eta, w0, max_iters, check_every, tol,
+                                                                             d_scalars, bt->d_next);
+    }
+#undef MLLP_SOLVE_R
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bfail((int)e, std::string("mllp_batch_solve: ") + cudaGetErrorString(e));
     return 0;

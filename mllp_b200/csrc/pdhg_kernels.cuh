@@ -493,10 +493,10 @@ __device__ __forceinline__ MatView global_view(const DevMat& M) { return global_
 // Layout at `base` (16 B aligned): desc[ntiles] | vals[res_steps*32] (double2) | idx[res_steps*32] (int2).
 // Returns the number of bytes used (multiple of 16).
 __device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_steps_cap, unsigned char* base,
-                                                  MatView& V)
+                                                  MatView& V, uint32_t cta)
 {
-    const uint32_t t0 = __ldg(M.cta_begin + blockIdx.x), t1 = __ldg(M.cta_begin + blockIdx.x + 1);
-    const uint32_t s0 = __ldg(M.cta_step_begin + blockIdx.x), s1 = __ldg(M.cta_step_begin + blockIdx.x + 1);
+    const uint32_t t0 = __ldg(M.cta_begin + cta), t1 = __ldg(M.cta_begin + cta + 1);
+    const uint32_t s0 = __ldg(M.cta_step_begin + cta), s1 = __ldg(M.cta_step_begin + cta + 1);
     const uint32_t nt = t1 - t0;
     const uint32_t rs = min(res_steps_cap, s1 - s0);
     int4* d_desc = reinterpret_cast<int4*>(base);
@@ -513,8 +513,12 @@ __device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_
     V.ridx = reinterpret_cast<const int2*>(d_idx);
     V.gvals = M.vals; V.gidx = M.idx;
     V.ntiles = nt; V.res_steps = rs; V.step0 = s0;
-    view_common(M, V, blockIdx.x);
+    view_common(M, V, cta);
     return nt * 16u + rs * 768u;
+}
+__device__ __forceinline__ uint32_t resident_view(const DevMat& M, uint32_t res_steps_cap, unsigned char* base, MatView& V)
+{
+    return resident_view(M, res_steps_cap, base, V, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -383,7 +383,8 @@ class BatchLP:
         out = (ctypes.c_int64 * 16)()
         _cabi.check(_cabi.lib().mllp_batch_info(self.handle, out), "mllp_batch_info")
         keys = ("count", "sum_m", "sum_n", "sum_nnz", "grid_ctas", "threads", "dyn_smem_bytes", "bytes_per_iter",
-                "instances_per_cta")
+                "instances_per_cta", "instances_per_cta_solve", "res_steps_A", "res_steps_AT", "res_steps_A_solve",
+                "res_steps_AT_solve", "dyn_smem_bytes_solve", "grid_ctas_solve")
         return dict(zip(keys, (int(v) for v in out)))
 
     def sigma_max(self, iters=50):

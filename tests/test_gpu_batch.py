@@ -105,6 +105,61 @@ def test_shared_matrix_batch_of_perturbed_instances():
         assert np.array_equal(res2[k][1], res[perm[k]][1]) and np.array_equal(res2[k][2], res[perm[k]][2])
 
 
+@pytest.mark.parametrize("name,B,RS", [("sc105", 37, (1, 2, 3, 4)), ("25fv47", 13, (1, 2, 3))])   # 4 x 25fv47 exceeds smem
+def test_shared_matrix_multi_rhs_is_bitwise_independent_of_group_size(name, B, RS, monkeypatch):
+    """R instances per CTA share every matrix step (multi-RHS); per instance the summation order is the one of
+    the one-instance walker, so iterates are bitwise equal for R = 1, 2, 3, 4 (B is not a multiple of R: tail group)."""
+    A, b, c = D.load_csr(name)
+    m, n = A.shape
+    rng = np.random.default_rng(7)
+    cb = c * (1 + 0.1 * rng.uniform(-1, 1, (B, n)))
+    bb = b * (1 + 0.1 * rng.uniform(0, 1, (B, m)))
+    out = {}
+    for R in RS:
+        monkeypatch.setenv("MLLP_BATCH_R", str(R))
+        bt = M.BatchLP([(A, A.data, b, c)], shared=True, count=B)
+        assert bt.info()["instances_per_cta"] == R
+        out[R] = M.pdhg_linear_program_batch([(A, A.data, b, c)], num_iters=120, handle=bt, shared=True, rhs_batch=bb,
+                                             coefs_batch=cb)
+        bt.close()
+    eta = 0.9 / O.power_iteration(A, 50)
+    for k in (0, B // 2, B - 1):
+        xo, yo = O.pdhg_run(A, bb[k], cb[k], np.zeros(n), np.zeros(m), eta, eta, 120)
+        assert rel(out[1][k][1], xo) < 1e-9 and rel(out[1][k][2], yo) < 1e-9
+        kk = O.kkt(A, bb[k], cb[k], xo, yo)
+        for R in RS:
+            inf = out[R][k][3]
+            assert abs(out[R][k][0] - kk[0]) <= 1e-6 * (1 + abs(kk[0])) and abs(inf["rel_kkt"] - kk[8]) <= 1e-6 * (1 + kk[8])
+    for R in RS[1:]:
+        for k in range(B):
+            assert np.array_equal(out[R][k][1], out[1][k][1]) and np.array_equal(out[R][k][2], out[1][k][2])
+
+
+def test_shared_matrix_solve_mode_multi_rhs(monkeypatch):
+    """solve mode, lockstep groups of R instances with per-instance restarts / termination vs the one-instance solver"""
+    A, b, c = D.load_csr("sc105")
+    m, n = A.shape
+    B = 9
+    rng = np.random.default_rng(11)
+    cb = c * (1 + 0.05 * rng.uniform(-1, 1, (B, n)))
+    bb = np.tile(b, (B, 1))
+    res = {}
+    for R in (1, 2, 4):
+        monkeypatch.setenv("MLLP_BATCH_R", str(R))
+        bt = M.BatchLP([(A, A.data, b, c)], shared=True, count=B)
+        assert bt.info()["instances_per_cta_solve"] == R
+        res[R] = M.solve_linear_program_batch([(A, A.data, b, c)], tol=1e-6, max_iters=200000, handle=bt, shared=True,
+                                              rhs_batch=bb, coefs_batch=cb)
+        bt.close()
+    for k in range(B):
+        for R in (1, 2, 4):
+            obj, x, y, inf = res[R][k]
+            assert inf["converged"] and inf["rel_kkt"] <= 1e-6
+            kk = O.kkt(A, bb[k], cb[k], x, y)
+            assert abs(kk[0] - obj) <= 1e-6 * (1 + abs(obj)) and kk[8] <= 1.01e-6
+            assert abs(obj - res[1][k][0]) <= 1e-5 * (1 + abs(res[1][k][0]))
+
+
 def test_batch_errors():
     A, b, c = D.load_csr("afiro")
     with pytest.raises(ValueError):
