@@ -220,6 +220,30 @@ int mllp_batch_solve(mllp_batch_t bt, double *d_x, double *d_y, const double *d_
                      const double *d_c, const double *d_eta, double w0, int32_t max_iters,
                      int32_t check_every, double tol, double *d_scalars, void *stream);
 
+/*
+ * Bipartite message passing over the LP's nonzeros: the forward pass of the reference's GNNModel
+ * (linear_program_methods.py:199-215, :238-251; five torch_geometric TransformerConv layers with heads = 1,
+ * 16 channels, edge_dim = 1, root weight and bias, alternating along the rows of A' and of A).  fp32 like the
+ * reference.  All pointers are device pointers; CSR arrays are those of the DESTINATION side (rows = destination
+ * nodes: A for variable->constraint passes, A' for constraint->variable passes), `d_values` the fp64 coefficients
+ * (cast to float per edge, as the reference's edge_attr).
+ *
+ * mllp_gnn_project: kv[j][0..15] = Wk h_j + bk, kv[j][16..31] = Wv h_j + bv for the n source nodes
+ *                   (h: n x din floats; params = Wk'[din][16] | bk[16] | Wv'[din][16] | bv[16], W' = transposed weight).
+ * mllp_gnn_conv:    out_i = sum_j softmax_j(q_i.(k_j + We a_ij) / 4) (v_j + We a_ij) + Ws h_i + bs, optional ReLU
+ *                   (params = Wq'[din][16] | bq[16] | Ws'[din][16] | bs[16] | We[16]).  Rows with more than `chunk`
+ *                   edges are listed in d_long_rows[nlong]; their chunks are d_items[nitems][3] = (row, first edge,
+ *                   end edge), row r owning items d_long_first[r] .. d_long_first[r+1]; d_scratch holds 96 floats per item.
+ * mllp_gnn_fc:      out[i] = w . h_i + b   (wb = w[16] | b).
+ */
+int mllp_gnn_project(int32_t n, const float *d_h, int32_t din, const float *d_params, float *d_kv, void *stream);
+int mllp_gnn_conv(int32_t nd, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                  const float *d_hdst, int32_t din, const float *d_kv_src, const float *d_params, float *d_hout,
+                  int32_t relu, int32_t chunk, int32_t nlong, const int32_t *d_long_rows,
+                  const int32_t *d_long_first, int32_t nitems, const int32_t *d_items, float *d_scratch,
+                  void *stream);
+int mllp_gnn_fc(int32_t n, const float *d_h, const float *d_wb, float *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ SIGNATURES = {
     "mllp_batch_estimate_norm": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
     "mllp_batch_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mllp_batch_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _dbl, _vp, _vp]),
+    "mllp_gnn_project": (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _vp]),
+    "mllp_gnn_conv": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp,
+                                     _vp, _vp]),
+    "mllp_gnn_fc": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
