@@ -117,6 +117,19 @@ int mllp_lp_info(mllp_lp_t lp, int64_t *out16);
  * out4: [0] ns / iteration of the first build, [1] of the build kept, [2] rounds run, [3] reserved. */
 int mllp_lp_tune_info(mllp_lp_t lp, double *out4);
 
+/* Launch geometry of the persistent kernels chosen by mllp_lp_create.  A grid barrier costs ~0.9 us, twice per
+ * iteration, so an LP whose phases are shorter than that runs on ONE thread-block cluster (<= 16 SMs, hardware
+ * cluster barrier) or on one CTA instead of the cooperative grid of one CTA per SM.  In the "broadcast" cluster
+ * geometry every CTA also keeps a full copy of the two gathered vectors in shared memory (a row update stores its
+ * entry into all copies over distributed shared memory), so nothing inside the iteration touches global memory.
+ * With tuning enabled the candidates are timed and the fastest is kept; environment MLLP_GEOM forces one
+ * (0 grid, 1 one CTA, 2..16 cluster, 101..116 broadcast cluster of 1..16 CTAs; 101 = one CTA with all vectors in
+ * shared memory).
+ * out12: [0] 0 = cooperative grid, 1 = cluster, 2 = one CTA, 3 = broadcast cluster; [1] CTAs; [2..10] measured
+ * ns / iteration of the grid, of a cluster of 16 / 8 / 4 CTAs, of one CTA and of a broadcast cluster of 16 / 8 / 4 / 1
+ * CTAs (0 = not tried); [11] reserved. */
+int mllp_lp_geometry(mllp_lp_t lp, double *out12);
+
 /* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */
 int mllp_spmv(mllp_lp_t lp, int trans, const double *d_in, double *d_out, void *stream);
 

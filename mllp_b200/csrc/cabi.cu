@@ -74,6 +74,7 @@ struct mllp_lp {
     std::vector<void*> mat_allocs;    // device arrays of the two tiled matrices (replaced by the tuning rounds)
     std::vector<void*>* sink = &allocs;
     double tune_ns[2] = {0.0, 0.0};   // measured ns / iteration before and after the tuning rounds
+    double geom_ns[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // geometry search: ns / iteration of grid, cluster 16 / 8 / 4, one CTA, broadcast cluster 16 / 8 / 4 / 1 (0 = not tried)
     int tune_rounds = 0;
     int32_t* d_orderX = nullptr;  // internal position k holds original column order[k]
     int32_t* d_orderY = nullptr;
@@ -256,30 +257,39 @@ static int configure_residency(mllp_lp* lp, const HostMat& HA, const HostMat& HA
                                bool resident)
 {
     const size_t desc_bytes = 16 * ((size_t)HA.max_cta_tiles + (size_t)HAT.max_cta_tiles);
+    const bool bcast = lp->d.sync_mode == SYNC_BCAST;
     // Own entries of the CTA's rows (y, b / x, c) resident in shared memory (parity kernel): only when (nearly) the whole
     // matrix share stays resident next to them (measured: ken-18 -2 %; on osa-60, where they would push matrix steps
-    // out of shared memory, +2 %).
+    // out of shared memory, +2 %).  SYNC_BCAST: always, with the anchors (6 arrays) and the two full vector copies.
     bool own = env_int("MLLP_OWN", 1) != 0 && resident && lp->nranks == 1 && !(lp->flags & MLLP_F_GRAPH_MODE);
-    size_t own_bytes = 16 * ((size_t)((HA.max_cta_rows + 1) & ~1) + (size_t)((HAT.max_cta_rows + 1) & ~1));
-    {
+    const size_t rows_a = (size_t)((HA.max_cta_rows + 1) & ~1), rows_at = (size_t)((HAT.max_cta_rows + 1) & ~1);
+    size_t own_bytes = 16 * (rows_a + rows_at);
+    if (bcast) {
+        own = true;
+        own_bytes = 24 * (rows_a + rows_at) + 8 * ((size_t)((lp->m + 1) & ~1) + (size_t)((lp->n + 1) & ~1));
+    } else {
         const size_t res_cap = (size_t)env_int("MLLP_RES_KB", 140) * 1024;
         const size_t all = 768 * ((size_t)HA.max_cta_steps + (size_t)HAT.max_cta_steps);
         if (env_int("MLLP_OWN", 1) < 2 && all + own_bytes > res_cap + res_cap / 7) own = false;   // MLLP_OWN=2 forces it (dev knob)
     }
     if (!own) own_bytes = 0;
-    lp->d.own_rows_A = own ? (uint32_t)((HA.max_cta_rows + 1) & ~1) : 0u;
-    lp->d.own_rows_AT = own ? (uint32_t)((HAT.max_cta_rows + 1) & ~1) : 0u;
+    lp->d.own_rows_A = own ? (uint32_t)rows_a : 0u;
+    lp->d.own_rows_AT = own ? (uint32_t)rows_at : 0u;
     lp->dyn_smem = desc_bytes + own_bytes;
     lp->d.res_steps_A = 0; lp->d.res_steps_AT = 0;
     if (resident) {
-        const size_t per_cta = (size_t)prop.sharedMemPerMultiprocessor / (size_t)bpsm;
+        const size_t per_cta = (size_t)prop.sharedMemPerMultiprocessor / (size_t)(lp->d.sync_mode == SYNC_GRID ? bpsm : 1);
         size_t budget = std::min<size_t>(per_cta - 1024, (size_t)prop.sharedMemPerBlockOptin);
         budget -= std::min<size_t>(budget, 6144);  // static shared memory of the kernels + slack
+        if (bcast && budget < desc_bytes + own_bytes)
+            return fail(MLLP_E_STATE, "mllp_lp_create: the vector copies of the broadcast geometry do not fit in shared memory");
         budget -= std::min<size_t>(budget, desc_bytes + own_bytes);
         // The gathered vectors are read through L1 (the grid barrier invalidates it), so part of
-        // the SM's 228 KB stays L1: cap the shared-memory share of the matrix.
-        const size_t res_cap = (size_t)env_int("MLLP_RES_KB", 140) * 1024;
-        budget = std::min<size_t>(budget, res_cap > own_bytes ? res_cap - own_bytes : 0);
+        // the SM's 228 KB stays L1: cap the shared-memory share of the matrix.  (SYNC_BCAST gathers from shared memory.)
+        if (!bcast) {
+            const size_t res_cap = (size_t)env_int("MLLP_RES_KB", 140) * 1024;
+            budget = std::min<size_t>(budget, res_cap > own_bytes ? res_cap - own_bytes : 0);
+        }
         // what is left keeps (a prefix of) each CTA's share of A' and A resident
         const size_t cap = budget / 768;
         size_t a = (size_t)HA.max_cta_steps, at = (size_t)HAT.max_cta_steps;
@@ -293,7 +303,12 @@ static int configure_residency(mllp_lp* lp, const HostMat& HA, const HostMat& HA
         lp->dyn_smem = desc_bytes + own_bytes + 768 * (a + at);
     }
     if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(persistent_set_smem(lp->bounds, lp->dyn_smem));
-    if (persistent_max_blocks_per_sm(lp->threads, lp->bounds, lp->dyn_smem) < bpsm)
+    if (lp->d.sync_mode == SYNC_CLUSTER || bcast) {
+        if (persistent_cluster_fits(lp->G, lp->threads, lp->bounds, lp->dyn_smem) != 1)
+            return fail(MLLP_E_STATE, "mllp_lp_create: a cluster of this many CTAs cannot be resident");
+        return 0;
+    }
+    if (persistent_max_blocks_per_sm(lp->threads, lp->bounds, lp->dyn_smem) < (lp->d.sync_mode == SYNC_CTA ? 1 : bpsm))
         return fail(MLLP_E_STATE, "mllp_lp_create: persistent grid does not fit with the chosen shared memory");
     return 0;
 }
@@ -463,16 +478,20 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
         const int64_t len = h_indptr[i + 1] - h_indptr[i];
         if (len > 512) heavy += len;
     }
-    {
-        const int64_t one_round = (int64_t)lp->G * (lp->threads / 32) * 256;
-        bp.max_steps = env_int("MLLP_MAX_STEPS", 2 * heavy >= one_round ? 4 : 8);
-    }
     if (bp.pref_steps < 1) bp.pref_steps = 1;
-    if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
-    if (bp.max_steps > 1024) bp.max_steps = 1024;
     bp.cluster = env_int("MLLP_CLUSTER", 1) != 0;
     bp.cluster_rounds = env_int("MLLP_CLUSTER_ROUNDS", 3);
     bp.contiguous = env_int("MLLP_CONTIGUOUS", 2 * heavy < nnz ? 1 : 0) != 0;
+    auto set_grid = [&](int G) {   // the parameters that depend on the number of CTAs
+        lp->G = G;
+        bp.num_ctas = G;
+        const int64_t one_round = (int64_t)G * (lp->threads / 32) * 256;
+        bp.max_steps = env_int("MLLP_MAX_STEPS", 2 * heavy >= one_round ? 4 : 8);
+        if (bp.max_steps < bp.pref_steps) bp.max_steps = bp.pref_steps;
+        if (bp.max_steps > 1024) bp.max_steps = 1024;
+    };
+    const int G_grid = lp->G;
+    set_grid(G_grid);
 
     int rc = 0;
     try {
@@ -566,10 +585,63 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
         };
         rc = body();
 
+        // Geometry of the persistent kernels (single GPU).  The grid barrier costs ~0.9 us and there are two per
+        // iteration; an LP whose phases are shorter than that runs faster on ONE thread-block cluster (<= 16 SMs,
+        // hardware cluster barrier) or on one CTA.  Candidates are built and timed (48 traced iterations on the zero
+        // state, like the tuning rounds), the fastest is kept.  MLLP_GEOM forces one: 0 grid, 1 one CTA, 2..16 cluster.
+        // The format (row order, dealing) depends on the CTA count, the arithmetic of a row does not: results of
+        // different geometries agree to rounding of the split rows' chunk sums.
+        auto build_geom = [&](int G, int mode) -> int {
+            set_grid(G);
+            lp->d.sync_mode = mode;
+            plan_orders(m, n, h_indptr, h_indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
+            HostMat nA, nAT;
+            build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, nA);
+            build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, nAT);
+            HA = std::move(nA); HAT = std::move(nAT);
+            free_mats(lp);
+            RC_OK(upload_mat(lp, HA, lp->d.A));
+            RC_OK(upload_mat(lp, HAT, lp->d.AT));
+            CUDA_OK(cudaMemcpy(lp->d_orderX, orderX.data(), orderX.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMemcpy(lp->d_orderY, orderY.data(), orderY.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            RC_OK(configure_residency(lp, HA, HAT, prop, bpsm, resident));
+            return 0;
+        };
+        const int tune = env_int("MLLP_TUNE", (flags & MLLP_F_NO_TUNE) ? 0 : 8);
+        if (rc == 0 && nranks == 1 && resident && m > 0 && n > 0) {
+            // candidate code: 0 grid, 1 one CTA, 2..16 cluster of c CTAs, 100 + c the same cluster with broadcast copies
+            auto mode_of = [](int c) { return c == 0 ? SYNC_GRID : c == 1 ? SYNC_CTA : c >= 100 ? SYNC_BCAST : SYNC_CLUSTER; };
+            auto ctas_of = [&](int c) { return c == 0 ? G_grid : c >= 100 ? std::min(c - 100, 16) : std::min(c, 16); };
+            auto select = [&]() -> int {
+                const int forced = env_int("MLLP_GEOM", -1);
+                if (forced == 0) return 0;
+                if (forced > 0) return build_geom(ctas_of(forced), mode_of(forced));
+                if (tune <= 0 || nnz > (int64_t)env_int("MLLP_GEOM_MAX_NNZ", 200000)) return 0;
+                PhaseTimes T;
+                RC_OK(measure_phases(lp, T));
+                double best = T.iter_ns;
+                int best_c = 0, cur = 0;
+                lp->geom_ns[0] = T.iter_ns;
+                const int cands[8] = {16, 8, 4, 1, 116, 108, 104, 101};
+                for (int q = 0; q < 8; ++q) {
+                    const int c = cands[q];
+                    if ((c == 1 || c == 101) && nnz > 30000) continue;
+                    if (c > 1 && c != 101 && persistent_cluster_fits(ctas_of(c), lp->threads, lp->bounds, 0) != 1) continue;
+                    if (build_geom(ctas_of(c), mode_of(c)) != 0) { cur = -1; continue; }   // does not fit: skip the candidate
+                    cur = c;
+                    RC_OK(measure_phases(lp, T));
+                    lp->geom_ns[q + 1] = T.iter_ns;
+                    if (T.iter_ns < 0.97 * best) { best = T.iter_ns; best_c = c; }
+                }
+                if (cur != best_c) RC_OK(build_geom(ctas_of(best_c), mode_of(best_c)));
+                return 0;
+            };
+            rc = select();
+        }
+
         // Tuning rounds (single GPU, persistent kernel): trace a few iterations on the zero state, feed the
         // per-CTA phase times back into the dealing of the regular tiles, rebuild, keep the fastest build.
         // The dealing does not change the summation order inside a row, so results are unaffected.
-        const int tune = env_int("MLLP_TUNE", (flags & MLLP_F_NO_TUNE) ? 0 : 8);
         const bool worth = (int64_t)HA.tiles.size() + (int64_t)HAT.tiles.size() >= 8 * (int64_t)lp->G;
         if (rc == 0 && tune > 0 && nranks == 1 && !(flags & MLLP_F_GRAPH_MODE) && worth) {
             auto tuning = [&]() -> int {
@@ -750,6 +822,15 @@ int mllp_lp_tune_info(mllp_lp_t lp, double* out4)
 {
     if (!lp || !out4) return fail(MLLP_E_INVALID, "mllp_lp_tune_info: null argument");
     out4[0] = lp->tune_ns[0]; out4[1] = lp->tune_ns[1]; out4[2] = (double)lp->tune_rounds; out4[3] = 0.0;
+    return 0;
+}
+
+int mllp_lp_geometry(mllp_lp_t lp, double* out12)
+{
+    if (!lp || !out12) return fail(MLLP_E_INVALID, "mllp_lp_geometry: null argument");
+    out12[0] = (double)lp->d.sync_mode; out12[1] = (double)lp->G;
+    for (int k = 0; k < 9; ++k) out12[2 + k] = lp->geom_ns[k];
+    out12[11] = 0.0;
     return 0;
 }
 

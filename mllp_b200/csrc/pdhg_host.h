@@ -23,6 +23,7 @@ int launch_eval_finalize(const DevLP& lp, int G, double* out, double iters, cuda
 int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s);
 int persistent_set_smem(bool bounds, size_t dyn_smem);
 int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem);
+int persistent_cluster_fits(int ctas, int threads, bool bounds, size_t dyn_smem);
 int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double tau, double sigma,
                            int iters, cudaStream_t s);
 int xchg_set_smem(bool bounds, size_t dyn_smem);

@@ -186,6 +186,7 @@ struct PersistentSmem {
     MatView VA, VAT;
     unsigned long long tag;   // tag of the last polled split-row join (one per phase call)
     double *ys, *bs, *xs, *cs; // own entries of the CTA's regular rows (parity kernel), or null
+    uint32_t used;             // bytes of the dynamic shared memory taken by the two matrix views
 };
 
 // CTA-local row slots of the regular tiles: written into the .split field of the shared-memory copy of
@@ -221,6 +222,7 @@ __device__ __forceinline__ void persistent_setup(const DevLP& lp, unsigned char*
     const uint32_t used = resident_view(lp.A, lp.res_steps_A, base, P.VA);
     const uint32_t used2 = resident_view(lp.AT, lp.res_steps_AT, base + used, P.VAT);
     P.ys = P.bs = P.xs = P.cs = nullptr;
+    P.used = used + used2;
     __syncthreads();
     if (own && lp.own_rows_A + lp.own_rows_AT > 0) {
         P.ys = reinterpret_cast<double*>(base + used + used2);
@@ -265,9 +267,9 @@ __global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double ta
         for (int it = 0; it < iters; ++it) {
             unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 4 : nullptr;
             phase_AT(lp, P, pop, acc);
-            grid_barrier(lp.barrier, target, tr);
+            sync_all(lp, target, tr);
             phase_A(lp, P, dop, acc);
-            grid_barrier(lp.barrier, target, tr ? tr + 2 : nullptr);
+            sync_all(lp, target, tr ? tr + 2 : nullptr);
         }
         copy_own<false>(P.VAT, lp.x, P.xs);   // y was published every iteration
         return;
@@ -277,9 +279,9 @@ __global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double ta
     for (int it = 0; it < iters; ++it) {
         unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 4 : nullptr;
         phase_AT(lp, P, pop, acc);
-        grid_barrier(lp.barrier, target, tr);
+        sync_all(lp, target, tr);
         phase_A(lp, P, dop, acc);
-        grid_barrier(lp.barrier, target, tr ? tr + 2 : nullptr);
+        sync_all(lp, target, tr ? tr + 2 : nullptr);
     }
 }
 
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
     // x0 = x, y0 = y
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < lp.n; k += gridDim.x * blockDim.x) lp.x0[k] = __ldcg(lp.x + k);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < lp.m; k += gridDim.x * blockDim.x) lp.y0[k] = __ldcg(lp.y + k);
-    grid_barrier(lp.barrier, target);
+    sync_all(lp, target);
 
     double w = w0, fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
     int k = 0, it = 0, restarts = 0, converged = 0;
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
             phase_AT(lp, P, op, acc);
             if (need_fpe) cta_reduce_store<1>(acc, redp + (size_t)blockIdx.x * NRED, smem);
         }
-        grid_barrier(lp.barrier, target);
+        sync_all(lp, target);
         {
             DualHalpernOp<BOUNDS> op{lp, sigma, lam};
             double acc[NRED];
@@ -354,11 +356,11 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
         }
         if (check) {
             // KKT at the new iterate needs the complete x and y
-            grid_barrier(lp.barrier, target);
+            sync_all(lp, target);
             eval_phases<BOUNDS>(lp, VA, VAT, lp.red + (size_t)((it & 1) * 4 + RED_EVALP) * RS,
                                 lp.red + (size_t)((it & 1) * 4 + RED_EVALD) * RS, smem);
         }
-        grid_barrier(lp.barrier, target);
+        sync_all(lp, target);
         ++it; ++k;
         if (need_fpe) {
             if (threadIdx.x < 32) {
@@ -394,12 +396,187 @@ __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, d
                 if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
                 for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lp.n; q += gridDim.x * blockDim.x) lp.x0[q] = __ldcg(lp.x + q);
                 for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lp.m; q += gridDim.x * blockDim.x) lp.y0[q] = __ldcg(lp.y + q);
-                grid_barrier(lp.barrier, target);
+                sync_all(lp, target);
                 k = 0; fpe_restart = -1.0; fpe_prev = INFINITY;
                 ++restarts;
             }
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int q = 0; q < 10; ++q) out[q] = kk[q];
+        out[10] = (double)it; out[11] = (double)restarts; out[12] = (double)converged;
+        out[13] = w; out[14] = fpe; out[15] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// SYNC_BCAST kernels: the grid is ONE thread-block cluster.  Dynamic shared memory:
+//   ycopy[m~] | xbcopy[n~] | ys | bs | y0s  (own_rows_A each) | xs | cs | x0s  (own_rows_AT each) | matrix views
+struct ClusterSmem {
+    double *ys, *bs, *y0s, *xs, *cs, *x0s, *ycopy, *xbcopy;
+};
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void cluster_setup(const DevLP& lp, unsigned char* dsm, PersistentSmem& P, ClusterSmem& C, bool anchors)
+{
+    // the copies come first: their shared-memory addresses must be the same in every CTA of the cluster (the matrix
+    // views that follow have CTA-dependent sizes)
+    double* q = reinterpret_cast<double*>(dsm);
+    const uint32_t ra = lp.own_rows_A, rat = lp.own_rows_AT;
+    C.ycopy = q; q += (lp.m + 1) & ~1;
+    C.xbcopy = q; q += (lp.n + 1) & ~1;
+    C.ys = q; q += ra; C.bs = q; q += ra; C.y0s = q; q += ra;
+    C.xs = q; q += rat; C.cs = q; q += rat; C.x0s = q; q += rat;
+    persistent_setup(lp, reinterpret_cast<unsigned char*>(q), P, false);
+    if (threadIdx.x == 0) assign_row_slots(P.VA);
+    if (threadIdx.x == 32) assign_row_slots(P.VAT);
+    __syncthreads();
+    copy_own<true>(P.VA, lp.y, C.ys);
+    copy_own<true>(P.VA, const_cast<double*>(lp.b), C.bs);
+    copy_own<true>(P.VAT, lp.x, C.xs);
+    copy_own<true>(P.VAT, const_cast<double*>(lp.c), C.cs);
+    if (anchors) {
+        copy_own<true>(P.VA, lp.y0, C.y0s);
+        copy_own<true>(P.VAT, lp.x0, C.x0s);
+    }
+    for (int k = threadIdx.x; k < lp.m; k += blockDim.x) C.ycopy[k] = __ldcg(lp.y + k);
+    // every CTA of the cluster has started and initialised its copies before anyone stores into them
+    cluster_barrier();
+}
+
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_pdhg_cluster(DevLP lp, double tau, double sigma, int iters)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    PersistentSmem P;
+    ClusterSmem C;
+    cluster_setup(lp, dsm, P, C, false);
+    const int nctas = (int)gridDim.x;
+    PrimalBcastOp<BOUNDS> pop{lp, tau, C.xs, C.cs, C.ycopy, Bcast{smem_u32(C.xbcopy), nctas}};
+    DualBcastOp<BOUNDS> dop{lp, sigma, C.ys, C.bs, C.xbcopy, Bcast{smem_u32(C.ycopy), nctas}};
+    unsigned target = 0;
+    double acc[NRED];
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 4 : nullptr;
+        phase_AT(lp, P, pop, acc);
+        sync_all(lp, target, tr);
+        phase_A(lp, P, dop, acc);
+        sync_all(lp, target, tr ? tr + 2 : nullptr);
+    }
+    copy_own<false>(P.VAT, lp.x, C.xs);
+    copy_own<false>(P.VA, lp.y, C.ys);
+}
+
+// Solve mode in the SYNC_BCAST geometry: k_solve_persistent's control flow; the iterates reach global memory only
+// for the KKT checks (every check_every iterations), which run on the global-memory evaluation path.
+template <bool BOUNDS>
+__global__ void __launch_bounds__(1024, 1) k_solve_cluster(DevLP lp, int G, double eta, double w0, int max_iters,
+                                                           int check_every, double tol, double* out)
+{
+    __shared__ double smem[32 * NRED];
+    __shared__ double bc[16];
+    extern __shared__ __align__(16) unsigned char dsm[];
+    PersistentSmem P;
+    ClusterSmem C;
+    // x0 = x, y0 = y (global), then the slots are filled from global memory
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < lp.n; k += gridDim.x * blockDim.x) lp.x0[k] = __ldcg(lp.x + k);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < lp.m; k += gridDim.x * blockDim.x) lp.y0[k] = __ldcg(lp.y + k);
+    cluster_barrier();
+    cluster_setup(lp, dsm, P, C, true);
+    const MatView& VA = P.VA;
+    const MatView& VAT = P.VAT;
+    const int nctas = (int)gridDim.x;
+    const Bcast xb{smem_u32(C.xbcopy), nctas}, yb{smem_u32(C.ycopy), nctas};
+    unsigned target = 0;
+    const size_t RS = (size_t)G * NRED;
+
+    double w = w0, fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
+    int k = 0, it = 0, restarts = 0, converged = 0;
+    double kk[10];
+    for (int q = 0; q < 10; ++q) kk[q] = 0.0;
+
+    while (it < max_iters) {
+        const double tau = eta / w, sigma = eta * w;
+        const double lam = (double)(k + 1) / (double)(k + 2);
+        const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iters);
+        const bool need_fpe = check || fpe_restart < 0.0;
+        double* redp = lp.red + (size_t)((it & 1) * 4 + RED_STEPP) * RS;
+        double* redd = lp.red + (size_t)((it & 1) * 4 + RED_STEPD) * RS;
+        {
+            PrimalHalpernBcastOp<BOUNDS> op{lp, tau, lam, C.xs, C.cs, C.x0s, C.ycopy, xb};
+            double acc[NRED];
+            acc[0] = 0.0;
+            phase_AT(lp, P, op, acc);
+            if (need_fpe) cta_reduce_store<1>(acc, redp + (size_t)blockIdx.x * NRED, smem);
+        }
+        sync_all(lp, target);
+        {
+            DualHalpernBcastOp<BOUNDS> op{lp, sigma, lam, C.ys, C.bs, C.y0s, C.xbcopy, yb};
+            double acc[NRED];
+            acc[0] = 0.0;
+            phase_A(lp, P, op, acc);
+            if (need_fpe) cta_reduce_store<1>(acc, redd + (size_t)blockIdx.x * NRED, smem);
+        }
+        if (check) {
+            // KKT at the new iterate: publish x and y, then the global-memory evaluation path
+            copy_own<false>(VAT, lp.x, C.xs);
+            copy_own<false>(VA, lp.y, C.ys);
+            sync_all(lp, target);
+            eval_phases<BOUNDS>(lp, VA, VAT, lp.red + (size_t)((it & 1) * 4 + RED_EVALP) * RS,
+                                lp.red + (size_t)((it & 1) * 4 + RED_EVALD) * RS, smem);
+        }
+        sync_all(lp, target);
+        ++it; ++k;
+        if (need_fpe) {
+            if (threadIdx.x < 32) {
+                const double dx2 = grid_sum(redp, G, 0), dy2 = grid_sum(redd, G, 0);
+                if (threadIdx.x == 0) bc[0] = sqrt(w * dx2 + dy2 / w);
+            }
+            __syncthreads();
+            fpe = bc[0];
+            __syncthreads();
+            if (fpe_restart < 0.0) fpe_restart = fpe;
+        }
+        if (check) {
+            const double* ep = lp.red + (size_t)(((it - 1) & 1) * 4 + RED_EVALP) * RS;
+            const double* ed = lp.red + (size_t)(((it - 1) & 1) * 4 + RED_EVALD) * RS;
+            if (threadIdx.x < 32) {
+                double s[10];
+                kkt_from_sums(ep, ed, G, s);
+                const double ddx2 = grid_sum(ep, G, 5), ddy2 = grid_sum(ed, G, 4);
+                if (threadIdx.x == 0) {
+                    for (int q = 0; q < 10; ++q) bc[q] = s[q];
+                    bc[10] = ddx2; bc[11] = ddy2;
+                }
+            }
+            __syncthreads();
+            for (int q = 0; q < 10; ++q) kk[q] = bc[q];
+            const double ddx = sqrt(bc[10]), ddy = sqrt(bc[11]);
+            __syncthreads();
+            if (kk[8] <= tol) { converged = 1; break; }
+            const bool do_restart = (fpe <= 0.2 * fpe_restart) || (fpe <= 0.8 * fpe_restart && fpe > fpe_prev) ||
+                                    ((double)k >= 0.36 * (double)it);
+            fpe_prev = fpe;
+            if (do_restart) {
+                if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
+                // x and y were published for the check: anchors in global memory and in the slots
+                for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lp.n; q += gridDim.x * blockDim.x) lp.x0[q] = __ldcg(lp.x + q);
+                for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lp.m; q += gridDim.x * blockDim.x) lp.y0[q] = __ldcg(lp.y + q);
+                for (uint32_t q = threadIdx.x; q < lp.own_rows_AT; q += blockDim.x) C.x0s[q] = C.xs[q];
+                for (uint32_t q = threadIdx.x; q < lp.own_rows_A; q += blockDim.x) C.y0s[q] = C.ys[q];
+                sync_all(lp, target);
+                k = 0; fpe_restart = -1.0; fpe_prev = INFINITY;
+                ++restarts;
+            }
+        }
+    }
+    copy_own<false>(VAT, lp.x, C.xs);
+    copy_own<false>(VA, lp.y, C.ys);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int q = 0; q < 10; ++q) out[q] = kk[q];
         out[10] = (double)it; out[11] = (double)restarts; out[12] = (double)converged;
@@ -486,16 +663,20 @@ int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, d
     return (int)cudaGetLastError();
 }
 
-static const void* persistent_fn(bool solve, bool bounds)
+static const void* persistent_fn(bool solve, bool bounds, bool bcast = false)
 {
+    if (bcast) {
+        if (solve) return bounds ? (const void*)k_solve_cluster<true> : (const void*)k_solve_cluster<false>;
+        return bounds ? (const void*)k_pdhg_cluster<true> : (const void*)k_pdhg_cluster<false>;
+    }
     if (solve) return bounds ? (const void*)k_solve_persistent<true> : (const void*)k_solve_persistent<false>;
     return bounds ? (const void*)k_pdhg_persistent<true> : (const void*)k_pdhg_persistent<false>;
 }
 
 int persistent_set_smem(bool bounds, size_t dyn_smem)
 {
-    for (int solve = 0; solve < 2; ++solve) {
-        cudaError_t e = cudaFuncSetAttribute(persistent_fn(solve, bounds), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    for (int k = 0; k < 4; ++k) {
+        cudaError_t e = cudaFuncSetAttribute(persistent_fn(k & 1, bounds, k >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;
@@ -513,14 +694,66 @@ int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem)
     return best;
 }
 
+// One launch of a persistent kernel in the geometry lp.sync_mode names: cooperative grid, ONE cluster of G CTAs, or
+// one CTA.
+static int launch_persistent_fn(const void* fn, int sync_mode, int G, int threads, size_t dyn_smem, void** args, cudaStream_t s)
+{
+    if (sync_mode == SYNC_GRID) {
+        CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, dyn_smem, s));
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = sync_mode == SYNC_CTA ? 1 : G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelExC(&cfg, fn, args));
+    return 0;
+}
+
+// Can ONE cluster of `ctas` CTAs of the persistent kernels (both modes) be resident with this much shared memory?
+// (Clusters above 8 CTAs are non-portable and need the opt-in attribute.)  Returns 1 / 0, or a negative CUDA error.
+int persistent_cluster_fits(int ctas, int threads, bool bounds, size_t dyn_smem)
+{
+    for (int k = 0; k < 4; ++k) {
+        const void* fn = persistent_fn(k & 1, bounds, k >> 1);
+        if (ctas > 8) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ctas);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = dyn_smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ctas;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
+        if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (n < 1) return 0;
+    }
+    return 1;
+}
+
 int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double tau, double sigma,
                            int iters, cudaStream_t s)
 {
-    CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
+    if (lp.sync_mode == SYNC_GRID) CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
     DevLP lpv = lp;
     void* args[] = {&lpv, &tau, &sigma, &iters};
-    CK(cudaLaunchCooperativeKernel(persistent_fn(false, bounds), dim3(G), dim3(threads), args, dyn_smem, s));
-    return 0;
+    return launch_persistent_fn(persistent_fn(false, bounds, lp.sync_mode == SYNC_BCAST), lp.sync_mode, G, threads, dyn_smem, args, s);
 }
 
 int xchg_set_smem(bool bounds, size_t dyn_smem)
@@ -544,11 +777,10 @@ int launch_pdhg_persistent_xchg(const DevLP& lp, const PeerInfo& pi, bool bounds
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
                             int max_iters, int check_every, double tol, double* out, cudaStream_t s)
 {
-    CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
+    if (lp.sync_mode == SYNC_GRID) CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
     DevLP lpv = lp;
     void* args[] = {&lpv, &G, &eta, &w0, &max_iters, &check_every, &tol, &out};
-    CK(cudaLaunchCooperativeKernel(persistent_fn(true, bounds), dim3(G), dim3(threads), args, dyn_smem, s));
-    return 0;
+    return launch_persistent_fn(persistent_fn(true, bounds, lp.sync_mode == SYNC_BCAST), lp.sync_mode, G, threads, dyn_smem, args, s);
 }
 
 }  // namespace mllp

@@ -66,7 +66,15 @@ struct DevLP {
     double* ctrl;       // control block (device doubles): CTRL_* slots
     unsigned long long join_base;  // tags of the polled split-row join start above this value
     unsigned long long* trace;  // dev tool: [iter][cta][4] barrier timestamps, or null
+    int sync_mode;      // how the CTAs of the persistent kernels meet between phases: SYNC_* below
 };
+// SYNC_GRID: cooperative grid of one CTA per SM, counter barrier in global memory (~0.9 us).  SYNC_CLUSTER: the
+// whole grid is ONE thread-block cluster (<= 16 CTAs) and meets on the hardware cluster barrier (~0.2 us): small and
+// mid-size LPs, whose phases are shorter than a grid barrier.  SYNC_CTA: one CTA, __syncthreads().
+// SYNC_BCAST: one cluster whose CTAs each keep a full copy of the two gathered vectors (y, xbar) in shared memory; a row
+// update stores its new entry into every CTA's copy over distributed shared memory, gathers are local LDS and the
+// rows' own entries (x, c, x0 / y, b, y0) stay in shared-memory slots: no global-memory traffic inside the iteration.
+constexpr int SYNC_GRID = 0, SYNC_CLUSTER = 1, SYNC_CTA = 2, SYNC_BCAST = 3;
 
 // Memory policies of the row ops.  GlobalMem: vectors live in global memory and are shared by
 // all CTAs (single-instance path).  SmemMem: vectors are the CTA's own shared-memory copies
@@ -75,6 +83,36 @@ struct GlobalMem {
     static __device__ __forceinline__ double ld_mut(const double* p) { return __ldcg(p); }  // L2-coherent
     static __device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }    // read-only path
     static __device__ __forceinline__ double gather(const double* p) { return __ldca(p); }  // L1, see tile_dot
+};
+// ClusterMem: the gathered vector is this CTA's shared-memory copy (SYNC_BCAST); own entries without a slot (rows of
+// split chunks) stay in global memory.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct ClusterMem {
+    static __device__ __forceinline__ double ld_mut(const double* p) { return __ldcg(p); }
+    static __device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }
+    static __device__ __forceinline__ double gather(const double* p)
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)) : "memory");
+        return v;
+    }
+};
+// One vector entry stored into the copies of all CTAs of the cluster (own copy included).
+struct Bcast {
+    uint32_t base;   // shared-memory address of the copy (the layout is the same in every CTA)
+    int nctas;
+    __device__ __forceinline__ void put(int r, double v) const
+    {
+        const uint32_t a = base + 8u * (uint32_t)r;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (q < nctas) {
+                uint32_t ra;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(q));   // volatile: never speculated for q >= nctas
+                asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+            }
+        }
+    }
 };
 struct SmemMem {
     static __device__ __forceinline__ double ld_mut(const double* p) { return *p; }
@@ -110,6 +148,28 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
         if (trace) trace[1] = global_ns();
     }
     __syncthreads();
+}
+
+// Phase boundary of the persistent kernels (see SYNC_*).  The cluster barrier's release / acquire pair orders the
+// phase's global-memory writes before the other CTAs' reads and invalidates L1 like the acquire poll of the grid
+// barrier does, so the L1-cached gathers stay valid; inside one CTA __syncthreads() gives the same guarantee.
+__device__ __forceinline__ void sync_all(const DevLP& lp, unsigned& target, unsigned long long* trace = nullptr)
+{
+    if (lp.sync_mode == SYNC_GRID) {
+        grid_barrier(lp.barrier, target, trace);
+        return;
+    }
+    if (trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace[0] = global_ns();
+    }
+    if (lp.sync_mode != SYNC_CTA && gridDim.x > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    if (trace && threadIdx.x == 0) trace[1] = global_ns();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -217,6 +277,125 @@ struct DualResOp {
         if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
         lp.y[r] = yn;    // y is the gather vector of the A' phase: always published
         if (slot >= 0) ys[slot] = yn;
+    }
+};
+
+// SYNC_BCAST ops: own entries in shared-memory slots (global memory for rows without a slot), the new entry of the
+// gathered vector goes to every CTA's copy.
+template <bool BOUNDS>
+struct PrimalBcastOp {
+    using Mem = ClusterMem;
+    static constexpr bool kSlots = true;
+    const DevLP& lp;
+    double tau;
+    double* xs;
+    const double* cs;
+    const double* ycopy;
+    Bcast xb;
+    struct Pre { double c, x; };
+    __device__ __forceinline__ const double* vec() const { return ycopy; }
+    __device__ __forceinline__ Pre prefetch(int r, int slot) const
+    {
+        if (slot >= 0) return {cs[slot], xs[slot]};
+        return {Mem::ld_ro(lp.c + r), Mem::ld_mut(lp.x + r)};
+    }
+    __device__ __forceinline__ void row(int r, int slot, double dot, const Pre& p, double*) const
+    {
+        const double g = p.c - dot;
+        double xn = p.x - tau * g;
+        if (BOUNDS) xn = fmin(fmax(xn, Mem::ld_ro(lp.lb + r)), Mem::ld_ro(lp.ub + r));
+        else xn = fmax(xn, 0.0);
+        xb.put(r, 2.0 * xn - p.x);
+        if (slot >= 0) xs[slot] = xn; else lp.x[r] = xn;
+    }
+};
+
+template <bool BOUNDS>
+struct DualBcastOp {
+    using Mem = ClusterMem;
+    static constexpr bool kSlots = true;
+    const DevLP& lp;
+    double sigma;
+    double* ys;
+    const double* bs;
+    const double* xbcopy;
+    Bcast yb;
+    struct Pre { double b, y; };
+    __device__ __forceinline__ const double* vec() const { return xbcopy; }
+    __device__ __forceinline__ Pre prefetch(int r, int slot) const
+    {
+        if (slot >= 0) return {bs[slot], ys[slot]};
+        return {Mem::ld_ro(lp.b + r), Mem::ld_mut(lp.y + r)};
+    }
+    __device__ __forceinline__ void row(int r, int slot, double dot, const Pre& p, double*) const
+    {
+        double yn = p.y + sigma * (p.b - dot);
+        if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
+        yb.put(r, yn);
+        if (slot >= 0) ys[slot] = yn; else lp.y[r] = yn;
+    }
+};
+
+template <bool BOUNDS>
+struct PrimalHalpernBcastOp {
+    using Mem = ClusterMem;
+    static constexpr bool kSlots = true;
+    const DevLP& lp;
+    double tau, lam;
+    double* xs;
+    const double* cs;
+    const double* x0s;
+    const double* ycopy;
+    Bcast xb;
+    struct Pre { double c, x, x0; };
+    __device__ __forceinline__ const double* vec() const { return ycopy; }
+    __device__ __forceinline__ Pre prefetch(int r, int slot) const
+    {
+        if (slot >= 0) return {cs[slot], xs[slot], x0s[slot]};
+        return {Mem::ld_ro(lp.c + r), Mem::ld_mut(lp.x + r), Mem::ld_mut(lp.x0 + r)};
+    }
+    __device__ __forceinline__ void row(int r, int slot, double dot, const Pre& p, double* acc) const
+    {
+        const double g = p.c - dot;
+        double xn = p.x - tau * g;
+        if (BOUNDS) xn = fmin(fmax(xn, Mem::ld_ro(lp.lb + r)), Mem::ld_ro(lp.ub + r));
+        else xn = fmax(xn, 0.0);
+        const double d = xn - p.x;
+        acc[0] += d * d;
+        const double xbv = 2.0 * xn - p.x;
+        xb.put(r, xbv);
+        const double xh = lam * xbv + (1.0 - lam) * p.x0;
+        if (slot >= 0) xs[slot] = xh; else lp.x[r] = xh;
+    }
+};
+
+template <bool BOUNDS>
+struct DualHalpernBcastOp {
+    using Mem = ClusterMem;
+    static constexpr bool kSlots = true;
+    const DevLP& lp;
+    double sigma, lam;
+    double* ys;
+    const double* bs;
+    const double* y0s;
+    const double* xbcopy;
+    Bcast yb;
+    struct Pre { double b, y, y0; };
+    __device__ __forceinline__ const double* vec() const { return xbcopy; }
+    __device__ __forceinline__ Pre prefetch(int r, int slot) const
+    {
+        if (slot >= 0) return {bs[slot], ys[slot], y0s[slot]};
+        return {Mem::ld_ro(lp.b + r), Mem::ld_mut(lp.y + r), Mem::ld_mut(lp.y0 + r)};
+    }
+    __device__ __forceinline__ void row(int r, int slot, double dot, const Pre& p, double* acc) const
+    {
+        double yn = p.y + sigma * (p.b - dot);
+        if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
+        const double d = yn - p.y;
+        acc[0] += d * d;
+        const double yh = lam * (2.0 * yn - p.y) + (1.0 - lam) * p.y0;
+        yb.put(r, yh);
+        if (slot >= 0) ys[slot] = yh; else lp.y[r] = yh;
     }
 };
 

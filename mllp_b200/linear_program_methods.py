@@ -146,6 +146,14 @@ class DeviceLP:
         _cabi.check(_cabi.lib().mllp_lp_tune_info(self.handle, out), "mllp_lp_tune_info")
         return {"ns_per_iter_first": out[0], "ns_per_iter_kept": out[1], "rounds": int(out[2])}
 
+    def geometry(self):
+        """Launch geometry of the persistent kernels (mllp_lp_geometry): cooperative grid, one cluster or one CTA."""
+        out = (ctypes.c_double * 12)()
+        _cabi.check(_cabi.lib().mllp_lp_geometry(self.handle, out), "mllp_lp_geometry")
+        names = ("grid", "cluster16", "cluster8", "cluster4", "cta", "bcast16", "bcast8", "bcast4", "bcast1")
+        return {"mode": ("grid", "cluster", "cta", "bcast")[int(out[0])], "ctas": int(out[1]),
+                "ns_per_iter": {k: out[2 + i] for i, k in enumerate(names) if out[2 + i] > 0}}
+
     def sigma_max(self, iters=50, stream=None):
         """||A||_2 estimate by power iteration on the device (cached)."""
         if self._sigma_max is None:

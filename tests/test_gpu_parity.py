@@ -228,3 +228,86 @@ def test_device_graph_builder_matches_reference_loop(torch_cuda):
         assert torch.equal(g["edge_attr"].cpu(), torch.tensor(A.data, dtype=torch.float).unsqueeze(-1))
         assert torch.equal(g["x_src"].cpu(), torch.tensor(c, dtype=torch.float).unsqueeze(-1))
         assert torch.equal(g["x_tgt"].cpu(), torch.tensor(b, dtype=torch.float).unsqueeze(-1))
+
+
+# Launch geometries of the persistent kernels (mllp_lp_geometry): cooperative grid, one cluster (hardware cluster
+# barrier), one CTA, and the broadcast cluster (vector copies in distributed shared memory).  mllp_lp_create picks
+# one by measurement; here each is forced and held to the same parity bar.
+GEOMS = [("0", "grid"), ("16", "cluster"), ("4", "cluster"), ("1", "cta"), ("116", "bcast"), ("108", "bcast"), ("101", "bcast")]
+
+
+@pytest.mark.parametrize("geom,mode", GEOMS)
+def test_launch_geometries_parity_and_solve(geom, mode, monkeypatch):
+    monkeypatch.setenv("MLLP_GEOM", geom)
+    # parity mode, standard form
+    A, b, c = D.load_csr("25fv47")
+    m, n = A.shape
+    lp = M.DeviceLP(A, A.data, m, n)
+    assert lp.geometry()["mode"] == mode
+    eta = 0.9 / O.power_iteration(A, 50)
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=500, tau=eta, sigma=eta, handle=lp)
+    xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, 500)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    scal_close(info, O.kkt(A, b, c, xo, yo))
+    # warm start on the same handle continues bitwise
+    _, xa, ya, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=100, tau=eta, sigma=eta, x0=x, y0=y, handle=lp)
+    _, xh, yh, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=50, tau=eta, sigma=eta, x0=x, y0=y, handle=lp)
+    _, xb, yb, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=50, tau=eta, sigma=eta, x0=xh, y0=yh, handle=lp)
+    assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    lp.close()
+    # general form (bounds and row senses)
+    A, b, c = D.load_csr("sc105")
+    m, n = A.shape
+    rng = np.random.default_rng(7)
+    lb = np.where(rng.random(n) < 0.3, -np.inf, rng.uniform(-1, 0, n))
+    ub = np.where(rng.random(n) < 0.3, np.inf, rng.uniform(0.5, 2, n))
+    kind = rng.integers(0, 3, m)
+    ylo, yhi = np.where(kind == 1, 0.0, -np.inf), np.where(kind == 2, 0.0, np.inf)
+    x0, y0 = rng.uniform(0, 0.4, n), np.clip(rng.standard_normal(m), ylo, yhi)
+    eta = 0.9 / O.power_iteration(A, 50)
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=400, tau=eta, sigma=0.5 * eta, lb=lb, ub=ub,
+                                            ylo=ylo, yhi=yhi, x0=x0, y0=y0)
+    xo, yo = O.pdhg_run(A, b, c, x0, y0, eta, 0.5 * eta, 400, lb, ub, ylo, yhi)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    # solve mode: same answer as the oracle's solve loop and HiGHS
+    A, b, c = D.load_csr("afiro")
+    m, n = A.shape
+    obj, x, y, info = M.solve_linear_program(A, A.data, b, c, tol=1e-6, max_iters=400000)
+    assert info["converged"] and abs(obj - HIGHS["afiro"]) <= 1e-4 * (1 + abs(HIGHS["afiro"]))
+    xs, ys, ks, si = O.pdhg_solve(A, b, c, np.zeros(n), np.zeros(m), info["eta"], max_iters=400000, tol=1e-6)
+    assert abs(ks[0] - obj) <= SCAL_TOL * (1 + abs(obj))
+    kk = O.kkt(A, b, c, x, y)
+    assert abs(kk[8] - info["rel_kkt"]) <= 1e-9
+
+
+@pytest.mark.parametrize("geom", ["8", "108"])
+def test_launch_geometries_split_rows(geom, monkeypatch):
+    """rows cut into chunks and rows spanning several CTAs of the cluster (polled join) in the cluster geometries"""
+    monkeypatch.setenv("MLLP_GEOM", geom)
+    rng = np.random.default_rng(11)
+    rows = [sp.random(1, 5000, density=d, random_state=int(10000 * d) + 3, format="csr")
+            for d in (0.0, 0.0004, 0.002, 0.01, 0.05, 0.2, 0.8)]
+    A = sp.vstack(rows * 9).tocsr()
+    A.data[:] = rng.standard_normal(A.nnz)
+    A.sort_indices()
+    m, n = A.shape
+    b, c = rng.standard_normal(m), rng.standard_normal(n)
+    eta = 0.9 / O.power_iteration(A, 50)
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=200, tau=eta, sigma=eta)
+    xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, 200)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    obj, x, y, info = M.solve_linear_program(A, A.data, b, c, tol=1e-30, max_iters=300, check_every=32)
+    xs, ys, ks, si = O.pdhg_solve(A, b, c, np.zeros(n), np.zeros(m), info["eta"], max_iters=300, tol=1e-30, check_every=32)
+    assert rel(x, xs) < 1e-7 and rel(y, ys) < 1e-7
+
+
+def test_geometry_is_chosen_by_measurement():
+    A, b, c = D.load_csr("afiro")
+    lp = M.DeviceLP(A, A.data, *A.shape)
+    g = lp.geometry()
+    assert g["mode"] != "grid" and "grid" in g["ns_per_iter"] and min(g["ns_per_iter"].values()) < g["ns_per_iter"]["grid"]
+    lp.close()
+    A, b, c = D.load_csr("ken-18")       # too large for one cluster: not even tried
+    lp = M.DeviceLP(A, A.data, *A.shape)
+    assert lp.geometry()["mode"] == "grid" and lp.geometry()["ctas"] >= 148
+    lp.close()
