@@ -236,25 +236,47 @@ int mllp_batch_solve(mllp_batch_t bt, double *d_x, double *d_y, const double *d_
 /*
  * Bipartite message passing over the LP's nonzeros: the forward pass of the reference's GNNModel
  * (linear_program_methods.py:199-215, :238-251; five torch_geometric TransformerConv layers with heads = 1,
- * 16 channels, edge_dim = 1, root weight and bias, alternating along the rows of A' and of A).  fp32 like the
- * reference.  All pointers are device pointers; CSR arrays are those of the DESTINATION side (rows = destination
- * nodes: A for variable->constraint passes, A' for constraint->variable passes), `d_values` the fp64 coefficients
- * (cast to float per edge, as the reference's edge_attr).
+ * 16 channels, edge_dim = 1, root weight and bias, alternating along the rows of A' and of A, ReLU, Linear(16, 1)).
+ * fp32 like the reference.  All pointers are device pointers.
  *
- * mllp_gnn_project: kv[j][0..15] = Wk h_j + bk, kv[j][16..31] = Wv h_j + bv for the n source nodes
- *                   (h: n x din floats; params = Wk'[din][16] | bk[16] | Wv'[din][16] | bv[16], W' = transposed weight).
- * mllp_gnn_conv:    out_i = sum_j softmax_j(q_i.(k_j + We a_ij) / 4) (v_j + We a_ij) + Ws h_i + bs, optional ReLU
- *                   (params = Wq'[din][16] | bq[16] | Ws'[din][16] | bs[16] | We[16]).  Rows with more than `chunk`
- *                   edges are listed in d_long_rows[nlong]; their chunks are d_items[nitems][3] = (row, first edge,
- *                   end edge), row r owning items d_long_first[r] .. d_long_first[r+1]; d_scratch holds 96 floats per item.
- * mllp_gnn_fc:      out[i] = w . h_i + b   (wb = w[16] | b).
+ * mllp_gnn_side: one direction of the graph as CSR of the DESTINATION side (rows = destination nodes: A' for the
+ * constraint->variable "w2s" passes, A for the variable->constraint "s2w" passes); `values` are the fp64 coefficients
+ * (cast to float per edge, as the reference's edge_attr).  `group` = lanes per destination row (4, 8, 16 or 32; pick
+ * about half the mean row length).  Rows with more than `chunk` edges are listed in long_rows[nlong]; their pieces
+ * are items[nitems][3] = (row, first edge, end edge), row r owning items long_first[r] .. long_first[r+1];
+ * scratch holds 20 floats per item.
  */
-int mllp_gnn_project(int32_t n, const float *d_h, int32_t din, const float *d_params, float *d_kv, void *stream);
-int mllp_gnn_conv(int32_t nd, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
-                  const float *d_hdst, int32_t din, const float *d_kv_src, const float *d_params, float *d_hout,
-                  int32_t relu, int32_t chunk, int32_t nlong, const int32_t *d_long_rows,
-                  const int32_t *d_long_first, int32_t nitems, const int32_t *d_items, float *d_scratch,
-                  void *stream);
+typedef struct mllp_gnn_side {
+    int32_t nd, ns, group, chunk;
+    const int32_t *indptr;
+    const int32_t *indices;
+    const double *values;
+    int32_t nlong, nitems;
+    const int32_t *long_rows;
+    const int32_t *long_first;
+    const int32_t *items;
+    float *scratch;
+} mllp_gnn_side;
+
+/* The whole forward in one call (9 launches, + 2 per conv with long rows): logit per variable into d_out[n].
+ * d_x1[n] = coefs, d_x2[m] = rhs as float32 (the reference's x1 / x2, :100-101).
+ * d_params: per conv, in the order gconv1_w2s, gconv1_s2w, gconv2_w2s, gconv2_s2w, gconv3_w2s, the block
+ *   Wq'[din][16] | bq[16] | Ws'[din][16] | bs[16] | Wk'[din][16] | bk[16] | Wv'[din][16] | bv[16] | We[16]
+ * (W' = transposed lin_*.weight; din = 1 for the first two convs, 16 after), then fc.weight[16] | fc.bias.
+ * d_work: mllp_gnn_workspace_floats(n, m) floats, caller-owned.  Asynchronous on `stream`. */
+int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m);
+int mllp_gnn_forward(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
+                     const float *d_params, float *d_work, float *d_out, void *stream);
+
+/* Building blocks of the forward (exposed for unit parity):
+ * mllp_gnn_project: out[j][0..15] = W1 h_j + b1, out[j][16..31] = W2 h_j + b2 for n nodes
+ *                   (h: n x din floats; params = W1'[din][16] | b1[16] | W2'[din][16] | b2[16]): the {q | skip} rows of
+ *                   the destination nodes (Wq, Ws) or the {k | v} rows of the source nodes (Wk, Wv) of a conv.
+ * mllp_gnn_conv:    out_i = sum_j softmax_j(q_i.(k_j + We a_ij) / 4) (v_j + We a_ij) + skip_i, optional ReLU.
+ * mllp_gnn_fc:      out[i] = w . h_i + b   (wb = w[16] | b). */
+int mllp_gnn_project(int32_t n, const float *d_h, int32_t din, const float *d_params, float *d_out, void *stream);
+int mllp_gnn_conv(const mllp_gnn_side *side, const float *d_qs_dst, const float *d_kv_src, const float *d_we,
+                  float *d_hout, int32_t relu, void *stream);
 int mllp_gnn_fc(int32_t n, const float *d_h, const float *d_wb, float *d_out, void *stream);
 
 #ifdef __cplusplus

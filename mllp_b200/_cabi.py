@@ -50,11 +50,20 @@ SIGNATURES = {
     "mllp_batch_estimate_norm": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
     "mllp_batch_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mllp_batch_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _dbl, _vp, _vp]),
+    "mllp_gnn_workspace_floats": (ctypes.c_int64, [_i32, _i32]),
+    "mllp_gnn_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mllp_gnn_project": (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _vp]),
-    "mllp_gnn_conv": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp,
-                                     _vp, _vp]),
+    "mllp_gnn_conv": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mllp_gnn_fc": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp]),
 }
+
+
+
+class GnnSide(ctypes.Structure):
+    """mllp_gnn_side of include/mllp_b200.h"""
+    _fields_ = [("nd", _i32), ("ns", _i32), ("group", _i32), ("chunk", _i32), ("indptr", _vp), ("indices", _vp), ("values", _vp),
+                ("nlong", _i32), ("nitems", _i32), ("long_rows", _vp), ("long_first", _vp), ("items", _vp), ("scratch", _vp)]
+
 
 _lib = None
 

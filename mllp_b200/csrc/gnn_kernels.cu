@@ -10,12 +10,18 @@
 //     alpha_ij = softmax_j( q_i . (k_j + e_ij) / sqrt(16) )   over the incoming edges j -> i of node i
 //     out_i = sum_j alpha_ij (v_j + e_ij) + Ws x_i + bs
 //
-// fp32, as the reference (dtype=torch.float, :90-91, :100).  One warp owns one destination node (a CSR row):
-// lanes 0-15 carry the key channels, lanes 16-31 the value channels, so ONE coalesced 128-byte load fetches a
-// source node's {k, v}; the softmax is computed online (running max / sum), so every edge is visited once and
-// nothing of size nnz is written.  Rows longer than a chunk (osa-60 has rows of 173 366 edges) are cut into
-// chunks (one warp each) whose partial (max, sum, acc) triples are merged in a fixed order by a second kernel.
-// HBM-bound gather work (hidden = 16): no tensor cores.
+// fp32, as the reference (dtype=torch.float, :90-91, :100).  Structure:
+//   * the four 16-wide linear maps of a layer are node-wise and run first (k_gnn_project*): {q | skip} rows for the
+//     destination nodes, {k | v} rows for the source nodes, 128 B per node;
+//   * the conv kernel gives every destination node (a CSR row) a group of S lanes (S = 4 .. 32, chosen from the
+//     mean row length like the lanes-per-row of the LP format); a lane owns every S-th edge of the row: it gathers
+//     the 64 B key row of the edge's source node, scores it against q, and folds the 64 B value row into its own
+//     online-softmax state (running max, sum, 16 accumulators).  Nothing crosses lanes inside the edge loop and
+//     nothing of size nnz is written; at the row end the group's states are merged (max butterfly, rescale,
+//     reduce-scatter of the 16 channels), so every edge costs ~2 warp instructions instead of a warp-wide reduction;
+//   * rows longer than `chunk` edges (osa-60 has rows of 173 366 edges) are cut into items (one warp each) whose
+//     partial states are merged in a fixed order by a second kernel.
+// HBM/L2-bound gather work (hidden = 16): no tensor cores.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -29,170 +35,280 @@ void set_last_error(const std::string& msg);
 namespace {
 constexpr int C = 16;              // channels
 constexpr unsigned FULLM = 0xffffffffu;
+constexpr int ITEM_FLOATS = 20;    // partial state of one item: m, l, pa, pad, acc[16]
 
-// packed parameters of one TransformerConv as the kernels read them (floats):
-//   conv: Wq[din][16] | bq[16] | Ws[din][16] | bs[16] | We[16]        (input-major: conflict-free, coalesced)
-//   proj: Wk[din][16] | bk[16] | Wv[din][16] | bv[16]
-struct Partial { float m, l, acc; };   // per lane: running max, running sum, accumulator of its channel
+// One lane's online-softmax state over the edges it has seen: running max m, sum l of exp(s - m), the same
+// weights times the edge attribute (pa) and times the value rows (acc).
+struct State {
+    float m, l, pa, acc[C];
+};
 
-// q_c and skip_c of destination node i for this lane's channel, and qe = q . We (all lanes)
-__device__ __forceinline__ void row_prologue(const float* __restrict__ hdst, int din, const float* __restrict__ sp, int i, int c,
-                                             float& q, float& skip, float& qe)
+__device__ __forceinline__ void load16(const float* __restrict__ p, float* r)
 {
-    const float* Wq = sp;
-    const float* bq = sp + din * C;
-    const float* Ws = bq + C;
-    const float* bs = Ws + din * C;
-    const float* We = bs + C;
-    q = bq[c];
-    skip = bs[c];
-    for (int d = 0; d < din; ++d) {
-        const float h = __ldg(hdst + (size_t)i * din + d);
-        q = fmaf(h, Wq[d * C + c], q);
-        skip = fmaf(h, Ws[d * C + c], skip);
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(q + k);
+        r[4 * k] = t.x; r[4 * k + 1] = t.y; r[4 * k + 2] = t.z; r[4 * k + 3] = t.w;
     }
-    float t = q * We[c];
-    for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(FULLM, t, o);   // both halves hold the same 16 channels
-    qe = t;
 }
 
-// edges [e0, e1) of one destination node, online softmax.  Lanes < 16: key channel c, lanes >= 16: value channel c.
-__device__ __forceinline__ Partial edge_loop(const int32_t* __restrict__ indices, const double* __restrict__ values,
-                                             const float* __restrict__ kv, int e0, int e1, float q, float qe, float we, int lane)
+// fold one edge (score s, attribute a, value row v) into the lane's state
+__device__ __forceinline__ void fold(State& st, float s, float a, const float* v)
 {
-    Partial P{-INFINITY, 0.0f, 0.0f};
-    for (int base = e0; base < e1; base += 32) {
-        const int e = base + lane;
-        const int j_l = e < e1 ? __ldg(indices + e) : 0;
-        const float a_l = e < e1 ? (float)__ldg(values + e) : 0.0f;   // edge_attr = float32(a_ij), as the reference casts it
-        const int cnt = min(32, e1 - base);
-        // the {k, v} rows of up to 4 edges are in flight together
-        for (int u0 = 0; u0 < cnt; u0 += 4) {
-            float x[4], a[4];
+    if (s > st.m) {   // new maximum: rescale what was accumulated (rare after the first edges)
+        const float sc = __expf(st.m - s);   // exp(-inf) = 0 on the first edge
+        st.l *= sc; st.pa *= sc;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int src = __shfl_sync(FULLM, j_l, (u0 + u) & 31);
-                a[u] = __shfl_sync(FULLM, a_l, (u0 + u) & 31);
-                x[u] = u0 + u < cnt ? __ldg(kv + (size_t)src * 32 + lane) : 0.0f;
-            }
+        for (int c = 0; c < C; ++c) st.acc[c] *= sc;
+        st.m = s;
+    }
+    const float p = __expf(s - st.m);
+    st.l += p;
+    st.pa = fmaf(p, a, st.pa);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (u0 + u >= cnt) break;
-                float t = lane < 16 ? q * x[u] : 0.0f;
-                for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(FULLM, t, o);
-                const float s = (__shfl_sync(FULLM, t, 0) + a[u] * qe) * 0.25f;   // / sqrt(16)
-                const float mn = fmaxf(P.m, s);
-                const float sc = expf(P.m - mn);   // exp(-inf) = 0 on the first edge
-                const float p = expf(s - mn);
-                P.l = P.l * sc + p;
-                P.acc = P.acc * sc + p * (x[u] + a[u] * we);
-                P.m = mn;
+    for (int c = 0; c < C; ++c) st.acc[c] = fmaf(p, v[c], st.acc[c]);
+}
+
+// edges [e0, e1) of one destination node, strided over the S lanes of its group (lane `gl` of the group); two
+// edges per lane are in flight together
+template <int S>
+__device__ __forceinline__ void edge_loop(const int32_t* __restrict__ indices, const double* __restrict__ values,
+                                          const float* __restrict__ kv, int e0, int e1, int gl, const float* q, float qe, State& st)
+{
+    for (int e = e0 + gl; e < e1; e += 2 * S) {
+        const int eb = e + S;
+        const bool two = eb < e1;
+        const int ja = __ldg(indices + e);
+        const int jb = two ? __ldg(indices + eb) : ja;
+        const float aa = (float)__ldg(values + e);     // edge_attr = float32(a_ij), as the reference casts it
+        const float ab = two ? (float)__ldg(values + eb) : 0.0f;
+        float ka[C], kb[C], va[C], vb[C];
+        load16(kv + (size_t)ja * 32, ka);
+        load16(kv + (size_t)jb * 32, kb);
+        load16(kv + (size_t)ja * 32 + C, va);
+        load16(kv + (size_t)jb * 32 + C, vb);
+        float sa = aa * qe, sb = ab * qe;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { sa = fmaf(q[c], ka[c], sa); sb = fmaf(q[c], kb[c], sb); }
+        fold(st, sa * 0.25f, aa, va);   // / sqrt(16)
+        if (two) fold(st, sb * 0.25f, ab, vb);
+    }
+}
+
+// Merge the states of the S lanes of a group.  On return lane `gl` holds, in acc[0 .. n), the group's sums of the
+// n = max(16 / S, 1) channels starting at `cbase`; l and pa are the group's sums in every lane.
+template <int S>
+__device__ __forceinline__ int merge_group(State& st, int gl, int& cbase)
+{
+    float M = st.m;
+#pragma unroll
+    for (int o = S / 2; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULLM, M, o));
+    const float sc = st.m == -INFINITY ? 0.0f : __expf(st.m - M);   // a lane that saw no edge contributes nothing
+    st.l *= sc; st.pa *= sc;
+#pragma unroll
+    for (int c = 0; c < C; ++c) st.acc[c] *= sc;
+    st.m = M;
+#pragma unroll
+    for (int o = S / 2; o > 0; o >>= 1) {
+        st.l += __shfl_xor_sync(FULLM, st.l, o);
+        st.pa += __shfl_xor_sync(FULLM, st.pa, o);
+    }
+    // reduce-scatter of the 16 channels: at every level a lane keeps one half of its channels and receives the
+    // partner's sums of that half
+    cbase = 0;
+    int cnt = C;
+#pragma unroll
+    for (int o = S / 2; o > 0; o >>= 1) {
+        if (cnt > 1) {
+            const int half = cnt / 2;
+            const bool upper = (gl & o) != 0;
+#pragma unroll
+            for (int k = 0; k < C / 2; ++k) {
+                if (k < half) {
+                    const float send = upper ? st.acc[k] : st.acc[k + half];
+                    const float keep = upper ? st.acc[k + half] : st.acc[k];
+                    st.acc[k] = keep + __shfl_xor_sync(FULLM, send, o);
+                }
             }
+            cbase += upper ? half : 0;
+            cnt = half;
+        } else {
+            st.acc[0] += __shfl_xor_sync(FULLM, st.acc[0], o);   // S = 32: both lanes of a pair hold the same channel
         }
     }
-    return P;
+    return cnt;
 }
 
-__device__ __forceinline__ void row_epilogue(float* __restrict__ hout, int i, int lane, const Partial& P, float skip, int relu)
+// out_i[c] = acc_c / l + (pa / l) We_c + skip_c  for this lane's channels
+template <int S>
+__device__ __forceinline__ void row_epilogue(float* __restrict__ hout, const float* __restrict__ qs, const float* we, int i, int gl,
+                                             const State& st, int cbase, int cnt, int relu)
 {
-    float o = (P.l > 0.0f ? P.acc / P.l : 0.0f) + skip;   // a node without incoming edges keeps only the root term
-    if (relu) o = fmaxf(o, 0.0f);
-    if (lane >= 16) hout[(size_t)i * C + (lane - 16)] = o;
-}
-
-// rows with at most `chunk` edges: one warp per row
-__global__ void __launch_bounds__(256) k_gnn_conv_rows(int nd, const int32_t* __restrict__ indptr,
-                                                       const int32_t* __restrict__ indices, const double* __restrict__ values,
-                                                       const float* __restrict__ hdst, int din, const float* __restrict__ kv,
-                                                       const float* __restrict__ params, float* __restrict__ hout, int chunk,
-                                                       int relu)
-{
-    extern __shared__ float sp[];
-    const int np = 2 * din * C + 3 * C;
-    for (int k = threadIdx.x; k < np; k += blockDim.x) sp[k] = params[k];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, c = lane & 15;
-    const float we = sp[2 * din * C + 2 * C + c];
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nd; i += warps) {
-        const int e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
-        if (e1 - e0 > chunk) continue;   // long row: k_gnn_conv_items + k_gnn_conv_merge
-        float q, skip, qe;
-        row_prologue(hdst, din, sp, i, c, q, skip, qe);
-        const Partial P = edge_loop(indices, values, kv, e0, e1, q, qe, we, lane);
-        row_epilogue(hout, i, lane, P, skip, relu);
+    if (S == 32 && (gl & 1)) return;   // the odd lane of a pair holds a copy
+    const float inv = st.l > 0.0f ? 1.0f / st.l : 0.0f;   // a node without incoming edges keeps only the root term
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < cnt) {
+            const int c = cbase + k;
+            float o = fmaf(st.pa * inv, we[c], st.acc[k] * inv) + __ldg(qs + (size_t)i * 32 + C + c);
+            if (relu) o = fmaxf(o, 0.0f);
+            hout[(size_t)i * C + c] = o;
+        }
     }
 }
 
-// long rows: item t = (row, first edge, last edge); one warp per item, partial -> scratch[t][3][32]
-__global__ void __launch_bounds__(256) k_gnn_conv_items(int nitems, const int32_t* __restrict__ items,
-                                                        const int32_t* __restrict__ indices, const double* __restrict__ values,
-                                                        const float* __restrict__ hdst, int din, const float* __restrict__ kv,
-                                                        const float* __restrict__ params, float* __restrict__ scratch)
+__device__ __forceinline__ void state_init(State& st)
 {
-    extern __shared__ float sp[];
-    const int np = 2 * din * C + 3 * C;
-    for (int k = threadIdx.x; k < np; k += blockDim.x) sp[k] = params[k];
+    st.m = -INFINITY; st.l = 0.0f; st.pa = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) st.acc[c] = 0.0f;
+}
+
+// rows with at most `chunk` edges: S lanes per row
+template <int S>
+__global__ void __launch_bounds__(256) k_gnn_conv_rows(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                       const double* __restrict__ values, const float* __restrict__ qs,
+                                                       const float* __restrict__ kv, const float* __restrict__ we_g,
+                                                       float* __restrict__ hout, int chunk, int relu)
+{
+    __shared__ float we[C];
+    if (threadIdx.x < C) we[threadIdx.x] = we_g[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31, c = lane & 15;
-    const float we = sp[2 * din * C + 2 * C + c];
+    const int lane = threadIdx.x & 31, gl = lane & (S - 1);
+    constexpr int RPW = 32 / S;   // rows per warp
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; base < nd; base += warps * RPW) {
+        const int i = base + lane / S;   // warp-uniform trip count: the merges below are warp-wide
+        int e0 = 0, e1 = 0;
+        if (i < nd) { e0 = __ldg(indptr + i); e1 = __ldg(indptr + i + 1); }
+        const bool live = i < nd && e1 - e0 <= chunk;   // long row: k_gnn_conv_items + k_gnn_conv_merge
+        State st;
+        state_init(st);
+        if (live && e1 > e0) {
+            float q[C];
+            load16(qs + (size_t)i * 32, q);
+            float qe = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) qe = fmaf(q[c], we[c], qe);
+            edge_loop<S>(indices, values, kv, e0, e1, gl, q, qe, st);
+        }
+        int cbase;
+        const int cnt = merge_group<S>(st, gl, cbase);
+        if (live) row_epilogue<S>(hout, qs, we, i, gl, st, cbase, cnt, relu);
+    }
+}
+
+// long rows: item t = (row, first edge, end edge); one warp per item, merged partial state -> scratch[t][20]
+__global__ void __launch_bounds__(256) k_gnn_conv_items(int nitems, const int32_t* __restrict__ items, const int32_t* __restrict__ indices,
+                                                        const double* __restrict__ values, const float* __restrict__ qs,
+                                                        const float* __restrict__ kv, const float* __restrict__ we_g,
+                                                        float* __restrict__ scratch)
+{
+    __shared__ float we[C];
+    if (threadIdx.x < C) we[threadIdx.x] = we_g[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nitems; t += warps) {
         const int i = __ldg(items + 3 * t), e0 = __ldg(items + 3 * t + 1), e1 = __ldg(items + 3 * t + 2);
-        float q, skip, qe;
-        row_prologue(hdst, din, sp, i, c, q, skip, qe);
-        const Partial P = edge_loop(indices, values, kv, e0, e1, q, qe, we, lane);
-        float* o = scratch + (size_t)t * 96;
-        o[lane] = P.m; o[32 + lane] = P.l; o[64 + lane] = P.acc;
+        float q[C];
+        load16(qs + (size_t)i * 32, q);
+        float qe = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) qe = fmaf(q[c], we[c], qe);
+        State st;
+        state_init(st);
+        edge_loop<32>(indices, values, kv, e0, e1, lane, q, qe, st);
+        int cbase;
+        merge_group<32>(st, lane, cbase);
+        float* o = scratch + (size_t)t * ITEM_FLOATS;
+        if (lane == 0) { o[0] = st.m; o[1] = st.l; o[2] = st.pa; o[3] = 0.0f; }
+        if (!(lane & 1)) o[4 + cbase] = st.acc[0];
     }
 }
 
-// long rows: merge the partials of row r's items [first[r], first[r+1]) in order, then the epilogue
+// long rows: merge the partial states of row r's items [first[r], first[r+1]) in order (lane c < 16 owns channel c),
+// then the epilogue
 __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t* __restrict__ long_rows,
                                                         const int32_t* __restrict__ first, const float* __restrict__ scratch,
-                                                        const float* __restrict__ hdst, int din, const float* __restrict__ params,
+                                                        const float* __restrict__ qs, const float* __restrict__ we_g,
                                                         float* __restrict__ hout, int relu)
 {
-    extern __shared__ float sp[];
-    const int np = 2 * din * C + 3 * C;
-    for (int k = threadIdx.x; k < np; k += blockDim.x) sp[k] = params[k];
-    __syncthreads();
     const int lane = threadIdx.x & 31, c = lane & 15;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nlong; r += warps) {
         const int i = __ldg(long_rows + r);
-        float q, skip, qe;
-        row_prologue(hdst, din, sp, i, c, q, skip, qe);
-        Partial P{-INFINITY, 0.0f, 0.0f};
+        float m = -INFINITY, l = 0.0f, pa = 0.0f, acc = 0.0f;
         for (int t = __ldg(first + r); t < __ldg(first + r + 1); ++t) {
-            const float* o = scratch + (size_t)t * 96;
-            const float m2 = o[lane], l2 = o[32 + lane], a2 = o[64 + lane];
-            const float mn = fmaxf(P.m, m2);
-            const float s1 = expf(P.m - mn), s2 = expf(m2 - mn);
-            P.l = P.l * s1 + l2 * s2;
-            P.acc = P.acc * s1 + a2 * s2;
-            P.m = mn;
+            const float* o = scratch + (size_t)t * ITEM_FLOATS;
+            const float m2 = o[0], l2 = o[1], pa2 = o[2], a2 = o[4 + c];
+            const float mn = fmaxf(m, m2);
+            const float s1 = m == -INFINITY ? 0.0f : __expf(m - mn), s2 = m2 == -INFINITY ? 0.0f : __expf(m2 - mn);
+            l = l * s1 + l2 * s2;
+            pa = pa * s1 + pa2 * s2;
+            acc = acc * s1 + a2 * s2;
+            m = mn;
         }
-        row_epilogue(hout, i, lane, P, skip, relu);
+        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+        float o = fmaf(pa * inv, __ldg(we_g + c), acc * inv) + __ldg(qs + (size_t)i * 32 + C + c);
+        if (relu) o = fmaxf(o, 0.0f);
+        if (lane < 16) hout[(size_t)i * C + c] = o;
     }
 }
 
-// {k, v} rows of the source nodes for the next conv: kv[j][0..15] = Wk h_j + bk, kv[j][16..31] = Wv h_j + bv
-__global__ void __launch_bounds__(256) k_gnn_project(int n, const float* __restrict__ h, int din, const float* __restrict__ params,
-                                                     float* __restrict__ kv)
+// Node-wise linear maps.  One warp per node; lane l < 16 computes channel l of the first map of a pair, lane
+// l >= 16 channel l - 16 of the second: out[j][0..15] = W1 h_j + b1, out[j][16..31] = W2 h_j + b2, with
+// params = W1'[din][16] | b1[16] | W2'[din][16] | b2[16] (W' = transposed weight: input-major, conflict-free).
+// A node set can feed two pairs at once (its {q | skip} rows as destination of one conv and its {k | v} rows as
+// source of the other conv of the layer), and both node sets of the graph share the launch.
+struct ProjJob {
+    const float* h;        // [n][din]
+    const float* pa;       // first pair of maps, or null
+    float* oa;             // [n][32]
+    const float* pb;       // second pair, or null
+    float* ob;
+    int n;
+};
+
+__global__ void __launch_bounds__(256) k_gnn_project(ProjJob j0, ProjJob j1, int din)
 {
-    extern __shared__ float sp[];
+    extern __shared__ float sp[];   // 4 parameter blocks of np floats
     const int np = 2 * din * C + 2 * C;
-    for (int k = threadIdx.x; k < np; k += blockDim.x) sp[k] = params[k];
+    const float* src[4] = {j0.pa, j0.pb, j1.pa, j1.pb};
+    for (int b = 0; b < 4; ++b)
+        if (src[b])
+            for (int k = threadIdx.x; k < np; k += blockDim.x) sp[b * np + k] = src[b][k];
     __syncthreads();
     const int lane = threadIdx.x & 31, c = lane & 15;
-    const float* W = lane < 16 ? sp : sp + din * C + C;
-    const float* bias = W + din * C;
+    const int woff = lane < 16 ? 0 : din * C + C;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
-        float o = bias[c];
-        for (int d = 0; d < din; ++d) o = fmaf(__ldg(h + (size_t)j * din + d), W[d * C + c], o);
-        kv[(size_t)j * 32 + lane] = o;
+    const int total = j0.n + j1.n;
+    // the node's feature row is fetched by ONE coalesced load (lane d holds h[d], din <= 32) and handed round by
+    // shuffles; the next node's row is in flight while this one is multiplied
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    auto fetch = [&](int ww) -> float {
+        if (ww >= total || lane >= din) return 0.0f;
+        const bool sec = ww >= j0.n;
+        return __ldg((sec ? j1.h : j0.h) + (size_t)(sec ? ww - j0.n : ww) * din + lane);
+    };
+    float hrow = fetch(w);
+    for (; w < total; w += warps) {
+        const float hnext = fetch(w + warps);
+        const bool second = w >= j0.n;
+        const int j = second ? w - j0.n : w;
+        const float* pA = sp + (second ? 2 : 0) * np + woff;
+        const float* pB = pA + np;
+        const bool ha = (second ? j1.pa : j0.pa) != nullptr, hb = (second ? j1.pb : j0.pb) != nullptr;
+        float oa = pA[din * C + c], ob = pB[din * C + c];
+        for (int d = 0; d < din; ++d) {
+            const float h = __shfl_sync(FULLM, hrow, d);
+            oa = fmaf(h, pA[d * C + c], oa);
+            ob = fmaf(h, pB[d * C + c], ob);
+        }
+        if (ha) (second ? j1.oa : j0.oa)[(size_t)j * 32 + lane] = oa;
+        if (hb) (second ? j1.ob : j0.ob)[(size_t)j * 32 + lane] = ob;
+        hrow = hnext;
     }
 }
 
@@ -218,6 +334,49 @@ int grid_for_warps(long long warps_needed)
     const long long blocks = (warps_needed + 7) / 8;
     return (int)(blocks < 1 ? 1 : blocks > 148 * 8 ? 148 * 8 : blocks);   // 8 CTAs of 256 threads per SM
 }
+int cuda_status(const char* what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return gfail((int)e, std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_project(const ProjJob& j0, const ProjJob& j1, int din, cudaStream_t s)
+{
+    if (j0.n + j1.n <= 0) return 0;
+    const size_t smem = 4 * (size_t)(2 * din * C + 2 * C) * sizeof(float);
+    k_gnn_project<<<grid_for_warps(j0.n + j1.n), 256, smem, s>>>(j0, j1, din);
+    return cuda_status("mllp_gnn: projection");
+}
+
+bool side_ok(const mllp_gnn_side* g)
+{
+    if (!g || g->nd < 0 || g->ns < 0 || !g->indptr) return false;
+    if (g->group != 4 && g->group != 8 && g->group != 16 && g->group != 32) return false;
+    if (g->chunk < 32) return false;
+    if (g->nlong > 0 && (!g->long_rows || !g->long_first || !g->items || !g->scratch || g->nitems < g->nlong)) return false;
+    return true;
+}
+
+int launch_conv(const mllp_gnn_side& g, const float* qs, const float* kv, const float* we, float* hout, int relu, cudaStream_t s)
+{
+    if (g.nd == 0) return 0;
+    const int grid = grid_for_warps(((long long)g.nd * g.group + 31) / 32);
+    switch (g.group) {
+        case 4: k_gnn_conv_rows<4><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
+        case 8: k_gnn_conv_rows<8><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
+        case 16: k_gnn_conv_rows<16><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
+        default: k_gnn_conv_rows<32><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
+    }
+    if (g.nlong > 0) {
+        k_gnn_conv_items<<<grid_for_warps(g.nitems), 256, 0, s>>>(g.nitems, g.items, g.indices, g.values, qs, kv, we, g.scratch);
+        k_gnn_conv_merge<<<grid_for_warps(g.nlong), 256, 0, s>>>(g.nlong, g.long_rows, g.long_first, g.scratch, qs, we, hout, relu);
+    }
+    return cuda_status("mllp_gnn: conv");
+}
+
+// floats of one conv's parameter block: Wq'|bq|Ws'|bs | Wk'|bk|Wv'|bv | We
+size_t conv_block(int din) { return 2 * (size_t)(2 * din * C + 2 * C) + C; }
 }  // namespace
 }  // namespace mllp
 
@@ -225,39 +384,18 @@ using namespace mllp;
 
 extern "C" {
 
-int mllp_gnn_project(int32_t n, const float* d_h, int32_t din, const float* d_params, float* d_kv, void* stream)
+int mllp_gnn_project(int32_t n, const float* d_h, int32_t din, const float* d_params, float* d_out, void* stream)
 {
-    if (n < 0 || din < 1 || din > 64 || !d_h || !d_params || !d_kv) return gfail(MLLP_E_INVALID, "mllp_gnn_project: bad argument");
-    if (n == 0) return 0;
-    k_gnn_project<<<grid_for_warps(n), 256, (2 * din * C + 2 * C) * sizeof(float), (cudaStream_t)stream>>>(n, d_h, din, d_params, d_kv);
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return gfail((int)e, std::string("mllp_gnn_project: ") + cudaGetErrorString(e));
-    return 0;
+    if (n < 0 || din < 1 || din > 32 || !d_h || !d_params || !d_out) return gfail(MLLP_E_INVALID, "mllp_gnn_project: bad argument (din must be 1 .. 32)");
+    const ProjJob j0{d_h, d_params, d_out, nullptr, nullptr, n}, j1{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    return launch_project(j0, j1, din, (cudaStream_t)stream);
 }
 
-int mllp_gnn_conv(int32_t nd, const int32_t* d_indptr, const int32_t* d_indices, const double* d_values, const float* d_hdst,
-                  int32_t din, const float* d_kv_src, const float* d_params, float* d_hout, int32_t relu, int32_t chunk,
-                  int32_t nlong, const int32_t* d_long_rows, const int32_t* d_long_first, int32_t nitems, const int32_t* d_items,
-                  float* d_scratch, void* stream)
+int mllp_gnn_conv(const mllp_gnn_side* side, const float* d_qs_dst, const float* d_kv_src, const float* d_we, float* d_hout,
+                  int32_t relu, void* stream)
 {
-    if (nd < 0 || din < 1 || din > 64 || !d_indptr || !d_hdst || !d_kv_src || !d_params || !d_hout || chunk < 32)
-        return gfail(MLLP_E_INVALID, "mllp_gnn_conv: bad argument");
-    if (nlong > 0 && (!d_long_rows || !d_long_first || !d_items || !d_scratch || nitems < nlong))
-        return gfail(MLLP_E_INVALID, "mllp_gnn_conv: long-row tables missing");
-    if (nd == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = (2 * din * C + 3 * C) * sizeof(float);
-    k_gnn_conv_rows<<<grid_for_warps(nd), 256, smem, s>>>(nd, d_indptr, d_indices, d_values, d_hdst, din, d_kv_src, d_params, d_hout,
-                                                          chunk, relu);
-    if (nlong > 0) {
-        k_gnn_conv_items<<<grid_for_warps(nitems), 256, smem, s>>>(nitems, d_items, d_indices, d_values, d_hdst, din, d_kv_src,
-                                                                   d_params, d_scratch);
-        k_gnn_conv_merge<<<grid_for_warps(nlong), 256, smem, s>>>(nlong, d_long_rows, d_long_first, d_scratch, d_hdst, din, d_params,
-                                                                  d_hout, relu);
-    }
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return gfail((int)e, std::string("mllp_gnn_conv: ") + cudaGetErrorString(e));
-    return 0;
+    if (!side_ok(side) || !d_qs_dst || !d_kv_src || !d_we || !d_hout) return gfail(MLLP_E_INVALID, "mllp_gnn_conv: bad argument");
+    return launch_conv(*side, d_qs_dst, d_kv_src, d_we, d_hout, relu, (cudaStream_t)stream);
 }
 
 int mllp_gnn_fc(int32_t n, const float* d_h, const float* d_wb, float* d_out, void* stream)
@@ -265,9 +403,58 @@ int mllp_gnn_fc(int32_t n, const float* d_h, const float* d_wb, float* d_out, vo
     if (n < 0 || !d_h || !d_wb || !d_out) return gfail(MLLP_E_INVALID, "mllp_gnn_fc: bad argument");
     if (n == 0) return 0;
     k_gnn_fc<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_h, d_wb, d_out);
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return gfail((int)e, std::string("mllp_gnn_fc: ") + cudaGetErrorString(e));
-    return 0;
+    return cuda_status("mllp_gnn_fc");
+}
+
+int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m) { return 96 * ((int64_t)n + (int64_t)m) + 64; }
+
+int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                     const float* d_params, float* d_work, float* d_out, void* stream)
+{
+    if (!side_ok(to_var) || !side_ok(to_con) || !d_x1 || !d_x2 || !d_params || !d_work || !d_out)
+        return gfail(MLLP_E_INVALID, "mllp_gnn_forward: bad argument");
+    const int n = to_var->nd, m = to_con->nd;
+    if (to_var->ns != m || to_con->ns != n) return gfail(MLLP_E_INVALID, "mllp_gnn_forward: the two sides do not describe one graph");
+    cudaStream_t s = (cudaStream_t)stream;
+    // workspace: two feature buffers and {q | skip}, {k | v} rows per node set
+    float* h1[2] = {d_work, d_work + (size_t)16 * n};
+    float* qs1 = d_work + (size_t)32 * n;
+    float* kv1 = qs1 + (size_t)32 * n;
+    float* base2 = d_work + (size_t)96 * n;
+    float* h2[2] = {base2, base2 + (size_t)16 * m};
+    float* qs2 = base2 + (size_t)32 * m;
+    float* kv2 = qs2 + (size_t)32 * m;
+    // parameter blocks: gconv1_w2s, gconv1_s2w (din 1), gconv2_w2s, gconv2_s2w, gconv3_w2s (din 16), fc
+    const float* P[5];
+    size_t off = 0;
+    for (int k = 0; k < 5; ++k) { P[k] = d_params + off; off += conv_block(k < 2 ? 1 : C); }
+    const float* fc = d_params + off;
+    auto dstp = [&](int k) { return P[k]; };
+    auto srcp = [&](int k) { return P[k] + (2 * (k < 2 ? 1 : C) * C + 2 * C); };
+    auto wep = [&](int k) { return P[k] + 2 * (2 * (k < 2 ? 1 : C) * C + 2 * C); };
+
+    const float* x1 = d_x1;
+    const float* x2 = d_x2;
+    int rc = 0;
+    for (int layer = 0; layer < 2 && rc == 0; ++layer) {
+        const int kw = 2 * layer, ks = 2 * layer + 1, din = layer == 0 ? 1 : C;
+        // variables: destination of the w2s conv, source of the s2w conv; constraints: the other way round
+        const ProjJob jv{x1, dstp(kw), qs1, srcp(ks), kv1, n}, jc{x2, dstp(ks), qs2, srcp(kw), kv2, m};
+        rc = launch_project(jv, jc, din, s);
+        if (rc == 0) rc = launch_conv(*to_var, qs1, kv2, wep(kw), h1[layer], 1, s);
+        if (rc == 0) rc = launch_conv(*to_con, qs2, kv1, wep(ks), h2[layer], 1, s);
+        x1 = h1[layer]; x2 = h2[layer];
+    }
+    if (rc == 0) {
+        const ProjJob jv{x1, dstp(4), qs1, nullptr, nullptr, n}, jc{x2, nullptr, nullptr, srcp(4), kv2, m};
+        rc = launch_project(jv, jc, C, s);
+    }
+    if (rc == 0) rc = launch_conv(*to_var, qs1, kv2, wep(4), h1[0], 1, s);
+    if (rc == 0 && n > 0) {
+        k_gnn_fc<<<(n + 255) / 256, 256, 0, s>>>(n, h1[0], fc, d_out);
+        rc = cuda_status("mllp_gnn_forward: fc");
+    }
+    return rc;
 }
 
 }  // extern "C"

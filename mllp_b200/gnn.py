@@ -15,7 +15,7 @@ from .linear_program_methods import _device_index, _torch_stream, csr_from_const
 
 C = 16
 CONVS = ("gconv1_w2s", "gconv1_s2w", "gconv2_w2s", "gconv2_s2w", "gconv3_w2s")
-CHUNK = 2048   # edges per warp before a row is cut into items
+CHUNK = 1024   # edges per warp before a row is cut into items
 
 
 def default_state(seed=0):
@@ -37,7 +37,8 @@ def default_state(seed=0):
 
 
 class _Side:
-    """CSR of one direction (rows = destination nodes) + the long-row tables, on the device."""
+    """CSR of one direction (rows = destination nodes) + the long-row tables, on the device, and the
+    ``mllp_gnn_side`` struct that describes them to the library."""
 
     def __init__(self, M, dev, torch):
         M = M.tocsr()
@@ -53,15 +54,23 @@ class _Side:
         for r in long_rows:
             k = -(-int(lens[r]) // CHUNK)
             step = -(-int(lens[r]) // k)
-            step = (step + 31) & ~31
+            step = (step + 63) & ~63
             for e0 in range(int(ip[r]), int(ip[r + 1]), step):
                 items.append((int(r), e0, min(e0 + step, int(ip[r + 1]))))
             first.append(len(items))
         self.nlong, self.nitems = len(long_rows), len(items)
         z = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32).reshape(-1) if len(a) else np.zeros(1, np.int32), device=dev)
         self.long_rows, self.first, self.items = z(long_rows), z(first), z(items)
-        self.scratch = torch.empty(max(1, 96 * self.nitems), dtype=torch.float32, device=dev)
+        self.scratch = torch.empty(max(1, 20 * self.nitems), dtype=torch.float32, device=dev)
         self.nnz = int(ip[-1])
+        # lanes per destination row: about half the mean length of the rows handled by the row kernel (two edges per
+        # lane are in flight), like the lanes-per-row choice of the LP format
+        reg = lens[(lens > 0) & (lens <= CHUNK)]
+        mean = float(reg.mean()) if reg.size else 1.0
+        self.group = 4 if mean <= 12 else 8 if mean <= 24 else 16 if mean <= 48 else 32
+        self.c = _cabi.GnnSide(self.nd, self.ns, self.group, CHUNK, self.indptr.data_ptr(), self.indices.data_ptr(),
+                               self.values.data_ptr(), self.nlong, self.nitems, self.long_rows.data_ptr(),
+                               self.first.data_ptr(), self.items.data_ptr(), self.scratch.data_ptr())
 
 
 class BipartiteGraph:
@@ -69,6 +78,7 @@ class BipartiteGraph:
     nonzero with attribute a_ij (linear_program_methods.py:89-103), held as CSR of A and of A'."""
 
     def __init__(self, constrs, constr_weights, rhs, coefs, device=0):
+        import ctypes
         import scipy.sparse as sp
         import torch
         self.device = _device_index(device)
@@ -83,13 +93,27 @@ class BipartiteGraph:
         self.to_var = _Side(A.T.tocsr(), dev, torch)  # constraint -> variable ("w2s"): rows of A'
         self.x1 = torch.as_tensor(np.asarray(coefs, dtype=np.float32).reshape(n, 1), device=dev)
         self.x2 = torch.as_tensor(np.asarray(rhs, dtype=np.float32).reshape(m, 1), device=dev)
+        self.work = torch.empty(int(_cabi.lib().mllp_gnn_workspace_floats(n, m)), dtype=torch.float32, device=dev)
+        self._byref = ctypes.byref
+
+
+def pack_conv(state, cv):
+    """(projection block of the destination side Wq'|bq|Ws'|bs, of the source side Wk'|bk|Wv'|bv, We) as float32"""
+    g = lambda part, kind: np.asarray(state["%s.%s.%s" % (cv, part, kind)], dtype=np.float32)
+    din = g("lin_query", "weight").shape[1]
+    for part in ("lin_key", "lin_query", "lin_value", "lin_skip"):
+        if g(part, "weight").shape != (C, din) or g(part, "bias").shape != (C,):
+            raise ValueError("%s.%s: expected weight (16, %d) and bias (16,)" % (cv, part, din))
+    if g("lin_edge", "weight").shape != (C, 1):
+        raise ValueError("%s.lin_edge.weight: expected (16, 1) (edge_dim = 1, no bias)" % cv)
+    blk = lambda a, b: np.concatenate([g(a, "weight").T.reshape(-1), g(a, "bias"), g(b, "weight").T.reshape(-1), g(b, "bias")])
+    return din, blk("lin_query", "lin_skip"), blk("lin_key", "lin_value"), g("lin_edge", "weight").reshape(-1)
 
 
 class GNNModel:
     """Parameters under the reference module's names; ``forward(g)`` = linear_program_methods.py:238-251."""
 
     def __init__(self, state_dict=None, device=0, seed=0):
-        import torch
         self.device = _device_index(device)
         self.load_state_dict(default_state(seed) if state_dict is None else state_dict)
 
@@ -98,60 +122,31 @@ class GNNModel:
         dev = torch.device("cuda", self.device)
         f = lambda a: np.asarray(a.detach().cpu().numpy() if hasattr(a, "detach") else a, dtype=np.float32)
         self.state = {k: f(v) for k, v in state_dict.items()}
-        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32).reshape(-1), device=dev)
-        self.conv_params, self.proj_params, self.din = {}, {}, {}
-        for cv in CONVS:
-            g = lambda part, kind: self.state["%s.%s.%s" % (cv, part, kind)]
-            din = g("lin_query", "weight").shape[1]
+        parts, self.din = [], {}
+        for k, cv in enumerate(CONVS):
+            din, dst, src, we = pack_conv(self.state, cv)
+            if din != (1 if k < 2 else C):
+                raise ValueError("%s: expected %d input channels" % (cv, 1 if k < 2 else C))
             self.din[cv] = din
-            for part in ("lin_key", "lin_query", "lin_value", "lin_skip"):
-                if g(part, "weight").shape != (C, din) or g(part, "bias").shape != (C,):
-                    raise ValueError("%s.%s: expected weight (16, %d) and bias (16,)" % (cv, part, din))
-            if g("lin_edge", "weight").shape != (C, 1):
-                raise ValueError("%s.lin_edge.weight: expected (16, 1) (edge_dim = 1, no bias)" % cv)
-            self.conv_params[cv] = t(np.concatenate([g("lin_query", "weight").T.reshape(-1), g("lin_query", "bias"),
-                                                     g("lin_skip", "weight").T.reshape(-1), g("lin_skip", "bias"),
-                                                     g("lin_edge", "weight").reshape(-1)]))
-            self.proj_params[cv] = t(np.concatenate([g("lin_key", "weight").T.reshape(-1), g("lin_key", "bias"),
-                                                     g("lin_value", "weight").T.reshape(-1), g("lin_value", "bias")]))
+            parts += [dst, src, we]
         if self.state["fc.weight"].shape != (1, C):
             raise ValueError("fc.weight: expected (1, 16)")
-        self.fc = t(np.concatenate([self.state["fc.weight"].reshape(-1), self.state["fc.bias"].reshape(-1)]))
-
-    def _conv(self, cv, side, h_src, h_dst, relu=True):
-        import torch
-        L = _cabi.lib()
-        dev = h_dst.device
-        st = _torch_stream(dev)
-        din = self.din[cv]
-        if h_src.shape != (side.ns, din) or h_dst.shape != (side.nd, din):
-            raise ValueError("%s: feature shapes do not match the graph" % cv)
-        kv = torch.empty(side.ns * 32, dtype=torch.float32, device=dev)
-        _cabi.check(L.mllp_gnn_project(side.ns, h_src.data_ptr(), din, self.proj_params[cv].data_ptr(), kv.data_ptr(), st),
-                    "mllp_gnn_project")
-        out = torch.empty(side.nd, C, dtype=torch.float32, device=dev)
-        _cabi.check(L.mllp_gnn_conv(side.nd, side.indptr.data_ptr(), side.indices.data_ptr(), side.values.data_ptr(),
-                                    h_dst.data_ptr(), din, kv.data_ptr(), self.conv_params[cv].data_ptr(), out.data_ptr(),
-                                    int(relu), CHUNK, side.nlong, side.long_rows.data_ptr(), side.first.data_ptr(),
-                                    side.nitems, side.items.data_ptr(), side.scratch.data_ptr(), st), "mllp_gnn_conv")
-        return out
+        parts += [self.state["fc.weight"].reshape(-1), self.state["fc.bias"].reshape(-1)]
+        self.params = torch.as_tensor(np.ascontiguousarray(np.concatenate(parts), dtype=np.float32), device=dev)
 
     def forward(self, g):
-        """logit per variable, float32 tensor (n,) on the graph's device; no host synchronisation."""
+        """logit per variable, float32 tensor (n,) on the graph's device; one library call, no host synchronisation."""
+        import ctypes
         import torch
         if not isinstance(g, BipartiteGraph):
             raise TypeError("GNNModel.forward expects a BipartiteGraph")   # the reference asserts its type too (:239)
-        x1, x2 = g.x1, g.x2
-        n1 = self._conv("gconv1_w2s", g.to_var, x2, x1)
-        n2 = self._conv("gconv1_s2w", g.to_con, x1, x2)
-        x1, x2 = n1, n2
-        n1 = self._conv("gconv2_w2s", g.to_var, x2, x1)
-        n2 = self._conv("gconv2_s2w", g.to_con, x1, x2)
-        x1, x2 = n1, n2
-        n1 = self._conv("gconv3_w2s", g.to_var, x2, x1)
-        out = torch.empty(g.n, dtype=torch.float32, device=n1.device)
-        _cabi.check(_cabi.lib().mllp_gnn_fc(g.n, n1.data_ptr(), self.fc.data_ptr(), out.data_ptr(), _torch_stream(n1.device)),
-                    "mllp_gnn_fc")
+        if g.device != self.device:
+            raise ValueError("graph and model live on different devices")
+        dev = g.x1.device
+        out = torch.empty(g.n, dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib().mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
+                                                 g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), out.data_ptr(),
+                                                 _torch_stream(dev)), "mllp_gnn_forward")
         return out
 
     __call__ = forward

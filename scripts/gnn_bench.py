@@ -1,9 +1,9 @@
 """Dev tool: time of one GNNModel forward (5 TransformerConv passes + fc) per instance, CUDA events.
 
 Bytes counted per forward (algorithmic, every array touched once per conv): per conv 12 B/nnz (fp64 value + int32
-index) + 4 B/row indptr + 128 B per source node ({k, v} written by the projection, read by the conv) + 4*din B per
-source and destination node (features in) + 64 B per destination node (features out); the gathered {k, v} rows are
-served by L2 (128 B per edge of L2 traffic, reported separately)."""
+index) + 4 B/row indptr + 2 x 128 B per source node ({k | v} written by the projection, read by the conv) + 2 x 128 B
+per destination node ({q | skip}) + 4*din B per source and destination node (features in) + 64 B per destination node
+(features out); the gathered {k | v} rows are served by L2 / L1 (128 B per edge, reported separately)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,7 +15,7 @@ def bytes_per_forward(m, n, nnz):
     tot = 0
     for k, (nd, ns) in enumerate([(n, m), (m, n), (n, m), (m, n), (n, m)]):
         din = 1 if k < 2 else 16
-        tot += 12 * nnz + 4 * (nd + 1) + 2 * 128 * ns + 4 * din * (ns + nd) + 64 * nd
+        tot += 12 * nnz + 4 * (nd + 1) + 2 * 128 * (ns + nd) + 4 * din * (ns + nd) + 64 * nd
     return tot + 64 * n + 4 * n
 
 
@@ -38,8 +38,14 @@ def main(names):
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts))
         B = bytes_per_forward(m, n, A.nnz)
-        print("%-8s m %6d n %6d nnz %7d: %.1f us / forward (cold L2), %.0f GB/s algorithmic, gather traffic %.0f GB/s"
-              % (name, m, n, A.nnz, ms * 1e3, B / ms / 1e6, 5 * 128 * A.nnz / ms / 1e6), flush=True)
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); model(g); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        warm = float(np.median(ts))
+        print("%-8s m %6d n %6d nnz %7d groups %d/%d: %.1f us / forward (L2 flushed; %.1f us warm), %.0f GB/s algorithmic, gather traffic %.0f GB/s"
+              % (name, m, n, A.nnz, g.to_var.group, g.to_con.group, ms * 1e3, warm * 1e3, B / ms / 1e6, 5 * 128 * A.nnz / ms / 1e6), flush=True)
 
 
 if __name__ == "__main__":
