@@ -257,11 +257,14 @@ __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t
     }
 }
 
-// Node-wise linear maps.  One warp per node; lane l < 16 computes channel l of the first map of a pair, lane
-// l >= 16 channel l - 16 of the second: out[j][0..15] = W1 h_j + b1, out[j][16..31] = W2 h_j + b2, with
-// params = W1'[din][16] | b1[16] | W2'[din][16] | b2[16] (W' = transposed weight: input-major, conflict-free).
+// Node-wise linear maps: out[j][0..15] = W1 h_j + b1, out[j][16..31] = W2 h_j + b2, with
+// params = W1'[din][16] | b1[16] | W2'[din][16] | b2[16] (W' = transposed weight: input-major).
 // A node set can feed two pairs at once (its {q | skip} rows as destination of one conv and its {k | v} rows as
 // source of the other conv of the layer), and both node sets of the graph share the launch.
+// k_gnn_project<DIN> (the model's widths, 1 and 16): one THREAD per (node, pair) -- the node's row in registers, the 32
+// outputs in registers, weights read as broadcast LDS.128 (one per 4 FMAs).  k_gnn_project_generic (any din <= 32, unit
+// parity only): one warp per node, lane l < 16 channel l of the first map, lane l >= 16 channel l - 16 of the second.
+// Both accumulate bias first, then inputs in ascending order: bitwise equal.
 struct ProjJob {
     const float* h;        // [n][din]
     const float* pa;       // first pair of maps, or null
@@ -271,7 +274,7 @@ struct ProjJob {
     int n;
 };
 
-__global__ void __launch_bounds__(256) k_gnn_project(ProjJob j0, ProjJob j1, int din)
+__global__ void __launch_bounds__(256) k_gnn_project_generic(ProjJob j0, ProjJob j1, int din)
 {
     extern __shared__ float sp[];   // 4 parameter blocks of np floats
     const int np = 2 * din * C + 2 * C;
@@ -312,6 +315,63 @@ __global__ void __launch_bounds__(256) k_gnn_project(ProjJob j0, ProjJob j1, int
     }
 }
 
+template <int DIN>
+__global__ void __launch_bounds__(128) k_gnn_project(ProjJob j0, ProjJob j1)
+{
+    extern __shared__ __align__(16) float sp[];   // 4 parameter blocks of NP floats
+    constexpr int NP = 2 * DIN * C + 2 * C;
+    const float* src[4] = {j0.pa, j0.pb, j1.pa, j1.pb};
+    for (int b = 0; b < 4; ++b)
+        if (src[b])
+            for (int k = threadIdx.x; k < NP; k += blockDim.x) sp[b * NP + k] = src[b][k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nb0 = (j0.n + 31) >> 5, nb1 = (j1.n + 31) >> 5;
+    const int units = 2 * (nb0 + nb1);   // unit = (node set, block of 32 nodes, pair of maps): one warp, a node per lane
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warps) {
+        const bool second = u >= 2 * nb0;
+        const int uu = second ? u - 2 * nb0 : u;
+        const int pair = uu & 1;
+        const int j = (uu >> 1) * 32 + lane;
+        const float* prm = second ? (pair ? j1.pb : j1.pa) : (pair ? j0.pb : j0.pa);
+        const int n = second ? j1.n : j0.n;
+        if (!prm || j >= n) continue;
+        float* out = (second ? (pair ? j1.ob : j1.oa) : (pair ? j0.ob : j0.oa)) + (size_t)j * 32;
+        const float* hp = (second ? j1.h : j0.h) + (size_t)j * DIN;
+        const float* w = sp + ((second ? 2 : 0) + pair) * NP;
+        float h[DIN];
+        if constexpr (DIN % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < DIN / 4; ++k) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(hp) + k);
+                h[4 * k] = t.x; h[4 * k + 1] = t.y; h[4 * k + 2] = t.z; h[4 * k + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) h[d] = __ldg(hp + d);
+        }
+        float acc[2 * C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { acc[c] = w[DIN * C + c]; acc[C + c] = w[2 * DIN * C + C + c]; }
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) {
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4) {
+                const float4 wa = *reinterpret_cast<const float4*>(w + d * C + 4 * c4);
+                const float4 wb = *reinterpret_cast<const float4*>(w + DIN * C + C + d * C + 4 * c4);
+                acc[4 * c4] = fmaf(h[d], wa.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(h[d], wa.y, acc[4 * c4 + 1]);
+                acc[4 * c4 + 2] = fmaf(h[d], wa.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(h[d], wa.w, acc[4 * c4 + 3]);
+                acc[C + 4 * c4] = fmaf(h[d], wb.x, acc[C + 4 * c4]); acc[C + 4 * c4 + 1] = fmaf(h[d], wb.y, acc[C + 4 * c4 + 1]);
+                acc[C + 4 * c4 + 2] = fmaf(h[d], wb.z, acc[C + 4 * c4 + 2]); acc[C + 4 * c4 + 3] = fmaf(h[d], wb.w, acc[C + 4 * c4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            reinterpret_cast<float4*>(out)[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+    }
+}
+
 // out[i] = w . h_i + b     (the model's final Linear(16, 1))
 __global__ void __launch_bounds__(256) k_gnn_fc(int n, const float* __restrict__ h, const float* __restrict__ wb, float* __restrict__ out)
 {
@@ -345,7 +405,15 @@ int launch_project(const ProjJob& j0, const ProjJob& j1, int din, cudaStream_t s
 {
     if (j0.n + j1.n <= 0) return 0;
     const size_t smem = 4 * (size_t)(2 * din * C + 2 * C) * sizeof(float);
-    k_gnn_project<<<grid_for_warps(j0.n + j1.n), 256, smem, s>>>(j0, j1, din);
+    if (din == 1 || din == C) {
+        const long long units = 2 * ((long long)((j0.n + 31) >> 5) + (long long)((j1.n + 31) >> 5));
+        const long long blocks = (units + 3) / 4;
+        const int grid = (int)(blocks < 1 ? 1 : blocks > 148 * 16 ? 148 * 16 : blocks);   // 16 CTAs of 128 threads per SM
+        if (din == 1) k_gnn_project<1><<<grid, 128, smem, s>>>(j0, j1);
+        else k_gnn_project<C><<<grid, 128, smem, s>>>(j0, j1);
+    } else {
+        k_gnn_project_generic<<<grid_for_warps(j0.n + j1.n), 256, smem, s>>>(j0, j1, din);
+    }
     return cuda_status("mllp_gnn: projection");
 }
 

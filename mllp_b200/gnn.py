@@ -15,7 +15,8 @@ from .linear_program_methods import _device_index, _torch_stream, csr_from_const
 
 C = 16
 CONVS = ("gconv1_w2s", "gconv1_s2w", "gconv2_w2s", "gconv2_s2w", "gconv3_w2s")
-CHUNK = 1024   # edges per warp before a row is cut into items
+CHUNK = 1024   # rows up to this many edges decide the lanes per row
+ITEM = 512     # edges per item (one warp) of the rows that are cut
 
 
 def default_state(seed=0):
@@ -49,10 +50,18 @@ class _Side:
         self.indices = torch.as_tensor(np.ascontiguousarray(M.indices, dtype=np.int32), device=dev)
         self.values = torch.as_tensor(np.ascontiguousarray(M.data, dtype=np.float64), device=dev)
         lens = np.diff(ip)
-        long_rows = np.nonzero(lens > CHUNK)[0].astype(np.int32)
+        # lanes per destination row: about half the mean row length (two edges per lane are in flight), like the
+        # lanes-per-row choice of the LP format.  A group walks rows of up to 16 edges per lane; longer rows (ken-18's
+        # A has 151 rows of ~300 edges among 105 127 rows of ~3: on 4 lanes they were a 100 us tail) are cut into items
+        # of at most ITEM edges, one warp each, whose partial softmax states are merged in a fixed order.
+        reg = lens[(lens > 0) & (lens <= CHUNK)]
+        mean = float(reg.mean()) if reg.size else 1.0
+        self.group = 4 if mean <= 12 else 8 if mean <= 24 else 16 if mean <= 48 else 32
+        self.row_max = max(16 * self.group, 128)   # (two more launches per conv only pay above ~128 edges)
+        long_rows = np.nonzero(lens > self.row_max)[0].astype(np.int32)
         items, first = [], [0]
         for r in long_rows:
-            k = -(-int(lens[r]) // CHUNK)
+            k = -(-int(lens[r]) // ITEM)
             step = -(-int(lens[r]) // k)
             step = (step + 63) & ~63
             for e0 in range(int(ip[r]), int(ip[r + 1]), step):
@@ -63,12 +72,7 @@ class _Side:
         self.long_rows, self.first, self.items = z(long_rows), z(first), z(items)
         self.scratch = torch.empty(max(1, 20 * self.nitems), dtype=torch.float32, device=dev)
         self.nnz = int(ip[-1])
-        # lanes per destination row: about half the mean length of the rows handled by the row kernel (two edges per
-        # lane are in flight), like the lanes-per-row choice of the LP format
-        reg = lens[(lens > 0) & (lens <= CHUNK)]
-        mean = float(reg.mean()) if reg.size else 1.0
-        self.group = 4 if mean <= 12 else 8 if mean <= 24 else 16 if mean <= 48 else 32
-        self.c = _cabi.GnnSide(self.nd, self.ns, self.group, CHUNK, self.indptr.data_ptr(), self.indices.data_ptr(),
+        self.c = _cabi.GnnSide(self.nd, self.ns, self.group, self.row_max, self.indptr.data_ptr(), self.indices.data_ptr(),
                                self.values.data_ptr(), self.nlong, self.nitems, self.long_rows.data_ptr(),
                                self.first.data_ptr(), self.items.data_ptr(), self.scratch.data_ptr())
 

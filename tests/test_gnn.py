@@ -73,14 +73,15 @@ def test_oracle_edge_cases():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["afiro", "sc105", "25fv47", "pilot87", "osa-60"])
+@pytest.mark.parametrize("name", ["afiro", "sc105", "25fv47", "pilot87", "ken-18", "osa-60"])
 def test_gpu_forward_matches_oracle(name):
-    """osa-60 exercises the long-row path (rows of up to 173 366 edges are cut into chunks and merged)"""
+    """pilot87, ken-18 and osa-60 exercise the cut rows (rows of up to 173 366 edges, items merged in a fixed order)"""
     import mllp_b200.gnn as GN
     A, b, c = D.load_csr(name)
     st = G.init_state(5)
     g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c)
-    assert (g.to_con.nlong > 0) == (np.diff(A.indptr).max() > GN.CHUNK)
+    assert (g.to_con.nlong > 0) == (np.diff(A.indptr).max() > g.to_con.row_max)
+    assert name not in ("pilot87", "ken-18", "osa-60") or g.to_con.nlong > 0   # rows of 384, 325 and 173 366 edges
     model = GN.GNNModel(st)
     out = model(g)
     assert out.shape == (A.shape[1],) and out.is_cuda and out.dtype.is_floating_point
@@ -106,3 +107,24 @@ def test_gpu_forward_edge_cases_and_errors():
         GN.GNNModel(bad)
     # default parameters load and run
     assert np.all(np.isfinite(GN.GNNModel(seed=2)(g).cpu().numpy()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("din", [1, 5, 16, 32])
+def test_gpu_projection_kernels(din):
+    """mllp_gnn_project: the thread-per-node kernels (din = 1, 16: the model's widths) and the generic warp-per-node
+    kernel against numpy; both accumulate bias first, then the inputs in ascending order."""
+    import torch
+    from mllp_b200 import _cabi
+    rng = np.random.default_rng(din)
+    n = 1000 + din   # not a multiple of 32
+    h = rng.standard_normal((n, din)).astype(np.float32)
+    W1, W2 = rng.standard_normal((16, din)).astype(np.float32), rng.standard_normal((16, din)).astype(np.float32)
+    b1, b2 = rng.standard_normal(16).astype(np.float32), rng.standard_normal(16).astype(np.float32)
+    params = np.concatenate([W1.T.reshape(-1), b1, W2.T.reshape(-1), b2]).astype(np.float32)
+    dh, dp = torch.as_tensor(h, device="cuda"), torch.as_tensor(params, device="cuda")
+    out = torch.full((n, 32), float("nan"), dtype=torch.float32, device="cuda")
+    _cabi.check(_cabi.lib().mllp_gnn_project(n, dh.data_ptr(), din, dp.data_ptr(), out.data_ptr(), None), "mllp_gnn_project")
+    torch.cuda.synchronize()
+    ref = np.concatenate([h.astype(np.float64) @ W1.T.astype(np.float64) + b1, h.astype(np.float64) @ W2.T.astype(np.float64) + b2], axis=1)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
