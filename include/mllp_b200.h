@@ -244,7 +244,7 @@ int mllp_batch_solve(mllp_batch_t bt, double *d_x, double *d_y, const double *d_
  * (cast to float per edge, as the reference's edge_attr).  `group` = lanes per destination row (4, 8, 16 or 32; pick
  * about half the mean row length).  Rows with more than `chunk` edges are listed in long_rows[nlong]; their pieces
  * are items[nitems][3] = (row, first edge, end edge), row r owning items long_first[r] .. long_first[r+1];
- * scratch holds 20 floats per item.
+ * scratch holds 20 floats per item (16-byte aligned).
  */
 typedef struct mllp_gnn_side {
     int32_t nd, ns, group, chunk;
@@ -258,26 +258,27 @@ typedef struct mllp_gnn_side {
     float *scratch;
 } mllp_gnn_side;
 
-/* The whole forward in one call (9 launches, + 2 per conv with long rows): logit per variable into d_out[n].
- * d_x1[n] = coefs, d_x2[m] = rhs as float32 (the reference's x1 / x2, :100-101).
- * d_params: per conv, in the order gconv1_w2s, gconv1_s2w, gconv2_w2s, gconv2_s2w, gconv3_w2s, the block
- *   Wq'[din][16] | bq[16] | Ws'[din][16] | bs[16] | Wk'[din][16] | bk[16] | Wv'[din][16] | bv[16] | We[16]
- * (W' = transposed lin_*.weight; din = 1 for the first two convs, 16 after), then fc.weight[16] | fc.bias.
- * d_work: mllp_gnn_workspace_floats(n, m) floats, caller-owned.  Asynchronous on `stream`. */
+/* The layer is evaluated without materialising query / key / value rows (see mllp_b200/csrc/gnn_kernels.cu): an edge
+ * gathers the feature row of its source node, the dense maps are applied once per destination node.  Parameter block
+ * of one conv with din input channels (1 or 16), mllp_gnn_conv_param_floats(din) floats, formed on the host from the
+ * module's weights (mllp_b200/gnn.py: pack_conv):
+ *   MQ[din][din] = (Wq' Wk) / 4 | vq[din] = (Wk' bq) / 4 | wq[din] = (Wq' We) / 4 | sq = (We . bq) / 4 | pad to 4 floats |
+ *   Wv'[din][16] | bv[16] | Ws'[din][16] | bs[16] | We[16]            (W' = transposed lin_*.weight, 1/4 = 1/sqrt(16))
+ *
+ * mllp_gnn_forward: the whole forward in one call (5 launches, + 2 per conv with cut rows): logit per variable into
+ * d_out[n].  d_x1[n] = coefs, d_x2[m] = rhs as float32 (the reference's x1 / x2, :100-101).  d_params: the blocks of
+ * gconv1_w2s, gconv1_s2w (din 1), gconv2_w2s, gconv2_s2w, gconv3_w2s (din 16), then fc.weight[16] | fc.bias (the final
+ * Linear(16, 1) is folded into the last conv).  d_work: mllp_gnn_workspace_floats(n, m) floats, caller-owned, 16-byte
+ * aligned.  Asynchronous on `stream`. */
+int64_t mllp_gnn_conv_param_floats(int32_t din);
 int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m);
 int mllp_gnn_forward(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
                      const float *d_params, float *d_work, float *d_out, void *stream);
 
-/* Building blocks of the forward (exposed for unit parity):
- * mllp_gnn_project: out[j][0..15] = W1 h_j + b1, out[j][16..31] = W2 h_j + b2 for n nodes
- *                   (h: n x din floats; params = W1'[din][16] | b1[16] | W2'[din][16] | b2[16]): the {q | skip} rows of
- *                   the destination nodes (Wq, Ws) or the {k | v} rows of the source nodes (Wk, Wv) of a conv.
- * mllp_gnn_conv:    out_i = sum_j softmax_j(q_i.(k_j + We a_ij) / 4) (v_j + We a_ij) + skip_i, optional ReLU.
- * mllp_gnn_fc:      out[i] = w . h_i + b   (wb = w[16] | b). */
-int mllp_gnn_project(int32_t n, const float *d_h, int32_t din, const float *d_params, float *d_out, void *stream);
-int mllp_gnn_conv(const mllp_gnn_side *side, const float *d_qs_dst, const float *d_kv_src, const float *d_we,
+/* One layer (exposed for unit parity): d_hout[nd][16] = [relu] TransformerConv(d_hsrc[ns][din] -> d_hdst[nd][din]) along
+ * `side`, d_params = the conv's block as above. */
+int mllp_gnn_conv(const mllp_gnn_side *side, int32_t din, const float *d_hdst, const float *d_hsrc, const float *d_params,
                   float *d_hout, int32_t relu, void *stream);
-int mllp_gnn_fc(int32_t n, const float *d_h, const float *d_wb, float *d_out, void *stream);
 
 #ifdef __cplusplus
 }

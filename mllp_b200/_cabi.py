@@ -52,9 +52,8 @@ SIGNATURES = {
     "mllp_batch_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _dbl, _vp, _vp]),
     "mllp_gnn_workspace_floats": (ctypes.c_int64, [_i32, _i32]),
     "mllp_gnn_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "mllp_gnn_project": (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _vp]),
-    "mllp_gnn_conv": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "mllp_gnn_fc": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp]),
+    "mllp_gnn_conv_param_floats": (ctypes.c_int64, [_i32]),
+    "mllp_gnn_conv": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
 }
 
 

@@ -10,17 +10,25 @@
 //     alpha_ij = softmax_j( q_i . (k_j + e_ij) / sqrt(16) )   over the incoming edges j -> i of node i
 //     out_i = sum_j alpha_ij (v_j + e_ij) + Ws x_i + bs
 //
-// fp32, as the reference (dtype=torch.float, :90-91, :100).  Structure:
-//   * the four 16-wide linear maps of a layer are node-wise and run first (k_gnn_project*): {q | skip} rows for the
-//     destination nodes, {k | v} rows for the source nodes, 128 B per node;
-//   * the conv kernel gives every destination node (a CSR row) a group of S lanes (S = 4 .. 32, chosen from the
-//     mean row length like the lanes-per-row of the LP format); a lane owns every S-th edge of the row: it gathers
-//     the 64 B key row of the edge's source node, scores it against q, and folds the 64 B value row into its own
-//     online-softmax state (running max, sum, 16 accumulators).  Nothing crosses lanes inside the edge loop and
-//     nothing of size nnz is written; at the row end the group's states are merged (max butterfly, rescale,
-//     reduce-scatter of the 16 channels), so every edge costs ~2 warp instructions instead of a warp-wide reduction;
-//   * rows longer than `chunk` edges (osa-60 has rows of 173 366 edges) are cut into items (one warp each) whose
-//     partial states are merged in a fixed order by a second kernel.
+// fp32, as the reference (dtype=torch.float, :90-91, :100).  The layer is evaluated WITHOUT materialising q, k or v:
+//
+//     q_i . k_j = (Wk' q_i) . x_j + q_i . bk        the second term is the same for all edges of i: it cancels in
+//                                                   the softmax, so the score of an edge is  qt_i . x_j + a_ij qe_i
+//                                                   with qt_i = Wk'(Wq x_i + bq) / 4,  qe_i = We . (Wq x_i + bq) / 4
+//     sum_j alpha_ij v_j = Wv (sum_j alpha_ij x_j) + bv
+//
+// so an edge gathers ONE feature row of its source node (64 B for 16 channels, 4 B in the first layer, instead of a
+// 128 B {k | v} row), costs din + din FMAs, and the four dense maps are applied once per destination node in the
+// prologue / epilogue of its row (din x din and 2 x din x 16 / lanes FMAs): no projection kernels, nothing of size
+// nodes x 32 or nnz is written.  The products Wq'Wk, Wk'bq, Wq'We are formed on the host (mllp_b200/gnn.py, float64,
+// rounded once).  Structure:
+//   * every destination node (a CSR row) has a group of S lanes (S = 4 .. 32, chosen from the mean row length like
+//     the lanes-per-row of the LP format); a lane owns every S-th edge of the row and folds it into its own
+//     online-softmax state (running max, sum, din accumulators), two edges in flight; at the row end the group's
+//     states are merged by a butterfly all-reduce and every lane finishes 16 / S output channels;
+//   * rows longer than `chunk` edges (osa-60 has rows of 173 366 edges, ken-18 151 rows of ~300 among 105 127 of ~3)
+//     are cut into items (one warp each) whose partial states are merged in a fixed order by a second kernel;
+//   * the final Linear(16, 1) is folded into the epilogue of the last conv.
 // HBM/L2-bound gather work (hidden = 16): no tensor cores.
 #include <cuda_runtime.h>
 
@@ -37,44 +45,96 @@ constexpr int C = 16;              // channels
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr int ITEM_FLOATS = 20;    // partial state of one item: m, l, pa, pad, acc[16]
 
-// One lane's online-softmax state over the edges it has seen: running max m, sum l of exp(s - m), the same
-// weights times the edge attribute (pa) and times the value rows (acc).
-struct State {
-    float m, l, pa, acc[C];
+// Parameter block of one conv (floats), see conv_offsets():
+//   MQ[din][din] (input-major: qt[o] += x[i] MQ[i][o]) | vq[din] | wq[din] | sq | pad to 4 |
+//   Wv'[din][16] | bv[16] | Ws'[din][16] | bs[16] | We[16]
+template <int DIN>
+struct Off {
+    static constexpr int mq = 0, vq = DIN * DIN, wq = vq + DIN, sq = wq + DIN;
+    static constexpr int wv = (sq + 1 + 3) & ~3, bv = wv + DIN * C, ws = bv + C, bs = ws + DIN * C, we = bs + C, total = we + C;
 };
 
-__device__ __forceinline__ void load16(const float* __restrict__ p, float* r)
+// One lane's online-softmax state over the edges it has seen: running max m, sum l of exp(s - m), the same
+// weights times the edge attribute (pa) and times the source feature rows (acc).
+template <int DIN>
+struct State {
+    float m, l, pa, acc[DIN];
+};
+
+template <int DIN>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float* r)
 {
-    const float4* q = reinterpret_cast<const float4*>(p);
+    if constexpr (DIN % 4 == 0) {
+        const float4* q = reinterpret_cast<const float4*>(p);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float4 t = __ldg(q + k);
-        r[4 * k] = t.x; r[4 * k + 1] = t.y; r[4 * k + 2] = t.z; r[4 * k + 3] = t.w;
+        for (int k = 0; k < DIN / 4; ++k) {
+            const float4 t = __ldg(q + k);
+            r[4 * k] = t.x; r[4 * k + 1] = t.y; r[4 * k + 2] = t.z; r[4 * k + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) r[d] = __ldg(p + d);
     }
 }
 
-// fold one edge (score s, attribute a, value row v) into the lane's state
-__device__ __forceinline__ void fold(State& st, float s, float a, const float* v)
+template <int DIN>
+__device__ __forceinline__ void state_init(State<DIN>& st)
+{
+    st.m = -INFINITY; st.l = 0.0f; st.pa = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DIN; ++d) st.acc[d] = 0.0f;
+}
+
+// fold one edge (score s, attribute a, source row x) into the lane's state
+template <int DIN>
+__device__ __forceinline__ void fold(State<DIN>& st, float s, float a, const float* x)
 {
     if (s > st.m) {   // new maximum: rescale what was accumulated (rare after the first edges)
         const float sc = __expf(st.m - s);   // exp(-inf) = 0 on the first edge
         st.l *= sc; st.pa *= sc;
 #pragma unroll
-        for (int c = 0; c < C; ++c) st.acc[c] *= sc;
+        for (int d = 0; d < DIN; ++d) st.acc[d] *= sc;
         st.m = s;
     }
     const float p = __expf(s - st.m);
     st.l += p;
     st.pa = fmaf(p, a, st.pa);
 #pragma unroll
-    for (int c = 0; c < C; ++c) st.acc[c] = fmaf(p, v[c], st.acc[c]);
+    for (int d = 0; d < DIN; ++d) st.acc[d] = fmaf(p, x[d], st.acc[d]);
+}
+
+// qt = (Wk'(Wq x + bq)) / 4 and qe = (We . (Wq x + bq)) / 4 of a destination node with feature row x
+template <int DIN>
+__device__ __forceinline__ void dst_prologue(const float* __restrict__ prm, const float* x, float* qt, float& qe)
+{
+    using O = Off<DIN>;
+    qe = prm[O::sq];
+#pragma unroll
+    for (int d = 0; d < DIN; ++d) { qt[d] = prm[O::vq + d]; qe = fmaf(x[d], prm[O::wq + d], qe); }
+    if constexpr (DIN % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < DIN; ++i) {
+#pragma unroll
+            for (int o4 = 0; o4 < DIN / 4; ++o4) {
+                const float4 w = *reinterpret_cast<const float4*>(prm + O::mq + i * DIN + 4 * o4);
+                qt[4 * o4] = fmaf(x[i], w.x, qt[4 * o4]); qt[4 * o4 + 1] = fmaf(x[i], w.y, qt[4 * o4 + 1]);
+                qt[4 * o4 + 2] = fmaf(x[i], w.z, qt[4 * o4 + 2]); qt[4 * o4 + 3] = fmaf(x[i], w.w, qt[4 * o4 + 3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < DIN; ++i)
+#pragma unroll
+            for (int o = 0; o < DIN; ++o) qt[o] = fmaf(x[i], prm[O::mq + i * DIN + o], qt[o]);
+    }
 }
 
 // edges [e0, e1) of one destination node, strided over the S lanes of its group (lane `gl` of the group); two
 // edges per lane are in flight together
-template <int S>
+template <int S, int DIN>
 __device__ __forceinline__ void edge_loop(const int32_t* __restrict__ indices, const double* __restrict__ values,
-                                          const float* __restrict__ kv, int e0, int e1, int gl, const float* q, float qe, State& st)
+                                          const float* __restrict__ hsrc, int e0, int e1, int gl, const float* qt, float qe,
+                                          State<DIN>& st)
 {
     for (int e = e0 + gl; e < e1; e += 2 * S) {
         const int eb = e + S;
@@ -83,23 +143,20 @@ __device__ __forceinline__ void edge_loop(const int32_t* __restrict__ indices, c
         const int jb = two ? __ldg(indices + eb) : ja;
         const float aa = (float)__ldg(values + e);     // edge_attr = float32(a_ij), as the reference casts it
         const float ab = two ? (float)__ldg(values + eb) : 0.0f;
-        float ka[C], kb[C], va[C], vb[C];
-        load16(kv + (size_t)ja * 32, ka);
-        load16(kv + (size_t)jb * 32, kb);
-        load16(kv + (size_t)ja * 32 + C, va);
-        load16(kv + (size_t)jb * 32 + C, vb);
+        float xa[DIN], xb[DIN];
+        load_row<DIN>(hsrc + (size_t)ja * DIN, xa);
+        load_row<DIN>(hsrc + (size_t)jb * DIN, xb);
         float sa = aa * qe, sb = ab * qe;
 #pragma unroll
-        for (int c = 0; c < C; ++c) { sa = fmaf(q[c], ka[c], sa); sb = fmaf(q[c], kb[c], sb); }
-        fold(st, sa * 0.25f, aa, va);   // / sqrt(16)
-        if (two) fold(st, sb * 0.25f, ab, vb);
+        for (int d = 0; d < DIN; ++d) { sa = fmaf(qt[d], xa[d], sa); sb = fmaf(qt[d], xb[d], sb); }
+        fold<DIN>(st, sa, aa, xa);
+        if (two) fold<DIN>(st, sb, ab, xb);
     }
 }
 
-// Merge the states of the S lanes of a group.  On return lane `gl` holds, in acc[0 .. n), the group's sums of the
-// n = max(16 / S, 1) channels starting at `cbase`; l and pa are the group's sums in every lane.
-template <int S>
-__device__ __forceinline__ int merge_group(State& st, int gl, int& cbase)
+// Merge the states of the S lanes of a group (butterfly all-reduce: every lane ends with the group's m, l, pa, acc).
+template <int S, int DIN>
+__device__ __forceinline__ void merge_group(State<DIN>& st)
 {
     float M = st.m;
 #pragma unroll
@@ -107,134 +164,141 @@ __device__ __forceinline__ int merge_group(State& st, int gl, int& cbase)
     const float sc = st.m == -INFINITY ? 0.0f : __expf(st.m - M);   // a lane that saw no edge contributes nothing
     st.l *= sc; st.pa *= sc;
 #pragma unroll
-    for (int c = 0; c < C; ++c) st.acc[c] *= sc;
+    for (int d = 0; d < DIN; ++d) st.acc[d] *= sc;
     st.m = M;
 #pragma unroll
     for (int o = S / 2; o > 0; o >>= 1) {
         st.l += __shfl_xor_sync(FULLM, st.l, o);
         st.pa += __shfl_xor_sync(FULLM, st.pa, o);
-    }
-    // reduce-scatter of the 16 channels: at every level a lane keeps one half of its channels and receives the
-    // partner's sums of that half
-    cbase = 0;
-    int cnt = C;
 #pragma unroll
-    for (int o = S / 2; o > 0; o >>= 1) {
-        if (cnt > 1) {
-            const int half = cnt / 2;
-            const bool upper = (gl & o) != 0;
-#pragma unroll
-            for (int k = 0; k < C / 2; ++k) {
-                if (k < half) {
-                    const float send = upper ? st.acc[k] : st.acc[k + half];
-                    const float keep = upper ? st.acc[k + half] : st.acc[k];
-                    st.acc[k] = keep + __shfl_xor_sync(FULLM, send, o);
-                }
-            }
-            cbase += upper ? half : 0;
-            cnt = half;
-        } else {
-            st.acc[0] += __shfl_xor_sync(FULLM, st.acc[0], o);   // S = 32: both lanes of a pair hold the same channel
-        }
+        for (int d = 0; d < DIN; ++d) st.acc[d] += __shfl_xor_sync(FULLM, st.acc[d], o);
     }
-    return cnt;
 }
 
-// out_i[c] = acc_c / l + (pa / l) We_c + skip_c  for this lane's channels
-template <int S>
-__device__ __forceinline__ void row_epilogue(float* __restrict__ hout, const float* __restrict__ qs, const float* we, int i, int gl,
-                                             const State& st, int cbase, int cnt, int relu)
+// channel c of the layer's output for a destination node with feature row x and merged state (l, pa, acc):
+//   out_c = (Wv acc)_c / l + bv_c [l > 0] + (pa / l) We_c + (Ws x)_c + bs_c
+template <int DIN>
+__device__ __forceinline__ float out_channel(const float* __restrict__ prm, int c, const float* x, const float* acc, float pa,
+                                             float inv, bool any, int relu)
 {
-    if (S == 32 && (gl & 1)) return;   // the odd lane of a pair holds a copy
-    const float inv = st.l > 0.0f ? 1.0f / st.l : 0.0f;   // a node without incoming edges keeps only the root term
+    using O = Off<DIN>;
+    float v = 0.0f, sk = prm[O::bs + c];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < cnt) {
-            const int c = cbase + k;
-            float o = fmaf(st.pa * inv, we[c], st.acc[k] * inv) + __ldg(qs + (size_t)i * 32 + C + c);
-            if (relu) o = fmaxf(o, 0.0f);
-            hout[(size_t)i * C + c] = o;
-        }
+    for (int d = 0; d < DIN; ++d) {
+        v = fmaf(acc[d], prm[O::wv + d * C + c], v);
+        sk = fmaf(x[d], prm[O::ws + d * C + c], sk);
     }
+    float o = fmaf(pa * inv, prm[O::we + c], v * inv) + (any ? prm[O::bv + c] : 0.0f) + sk;
+    if (relu) o = fmaxf(o, 0.0f);
+    return o;
 }
 
-__device__ __forceinline__ void state_init(State& st)
-{
-    st.m = -INFINITY; st.l = 0.0f; st.pa = 0.0f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) st.acc[c] = 0.0f;
-}
-
-// rows with at most `chunk` edges: S lanes per row
-template <int S>
+// rows with at most `chunk` edges: S lanes per row.  hout (nd x 16) and / or, with `fc` (= w[16] | b), the folded final
+// linear layer fc_out[i] = w . out_i + b.
+template <int S, int DIN>
 __global__ void __launch_bounds__(256) k_gnn_conv_rows(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                                       const double* __restrict__ values, const float* __restrict__ qs,
-                                                       const float* __restrict__ kv, const float* __restrict__ we_g,
-                                                       float* __restrict__ hout, int chunk, int relu)
+                                                       const double* __restrict__ values, const float* __restrict__ hdst,
+                                                       const float* __restrict__ hsrc, const float* __restrict__ prm_g,
+                                                       float* __restrict__ hout, int chunk, int relu,
+                                                       const float* __restrict__ fc, float* __restrict__ fc_out)
 {
-    __shared__ float we[C];
-    if (threadIdx.x < C) we[threadIdx.x] = we_g[threadIdx.x];
+    using O = Off<DIN>;
+    __shared__ __align__(16) float prm[O::total + C + 4];
+    for (int k = threadIdx.x; k < O::total; k += blockDim.x) prm[k] = prm_g[k];
+    if (fc && threadIdx.x <= C) prm[O::total + threadIdx.x] = fc[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, gl = lane & (S - 1);
-    constexpr int RPW = 32 / S;   // rows per warp
+    constexpr int RPW = 32 / S;                 // rows per warp
+    constexpr int CNT = S <= C ? C / S : 1;     // output channels per lane (S = 32: lane pairs share a channel)
+    const int c0 = S <= C ? gl * CNT : (gl >> 1);
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; base < nd; base += warps * RPW) {
         const int i = base + lane / S;   // warp-uniform trip count: the merges below are warp-wide
         int e0 = 0, e1 = 0;
         if (i < nd) { e0 = __ldg(indptr + i); e1 = __ldg(indptr + i + 1); }
         const bool live = i < nd && e1 - e0 <= chunk;   // long row: k_gnn_conv_items + k_gnn_conv_merge
-        State st;
-        state_init(st);
-        if (live && e1 > e0) {
-            float q[C];
-            load16(qs + (size_t)i * 32, q);
-            float qe = 0.0f;
+        State<DIN> st;
+        state_init<DIN>(st);
+        float x[DIN];
 #pragma unroll
-            for (int c = 0; c < C; ++c) qe = fmaf(q[c], we[c], qe);
-            edge_loop<S>(indices, values, kv, e0, e1, gl, q, qe, st);
+        for (int d = 0; d < DIN; ++d) x[d] = 0.0f;
+        if (live) load_row<DIN>(hdst + (size_t)i * DIN, x);
+        if (live && e1 > e0) {
+            float qt[DIN], qe;
+            dst_prologue<DIN>(prm, x, qt, qe);
+            edge_loop<S, DIN>(indices, values, hsrc, e0, e1, gl, qt, qe, st);
         }
-        int cbase;
-        const int cnt = merge_group<S>(st, gl, cbase);
-        if (live) row_epilogue<S>(hout, qs, we, i, gl, st, cbase, cnt, relu);
+        merge_group<S, DIN>(st);
+        const bool any = st.l > 0.0f;
+        const float inv = any ? 1.0f / st.l : 0.0f;   // a node without incoming edges keeps only the root term
+        float o[CNT], part = 0.0f;
+#pragma unroll
+        for (int k = 0; k < CNT; ++k) {
+            o[k] = out_channel<DIN>(prm, c0 + k, x, st.acc, st.pa, inv, any, relu);
+            part = fmaf(o[k], prm[O::total + c0 + k], part);
+        }
+        const bool writer = live && !(S == 32 && (gl & 1));
+        if (writer && hout) {
+            if constexpr (CNT == 4) {
+                *reinterpret_cast<float4*>(hout + (size_t)i * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < CNT; ++k) hout[(size_t)i * C + c0 + k] = o[k];
+            }
+        }
+        if (fc) {   // warp-uniform
+            if (S == 32 && (gl & 1)) part = 0.0f;
+#pragma unroll
+            for (int w = S / 2; w > 0; w >>= 1) part += __shfl_xor_sync(FULLM, part, w);
+            if (live && gl == 0) fc_out[i] = part + prm[O::total + C];
+        }
     }
 }
 
 // long rows: item t = (row, first edge, end edge); one warp per item, merged partial state -> scratch[t][20]
+template <int DIN>
 __global__ void __launch_bounds__(256) k_gnn_conv_items(int nitems, const int32_t* __restrict__ items, const int32_t* __restrict__ indices,
-                                                        const double* __restrict__ values, const float* __restrict__ qs,
-                                                        const float* __restrict__ kv, const float* __restrict__ we_g,
+                                                        const double* __restrict__ values, const float* __restrict__ hdst,
+                                                        const float* __restrict__ hsrc, const float* __restrict__ prm_g,
                                                         float* __restrict__ scratch)
 {
-    __shared__ float we[C];
-    if (threadIdx.x < C) we[threadIdx.x] = we_g[threadIdx.x];
+    using O = Off<DIN>;
+    __shared__ __align__(16) float prm[O::wv];   // the prologue's part of the block
+    for (int k = threadIdx.x; k < O::wv; k += blockDim.x) prm[k] = prm_g[k];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nitems; t += warps) {
         const int i = __ldg(items + 3 * t), e0 = __ldg(items + 3 * t + 1), e1 = __ldg(items + 3 * t + 2);
-        float q[C];
-        load16(qs + (size_t)i * 32, q);
-        float qe = 0.0f;
+        float x[DIN], qt[DIN], qe;
+        load_row<DIN>(hdst + (size_t)i * DIN, x);
+        dst_prologue<DIN>(prm, x, qt, qe);
+        State<DIN> st;
+        state_init<DIN>(st);
+        edge_loop<32, DIN>(indices, values, hsrc, e0, e1, lane, qt, qe, st);
+        merge_group<32, DIN>(st);
+        if (lane == 0) {
+            float4* o = reinterpret_cast<float4*>(scratch + (size_t)t * ITEM_FLOATS);
+            o[0] = make_float4(st.m, st.l, st.pa, 0.0f);
+            float a[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) qe = fmaf(q[c], we[c], qe);
-        State st;
-        state_init(st);
-        edge_loop<32>(indices, values, kv, e0, e1, lane, q, qe, st);
-        int cbase;
-        merge_group<32>(st, lane, cbase);
-        float* o = scratch + (size_t)t * ITEM_FLOATS;
-        if (lane == 0) { o[0] = st.m; o[1] = st.l; o[2] = st.pa; o[3] = 0.0f; }
-        if (!(lane & 1)) o[4 + cbase] = st.acc[0];
+            for (int d = 0; d < C; ++d) a[d] = d < DIN ? st.acc[d < DIN ? d : 0] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[1 + k] = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
+        }
     }
 }
 
-// long rows: merge the partial states of row r's items [first[r], first[r+1]) in order (lane c < 16 owns channel c),
-// then the epilogue
+// long rows: merge the partial states of row r's items [first[r], first[r+1]) in order (lane d < din owns acc_d), then
+// the epilogue (lane c < 16 finishes channel c; acc and x are handed round by shuffles)
+template <int DIN>
 __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t* __restrict__ long_rows,
                                                         const int32_t* __restrict__ first, const float* __restrict__ scratch,
-                                                        const float* __restrict__ qs, const float* __restrict__ we_g,
-                                                        float* __restrict__ hout, int relu)
+                                                        const float* __restrict__ hdst, const float* __restrict__ prm,
+                                                        float* __restrict__ hout, int relu, const float* __restrict__ fc,
+                                                        float* __restrict__ fc_out)
 {
+    using O = Off<DIN>;
     const int lane = threadIdx.x & 31, c = lane & 15;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nlong; r += warps) {
@@ -250,142 +314,26 @@ __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t
             acc = acc * s1 + a2 * s2;
             m = mn;
         }
-        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-        float o = fmaf(pa * inv, __ldg(we_g + c), acc * inv) + __ldg(qs + (size_t)i * 32 + C + c);
-        if (relu) o = fmaxf(o, 0.0f);
-        if (lane < 16) hout[(size_t)i * C + c] = o;
-    }
-}
-
-// Node-wise linear maps: out[j][0..15] = W1 h_j + b1, out[j][16..31] = W2 h_j + b2, with
-// params = W1'[din][16] | b1[16] | W2'[din][16] | b2[16] (W' = transposed weight: input-major).
-// A node set can feed two pairs at once (its {q | skip} rows as destination of one conv and its {k | v} rows as
-// source of the other conv of the layer), and both node sets of the graph share the launch.
-// k_gnn_project<DIN> (the model's widths, 1 and 16): one THREAD per (node, pair) -- the node's row in registers, the 32
-// outputs in registers, weights read as broadcast LDS.128 (one per 4 FMAs).  k_gnn_project_generic (any din <= 32, unit
-// parity only): one warp per node, lane l < 16 channel l of the first map, lane l >= 16 channel l - 16 of the second.
-// Both accumulate bias first, then inputs in ascending order: bitwise equal.
-struct ProjJob {
-    const float* h;        // [n][din]
-    const float* pa;       // first pair of maps, or null
-    float* oa;             // [n][32]
-    const float* pb;       // second pair, or null
-    float* ob;
-    int n;
-};
-
-__global__ void __launch_bounds__(256) k_gnn_project_generic(ProjJob j0, ProjJob j1, int din)
-{
-    extern __shared__ float sp[];   // 4 parameter blocks of np floats
-    const int np = 2 * din * C + 2 * C;
-    const float* src[4] = {j0.pa, j0.pb, j1.pa, j1.pb};
-    for (int b = 0; b < 4; ++b)
-        if (src[b])
-            for (int k = threadIdx.x; k < np; k += blockDim.x) sp[b * np + k] = src[b][k];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, c = lane & 15;
-    const int woff = lane < 16 ? 0 : din * C + C;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    const int total = j0.n + j1.n;
-    // the node's feature row is fetched by ONE coalesced load (lane d holds h[d], din <= 32) and handed round by
-    // shuffles; the next node's row is in flight while this one is multiplied
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    auto fetch = [&](int ww) -> float {
-        if (ww >= total || lane >= din) return 0.0f;
-        const bool sec = ww >= j0.n;
-        return __ldg((sec ? j1.h : j0.h) + (size_t)(sec ? ww - j0.n : ww) * din + lane);
-    };
-    float hrow = fetch(w);
-    for (; w < total; w += warps) {
-        const float hnext = fetch(w + warps);
-        const bool second = w >= j0.n;
-        const int j = second ? w - j0.n : w;
-        const float* pA = sp + (second ? 2 : 0) * np + woff;
-        const float* pB = pA + np;
-        const bool ha = (second ? j1.pa : j0.pa) != nullptr, hb = (second ? j1.pb : j0.pb) != nullptr;
-        float oa = pA[din * C + c], ob = pB[din * C + c];
-        for (int d = 0; d < din; ++d) {
-            const float h = __shfl_sync(FULLM, hrow, d);
-            oa = fmaf(h, pA[d * C + c], oa);
-            ob = fmaf(h, pB[d * C + c], ob);
-        }
-        if (ha) (second ? j1.oa : j0.oa)[(size_t)j * 32 + lane] = oa;
-        if (hb) (second ? j1.ob : j0.ob)[(size_t)j * 32 + lane] = ob;
-        hrow = hnext;
-    }
-}
-
-template <int DIN>
-__global__ void __launch_bounds__(128) k_gnn_project(ProjJob j0, ProjJob j1)
-{
-    extern __shared__ __align__(16) float sp[];   // 4 parameter blocks of NP floats
-    constexpr int NP = 2 * DIN * C + 2 * C;
-    const float* src[4] = {j0.pa, j0.pb, j1.pa, j1.pb};
-    for (int b = 0; b < 4; ++b)
-        if (src[b])
-            for (int k = threadIdx.x; k < NP; k += blockDim.x) sp[b * NP + k] = src[b][k];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int nb0 = (j0.n + 31) >> 5, nb1 = (j1.n + 31) >> 5;
-    const int units = 2 * (nb0 + nb1);   // unit = (node set, block of 32 nodes, pair of maps): one warp, a node per lane
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warps) {
-        const bool second = u >= 2 * nb0;
-        const int uu = second ? u - 2 * nb0 : u;
-        const int pair = uu & 1;
-        const int j = (uu >> 1) * 32 + lane;
-        const float* prm = second ? (pair ? j1.pb : j1.pa) : (pair ? j0.pb : j0.pa);
-        const int n = second ? j1.n : j0.n;
-        if (!prm || j >= n) continue;
-        float* out = (second ? (pair ? j1.ob : j1.oa) : (pair ? j0.ob : j0.oa)) + (size_t)j * 32;
-        const float* hp = (second ? j1.h : j0.h) + (size_t)j * DIN;
-        const float* w = sp + ((second ? 2 : 0) + pair) * NP;
-        float h[DIN];
-        if constexpr (DIN % 4 == 0) {
-#pragma unroll
-            for (int k = 0; k < DIN / 4; ++k) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(hp) + k);
-                h[4 * k] = t.x; h[4 * k + 1] = t.y; h[4 * k + 2] = t.z; h[4 * k + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) h[d] = __ldg(hp + d);
-        }
-        float acc[2 * C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) { acc[c] = w[DIN * C + c]; acc[C + c] = w[2 * DIN * C + C + c]; }
+        const bool any = l > 0.0f;
+        const float inv = any ? 1.0f / l : 0.0f;
+        const float xmine = lane < DIN ? __ldg(hdst + (size_t)i * DIN + lane) : 0.0f;
+        float v = 0.0f, sk = __ldg(prm + O::bs + c);
 #pragma unroll
         for (int d = 0; d < DIN; ++d) {
-#pragma unroll
-            for (int c4 = 0; c4 < C / 4; ++c4) {
-                const float4 wa = *reinterpret_cast<const float4*>(w + d * C + 4 * c4);
-                const float4 wb = *reinterpret_cast<const float4*>(w + DIN * C + C + d * C + 4 * c4);
-                acc[4 * c4] = fmaf(h[d], wa.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(h[d], wa.y, acc[4 * c4 + 1]);
-                acc[4 * c4 + 2] = fmaf(h[d], wa.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(h[d], wa.w, acc[4 * c4 + 3]);
-                acc[C + 4 * c4] = fmaf(h[d], wb.x, acc[C + 4 * c4]); acc[C + 4 * c4 + 1] = fmaf(h[d], wb.y, acc[C + 4 * c4 + 1]);
-                acc[C + 4 * c4 + 2] = fmaf(h[d], wb.z, acc[C + 4 * c4 + 2]); acc[C + 4 * c4 + 3] = fmaf(h[d], wb.w, acc[C + 4 * c4 + 3]);
-            }
+            const float ad = __shfl_sync(FULLM, acc, d), xd = __shfl_sync(FULLM, xmine, d);
+            v = fmaf(ad, __ldg(prm + O::wv + d * C + c), v);
+            sk = fmaf(xd, __ldg(prm + O::ws + d * C + c), sk);
         }
+        float o = fmaf(pa * inv, __ldg(prm + O::we + c), v * inv) + (any ? __ldg(prm + O::bv + c) : 0.0f) + sk;
+        if (relu) o = fmaxf(o, 0.0f);
+        if (lane < 16 && hout) hout[(size_t)i * C + c] = o;
+        if (fc) {
+            float part = lane < 16 ? o * __ldg(fc + c) : 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            reinterpret_cast<float4*>(out)[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+            for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(FULLM, part, w);
+            if (lane == 0) fc_out[i] = part + __ldg(fc + C);
+        }
     }
-}
-
-// out[i] = w . h_i + b     (the model's final Linear(16, 1))
-__global__ void __launch_bounds__(256) k_gnn_fc(int n, const float* __restrict__ h, const float* __restrict__ wb, float* __restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4* r = reinterpret_cast<const float4*>(h + (size_t)i * C);
-    float o = __ldg(wb + C);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float4 v = __ldg(r + k);
-        o = fmaf(v.x, __ldg(wb + 4 * k), o); o = fmaf(v.y, __ldg(wb + 4 * k + 1), o);
-        o = fmaf(v.z, __ldg(wb + 4 * k + 2), o); o = fmaf(v.w, __ldg(wb + 4 * k + 3), o);
-    }
-    out[i] = o;
 }
 
 int gfail(int code, const std::string& msg) { set_last_error(msg); return code; }
@@ -401,22 +349,6 @@ int cuda_status(const char* what)
     return 0;
 }
 
-int launch_project(const ProjJob& j0, const ProjJob& j1, int din, cudaStream_t s)
-{
-    if (j0.n + j1.n <= 0) return 0;
-    const size_t smem = 4 * (size_t)(2 * din * C + 2 * C) * sizeof(float);
-    if (din == 1 || din == C) {
-        const long long units = 2 * ((long long)((j0.n + 31) >> 5) + (long long)((j1.n + 31) >> 5));
-        const long long blocks = (units + 3) / 4;
-        const int grid = (int)(blocks < 1 ? 1 : blocks > 148 * 16 ? 148 * 16 : blocks);   // 16 CTAs of 128 threads per SM
-        if (din == 1) k_gnn_project<1><<<grid, 128, smem, s>>>(j0, j1);
-        else k_gnn_project<C><<<grid, 128, smem, s>>>(j0, j1);
-    } else {
-        k_gnn_project_generic<<<grid_for_warps(j0.n + j1.n), 256, smem, s>>>(j0, j1, din);
-    }
-    return cuda_status("mllp_gnn: projection");
-}
-
 bool side_ok(const mllp_gnn_side* g)
 {
     if (!g || g->nd < 0 || g->ns < 0 || !g->indptr) return false;
@@ -426,25 +358,35 @@ bool side_ok(const mllp_gnn_side* g)
     return true;
 }
 
-int launch_conv(const mllp_gnn_side& g, const float* qs, const float* kv, const float* we, float* hout, int relu, cudaStream_t s)
+template <int DIN>
+int launch_conv_din(const mllp_gnn_side& g, const float* hdst, const float* hsrc, const float* prm, float* hout, int relu,
+                    const float* fc, float* fc_out, cudaStream_t s)
 {
-    if (g.nd == 0) return 0;
     const int grid = grid_for_warps(((long long)g.nd * g.group + 31) / 32);
+#define MLLP_CONV_ROWS(SS) \
+    k_gnn_conv_rows<SS, DIN><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, hdst, hsrc, prm, hout, g.chunk, relu, fc, fc_out)
     switch (g.group) {
-        case 4: k_gnn_conv_rows<4><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
-        case 8: k_gnn_conv_rows<8><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
-        case 16: k_gnn_conv_rows<16><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
-        default: k_gnn_conv_rows<32><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, qs, kv, we, hout, g.chunk, relu); break;
+        case 4: MLLP_CONV_ROWS(4); break;
+        case 8: MLLP_CONV_ROWS(8); break;
+        case 16: MLLP_CONV_ROWS(16); break;
+        default: MLLP_CONV_ROWS(32); break;
     }
+#undef MLLP_CONV_ROWS
     if (g.nlong > 0) {
-        k_gnn_conv_items<<<grid_for_warps(g.nitems), 256, 0, s>>>(g.nitems, g.items, g.indices, g.values, qs, kv, we, g.scratch);
-        k_gnn_conv_merge<<<grid_for_warps(g.nlong), 256, 0, s>>>(g.nlong, g.long_rows, g.long_first, g.scratch, qs, we, hout, relu);
+        k_gnn_conv_items<DIN><<<grid_for_warps(g.nitems), 256, 0, s>>>(g.nitems, g.items, g.indices, g.values, hdst, hsrc, prm, g.scratch);
+        k_gnn_conv_merge<DIN><<<grid_for_warps(g.nlong), 256, 0, s>>>(g.nlong, g.long_rows, g.long_first, g.scratch, hdst, prm, hout,
+                                                                     relu, fc, fc_out);
     }
     return cuda_status("mllp_gnn: conv");
 }
 
-// floats of one conv's parameter block: Wq'|bq|Ws'|bs | Wk'|bk|Wv'|bv | We
-size_t conv_block(int din) { return 2 * (size_t)(2 * din * C + 2 * C) + C; }
+int launch_conv(const mllp_gnn_side& g, int din, const float* hdst, const float* hsrc, const float* prm, float* hout, int relu,
+                const float* fc, float* fc_out, cudaStream_t s)
+{
+    if (g.nd == 0) return 0;
+    if (din == 1) return launch_conv_din<1>(g, hdst, hsrc, prm, hout, relu, fc, fc_out, s);
+    return launch_conv_din<C>(g, hdst, hsrc, prm, hout, relu, fc, fc_out, s);
+}
 }  // namespace
 }  // namespace mllp
 
@@ -452,29 +394,20 @@ using namespace mllp;
 
 extern "C" {
 
-int mllp_gnn_project(int32_t n, const float* d_h, int32_t din, const float* d_params, float* d_out, void* stream)
+int64_t mllp_gnn_conv_param_floats(int32_t din)
 {
-    if (n < 0 || din < 1 || din > 32 || !d_h || !d_params || !d_out) return gfail(MLLP_E_INVALID, "mllp_gnn_project: bad argument (din must be 1 .. 32)");
-    const ProjJob j0{d_h, d_params, d_out, nullptr, nullptr, n}, j1{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-    return launch_project(j0, j1, din, (cudaStream_t)stream);
+    return din == 1 ? Off<1>::total : din == C ? Off<C>::total : -1;
 }
 
-int mllp_gnn_conv(const mllp_gnn_side* side, const float* d_qs_dst, const float* d_kv_src, const float* d_we, float* d_hout,
-                  int32_t relu, void* stream)
+int mllp_gnn_conv(const mllp_gnn_side* side, int32_t din, const float* d_hdst, const float* d_hsrc, const float* d_params,
+                  float* d_hout, int32_t relu, void* stream)
 {
-    if (!side_ok(side) || !d_qs_dst || !d_kv_src || !d_we || !d_hout) return gfail(MLLP_E_INVALID, "mllp_gnn_conv: bad argument");
-    return launch_conv(*side, d_qs_dst, d_kv_src, d_we, d_hout, relu, (cudaStream_t)stream);
+    if (!side_ok(side) || (din != 1 && din != C) || !d_hdst || !d_hsrc || !d_params || !d_hout)
+        return gfail(MLLP_E_INVALID, "mllp_gnn_conv: bad argument (din must be 1 or 16)");
+    return launch_conv(*side, din, d_hdst, d_hsrc, d_params, d_hout, relu, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int mllp_gnn_fc(int32_t n, const float* d_h, const float* d_wb, float* d_out, void* stream)
-{
-    if (n < 0 || !d_h || !d_wb || !d_out) return gfail(MLLP_E_INVALID, "mllp_gnn_fc: bad argument");
-    if (n == 0) return 0;
-    k_gnn_fc<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_h, d_wb, d_out);
-    return cuda_status("mllp_gnn_fc");
-}
-
-int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m) { return 96 * ((int64_t)n + (int64_t)m) + 64; }
+int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m) { return 32 * ((int64_t)n + (int64_t)m) + 64; }
 
 int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
                      const float* d_params, float* d_work, float* d_out, void* stream)
@@ -484,44 +417,21 @@ int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, c
     const int n = to_var->nd, m = to_con->nd;
     if (to_var->ns != m || to_con->ns != n) return gfail(MLLP_E_INVALID, "mllp_gnn_forward: the two sides do not describe one graph");
     cudaStream_t s = (cudaStream_t)stream;
-    // workspace: two feature buffers and {q | skip}, {k | v} rows per node set
+    // workspace: two feature buffers per node set (16 B aligned: n and m are multiplied by 16 floats)
     float* h1[2] = {d_work, d_work + (size_t)16 * n};
-    float* qs1 = d_work + (size_t)32 * n;
-    float* kv1 = qs1 + (size_t)32 * n;
-    float* base2 = d_work + (size_t)96 * n;
-    float* h2[2] = {base2, base2 + (size_t)16 * m};
-    float* qs2 = base2 + (size_t)32 * m;
-    float* kv2 = qs2 + (size_t)32 * m;
+    float* h2[2] = {d_work + (size_t)32 * n, d_work + (size_t)32 * n + (size_t)16 * m};
     // parameter blocks: gconv1_w2s, gconv1_s2w (din 1), gconv2_w2s, gconv2_s2w, gconv3_w2s (din 16), fc
     const float* P[5];
     size_t off = 0;
-    for (int k = 0; k < 5; ++k) { P[k] = d_params + off; off += conv_block(k < 2 ? 1 : C); }
+    for (int k = 0; k < 5; ++k) { P[k] = d_params + off; off += (size_t)(k < 2 ? Off<1>::total : Off<C>::total); }
     const float* fc = d_params + off;
-    auto dstp = [&](int k) { return P[k]; };
-    auto srcp = [&](int k) { return P[k] + (2 * (k < 2 ? 1 : C) * C + 2 * C); };
-    auto wep = [&](int k) { return P[k] + 2 * (2 * (k < 2 ? 1 : C) * C + 2 * C); };
-
-    const float* x1 = d_x1;
-    const float* x2 = d_x2;
-    int rc = 0;
-    for (int layer = 0; layer < 2 && rc == 0; ++layer) {
-        const int kw = 2 * layer, ks = 2 * layer + 1, din = layer == 0 ? 1 : C;
-        // variables: destination of the w2s conv, source of the s2w conv; constraints: the other way round
-        const ProjJob jv{x1, dstp(kw), qs1, srcp(ks), kv1, n}, jc{x2, dstp(ks), qs2, srcp(kw), kv2, m};
-        rc = launch_project(jv, jc, din, s);
-        if (rc == 0) rc = launch_conv(*to_var, qs1, kv2, wep(kw), h1[layer], 1, s);
-        if (rc == 0) rc = launch_conv(*to_con, qs2, kv1, wep(ks), h2[layer], 1, s);
-        x1 = h1[layer]; x2 = h2[layer];
-    }
-    if (rc == 0) {
-        const ProjJob jv{x1, dstp(4), qs1, nullptr, nullptr, n}, jc{x2, nullptr, nullptr, srcp(4), kv2, m};
-        rc = launch_project(jv, jc, C, s);
-    }
-    if (rc == 0) rc = launch_conv(*to_var, qs1, kv2, wep(4), h1[0], 1, s);
-    if (rc == 0 && n > 0) {
-        k_gnn_fc<<<(n + 255) / 256, 256, 0, s>>>(n, h1[0], fc, d_out);
-        rc = cuda_status("mllp_gnn_forward: fc");
-    }
+    // variables are the destination of the w2s convs and the source of the s2w convs; both convs of a layer read the
+    // layer's input features (:241-246)
+    int rc = launch_conv(*to_var, 1, d_x1, d_x2, P[0], h1[0], 1, nullptr, nullptr, s);
+    if (rc == 0) rc = launch_conv(*to_con, 1, d_x2, d_x1, P[1], h2[0], 1, nullptr, nullptr, s);
+    if (rc == 0) rc = launch_conv(*to_var, C, h1[0], h2[0], P[2], h1[1], 1, nullptr, nullptr, s);
+    if (rc == 0) rc = launch_conv(*to_con, C, h2[0], h1[0], P[3], h2[1], 1, nullptr, nullptr, s);
+    if (rc == 0) rc = launch_conv(*to_var, C, h1[1], h2[1], P[4], nullptr, 1, fc, d_out, s);
     return rc;
 }
 

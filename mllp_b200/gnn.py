@@ -102,7 +102,10 @@ class BipartiteGraph:
 
 
 def pack_conv(state, cv):
-    """(projection block of the destination side Wq'|bq|Ws'|bs, of the source side Wk'|bk|Wv'|bv, We) as float32"""
+    """(din, parameter block of one conv as float32) in the layout of include/mllp_b200.h: the layer is evaluated
+    without materialising query / key / value rows, so the products Wq'Wk, Wk'bq, Wq'We and We.bq (all with the
+    1/sqrt(16) of the attention score folded in) are formed here, in float64, and rounded once.  lin_key.bias adds the
+    same amount to every score of a destination node and cancels in the softmax."""
     g = lambda part, kind: np.asarray(state["%s.%s.%s" % (cv, part, kind)], dtype=np.float32)
     din = g("lin_query", "weight").shape[1]
     for part in ("lin_key", "lin_query", "lin_value", "lin_skip"):
@@ -110,8 +113,17 @@ def pack_conv(state, cv):
             raise ValueError("%s.%s: expected weight (16, %d) and bias (16,)" % (cv, part, din))
     if g("lin_edge", "weight").shape != (C, 1):
         raise ValueError("%s.lin_edge.weight: expected (16, 1) (edge_dim = 1, no bias)" % cv)
-    blk = lambda a, b: np.concatenate([g(a, "weight").T.reshape(-1), g(a, "bias"), g(b, "weight").T.reshape(-1), g(b, "bias")])
-    return din, blk("lin_query", "lin_skip"), blk("lin_key", "lin_value"), g("lin_edge", "weight").reshape(-1)
+    d = lambda part, kind: g(part, kind).astype(np.float64)
+    Wq, bq, Wk = d("lin_query", "weight"), d("lin_query", "bias"), d("lin_key", "weight")
+    We = d("lin_edge", "weight").reshape(-1)
+    head = np.concatenate([(Wq.T @ Wk).reshape(-1) / 4.0, (Wk.T @ bq) / 4.0, (Wq.T @ We) / 4.0, [(We @ bq) / 4.0]])
+    head = np.concatenate([head, np.zeros(-len(head) % 4)])
+    tail = np.concatenate([d("lin_value", "weight").T.reshape(-1), d("lin_value", "bias"),
+                           d("lin_skip", "weight").T.reshape(-1), d("lin_skip", "bias"), We])
+    blk = np.concatenate([head, tail]).astype(np.float32)
+    if len(blk) != int(_cabi.lib().mllp_gnn_conv_param_floats(din)):
+        raise ValueError("%s: %d input channels are not supported (1 or 16)" % (cv, din))
+    return din, blk
 
 
 class GNNModel:
@@ -128,11 +140,11 @@ class GNNModel:
         self.state = {k: f(v) for k, v in state_dict.items()}
         parts, self.din = [], {}
         for k, cv in enumerate(CONVS):
-            din, dst, src, we = pack_conv(self.state, cv)
+            din, blk = pack_conv(self.state, cv)
             if din != (1 if k < 2 else C):
                 raise ValueError("%s: expected %d input channels" % (cv, 1 if k < 2 else C))
             self.din[cv] = din
-            parts += [dst, src, we]
+            parts.append(blk)
         if self.state["fc.weight"].shape != (1, C):
             raise ValueError("fc.weight: expected (1, 16)")
         parts += [self.state["fc.weight"].reshape(-1), self.state["fc.bias"].reshape(-1)]

@@ -1,9 +1,9 @@
-"""Dev tool: time of one GNNModel forward (5 TransformerConv passes + fc) per instance, CUDA events.
+"""Dev tool: time of one GNNModel forward (5 TransformerConv passes, fc folded into the last) per instance, CUDA events.
 
 Bytes counted per forward (algorithmic, every array touched once per conv): per conv 12 B/nnz (fp64 value + int32
-index) + 4 B/row indptr + 2 x 128 B per source node ({k | v} written by the projection, read by the conv) + 2 x 128 B
-per destination node ({q | skip}) + 4*din B per source and destination node (features in) + 64 B per destination node
-(features out); the gathered {k | v} rows are served by L2 / L1 (128 B per edge, reported separately)."""
+index) + 4 B/row indptr + 4*din B per source and destination node (features in) + 64 B per destination node (features
+out; 4 B for the last conv, whose output is the logit); the gathered source rows (4*din B per edge) are served by
+L2 / L1 and reported separately."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,8 +15,12 @@ def bytes_per_forward(m, n, nnz):
     tot = 0
     for k, (nd, ns) in enumerate([(n, m), (m, n), (n, m), (m, n), (n, m)]):
         din = 1 if k < 2 else 16
-        tot += 12 * nnz + 4 * (nd + 1) + 2 * 128 * (ns + nd) + 4 * din * (ns + nd) + 64 * nd
-    return tot + 64 * n + 4 * n
+        tot += 12 * nnz + 4 * (nd + 1) + 4 * din * (ns + nd) + (64 if k < 4 else 4) * nd
+    return tot
+
+
+def gather_bytes(nnz):
+    return nnz * (2 * 4 + 3 * 64)
 
 
 def main(names):
@@ -45,7 +49,7 @@ def main(names):
             ts.append(e0.elapsed_time(e1))
         warm = float(np.median(ts))
         print("%-8s m %6d n %6d nnz %7d groups %d/%d: %.1f us / forward (L2 flushed; %.1f us warm), %.0f GB/s algorithmic, gather traffic %.0f GB/s"
-              % (name, m, n, A.nnz, g.to_var.group, g.to_con.group, ms * 1e3, warm * 1e3, B / ms / 1e6, 5 * 128 * A.nnz / ms / 1e6), flush=True)
+              % (name, m, n, A.nnz, g.to_var.group, g.to_con.group, ms * 1e3, warm * 1e3, B / ms / 1e6, gather_bytes(A.nnz) / ms / 1e6), flush=True)
 
 
 if __name__ == "__main__":

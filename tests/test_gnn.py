@@ -110,21 +110,29 @@ def test_gpu_forward_edge_cases_and_errors():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("din", [1, 5, 16, 32])
-def test_gpu_projection_kernels(din):
-    """mllp_gnn_project: the thread-per-node kernels (din = 1, 16: the model's widths) and the generic warp-per-node
-    kernel against numpy; both accumulate bias first, then the inputs in ascending order."""
+@pytest.mark.parametrize("din,name", [(1, "25fv47"), (16, "25fv47"), (16, "pilot87")])
+def test_gpu_single_conv_matches_oracle(din, name):
+    """mllp_gnn_conv (one TransformerConv along the rows of A, no ReLU) on random features against the oracle's layer"""
     import torch
+    import mllp_b200.gnn as GN
     from mllp_b200 import _cabi
+    import ctypes
+    A, b, c = D.load_csr(name)
+    m, n = A.shape
     rng = np.random.default_rng(din)
-    n = 1000 + din   # not a multiple of 32
-    h = rng.standard_normal((n, din)).astype(np.float32)
-    W1, W2 = rng.standard_normal((16, din)).astype(np.float32), rng.standard_normal((16, din)).astype(np.float32)
-    b1, b2 = rng.standard_normal(16).astype(np.float32), rng.standard_normal(16).astype(np.float32)
-    params = np.concatenate([W1.T.reshape(-1), b1, W2.T.reshape(-1), b2]).astype(np.float32)
-    dh, dp = torch.as_tensor(h, device="cuda"), torch.as_tensor(params, device="cuda")
-    out = torch.full((n, 32), float("nan"), dtype=torch.float32, device="cuda")
-    _cabi.check(_cabi.lib().mllp_gnn_project(n, dh.data_ptr(), din, dp.data_ptr(), out.data_ptr(), None), "mllp_gnn_project")
+    st = G.init_state(9)
+    cv = "gconv1_s2w" if din == 1 else "gconv2_s2w"
+    xs, xd = rng.standard_normal((n, din)).astype(np.float32), rng.standard_normal((m, din)).astype(np.float32)
+    g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c)
+    d, blk = GN.pack_conv(st, cv)
+    assert d == din
+    t = lambda a: torch.as_tensor(a, device="cuda")
+    dxs, dxd, dp = t(xs), t(xd), t(blk)
+    out = torch.full((m, 16), float("nan"), dtype=torch.float32, device="cuda")
+    _cabi.check(_cabi.lib().mllp_gnn_conv(ctypes.byref(g.to_con.c), din, dxd.data_ptr(), dxs.data_ptr(), dp.data_ptr(),
+                                          out.data_ptr(), 0, None), "mllp_gnn_conv")
     torch.cuda.synchronize()
-    ref = np.concatenate([h.astype(np.float64) @ W1.T.astype(np.float64) + b1, h.astype(np.float64) @ W2.T.astype(np.float64) + b2], axis=1)
-    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    var = A.indices.astype(np.int64)
+    con = np.repeat(np.arange(m, dtype=np.int64), np.diff(A.indptr))
+    ref = G.transformer_conv(st, cv, xs, xd, var, con, A.data.astype(np.float32))
+    assert close(out.cpu().numpy(), ref)
