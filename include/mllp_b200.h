@@ -241,8 +241,9 @@ int mllp_batch_solve(mllp_batch_t bt, double *d_x, double *d_y, const double *d_
  *
  * mllp_gnn_side: one direction of the graph as CSR of the DESTINATION side (rows = destination nodes: A' for the
  * constraint->variable "w2s" passes, A for the variable->constraint "s2w" passes); `values` are the fp64 coefficients
- * (cast to float per edge, as the reference's edge_attr).  `group` = lanes per destination row (4, 8, 16 or 32; pick
- * about half the mean row length).  Rows with more than `chunk` edges are listed in long_rows[nlong]; their pieces
+ * (cast to float per edge, as the reference's edge_attr).  `group` = lanes per destination row (1, 2, 4, 8, 16
+ * or 32; about an eighth of the 90th-percentile row length, every lane walks its edges two at a time).  Rows with more
+ * than `chunk` (>= 16) edges are listed in long_rows[nlong]; their pieces
  * are items[nitems][3] = (row, first edge, end edge), row r owning items long_first[r] .. long_first[r+1];
  * scratch holds 20 floats per item (16-byte aligned).
  */

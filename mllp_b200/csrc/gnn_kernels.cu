@@ -22,8 +22,9 @@
 // prologue / epilogue of its row (din x din and 2 x din x 16 / lanes FMAs): no projection kernels, nothing of size
 // nodes x 32 or nnz is written.  The products Wq'Wk, Wk'bq, Wq'We are formed on the host (mllp_b200/gnn.py, float64,
 // rounded once).  Structure:
-//   * every destination node (a CSR row) has a group of S lanes (S = 4 .. 32, chosen from the mean row length like
-//     the lanes-per-row of the LP format); a lane owns every S-th edge of the row and folds it into its own
+//   * every destination node (a CSR row) has a group of S lanes (S = 1 .. 32, chosen from the row lengths like the
+//     lanes-per-row of the LP format: one lane per row when rows hold a handful of edges, as A' of the large Netlib
+//     instances does); a lane owns every S-th edge of the row and folds it into its own
 //     online-softmax state (running max, sum, din accumulators), two edges in flight; at the row end the group's
 //     states are merged by a butterfly all-reduce and every lane finishes 16 / S output channels;
 //   * rows longer than `chunk` edges (osa-60 has rows of 173 366 edges, ken-18 151 rows of ~300 among 105 127 of ~3)
@@ -103,29 +104,65 @@ __device__ __forceinline__ void fold(State<DIN>& st, float s, float a, const flo
     for (int d = 0; d < DIN; ++d) st.acc[d] = fmaf(p, x[d], st.acc[d]);
 }
 
-// qt = (Wk'(Wq x + bq)) / 4 and qe = (We . (Wq x + bq)) / 4 of a destination node with feature row x
-template <int DIN>
-__device__ __forceinline__ void dst_prologue(const float* __restrict__ prm, const float* x, float* qt, float& qe)
+// qt = (Wk'(Wq x + bq)) / 4 and qe = (We . (Wq x + bq)) / 4 of a destination node with feature row x.  The S lanes of the
+// node's group share the din x din product: lane gl forms din / S entries of qt, a round of shuffles hands them round.
+template <int S, int DIN>
+__device__ __forceinline__ void dst_prologue(const float* __restrict__ prm, const float* x, int gl, float* qt, float& qe)
 {
     using O = Off<DIN>;
     qe = prm[O::sq];
-#pragma unroll
-    for (int d = 0; d < DIN; ++d) { qt[d] = prm[O::vq + d]; qe = fmaf(x[d], prm[O::wq + d], qe); }
     if constexpr (DIN % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < DIN; ++i) {
-#pragma unroll
-            for (int o4 = 0; o4 < DIN / 4; ++o4) {
-                const float4 w = *reinterpret_cast<const float4*>(prm + O::mq + i * DIN + 4 * o4);
-                qt[4 * o4] = fmaf(x[i], w.x, qt[4 * o4]); qt[4 * o4 + 1] = fmaf(x[i], w.y, qt[4 * o4 + 1]);
-                qt[4 * o4 + 2] = fmaf(x[i], w.z, qt[4 * o4 + 2]); qt[4 * o4 + 3] = fmaf(x[i], w.w, qt[4 * o4 + 3]);
-            }
+        for (int d4 = 0; d4 < DIN / 4; ++d4) {
+            const float4 w = *reinterpret_cast<const float4*>(prm + O::wq + 4 * d4);
+            qe = fmaf(x[4 * d4], w.x, qe); qe = fmaf(x[4 * d4 + 1], w.y, qe);
+            qe = fmaf(x[4 * d4 + 2], w.z, qe); qe = fmaf(x[4 * d4 + 3], w.w, qe);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < DIN; ++i)
+        for (int d = 0; d < DIN; ++d) qe = fmaf(x[d], prm[O::wq + d], qe);
+    }
+    if constexpr (DIN >= 4 * S && DIN % 4 == 0) {
+        constexpr int PER = DIN / S;          // entries of qt per lane (a multiple of 4)
+        float mine[PER];
 #pragma unroll
-            for (int o = 0; o < DIN; ++o) qt[o] = fmaf(x[i], prm[O::mq + i * DIN + o], qt[o]);
+        for (int k = 0; k < PER; ++k) mine[k] = prm[O::vq + gl * PER + k];
+#pragma unroll
+        for (int i = 0; i < DIN; ++i) {
+#pragma unroll
+            for (int k4 = 0; k4 < PER / 4; ++k4) {
+                const float4 w = *reinterpret_cast<const float4*>(prm + O::mq + i * DIN + gl * PER + 4 * k4);
+                mine[4 * k4] = fmaf(x[i], w.x, mine[4 * k4]); mine[4 * k4 + 1] = fmaf(x[i], w.y, mine[4 * k4 + 1]);
+                mine[4 * k4 + 2] = fmaf(x[i], w.z, mine[4 * k4 + 2]); mine[4 * k4 + 3] = fmaf(x[i], w.w, mine[4 * k4 + 3]);
+            }
+        }
+        if constexpr (S == 1) {
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) qt[d] = mine[d];
+        } else {
+            const int base = (threadIdx.x & 31) & ~(S - 1);
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) qt[d] = __shfl_sync(FULLM, mine[d % PER], base + d / PER);
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) qt[d] = prm[O::vq + d];
+        if constexpr (DIN % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < DIN; ++i) {
+#pragma unroll
+                for (int o4 = 0; o4 < DIN / 4; ++o4) {
+                    const float4 w = *reinterpret_cast<const float4*>(prm + O::mq + i * DIN + 4 * o4);
+                    qt[4 * o4] = fmaf(x[i], w.x, qt[4 * o4]); qt[4 * o4 + 1] = fmaf(x[i], w.y, qt[4 * o4 + 1]);
+                    qt[4 * o4 + 2] = fmaf(x[i], w.z, qt[4 * o4 + 2]); qt[4 * o4 + 3] = fmaf(x[i], w.w, qt[4 * o4 + 3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DIN; ++i)
+#pragma unroll
+                for (int o = 0; o < DIN; ++o) qt[o] = fmaf(x[i], prm[O::mq + i * DIN + o], qt[o]);
+        }
     }
 }
 
@@ -175,28 +212,48 @@ __device__ __forceinline__ void merge_group(State<DIN>& st)
     }
 }
 
-// channel c of the layer's output for a destination node with feature row x and merged state (l, pa, acc):
+// channels c0 .. c0 + CNT of the layer's output for a destination node with feature row x and merged state (l, pa, acc):
 //   out_c = (Wv acc)_c / l + bv_c [l > 0] + (pa / l) We_c + (Ws x)_c + bs_c
-template <int DIN>
-__device__ __forceinline__ float out_channel(const float* __restrict__ prm, int c, const float* x, const float* acc, float pa,
-                                             float inv, bool any, int relu)
+template <int DIN, int CNT>
+__device__ __forceinline__ void out_channels(const float* __restrict__ prm, int c0, const float* x, const float* acc, float pa,
+                                             float inv, bool any, int relu, float* o)
 {
     using O = Off<DIN>;
-    float v = 0.0f, sk = prm[O::bs + c];
+    float v[CNT], sk[CNT];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) { v[k] = 0.0f; sk[k] = prm[O::bs + c0 + k]; }
 #pragma unroll
     for (int d = 0; d < DIN; ++d) {
-        v = fmaf(acc[d], prm[O::wv + d * C + c], v);
-        sk = fmaf(x[d], prm[O::ws + d * C + c], sk);
+        if constexpr (CNT == 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(prm + O::wv + d * C + c0);
+            const float4 ws = *reinterpret_cast<const float4*>(prm + O::ws + d * C + c0);
+            v[0] = fmaf(acc[d], wv.x, v[0]); v[1] = fmaf(acc[d], wv.y, v[1]); v[2] = fmaf(acc[d], wv.z, v[2]); v[3] = fmaf(acc[d], wv.w, v[3]);
+            sk[0] = fmaf(x[d], ws.x, sk[0]); sk[1] = fmaf(x[d], ws.y, sk[1]); sk[2] = fmaf(x[d], ws.z, sk[2]); sk[3] = fmaf(x[d], ws.w, sk[3]);
+        } else if constexpr (CNT == 2) {
+            const float2 wv = *reinterpret_cast<const float2*>(prm + O::wv + d * C + c0);
+            const float2 ws = *reinterpret_cast<const float2*>(prm + O::ws + d * C + c0);
+            v[0] = fmaf(acc[d], wv.x, v[0]); v[1] = fmaf(acc[d], wv.y, v[1]);
+            sk[0] = fmaf(x[d], ws.x, sk[0]); sk[1] = fmaf(x[d], ws.y, sk[1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < CNT; ++k) {
+                v[k] = fmaf(acc[d], prm[O::wv + d * C + c0 + k], v[k]);
+                sk[k] = fmaf(x[d], prm[O::ws + d * C + c0 + k], sk[k]);
+            }
+        }
     }
-    float o = fmaf(pa * inv, prm[O::we + c], v * inv) + (any ? prm[O::bv + c] : 0.0f) + sk;
-    if (relu) o = fmaxf(o, 0.0f);
-    return o;
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) {
+        float r = fmaf(pa * inv, prm[O::we + c0 + k], v[k] * inv) + (any ? prm[O::bv + c0 + k] : 0.0f) + sk[k];
+        if (relu) r = fmaxf(r, 0.0f);
+        o[k] = r;
+    }
 }
 
 // rows with at most `chunk` edges: S lanes per row.  hout (nd x 16) and / or, with `fc` (= w[16] | b), the folded final
 // linear layer fc_out[i] = w . out_i + b.
 template <int S, int DIN>
-__global__ void __launch_bounds__(256) k_gnn_conv_rows(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+__global__ void __launch_bounds__(256, 3) k_gnn_conv_rows(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                        const double* __restrict__ values, const float* __restrict__ hdst,
                                                        const float* __restrict__ hsrc, const float* __restrict__ prm_g,
                                                        float* __restrict__ hout, int chunk, int relu,
@@ -219,31 +276,37 @@ __global__ void __launch_bounds__(256) k_gnn_conv_rows(int nd, const int32_t* __
         const bool live = i < nd && e1 - e0 <= chunk;   // long row: k_gnn_conv_items + k_gnn_conv_merge
         State<DIN> st;
         state_init<DIN>(st);
-        float x[DIN];
+        {
+            float x[DIN], qt[DIN], qe;
 #pragma unroll
-        for (int d = 0; d < DIN; ++d) x[d] = 0.0f;
-        if (live) load_row<DIN>(hdst + (size_t)i * DIN, x);
-        if (live && e1 > e0) {
-            float qt[DIN], qe;
-            dst_prologue<DIN>(prm, x, qt, qe);
-            edge_loop<S, DIN>(indices, values, hsrc, e0, e1, gl, qt, qe, st);
+            for (int d = 0; d < DIN; ++d) x[d] = 0.0f;
+            if (live) load_row<DIN>(hdst + (size_t)i * DIN, x);
+            dst_prologue<S, DIN>(prm, x, gl, qt, qe);   // (warp-wide: the group's lanes exchange their parts)
+            if (live && e1 > e0) edge_loop<S, DIN>(indices, values, hsrc, e0, e1, gl, qt, qe, st);
         }
         merge_group<S, DIN>(st);
         const bool any = st.l > 0.0f;
         const float inv = any ? 1.0f / st.l : 0.0f;   // a node without incoming edges keeps only the root term
-        float o[CNT], part = 0.0f;
+        float x[DIN];   // read again (L1) rather than kept in registers across the edge loop
 #pragma unroll
-        for (int k = 0; k < CNT; ++k) {
-            o[k] = out_channel<DIN>(prm, c0 + k, x, st.acc, st.pa, inv, any, relu);
-            part = fmaf(o[k], prm[O::total + c0 + k], part);
-        }
+        for (int d = 0; d < DIN; ++d) x[d] = 0.0f;
+        if (live) load_row<DIN>(hdst + (size_t)i * DIN, x);
+        float part = 0.0f;
         const bool writer = live && !(S == 32 && (gl & 1));
-        if (writer && hout) {
-            if constexpr (CNT == 4) {
-                *reinterpret_cast<float4*>(hout + (size_t)i * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
+        constexpr int STEP = CNT >= 4 ? 4 : CNT;   // channels finished together (a float4 of weights per input channel)
 #pragma unroll
-                for (int k = 0; k < CNT; ++k) hout[(size_t)i * C + c0 + k] = o[k];
+        for (int k0 = 0; k0 < CNT; k0 += STEP) {
+            float o[STEP];
+            out_channels<DIN, STEP>(prm, c0 + k0, x, st.acc, st.pa, inv, any, relu, o);
+#pragma unroll
+            for (int k = 0; k < STEP; ++k) part = fmaf(o[k], prm[O::total + c0 + k0 + k], part);
+            if (writer && hout) {
+                if constexpr (STEP == 4) {
+                    *reinterpret_cast<float4*>(hout + (size_t)i * C + c0 + k0) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < STEP; ++k) hout[(size_t)i * C + c0 + k0 + k] = o[k];
+                }
             }
         }
         if (fc) {   // warp-uniform
@@ -272,7 +335,7 @@ __global__ void __launch_bounds__(256) k_gnn_conv_items(int nitems, const int32_
         const int i = __ldg(items + 3 * t), e0 = __ldg(items + 3 * t + 1), e1 = __ldg(items + 3 * t + 2);
         float x[DIN], qt[DIN], qe;
         load_row<DIN>(hdst + (size_t)i * DIN, x);
-        dst_prologue<DIN>(prm, x, qt, qe);
+        dst_prologue<32, DIN>(prm, x, lane, qt, qe);
         State<DIN> st;
         state_init<DIN>(st);
         edge_loop<32, DIN>(indices, values, hsrc, e0, e1, lane, qt, qe, st);
@@ -352,8 +415,8 @@ int cuda_status(const char* what)
 bool side_ok(const mllp_gnn_side* g)
 {
     if (!g || g->nd < 0 || g->ns < 0 || !g->indptr) return false;
-    if (g->group != 4 && g->group != 8 && g->group != 16 && g->group != 32) return false;
-    if (g->chunk < 32) return false;
+    if (g->group != 1 && g->group != 2 && g->group != 4 && g->group != 8 && g->group != 16 && g->group != 32) return false;
+    if (g->chunk < 16) return false;
     if (g->nlong > 0 && (!g->long_rows || !g->long_first || !g->items || !g->scratch || g->nitems < g->nlong)) return false;
     return true;
 }
@@ -362,10 +425,20 @@ template <int DIN>
 int launch_conv_din(const mllp_gnn_side& g, const float* hdst, const float* hsrc, const float* prm, float* hout, int relu,
                     const float* fc, float* fc_out, cudaStream_t s)
 {
-    const int grid = grid_for_warps(((long long)g.nd * g.group + 31) / 32);
-#define MLLP_CONV_ROWS(SS) \
-    k_gnn_conv_rows<SS, DIN><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, hdst, hsrc, prm, hout, g.chunk, relu, fc, fc_out)
+    // one wave of resident CTAs (the kernel walks its rows with a grid stride)
+    const long long want = (((long long)g.nd * g.group + 31) / 32 + 7) / 8;
+#define MLLP_CONV_ROWS(SS)                                                                                                   \
+    do {                                                                                                                     \
+        static int per_sm = 0;                                                                                               \
+        if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gnn_conv_rows<SS, DIN>, 256, 0) != cudaSuccess || per_sm < 1)) \
+            per_sm = 1;                                                                                                      \
+        const long long cap = 148LL * per_sm;                                                                                \
+        const int grid = (int)(want < 1 ? 1 : want > cap ? cap : want);                                                      \
+        k_gnn_conv_rows<SS, DIN><<<grid, 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, hdst, hsrc, prm, hout, g.chunk, relu, fc, fc_out); \
+    } while (0)
     switch (g.group) {
+        case 1: MLLP_CONV_ROWS(1); break;
+        case 2: MLLP_CONV_ROWS(2); break;
         case 4: MLLP_CONV_ROWS(4); break;
         case 8: MLLP_CONV_ROWS(8); break;
         case 16: MLLP_CONV_ROWS(16); break;

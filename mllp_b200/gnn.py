@@ -41,7 +41,7 @@ class _Side:
     """CSR of one direction (rows = destination nodes) + the long-row tables, on the device, and the
     ``mllp_gnn_side`` struct that describes them to the library."""
 
-    def __init__(self, M, dev, torch):
+    def __init__(self, M, dev, torch, group=None):
         M = M.tocsr()
         M.sort_indices()
         self.nd, self.ns = M.shape
@@ -50,14 +50,25 @@ class _Side:
         self.indices = torch.as_tensor(np.ascontiguousarray(M.indices, dtype=np.int32), device=dev)
         self.values = torch.as_tensor(np.ascontiguousarray(M.data, dtype=np.float64), device=dev)
         lens = np.diff(ip)
-        # lanes per destination row: about half the mean row length (two edges per lane are in flight), like the
-        # lanes-per-row choice of the LP format.  A group walks rows of up to 16 edges per lane; longer rows (ken-18's
-        # A has 151 rows of ~300 edges among 105 127 rows of ~3: on 4 lanes they were a 100 us tail) are cut into items
-        # of at most ITEM edges, one warp each, whose partial softmax states are merged in a fixed order.
+        # lanes per destination row, like the lanes-per-row choice of the LP format: a lane walks its edges two at a
+        # time, so one lane serves rows of a handful of edges (A' of ken-18 / pds-20 / osa-60: 2 - 6 per row) with no
+        # idle lanes and no merge; S = 2^k >= p90(row length) / 8.  Rows above row_max edges (ken-18's A has 151 rows of
+        # ~300 edges among 105 127 of ~3: on 4 lanes they were a 100 us tail) are cut into items of at most ITEM edges,
+        # one warp each, whose partial softmax states are merged in a fixed order; the two extra launches only pay above
+        # ~128 edges when the group is already wide.
         reg = lens[(lens > 0) & (lens <= CHUNK)]
-        mean = float(reg.mean()) if reg.size else 1.0
-        self.group = 4 if mean <= 12 else 8 if mean <= 24 else 16 if mean <= 48 else 32
-        self.row_max = max(16 * self.group, 128)   # (two more launches per conv only pay above ~128 edges)
+        p90 = float(np.percentile(reg, 90)) if reg.size else 1.0
+        self.group = 1
+        while self.group < 32 and 8 * self.group < p90:
+            self.group *= 2
+        # a small graph does not fill the GPU's lanes: wider groups then only shorten the per-row edge chain
+        while self.group < 32 and self.group < p90 and 2 * self.group * self.nd <= 148 * 768:
+            self.group *= 2
+        if group is not None:   # tests: force the lanes per row
+            if group not in (1, 2, 4, 8, 16, 32):
+                raise ValueError("group must be 1, 2, 4, 8, 16 or 32")
+            self.group = int(group)
+        self.row_max = 32 * self.group if self.group <= 2 else max(16 * self.group, 128)
         long_rows = np.nonzero(lens > self.row_max)[0].astype(np.int32)
         items, first = [], [0]
         for r in long_rows:
@@ -81,7 +92,7 @@ class BipartiteGraph:
     """The LP as the reference's bipartite graph: x1 = coefs (variables), x2 = rhs (constraints), one edge per
     nonzero with attribute a_ij (linear_program_methods.py:89-103), held as CSR of A and of A'."""
 
-    def __init__(self, constrs, constr_weights, rhs, coefs, device=0):
+    def __init__(self, constrs, constr_weights, rhs, coefs, device=0, groups=None):
         import ctypes
         import scipy.sparse as sp
         import torch
@@ -93,8 +104,9 @@ class BipartiteGraph:
             raise ValueError("constrs has %d rows, rhs has %d" % (ip.shape[0] - 1, m))
         A = sp.csr_matrix((vv, ii, ip), shape=(m, n))
         self.m, self.n, self.nnz = m, n, int(A.nnz)
-        self.to_con = _Side(A, dev, torch)            # variable -> constraint ("s2w"): rows of A
-        self.to_var = _Side(A.T.tocsr(), dev, torch)  # constraint -> variable ("w2s"): rows of A'
+        gv, gc = groups if groups is not None else (None, None)
+        self.to_con = _Side(A, dev, torch, gc)            # variable -> constraint ("s2w"): rows of A
+        self.to_var = _Side(A.T.tocsr(), dev, torch, gv)  # constraint -> variable ("w2s"): rows of A'
         self.x1 = torch.as_tensor(np.asarray(coefs, dtype=np.float32).reshape(n, 1), device=dev)
         self.x2 = torch.as_tensor(np.asarray(rhs, dtype=np.float32).reshape(m, 1), device=dev)
         self.work = torch.empty(int(_cabi.lib().mllp_gnn_workspace_floats(n, m)), dtype=torch.float32, device=dev)

@@ -136,3 +136,17 @@ def test_gpu_single_conv_matches_oracle(din, name):
     con = np.repeat(np.arange(m, dtype=np.int64), np.diff(A.indptr))
     ref = G.transformer_conv(st, cv, xs, xd, var, con, A.data.astype(np.float32))
     assert close(out.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])
+def test_gpu_forward_every_lane_group(group):
+    """every lanes-per-row instantiation of the conv kernel (the graph normally picks it from the row lengths), with rows
+    above the group's limit going through the cut-row kernels"""
+    import mllp_b200.gnn as GN
+    A, b, c = D.load_csr("25fv47")
+    st = G.init_state(group)
+    g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c, groups=(group, group))
+    assert g.to_var.group == group and g.to_con.group == group
+    out = GN.GNNModel(st)(g).cpu().numpy()
+    assert close(out, G.gnn_forward(st, A, b, c))
