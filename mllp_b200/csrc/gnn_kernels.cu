@@ -352,8 +352,9 @@ __global__ void __launch_bounds__(256) k_gnn_conv_items(int nitems, const int32_
     }
 }
 
-// long rows: merge the partial states of row r's items [first[r], first[r+1]) in order (lane d < din owns acc_d), then
-// the epilogue (lane c < 16 finishes channel c; acc and x are handed round by shuffles)
+// long rows: merge the partial states of row r's items [first[r], first[r+1]) -- lane k folds items k, k + 32, ... in
+// order, then the 32 lanes' states are merged by the butterfly (a fixed order: osa-60's longest row has 340 items, one
+// after the other they were a 140 us chain of dependent loads) -- then the epilogue (lane c < 16 finishes channel c)
 template <int DIN>
 __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t* __restrict__ long_rows,
                                                         const int32_t* __restrict__ first, const float* __restrict__ scratch,
@@ -361,37 +362,45 @@ __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t
                                                         float* __restrict__ hout, int relu, const float* __restrict__ fc,
                                                         float* __restrict__ fc_out)
 {
-    using O = Off<DIN>;
     const int lane = threadIdx.x & 31, c = lane & 15;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nlong; r += warps) {
         const int i = __ldg(long_rows + r);
-        float m = -INFINITY, l = 0.0f, pa = 0.0f, acc = 0.0f;
-        for (int t = __ldg(first + r); t < __ldg(first + r + 1); ++t) {
-            const float* o = scratch + (size_t)t * ITEM_FLOATS;
-            const float m2 = o[0], l2 = o[1], pa2 = o[2], a2 = o[4 + c];
-            const float mn = fmaxf(m, m2);
-            const float s1 = m == -INFINITY ? 0.0f : __expf(m - mn), s2 = m2 == -INFINITY ? 0.0f : __expf(m2 - mn);
-            l = l * s1 + l2 * s2;
-            pa = pa * s1 + pa2 * s2;
-            acc = acc * s1 + a2 * s2;
-            m = mn;
-        }
-        const bool any = l > 0.0f;
-        const float inv = any ? 1.0f / l : 0.0f;
-        const float xmine = lane < DIN ? __ldg(hdst + (size_t)i * DIN + lane) : 0.0f;
-        float v = 0.0f, sk = __ldg(prm + O::bs + c);
+        const int t1 = __ldg(first + r + 1);
+        State<DIN> st;
+        state_init<DIN>(st);
+#pragma unroll 2
+        for (int t = __ldg(first + r) + lane; t < t1; t += 32) {
+            const float4* o = reinterpret_cast<const float4*>(scratch + (size_t)t * ITEM_FLOATS);
+            const float4 h = o[0];   // m, l, pa
+            float a2[DIN];
+            if constexpr (DIN % 4 == 0) {
 #pragma unroll
-        for (int d = 0; d < DIN; ++d) {
-            const float ad = __shfl_sync(FULLM, acc, d), xd = __shfl_sync(FULLM, xmine, d);
-            v = fmaf(ad, __ldg(prm + O::wv + d * C + c), v);
-            sk = fmaf(xd, __ldg(prm + O::ws + d * C + c), sk);
+                for (int k = 0; k < DIN / 4; ++k) {
+                    const float4 q = o[1 + k];
+                    a2[4 * k] = q.x; a2[4 * k + 1] = q.y; a2[4 * k + 2] = q.z; a2[4 * k + 3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < DIN; ++d) a2[d] = scratch[(size_t)t * ITEM_FLOATS + 4 + d];
+            }
+            const float mn = fmaxf(st.m, h.x);
+            const float s1 = st.m == -INFINITY ? 0.0f : __expf(st.m - mn), s2 = h.x == -INFINITY ? 0.0f : __expf(h.x - mn);
+            st.l = st.l * s1 + h.y * s2;
+            st.pa = st.pa * s1 + h.z * s2;
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) st.acc[d] = st.acc[d] * s1 + a2[d] * s2;
+            st.m = mn;
         }
-        float o = fmaf(pa * inv, __ldg(prm + O::we + c), v * inv) + (any ? __ldg(prm + O::bv + c) : 0.0f) + sk;
-        if (relu) o = fmaxf(o, 0.0f);
-        if (lane < 16 && hout) hout[(size_t)i * C + c] = o;
+        merge_group<32, DIN>(st);
+        const bool any = st.l > 0.0f;
+        const float inv = any ? 1.0f / st.l : 0.0f;
+        float x[DIN], o1[1];
+        load_row<DIN>(hdst + (size_t)i * DIN, x);
+        out_channels<DIN, 1>(prm, c, x, st.acc, st.pa, inv, any, relu, o1);
+        if (lane < 16 && hout) hout[(size_t)i * C + c] = o1[0];
         if (fc) {
-            float part = lane < 16 ? o * __ldg(fc + c) : 0.0f;
+            float part = lane < 16 ? o1[0] * __ldg(fc + c) : 0.0f;
 #pragma unroll
             for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(FULLM, part, w);
             if (lane == 0) fc_out[i] = part + __ldg(fc + C);
