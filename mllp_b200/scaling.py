@@ -43,32 +43,41 @@ def scale_lp(A, b, c, lb=None, ub=None, ruiz_iters=10):
     return out
 
 
-def solve_mps(path, *, tol=1e-6, max_iters=400000, check_every=64, device=0, scale=True):
-    """Read an MPS file (with row senses, bounds, ranges), precondition, solve on the GPU in
-    solve mode and return (objective incl. offset, x, y, info) in the ORIGINAL variables.
-    info['rel_kkt_original'] is the KKT error re-evaluated on the unscaled LP on the device."""
+def solve_scaled(A, b, c, *, lb=None, ub=None, ylo=None, yhi=None, tol=1e-6, max_iters=400000, check_every=64, device=0,
+                 scale=True):
+    """Precondition (Ruiz + Pock-Chambolle), solve on the GPU in solve mode and return (objective, x, y, info) in the
+    ORIGINAL variables; info['rel_kkt_original'] is the KKT error re-evaluated on the unscaled LP on the device."""
     from .linear_program_methods import DeviceLP, pdhg_linear_program, solve_linear_program
-    from .mps import read_mps
-    lp = read_mps(path)
-    A, b, c = lp["A"], lp["b"], lp["c"]
+    A = sp.csr_matrix(A)
     m, n = A.shape
     if scale:
-        s = scale_lp(A, b, c, lp["lb"], lp["ub"])
+        s = scale_lp(A, b, c, lb, ub)
     else:
-        s = {"A": A, "b": b, "c": c, "lb": lp["lb"], "ub": lp["ub"], "dr": np.ones(m), "dc": np.ones(n)}
-    h = DeviceLP(s["A"], s["A"].data, m, n, lb=s["lb"], ub=s["ub"], ylo=lp["ylo"], yhi=lp["yhi"], device=device)
+        s = {"A": A, "b": b, "c": c, "lb": lb, "ub": ub, "dr": np.ones(m), "dc": np.ones(n)}
+    h = DeviceLP(s["A"], s["A"].data, m, n, lb=s["lb"], ub=s["ub"], ylo=ylo, yhi=yhi, device=device)
     obj, xs, ys, info = solve_linear_program(s["A"], s["A"].data, s["b"], s["c"], tol=tol, max_iters=max_iters,
                                              check_every=check_every, handle=h)
     x, y = s["dc"] * xs, s["dr"] * ys
     h.close()
-    h0 = DeviceLP(A, A.data, m, n, lb=lp["lb"], ub=lp["ub"], ylo=lp["ylo"], yhi=lp["yhi"], device=device)
+    h0 = DeviceLP(A, A.data, m, n, lb=lb, ub=ub, ylo=ylo, yhi=yhi, device=device)
     _, _, _, i0 = pdhg_linear_program(A, A.data, b, c, num_iters=0, tau=1.0, sigma=1.0, x0=x, y0=y, handle=h0)
     h0.close()
     info = dict(info)
     info.pop("handle", None)
     info["rel_kkt_original"] = i0["rel_kkt"]
+    return i0["pobj"], x, y, info
+
+
+def solve_mps(path, *, tol=1e-6, max_iters=400000, check_every=64, device=0, scale=True):
+    """Read an MPS file (with row senses, bounds, ranges), precondition, solve on the GPU in
+    solve mode and return (objective incl. offset, x, y, info) in the ORIGINAL variables.
+    info['rel_kkt_original'] is the KKT error re-evaluated on the unscaled LP on the device."""
+    from .mps import read_mps
+    lp = read_mps(path)
+    pobj, x, y, info = solve_scaled(lp["A"], lp["b"], lp["c"], lb=lp["lb"], ub=lp["ub"], ylo=lp["ylo"], yhi=lp["yhi"], tol=tol,
+                                    max_iters=max_iters, check_every=check_every, device=device, scale=scale)
     info["offset"] = lp["offset"]
-    objective = i0["pobj"] + lp["offset"]
+    objective = pobj + lp["offset"]
     if lp["maximize"]:
         objective = -objective
     return objective, x, y, info

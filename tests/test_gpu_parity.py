@@ -311,3 +311,17 @@ def test_geometry_is_chosen_by_measurement():
     lp = M.DeviceLP(A, A.data, *A.shape)
     assert lp.geometry()["mode"] == "grid" and lp.geometry()["ctas"] >= 148
     lp.close()
+
+
+@pytest.mark.parametrize("name", ["dfl001", "pds-20"])
+def test_preconditioned_solve_reaches_highs_optimum_on_config_instances(name):
+    """mid-size / large config instances: Ruiz + Pock-Chambolle scaling on the host, solve mode on
+    the device, objective and KKT error re-evaluated on the unscaled LP"""
+    from mllp_b200.scaling import solve_scaled
+    A, b, c = D.load_csr(name)
+    obj, x, y, info = solve_scaled(A, b, c, tol=1e-6, max_iters=400000)
+    assert info["converged"]
+    assert abs(obj - HIGHS[name]) <= 1e-5 * (1 + abs(HIGHS[name]))
+    assert info["rel_kkt_original"] <= 1e-4 and np.all(x >= 0)
+    kk = O.kkt(A, b, c, x, y)
+    assert abs(kk[0] - obj) <= SCAL_TOL * (1 + abs(obj))
