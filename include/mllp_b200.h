@@ -276,6 +276,17 @@ int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m);
 int mllp_gnn_forward(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
                      const float *d_params, float *d_work, float *d_out, void *stream);
 
+/* The same forward as a replayable plan: the launches are captured once into a CUDA graph (the two convs of a layer,
+ * which are independent, on parallel branches), mllp_gnn_plan_run replays it on `stream` with one graph launch -- for the
+ * small Netlib graphs the forward is launch-bound (afiro: ~10 launches of a few microseconds each).  The plan keeps the
+ * POINTERS it was created with (sides, x1, x2, params, work, out): they must stay valid and in place, their contents may
+ * change between runs.  Create on the device that owns the buffers. */
+typedef struct mllp_gnn_plan *mllp_gnn_plan_t;
+int mllp_gnn_plan_create(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
+                         const float *d_params, float *d_work, float *d_out, mllp_gnn_plan_t *out);
+int mllp_gnn_plan_run(mllp_gnn_plan_t plan, void *stream);
+int mllp_gnn_plan_destroy(mllp_gnn_plan_t plan);
+
 /* One layer (exposed for unit parity): d_hout[nd][16] = [relu] TransformerConv(d_hsrc[ns][din] -> d_hdst[nd][din]) along
  * `side`, d_params = the conv's block as above. */
 int mllp_gnn_conv(const mllp_gnn_side *side, int32_t din, const float *d_hdst, const float *d_hsrc, const float *d_params,

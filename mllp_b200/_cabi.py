@@ -52,6 +52,9 @@ SIGNATURES = {
     "mllp_batch_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i32, _i32, _dbl, _vp, _vp]),
     "mllp_gnn_workspace_floats": (ctypes.c_int64, [_i32, _i32]),
     "mllp_gnn_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mllp_gnn_plan_create": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "mllp_gnn_plan_run": (ctypes.c_int, [_vp, _vp]),
+    "mllp_gnn_plan_destroy": (ctypes.c_int, [_vp]),
     "mllp_gnn_conv_param_floats": (ctypes.c_int64, [_i32]),
     "mllp_gnn_conv": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
 }

@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <new>
 #include <string>
 
 #include "../../include/mllp_b200.h"
@@ -491,14 +492,12 @@ int mllp_gnn_conv(const mllp_gnn_side* side, int32_t din, const float* d_hdst, c
 
 int64_t mllp_gnn_workspace_floats(int32_t n, int32_t m) { return 32 * ((int64_t)n + (int64_t)m) + 64; }
 
-int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
-                     const float* d_params, float* d_work, float* d_out, void* stream)
+// The launches of one forward.  With a second stream the two convs of a layer (independent: both read the layer's
+// input features, :241-246) run side by side: fork / join by events (used under stream capture by the plan).
+static int forward_impl(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                        const float* d_params, float* d_work, float* d_out, cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev)
 {
-    if (!side_ok(to_var) || !side_ok(to_con) || !d_x1 || !d_x2 || !d_params || !d_work || !d_out)
-        return gfail(MLLP_E_INVALID, "mllp_gnn_forward: bad argument");
     const int n = to_var->nd, m = to_con->nd;
-    if (to_var->ns != m || to_con->ns != n) return gfail(MLLP_E_INVALID, "mllp_gnn_forward: the two sides do not describe one graph");
-    cudaStream_t s = (cudaStream_t)stream;
     // workspace: two feature buffers per node set (16 B aligned: n and m are multiplied by 16 floats)
     float* h1[2] = {d_work, d_work + (size_t)16 * n};
     float* h2[2] = {d_work + (size_t)32 * n, d_work + (size_t)32 * n + (size_t)16 * m};
@@ -507,14 +506,106 @@ int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, c
     size_t off = 0;
     for (int k = 0; k < 5; ++k) { P[k] = d_params + off; off += (size_t)(k < 2 ? Off<1>::total : Off<C>::total); }
     const float* fc = d_params + off;
-    // variables are the destination of the w2s convs and the source of the s2w convs; both convs of a layer read the
-    // layer's input features (:241-246)
-    int rc = launch_conv(*to_var, 1, d_x1, d_x2, P[0], h1[0], 1, nullptr, nullptr, s);
-    if (rc == 0) rc = launch_conv(*to_con, 1, d_x2, d_x1, P[1], h2[0], 1, nullptr, nullptr, s);
-    if (rc == 0) rc = launch_conv(*to_var, C, h1[0], h2[0], P[2], h1[1], 1, nullptr, nullptr, s);
-    if (rc == 0) rc = launch_conv(*to_con, C, h2[0], h1[0], P[3], h2[1], 1, nullptr, nullptr, s);
-    if (rc == 0) rc = launch_conv(*to_var, C, h1[1], h2[1], P[4], nullptr, 1, fc, d_out, s);
+    const float* in1 = d_x1;
+    const float* in2 = d_x2;
+    int rc = 0;
+    // variables are the destination of the w2s convs and the source of the s2w convs
+    for (int layer = 0; layer < 2 && rc == 0; ++layer) {
+        const int din = layer == 0 ? 1 : C;
+        cudaStream_t sb = s;
+        if (s2) {
+            if (cudaEventRecord(ev[2 * layer], s) != cudaSuccess || cudaStreamWaitEvent(s2, ev[2 * layer], 0) != cudaSuccess)
+                return cuda_status("mllp_gnn: fork");
+            sb = s2;
+        }
+        rc = launch_conv(*to_var, din, in1, in2, P[2 * layer], h1[layer], 1, nullptr, nullptr, s);
+        if (rc == 0) rc = launch_conv(*to_con, din, in2, in1, P[2 * layer + 1], h2[layer], 1, nullptr, nullptr, sb);
+        if (s2 && rc == 0) {
+            if (cudaEventRecord(ev[2 * layer + 1], s2) != cudaSuccess || cudaStreamWaitEvent(s, ev[2 * layer + 1], 0) != cudaSuccess)
+                return cuda_status("mllp_gnn: join");
+        }
+        in1 = h1[layer]; in2 = h2[layer];
+    }
+    if (rc == 0) rc = launch_conv(*to_var, C, in1, in2, P[4], nullptr, 1, fc, d_out, s);
     return rc;
+}
+
+static int forward_args_ok(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                           const float* d_params, float* d_work, float* d_out, const char* who)
+{
+    if (!side_ok(to_var) || !side_ok(to_con) || !d_x1 || !d_x2 || !d_params || !d_work || !d_out)
+        return gfail(MLLP_E_INVALID, std::string(who) + ": bad argument");
+    if (to_var->ns != to_con->nd || to_con->ns != to_var->nd)
+        return gfail(MLLP_E_INVALID, std::string(who) + ": the two sides do not describe one graph");
+    return 0;
+}
+
+int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                     const float* d_params, float* d_work, float* d_out, void* stream)
+{
+    const int rc = forward_args_ok(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, "mllp_gnn_forward");
+    if (rc != 0) return rc;
+    return forward_impl(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+struct mllp_gnn_plan {
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+};
+
+int mllp_gnn_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                         const float* d_params, float* d_work, float* d_out, mllp_gnn_plan_t* out)
+{
+    if (!out) return gfail(MLLP_E_INVALID, "mllp_gnn_plan_create: null output");
+    *out = nullptr;
+    int rc = forward_args_ok(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, "mllp_gnn_plan_create");
+    if (rc != 0) return rc;
+    cudaStream_t s = nullptr, s2 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph = nullptr;
+    mllp_gnn_plan* plan = new (std::nothrow) mllp_gnn_plan();
+    if (!plan) return gfail(MLLP_E_NOMEM, "mllp_gnn_plan_create: out of host memory");
+    auto cleanup = [&]() {
+        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+        if (graph) cudaGraphDestroy(graph);
+        if (s2) cudaStreamDestroy(s2);
+        if (s) cudaStreamDestroy(s);
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cleanup(); delete plan; return gfail((int)e, std::string("mllp_gnn_plan_create: ") + cudaGetErrorString(e)); }
+    rc = forward_impl(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, s, s2, ev);
+    e = cudaStreamEndCapture(s, &graph);
+    if (rc == 0 && e != cudaSuccess) rc = gfail((int)e, std::string("mllp_gnn_plan_create: capture: ") + cudaGetErrorString(e));
+    if (rc == 0) {
+        size_t nodes = 0;
+        cudaGraphGetNodes(graph, nullptr, &nodes);
+        plan->launches = (int)nodes;
+        e = cudaGraphInstantiate(&plan->exec, graph, 0);
+        if (e != cudaSuccess) rc = gfail((int)e, std::string("mllp_gnn_plan_create: instantiate: ") + cudaGetErrorString(e));
+    }
+    cleanup();
+    if (rc != 0) { cudaGetLastError(); delete plan; return rc; }
+    *out = plan;
+    return 0;
+}
+
+int mllp_gnn_plan_run(mllp_gnn_plan_t plan, void* stream)
+{
+    if (!plan || !plan->exec) return gfail(MLLP_E_INVALID, "mllp_gnn_plan_run: null plan");
+    const cudaError_t e = cudaGraphLaunch(plan->exec, (cudaStream_t)stream);
+    if (e != cudaSuccess) return gfail((int)e, std::string("mllp_gnn_plan_run: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int mllp_gnn_plan_destroy(mllp_gnn_plan_t plan)
+{
+    if (!plan) return 0;
+    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    delete plan;
+    return 0;
 }
 
 }  // extern "C"

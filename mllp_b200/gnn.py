@@ -110,7 +110,19 @@ class BipartiteGraph:
         self.x1 = torch.as_tensor(np.asarray(coefs, dtype=np.float32).reshape(n, 1), device=dev)
         self.x2 = torch.as_tensor(np.asarray(rhs, dtype=np.float32).reshape(m, 1), device=dev)
         self.work = torch.empty(int(_cabi.lib().mllp_gnn_workspace_floats(n, m)), dtype=torch.float32, device=dev)
-        self._byref = ctypes.byref
+        self._plans = {}   # parameter buffer -> (mllp_gnn_plan_t, output buffer, parameters)
+
+    def close(self):
+        """release the captured forward plans (the device arrays go with the object)"""
+        for plan, _, _ in self._plans.values():
+            _cabi.lib().mllp_gnn_plan_destroy(plan)
+        self._plans = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pack_conv(state, cv):
@@ -162,8 +174,10 @@ class GNNModel:
         parts += [self.state["fc.weight"].reshape(-1), self.state["fc.bias"].reshape(-1)]
         self.params = torch.as_tensor(np.ascontiguousarray(np.concatenate(parts), dtype=np.float32), device=dev)
 
-    def forward(self, g):
-        """logit per variable, float32 tensor (n,) on the graph's device; one library call, no host synchronisation."""
+    def forward(self, g, use_plan=True):
+        """logit per variable, float32 tensor (n,) on the graph's device; no host synchronisation.  With ``use_plan`` the
+        launches are captured once per (graph, parameters) into a CUDA graph (mllp_gnn_plan_*: the two convs of a layer on
+        parallel branches) and replayed with one launch; otherwise one mllp_gnn_forward call (5 - 11 launches)."""
         import ctypes
         import torch
         if not isinstance(g, BipartiteGraph):
@@ -171,10 +185,24 @@ class GNNModel:
         if g.device != self.device:
             raise ValueError("graph and model live on different devices")
         dev = g.x1.device
-        out = torch.empty(g.n, dtype=torch.float32, device=dev)
-        _cabi.check(_cabi.lib().mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
-                                                 g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), out.data_ptr(),
-                                                 _torch_stream(dev)), "mllp_gnn_forward")
-        return out
+        L = _cabi.lib()
+        if not use_plan:
+            out = torch.empty(g.n, dtype=torch.float32, device=dev)
+            _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
+                                           g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), out.data_ptr(),
+                                           _torch_stream(dev)), "mllp_gnn_forward")
+            return out
+        key = self.params.data_ptr()
+        entry = g._plans.get(key)
+        if entry is None:
+            buf = torch.empty(g.n, dtype=torch.float32, device=dev)
+            plan = ctypes.c_void_p()
+            with torch.cuda.device(dev):
+                _cabi.check(L.mllp_gnn_plan_create(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
+                                                   g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), buf.data_ptr(),
+                                                   ctypes.byref(plan)), "mllp_gnn_plan_create")
+            entry = g._plans[key] = (plan, buf, self.params)   # the plan holds these pointers: keep the tensors alive
+        _cabi.check(L.mllp_gnn_plan_run(entry[0], _torch_stream(dev)), "mllp_gnn_plan_run")
+        return entry[1].clone()
 
     __call__ = forward

@@ -48,8 +48,15 @@ def main(names):
             e0.record(); model(g); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         warm = float(np.median(ts))
-        print("%-8s m %6d n %6d nnz %7d groups %d/%d: %.1f us / forward (L2 flushed; %.1f us warm), %.0f GB/s algorithmic, gather traffic %.0f GB/s"
-              % (name, m, n, A.nnz, g.to_var.group, g.to_con.group, ms * 1e3, warm * 1e3, B / ms / 1e6, gather_bytes(A.nnz) / ms / 1e6), flush=True)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); model.forward(g, use_plan=False); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        plain = float(np.median(ts))
+        print("%-8s m %6d n %6d nnz %7d groups %d/%d: %.1f us / forward (L2 flushed; %.1f us warm; %.1f us as separate launches), %.0f GB/s algorithmic, gather traffic %.0f GB/s"
+              % (name, m, n, A.nnz, g.to_var.group, g.to_con.group, ms * 1e3, warm * 1e3, plain * 1e3, B / ms / 1e6, gather_bytes(A.nnz) / ms / 1e6), flush=True)
 
 
 if __name__ == "__main__":

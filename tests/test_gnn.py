@@ -150,3 +150,23 @@ def test_gpu_forward_every_lane_group(group):
     assert g.to_var.group == group and g.to_con.group == group
     out = GN.GNNModel(st)(g).cpu().numpy()
     assert close(out, G.gnn_forward(st, A, b, c))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["afiro", "pilot87", "ken-18"])
+def test_gpu_forward_plan_replays_bitwise(name):
+    """the captured forward (CUDA graph, the two convs of a layer on parallel branches) gives the bits of the plain
+    launches, replays after the inputs changed in place, and one graph serves several parameter sets"""
+    import torch
+    import mllp_b200.gnn as GN
+    A, b, c = D.load_csr(name)
+    g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c)
+    m1, m2 = GN.GNNModel(G.init_state(5)), GN.GNNModel(G.init_state(6))
+    plain1, plain2 = m1.forward(g, use_plan=False).cpu().numpy(), m2.forward(g, use_plan=False).cpu().numpy()
+    for _ in range(3):
+        assert np.array_equal(m1(g).cpu().numpy(), plain1) and np.array_equal(m2(g).cpu().numpy(), plain2)
+    assert close(plain1, G.gnn_forward(m1.state, A, b, c))
+    g.x2.mul_(0.5)   # new right-hand sides in place: the plan reads the same buffers
+    torch.cuda.synchronize()
+    assert close(m1(g).cpu().numpy(), G.gnn_forward(m1.state, A, 0.5 * b, c))
+    g.close()
