@@ -476,11 +476,60 @@ def pdhg_linear_program_batch(instances, *, num_iters, x0=None, y0=None, tau=Non
     return _batch_results(bt, x, y, scal, {"tau": tau_t.cpu().numpy(), "sigma": sigma_t.cpu().numpy()})
 
 
+def _scaled_batch(instances, shared, rhs_batch, coefs_batch):
+    """Ruiz + Pock-Chambolle scaling of every distinct matrix of a batch (mllp_b200/scaling.py): returns the scaled
+    instances / batches and the per-instance scaling vectors (dr, dc)."""
+    import scipy.sparse as sp
+    from .scaling import ruiz_pock_chambolle
+    cache, out, scal = {}, [], []
+    for constrs, weights, rhs, coefs in ([instances[0]] if shared else instances):
+        key = id(weights)
+        if key not in cache:
+            n = len(coefs) if np.ndim(coefs) == 1 else np.shape(coefs)[-1]
+            ip, ii, vv = csr_from_constrs(constrs, weights, n)
+            A = sp.csr_matrix((vv, ii, ip), shape=(ip.shape[0] - 1, n))
+            dr, dc = ruiz_pock_chambolle(A)
+            As = (sp.diags(dr) @ A @ sp.diags(dc)).tocsr()
+            As.sort_indices()
+            cache[key] = (As, dr, dc)
+        As, dr, dc = cache[key]
+        out.append((As, As.data, dr * np.asarray(rhs, dtype=np.float64), dc * np.asarray(coefs, dtype=np.float64)))
+        scal.append((dr, dc))
+    if shared:
+        dr, dc = scal[0]
+        rhs_batch = np.asarray(rhs_batch, dtype=np.float64) * dr
+        coefs_batch = np.asarray(coefs_batch, dtype=np.float64) * dc
+        scal = scal * len(rhs_batch)
+    return out, rhs_batch, coefs_batch, scal
+
+
 def solve_linear_program_batch(instances, *, tol=1e-6, max_iters=200000, check_every=64, x0=None, y0=None, eta=None,
-                               primal_weight=1.0, device=0, handle=None, shared=False, rhs_batch=None, coefs_batch=None):
+                               primal_weight=1.0, device=0, handle=None, shared=False, rhs_batch=None, coefs_batch=None,
+                               scale=False):
     """Solve mode on a whole batch in one launch; every instance restarts and terminates on
-    its own.  Returns a list of ``(objective, x, y, info)``."""
+    its own.  Returns a list of ``(objective, x, y, info)``.  ``scale=True``: every distinct matrix is preconditioned
+    (Ruiz + Pock-Chambolle, on the host) before the solve -- typically 2-4x fewer iterations on the Netlib instances --;
+    termination is then decided on the scaled LP, the returned x, y, objective and info['rel_kkt_original'] (evaluated
+    on the device by a zero-iteration run of the unscaled batch) refer to the ORIGINAL LP."""
     import torch
+    if scale:
+        if handle is not None or x0 is not None or y0 is not None:
+            raise ValueError("scale=True builds its own batch handle and starts from zero")
+        s_inst, s_rhs, s_coefs, scal = _scaled_batch(instances, shared, rhs_batch, coefs_batch)
+        res = solve_linear_program_batch(s_inst, tol=tol, max_iters=max_iters, check_every=check_every, eta=eta,
+                                         primal_weight=primal_weight, device=device, shared=shared, rhs_batch=s_rhs,
+                                         coefs_batch=s_coefs)
+        xs = [dc * r[1] for r, (dr, dc) in zip(res, scal)]
+        ys = [dr * r[2] for r, (dr, dc) in zip(res, scal)]
+        orig = pdhg_linear_program_batch(instances, num_iters=0, x0=xs, y0=ys, tau=1.0, sigma=1.0, device=device, shared=shared,
+                                         rhs_batch=rhs_batch, coefs_batch=coefs_batch)
+        out = []
+        for r, o, x, y in zip(res, orig, xs, ys):
+            info = dict(r[3])
+            info["rel_kkt_original"] = o[3]["rel_kkt"]
+            info["pobj"], info["dobj"] = o[3]["pobj"], o[3]["dobj"]
+            out.append((o[0], x, y, info))
+        return out
     bt = handle if handle is not None else BatchLP(instances, shared=shared,
                                                    count=None if not shared else len(rhs_batch), device=device)
     b, c, x, y, dev = _batch_vectors(bt, instances, rhs_batch, coefs_batch, x0, y0)

@@ -169,3 +169,27 @@ def test_batch_errors():
     Abig = sp.random(10, big_n, density=1e-3, format="csr", random_state=1)
     with pytest.raises(RuntimeError, match="shared memory"):
         M.BatchLP([(Abig, Abig.data, np.zeros(10), np.zeros(big_n))])
+
+
+def test_preconditioned_batch_solve_matches_highs_with_fewer_iterations():
+    """scale=True: Ruiz + Pock-Chambolle per distinct matrix on the host, one solve launch on the scaled batch, results and
+    KKT error reported for the ORIGINAL LPs"""
+    names = ["sc50a", "sc105", "adlittle", "blend", "share2b"]
+    insts, mats = load_batch(names)
+    plain = M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000)
+    res = M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000, scale=True)
+    for nm, (A, b, c), (obj, x, y, inf) in zip(names, mats, res):
+        assert inf["converged"] and inf["rel_kkt"] <= 1e-6 and inf["rel_kkt_original"] <= 1e-4
+        assert abs(obj - HIGHS[nm]) <= 1e-4 * (1 + abs(HIGHS[nm]))
+        kk = O.kkt(A, b, c, x, y)
+        assert abs(kk[0] - obj) <= 1e-6 * (1 + abs(obj)) and abs(kk[8] - inf["rel_kkt_original"]) <= 1e-9
+    assert sum(r[3]["iters"] for r in res) < sum(r[3]["iters"] for r in plain)
+    # shared matrix: perturbed costs of one LP
+    A, b, c = mats[1]
+    rng = np.random.default_rng(3)
+    cb = c * (1 + 0.05 * rng.uniform(-1, 1, (8, c.shape[0])))
+    bb = np.tile(b, (8, 1))
+    res = M.solve_linear_program_batch([insts[1]], tol=1e-6, max_iters=400000, shared=True, rhs_batch=bb, coefs_batch=cb, scale=True)
+    ref = M.solve_linear_program_batch([insts[1]], tol=1e-6, max_iters=400000, shared=True, rhs_batch=bb, coefs_batch=cb)
+    for (obj, x, y, inf), (obj0, _, _, inf0) in zip(res, ref):
+        assert inf["converged"] and abs(obj - obj0) <= 1e-4 * (1 + abs(obj0)) and np.all(x >= -1e-12)
