@@ -130,6 +130,18 @@ int mllp_lp_tune_info(mllp_lp_t lp, double *out4);
  * CTAs (0 = not tried); [11] reserved. */
 int mllp_lp_geometry(mllp_lp_t lp, double *out12);
 
+/* Block-angular LPs (independent blocks coupled by a few long "linking" rows, e.g. the multicommodity-flow instances
+ * ken-*): mllp_lp_create looks for the structure (rows more than 8x longer than the mean set aside, connected
+ * components of the rest) and, when there are enough blocks to fill the grid, builds a second image of the LP in which
+ * whole blocks are dealt to CTAs.  The parity kernel then keeps every CTA's blocks and iterates in shared memory, meets
+ * with __syncthreads() only, and exchanges the linking rows' partial products and dual values as tagged 16-byte words
+ * (two L2 hops per iteration instead of two grid barriers).  Both kernels are timed at create time, the faster is
+ * used by mllp_pdhg_run (MLLP_BLOCKS=0 / 1 disables / forces it); iterates agree with the grid kernel to rounding.
+ * out8: [0] 1 if mllp_pdhg_run uses the block kernel, [1] blocks (components), [2] linking rows, [3] their nonzeros,
+ * [4] shared memory per CTA, [5] / [6] measured ns per iteration of the grid kernel / of the block kernel,
+ * [7] 1 if the structure was found and the image built. */
+int mllp_lp_blocks_info(mllp_lp_t lp, double *out8);
+
 /* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */
 int mllp_spmv(mllp_lp_t lp, int trans, const double *d_in, double *d_out, void *stream);
 

@@ -76,6 +76,9 @@ struct mllp_lp {
     double tune_ns[2] = {0.0, 0.0};   // measured ns / iteration before and after the tuning rounds
     double geom_ns[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // geometry search: ns / iteration of grid, cluster 16 / 8 / 4, one CTA, broadcast cluster 16 / 8 / 4 / 1 (0 = not tried)
     int tune_rounds = 0;
+    BlockPlan* blocks = nullptr;      // block-angular structure (blocks.cu), or null
+    bool use_blocks = false;          // the parity kernel runs on it (chosen by timing both)
+    double blocks_ns[2] = {0.0, 0.0}; // ns / iteration of the grid kernel and of the block kernel
     int32_t* d_orderX = nullptr;  // internal position k holds original column order[k]
     int32_t* d_orderY = nullptr;
     double* tmp_n = nullptr;
@@ -368,6 +371,38 @@ static int measure_phases(mllp_lp* lp, PhaseTimes& T)
         t1 = std::max(t1, at(iters - 1, g, 3));
     }
     T.iter_ns = (double)(long long)(t1 - t0) / (iters - skip);
+    return 0;
+}
+
+// One launch of `iters` parity iterations on the handle's internal state: the block kernel when the LP is block-angular
+// and it measured faster, else the persistent kernel of the chosen geometry.
+static int launch_parity(mllp_lp* lp, double tau, double sigma, int iters, cudaStream_t s)
+{
+    lp->d.join_base = lp->join_epoch;
+    lp->join_epoch += 2ull * (unsigned long long)iters + 2ull;
+    if (lp->use_blocks && lp->blocks)
+        return blocks_run(lp->blocks, lp->d.x, lp->d.y, lp->d.b, lp->d.c, tau, sigma, iters, lp->d.join_base, s);
+    return launch_pdhg_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, iters, s);
+}
+
+// ns per parity iteration as currently configured (CUDA events around one launch of `iters` iterations on the handle's
+// internal state, after a short warm-up launch).
+static int time_parity(mllp_lp* lp, int iters, double& ns_per_iter)
+{
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    int rc = launch_parity(lp, 1.0, 1.0, 16, 0);
+    if (rc == 0) rc = (int)cudaEventRecord(e0, 0);
+    if (rc == 0) rc = launch_parity(lp, 1.0, 1.0, iters, 0);
+    if (rc == 0) rc = (int)cudaEventRecord(e1, 0);
+    if (rc == 0) rc = (int)cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (rc == 0) rc = (int)cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "timed parity run");
+    ns_per_iter = (double)ms * 1e6 / (double)iters;
     return 0;
 }
 
@@ -688,6 +723,41 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             rc = tuning();
         }
 
+        // Block-angular LPs (ken-18: 475 independent blocks + 151 linking rows): the block kernel of blocks.cu keeps every
+        // CTA's blocks in shared memory and needs no grid barrier.  Built when the structure is there (standard form,
+        // single GPU, cooperative grid), timed against the grid kernel on the zero state, kept when faster.
+        // MLLP_BLOCKS = 0 / 1 disables / forces it.
+        if (rc == 0 && nranks == 1 && resident && !lp->bounds && lp->d.sync_mode == SYNC_GRID && m > 0 && n > 0 &&
+            env_int("MLLP_BLOCKS", tune > 0 ? -1 : 0) != 0) {
+            auto pick = [&]() -> int {
+                RC_OK(blocks_create(m, n, h_indptr, h_indices, h_values, posX.data(), posY.data(), device, prop.multiProcessorCount,
+                                    &lp->blocks));
+                if (!lp->blocks) return 0;
+                if (env_int("MLLP_BLOCKS", -1) == 1) { lp->use_blocks = true; return 0; }
+                double t_grid = 0, t_blk = 0;
+                lp->use_blocks = false;
+                RC_OK(time_parity(lp, 200, t_grid));
+                lp->use_blocks = true;
+                // the block kernel's work per CTA is small: fewer threads mean cheaper CTA barriers, more threads fewer rounds
+                int best_threads = 1024;
+                if (getenv("MLLP_BLOCKS_THREADS") == nullptr) {
+                    for (int th : {1024, 512}) {
+                        double t = 0;
+                        blocks_set_threads(lp->blocks, th);
+                        RC_OK(time_parity(lp, 200, t));
+                        if (t_blk == 0 || t < t_blk) { t_blk = t; best_threads = th; }
+                    }
+                    blocks_set_threads(lp->blocks, best_threads);
+                } else {
+                    RC_OK(time_parity(lp, 200, t_blk));
+                }
+                lp->blocks_ns[0] = t_grid; lp->blocks_ns[1] = t_blk;
+                lp->use_blocks = t_blk < 0.97 * t_grid;
+                return 0;
+            };
+            rc = pick();
+        }
+
         int64_t* I = lp->info;
         I[0] = m; I[1] = n; I[2] = nranks > 1 ? HA.nnz_emitted : nnz;
         I[3] = (int64_t)HA.tiles.size(); I[4] = (int64_t)HAT.tiles.size();
@@ -805,6 +875,7 @@ int mllp_lp_destroy(mllp_lp_t lp)
     for (void* p : lp->ipc_opened) cudaIpcCloseMemHandle(p);
     if (lp->comm) { NcclApi* api = nccl_api(); if (api) api->comm_destroy(lp->comm); }
     if (lp->graph) cudaGraphExecDestroy(lp->graph);
+    blocks_destroy(lp->blocks);
     for (void* p : lp->allocs) cudaFree(p);
     for (void* p : lp->mat_allocs) cudaFree(p);
     delete lp;
@@ -822,6 +893,16 @@ int mllp_lp_tune_info(mllp_lp_t lp, double* out4)
 {
     if (!lp || !out4) return fail(MLLP_E_INVALID, "mllp_lp_tune_info: null argument");
     out4[0] = lp->tune_ns[0]; out4[1] = lp->tune_ns[1]; out4[2] = (double)lp->tune_rounds; out4[3] = 0.0;
+    return 0;
+}
+
+int mllp_lp_blocks_info(mllp_lp_t lp, double* out8)
+{
+    if (!lp || !out8) return fail(MLLP_E_INVALID, "mllp_lp_blocks_info: null argument");
+    int64_t b[4];
+    blocks_info(lp->blocks, b);
+    out8[0] = lp->use_blocks ? 1.0 : 0.0; out8[1] = (double)b[0]; out8[2] = (double)b[1]; out8[3] = (double)b[2];
+    out8[4] = (double)(b[3] & 0xffffffffll); out8[5] = lp->blocks_ns[0]; out8[6] = lp->blocks_ns[1]; out8[7] = lp->blocks ? 1.0 : 0.0;
     return 0;
 }
 
@@ -938,9 +1019,7 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
             RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));
         }
     } else if (num_iters > 0) {
-        lp->d.join_base = lp->join_epoch;
-        lp->join_epoch += 2ull * (unsigned long long)num_iters + 2ull;
-        RC_OK(launch_pdhg_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, num_iters, s));
+        RC_OK(launch_parity(lp, tau, sigma, num_iters, s));
     }
     if (d_scalars) RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, (double)num_iters, s));
     RC_OK(store_solution(lp, d_x, d_y, s));

@@ -31,4 +31,14 @@ int launch_pdhg_persistent_xchg(const DevLP& lp, const PeerInfo& pi, bool bounds
                                 double tau, double sigma, int iters, unsigned epoch, cudaStream_t s);
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
                             int max_iters, int check_every, double tol, double* out, cudaStream_t s);
+
+// blocks.cu: block-angular LPs (components dealt to CTAs, linking rows through tagged words; no grid barrier)
+struct BlockPlan;
+int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, const int32_t* posX,
+                  const int32_t* posY, int device, int G, BlockPlan** out);   // *out == nullptr: no usable structure
+int blocks_run(BlockPlan* bp, double* gx, double* gy, const double* gb, const double* gc, double tau, double sigma, int iters,
+               unsigned long long tag0, cudaStream_t s);
+void blocks_info(const BlockPlan* bp, int64_t* out4);   // components, linking rows, linking nonzeros, shared memory | threads << 32
+int blocks_set_threads(BlockPlan* bp, int threads);
+void blocks_destroy(BlockPlan* bp);
 }  // namespace mllp

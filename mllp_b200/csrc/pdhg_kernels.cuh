@@ -120,6 +120,19 @@ struct SmemMem {
     static __device__ __forceinline__ double gather(const double* p) { return *p; }
 };
 
+// Tagged 16-byte words {bits(value), bits(value) ^ tag}: value and validity travel in ONE 128-bit access, so no fence
+// orders them -- a word whose halves do not xor to the expected tag is stale or torn and is simply read again.  (The
+// polled join of split rows below and the linking rows of blocks.cu cross CTAs this way.)
+__device__ __forceinline__ void ld_tagged(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_tagged(unsigned long long* p, double v, unsigned long long tag)
+{
+    const unsigned long long a = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // Grid barrier for the persistent cooperative kernel: monotonic counter, one arrival per
 // CTA (release), acquire-poll.  `target` lives in thread 0's register.

@@ -154,6 +154,13 @@ class DeviceLP:
         return {"mode": ("grid", "cluster", "cta", "bcast")[int(out[0])], "ctas": int(out[1]),
                 "ns_per_iter": {k: out[2 + i] for i, k in enumerate(names) if out[2 + i] > 0}}
 
+    def blocks_info(self):
+        """Block-angular structure found by mllp_lp_create and whether the parity kernel runs on it (mllp_lp_blocks_info)."""
+        out = (ctypes.c_double * 8)()
+        _cabi.check(_cabi.lib().mllp_lp_blocks_info(self.handle, out), "mllp_lp_blocks_info")
+        return {"used": bool(out[0]), "found": bool(out[7]), "blocks": int(out[1]), "linking_rows": int(out[2]),
+                "linking_nnz": int(out[3]), "smem_bytes": int(out[4]), "ns_per_iter_grid": out[5], "ns_per_iter_blocks": out[6]}
+
     def sigma_max(self, iters=50, stream=None):
         """||A||_2 estimate by power iteration on the device (cached)."""
         if self._sigma_max is None:

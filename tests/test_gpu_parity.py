@@ -327,3 +327,67 @@ def test_preconditioned_solve_reaches_highs_optimum_on_config_instances(name):
     assert np.linalg.norm(np.minimum(x, 0.0)) <= 1e-6 * (1 + np.linalg.norm(x))
     kk = O.kkt(A, b, c, x, y)
     assert abs(kk[0] - obj) <= SCAL_TOL * (1 + abs(obj))
+
+
+def _block_angular(nblocks=400, seed=5):
+    """random block-angular LP: nblocks independent blocks (5 x 8, one of them with an empty row and an unused column)
+    coupled by 6 dense linking rows; a few columns occur in linking rows only"""
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for k in range(nblocks):
+        Bk = sp.random(5, 8, density=0.45, random_state=seed + k, format="csr")
+        Bk.data[:] = rng.standard_normal(Bk.nnz)
+        blocks.append(Bk)
+    D0 = sp.block_diag(blocks, format="csr")
+    extra = sp.csr_matrix((D0.shape[0], 12))                       # columns seen by the linking rows only
+    top = sp.hstack([D0, extra]).tocsr()
+    link = sp.random(6, top.shape[1], density=0.3, random_state=seed + 9999, format="csr")
+    link.data[:] = rng.standard_normal(link.nnz)
+    A = sp.vstack([top[:700], link[:3], top[700:], link[3:]]).tocsr()   # linking rows in the middle and at the end
+    A.sort_indices()
+    return A, rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[1])
+
+
+@pytest.mark.parametrize("name,K", [("ken-18", 600), ("synthetic", 300)])
+def test_block_angular_kernel_matches_oracle_and_grid_kernel(name, K, monkeypatch):
+    """blocks.cu: components dealt to CTAs, iterates in shared memory, linking rows through tagged words -- against the
+    oracle and against the grid kernel of the same handle type; warm start continues bitwise"""
+    A, b, c = _block_angular() if name == "synthetic" else D.load_csr(name)
+    m, n = A.shape
+    eta = 0.9 / O.power_iteration(A, 50)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MLLP_BLOCKS", mode)
+        monkeypatch.setenv("MLLP_GEOM", "0")
+        lp = M.DeviceLP(A, A.data, m, n)
+        bi = lp.blocks_info()
+        assert bi["used"] == (mode == "1") and (mode == "0" or (bi["found"] and bi["blocks"] >= 296 and bi["linking_rows"] >= 6))
+        _, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=K, tau=eta, sigma=eta, handle=lp)
+        _, xh, yh, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=K // 2, tau=eta, sigma=eta, handle=lp)
+        _, x2, y2, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=K - K // 2, tau=eta, sigma=eta, x0=xh, y0=yh, handle=lp)
+        assert np.array_equal(x, x2) and np.array_equal(y, y2)
+        res[mode] = (x, y, info)
+        lp.close()
+    xo, yo = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, K)
+    x, y, info = res["1"]
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    scal_close(info, O.kkt(A, b, c, xo, yo))
+    assert rel(x, res["0"][0]) < 1e-12 and rel(y, res["0"][1]) < 1e-12
+
+
+def test_block_angular_kernel_is_chosen_by_measurement_and_only_where_it_applies(monkeypatch):
+    monkeypatch.delenv("MLLP_BLOCKS", raising=False)
+    A, b, c = D.load_csr("ken-18")                  # 475 blocks + 151 linking rows: built and timed against the grid kernel
+    lp = M.DeviceLP(A, A.data, *A.shape)
+    bi = lp.blocks_info()
+    assert bi["found"] and bi["blocks"] == 475 and bi["linking_rows"] == 151 and bi["ns_per_iter_grid"] > 0
+    assert bi["used"] == (bi["ns_per_iter_blocks"] < 0.97 * bi["ns_per_iter_grid"])
+    lp.close()
+    A, b, c = D.load_csr("pds-20")                  # one giant component: no block structure
+    lp = M.DeviceLP(A, A.data, *A.shape)
+    assert not lp.blocks_info()["found"] and not lp.blocks_info()["used"]
+    lp.close()
+    A, b, c = D.load_csr("sc105")                   # general form keeps the grid / cluster kernels
+    lp = M.DeviceLP(A, A.data, *A.shape, lb=np.zeros(A.shape[1]), ub=np.ones(A.shape[1]))
+    assert not lp.blocks_info()["used"]
+    lp.close()
