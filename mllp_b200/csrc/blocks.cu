@@ -112,7 +112,7 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
     const int n = G.n, m = G.m, nlong = G.nlong, nlink = B.nlink, nctas = (int)gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int wc = G.wc;                                              // entry slots per column
-    const int pw = min(max((nlink + 31) >> 5, 1), nwarps / 4);        // warps that serve the linking rows
+    const int pw = min(max((nlink + 31) >> 5, 1), nwarps / 2);        // warps that serve the linking rows (a thread per row)
     const int rw = nwarps - pw;                                       // warps that walk the block
     const int nlc = G.nlc;                                            // leading columns with linking entries
     // shared memory: x | xbar | c | yy = (y of the block rows | duals of the linking rows) | b | colval | rowval | lval |
