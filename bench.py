@@ -357,6 +357,7 @@ def main():
     weights = A.data
     lp = M.device_lp(constrs, weights, b, c, device=local)   # built once, as in the loader
     info = lp.info()
+    geom, blocks = lp.geometry(), lp.blocks_info()
     eta = 0.9 / lp.sigma_max()
     KI = args.iters_per_step
     L = _cabi.lib()
@@ -448,11 +449,16 @@ def main():
             "config": {"workload": args.workload, "m": m, "n": n, "nnz": int(A.nnz), "mode": "parity (fixed step PDHG)",
                        "iters_per_step": KI, "bytes_per_iter": bytes_iter, "parallelism": "dp%d (independent LPs, no collective)" % world,
                        "l2": "flushed between steps (256 MiB write); inside a step the iterations reuse the L2-resident matrix by design",
-                       "grid_ctas": info["grid_ctas"], "threads": info["threads"], "final_pobj": float(final_scal[0]),
+                       "grid_ctas": info["grid_ctas"], "threads": info["threads"], "geometry": geom["mode"],
+                       "block_angular": ({"blocks": blocks["blocks"], "linking_rows": blocks["linking_rows"],
+                                          "ns_per_iter_grid_kernel": blocks["ns_per_iter_grid"],
+                                          "ns_per_iter_block_kernel": blocks["ns_per_iter_blocks"]} if blocks["used"] else None),
+                       "final_pobj": float(final_scal[0]),
                        "final_rel_kkt": float(final_scal[8])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload, KI), "algorithmic_bytes_per_launch": bytes_iter * KI,
-                         "kernel": "k_pdhg_persistent (one launch = %d iterations)" % KI,
+                         "kernel": "%s (one launch = %d iterations)" % (
+                             "k_pdhg_blocks" if blocks["used"] else "k_pdhg_persistent" if geom["mode"] == "grid" else "k_pdhg_cluster", KI),
                          "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
                          "note": "achieved = (24 nnz + 36 m + 44 n + 8) B x iterations / CUDA-event time of the step; the working set is L2-resident so DRAM traffic is far below the algorithmic bytes"},
             "clocks": clocks, "gpu_launches": 9 * args.steps, "wall_ms_per_step": wall_ms / args.steps,

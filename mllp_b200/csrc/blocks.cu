@@ -97,6 +97,20 @@ __device__ __forceinline__ double poll_tagged(const unsigned long long* p, unsig
     }
 }
 
+// where CTA g's part of linking row r lives: CTA-major (a CTA's nlink parts are one contiguous, fully coalesced store;
+// a finisher then reads nctas scattered words) or row-major (MLLP_PART_ROW_MAJOR: the other way round)
+#ifdef MLLP_PART_ROW_MAJOR
+#define PART_AT(r, g) ((size_t)(r) * nctas + (size_t)(g))
+#else
+#define PART_AT(r, g) ((size_t)(g) * nlink + (size_t)(r))
+#endif
+// where linking row r's dual for CTA g lives: row-major (the finisher's nctas copies are one contiguous store, a CTA
+// reads nlink scattered words) or CTA-major (MLLP_MAIL_CTA_MAJOR: a CTA's mailbox is contiguous)
+#ifdef MLLP_MAIL_CTA_MAJOR
+#define MAIL_AT(r, g) ((size_t)(g) * nlink + (size_t)(r))
+#else
+#define MAIL_AT(r, g) ((size_t)(r) * nctas + (size_t)(g))
+#endif
 constexpr int MAX_FIN = 32;   // linking rows finished per CTA (one warp each)
 constexpr int FIN_BATCH = 8;  // parts per lane in flight together (8 x 32 = 256 CTAs per round)
 
@@ -187,7 +201,7 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
             for (int r = (int)blockDim.x - 1 - (int)threadIdx.x; r < nlink; r += 32 * pw) {
                 double s = 0.0;
                 for (int e = lptr[r]; e < lptr[r + 1]; ++e) s = fma(lval[e], sxbar[lidx[e]], s);
-                st_tagged(B.partial + 2 * ((size_t)r * nctas + blockIdx.x), s, tag);
+                st_tagged(B.partial + 2 * PART_AT(r, blockIdx.x), s, tag);
             }
             if (tr && threadIdx.x == blockDim.x - 1) tr[1] = global_ns();   // this CTA's parts are published
             // ... the rows this CTA finishes: all parts, fixed order (lane-strided ascending, then butterfly); a lane's
@@ -195,7 +209,7 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
             for (int w = nwarps - 1 - warp; w < MAX_FIN && !(B.dbg & 1); w += pw) {
                 const int r = (int)blockIdx.x + w * nctas;
                 if (r >= nlink) break;
-                const unsigned long long* row = B.partial + 2 * (size_t)r * nctas;
+
                 double s = 0.0;
                 for (int k0 = 0; k0 < nctas; k0 += 32 * FIN_BATCH) {
                     unsigned long long a[FIN_BATCH], b[FIN_BATCH];
@@ -211,7 +225,7 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
                         if (spins && B.poll_gap) __nanosleep((unsigned)B.poll_gap);
 #pragma unroll
                         for (int u = 0; u < FIN_BATCH; ++u)
-                            if (stale & (1u << u)) ld_tagged(row + 2 * (size_t)(k0 + 32 * u + lane), a[u], b[u]);
+                            if (stale & (1u << u)) ld_tagged(B.partial + 2 * PART_AT(r, k0 + 32 * u + lane), a[u], b[u]);
 #pragma unroll
                         for (int u = 0; u < FIN_BATCH; ++u)
                             if ((stale & (1u << u)) && (a[u] ^ b[u]) == tag) stale &= ~(1u << u);
@@ -234,12 +248,12 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
                 // delayed the store everybody was waiting for)
                 const double yn = __shfl_sync(FULL, lane == 0 ? fin_y[w] + sigma * (fin_b[w] - s) : 0.0, 0);
                 if (lane == 0) fin_y[w] = yn;
-                for (int k = lane; k < nctas; k += 32) st_tagged(B.ylink + 2 * ((size_t)k * nlink + r), yn, tag);
+                for (int k = lane; k < nctas; k += 32) st_tagged(B.ylink + 2 * MAIL_AT(r, k), yn, tag);
                 if (tr && w == 0 && lane == 0) tr[2] = global_ns();   // this CTA's first linking row is finished and sent
             }
             // ... and the new duals of all linking rows, from this CTA's mailbox
             for (int r = (int)blockDim.x - 1 - (int)threadIdx.x; r < nlink && !(B.dbg & 1); r += 32 * pw)
-                syy[m + r] = poll_tagged(B.ylink + 2 * ((size_t)blockIdx.x * nlink + r), tag, B.abort_flag, (unsigned)B.poll_gap);
+                syy[m + r] = poll_tagged(B.ylink + 2 * MAIL_AT(r, blockIdx.x), tag, B.abort_flag, (unsigned)B.poll_gap);
             if (tr && threadIdx.x == blockDim.x - 1) tr[3] = global_ns();   // all duals received (by the last warp)
         } else {
             // (2b) meanwhile the other warps update the remaining columns (none of them reads a linking row's dual) ...

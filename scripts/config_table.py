@@ -44,7 +44,7 @@ def main(out_path):
         g = lp.geometry()
         bpi = lp.info()["bytes_per_iter"]
         rows.append("| %s | %dx%d | %d | %s x%d | %.2f | %.3g | %d | %.0f | %.3f | %.3g | %.1e |" % (
-            name, m, n, A.nnz, g["mode"], g["ctas"], us, 1e6 / us, bpi, bpi / us / 1e3, bpi / us / 1e3 / hbm, cpu, err))
+            name, m, n, A.nnz, "blocks" if lp.blocks_info()["used"] else g["mode"], g["ctas"], us, 1e6 / us, bpi, bpi / us / 1e3, bpi / us / 1e3 / hbm, cpu, err))
         print(rows[-1], flush=True)
         lp.close()
     open(out_path, "w").write("\n".join(rows) + "\n")
