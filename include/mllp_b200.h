@@ -142,6 +142,14 @@ int mllp_lp_geometry(mllp_lp_t lp, double *out12);
  * [7] 1 if the structure was found and the image built. */
 int mllp_lp_blocks_info(mllp_lp_t lp, double *out8);
 
+/* Host-only check of the block images (no GPU; used by the CPU tests): every row and column is placed exactly once,
+ * and the products A xbar and A'y replayed from the groups' lists equal the plain CSR products.
+ * out8: [0] 1 if the matrix has a usable block structure for G groups, [1] components, [2] linking rows, [3] their
+ * nonzeros, [4] worst relative error of A xbar, [5] of A'y, [6] shared memory per CTA (bytes), [7] largest group's
+ * columns. */
+int mllp_blocks_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices,
+                          const double *values, int32_t G, double *out8);
+
 /* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */
 int mllp_spmv(mllp_lp_t lp, int trans, const double *d_in, double *d_out, void *stream);
 

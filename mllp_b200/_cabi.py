@@ -39,6 +39,7 @@ SIGNATURES = {
     "mllp_lp_tune_info": (ctypes.c_int, [_vp, _vp]),
     "mllp_lp_geometry": (ctypes.c_int, [_vp, _vp]),
     "mllp_lp_blocks_info": (ctypes.c_int, [_vp, _vp]),
+    "mllp_blocks_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mllp_spmv": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
     "mllp_estimate_norm": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_dbl), _vp]),
     "mllp_pdhg_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),

@@ -359,22 +359,34 @@ void blocks_info(const BlockPlan* bp, int64_t* out4)
     out4[3] = bp ? (int64_t)bp->smem + ((int64_t)bp->threads << 32) : 0;   // shared memory | threads << 32
 }
 
-// Returns 0 with *out == nullptr when the matrix has no usable block structure (not an error).
-int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, const int32_t* posX,
-                  const int32_t* posY, int device, int G, BlockPlan** out)
+// Host image of the block structure: linking rows, groups of components, every group's lists (no CUDA involved).
+struct HostGroups {
+    int G = 0, nlink = 0, ncomp = 0;
+    int64_t link_nnz = 0;
+    std::vector<int32_t> link_rows;                  // original row ids, ascending
+    std::vector<std::vector<int32_t>> rows, cols;    // per group: original ids in local order
+    struct Img {
+        int wc = 0, nlong = 0, nlc = 0;
+        std::vector<int32_t> colidx, rowptr, rowidx, lptr, lidx;
+        std::vector<double> colval, rowval, lval;
+    };
+    std::vector<Img> img;
+    int max_m = 0, max_n = 0, max_c = 0, max_r = 0, max_l = 0;
+};
+
+// false: the matrix has no usable block structure
+static bool build_groups(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, int G, HostGroups& H)
 {
-    *out = nullptr;
     const int64_t nnz = indptr[m];
-    if (m < 1 || n < 1 || nnz < 1 || G < 2) return 0;
+    if (m < 1 || n < 1 || nnz < 1 || G < 2) return false;
     // 1. linking rows: far longer than the typical row
     const double mean = (double)nnz / (double)m;
     const int thr = env_i("MLLP_BLOCKS_ROW", (int)std::max(32.0, 8.0 * mean));
-    std::vector<int32_t> link_rows, link_id((size_t)m, -1);
-    int64_t link_nnz = 0;
+    std::vector<int32_t> link_id((size_t)m, -1);
     for (int i = 0; i < m; ++i)
-        if (indptr[i + 1] - indptr[i] > thr) { link_id[i] = (int32_t)link_rows.size(); link_rows.push_back(i); link_nnz += indptr[i + 1] - indptr[i]; }
-    const int nlink = (int)link_rows.size();
-    if (nlink > MAX_FIN * G || 2 * link_nnz > nnz) return 0;
+        if (indptr[i + 1] - indptr[i] > thr) { link_id[i] = (int32_t)H.link_rows.size(); H.link_rows.push_back(i); H.link_nnz += indptr[i + 1] - indptr[i]; }
+    const int nlink = H.nlink = (int)H.link_rows.size();
+    if (nlink > MAX_FIN * G || 2 * H.link_nnz > nnz) return false;
     // 2. connected components of the rest (rows 0 .. m-1, columns m .. m+n-1)
     UnionFind uf((size_t)m + (size_t)n);
     for (int i = 0; i < m; ++i) {
@@ -390,8 +402,8 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
         comp_of[v] = comp_of[r];
         comp_cost[comp_of[v]] += 1 + (v < m ? indptr[v + 1] - indptr[v] : 0);
     }
-    const int ncomp = (int)comp_cost.size();
-    if (ncomp < 2 * G) return 0;   // not enough independent pieces to balance a grid
+    const int ncomp = H.ncomp = (int)comp_cost.size();
+    if (ncomp < 2 * G) return false;   // not enough independent pieces to balance a grid
     // 3. components to groups: longest processing time first
     std::vector<int32_t> by_cost((size_t)ncomp);
     std::iota(by_cost.begin(), by_cost.end(), 0);
@@ -408,18 +420,19 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
             pq.push(l);
         }
     }
-    // 4. local orders: rows and columns of a group sorted by length (threads of a warp then loop alike)
+    // 4. local orders: rows sorted by length (threads of a warp then loop alike), columns with linking entries first
     std::vector<int32_t> col_len((size_t)n, 0);
     for (int64_t q = 0; q < nnz; ++q) ++col_len[indices[q]];
     std::vector<char> col_link((size_t)n, 0);
-    for (int i : link_rows)
+    for (int i : H.link_rows)
         for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) col_link[indices[q]] = 1;
-    std::vector<std::vector<int32_t>> rows((size_t)G), cols((size_t)G);
+    H.G = G;
+    H.rows.assign((size_t)G, {}); H.cols.assign((size_t)G, {}); H.img.assign((size_t)G, {});
+    auto& rows = H.rows; auto& cols = H.cols;
     for (int i = 0; i < m; ++i)
         if (link_id[i] < 0) rows[group_of[comp_of[i]]].push_back(i);
     for (int j = 0; j < n; ++j) cols[group_of[comp_of[m + j]]].push_back(j);
     std::vector<int32_t> local_row((size_t)m, -1), local_col((size_t)n, -1), col_group((size_t)n, 0);
-    int max_m = 0, max_n = 0;
     for (int g = 0; g < G; ++g) {
         std::stable_sort(rows[g].begin(), rows[g].end(), [&](int32_t a, int32_t b) { return indptr[a + 1] - indptr[a] > indptr[b + 1] - indptr[b]; });
         std::stable_sort(cols[g].begin(), cols[g].end(), [&](int32_t a, int32_t b) {
@@ -427,136 +440,139 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
         });
         for (size_t k = 0; k < rows[g].size(); ++k) local_row[rows[g][k]] = (int32_t)k;
         for (size_t k = 0; k < cols[g].size(); ++k) { local_col[cols[g][k]] = (int32_t)k; col_group[cols[g][k]] = g; }
-        max_m = std::max<int>(max_m, (int)rows[g].size());
-        max_n = std::max<int>(max_n, (int)cols[g].size());
+        H.max_m = std::max<int>(H.max_m, (int)rows[g].size());
+        H.max_n = std::max<int>(H.max_n, (int)cols[g].size());
     }
+    // 5. the groups' lists.  Transpose once: entries of every column in original row order
+    std::vector<int64_t> tptr((size_t)n + 1, 0);
+    for (int64_t q = 0; q < nnz; ++q) ++tptr[indices[q] + 1];
+    for (int j = 0; j < n; ++j) tptr[j + 1] += tptr[j];
+    std::vector<int32_t> trow((size_t)nnz);
+    std::vector<double> tval((size_t)nnz);
+    {
+        std::vector<int64_t> cur(tptr.begin(), tptr.end() - 1);
+        for (int i = 0; i < m; ++i)
+            for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) { const int64_t at = cur[indices[q]]++; trow[at] = i; tval[at] = values[q]; }
+    }
+    for (int g = 0; g < G; ++g) {
+        HostGroups::Img& I = H.img[g];
+        const int mg = (int)rows[g].size(), ng = (int)cols[g].size();
+        for (int j : cols[g]) { I.wc = std::max<int>(I.wc, (int)(tptr[j + 1] - tptr[j])); I.nlc += col_link[j] ? 1 : 0; }
+        I.colidx.assign((size_t)I.wc * ng, 0);
+        I.colval.assign((size_t)I.wc * ng, 0.0);
+        for (int k = 0; k < ng; ++k) {
+            const int j = cols[g][k];
+            int e = 0;
+            for (int64_t q = tptr[j]; q < tptr[j + 1]; ++q, ++e) {
+                const int i = trow[q];
+                I.colidx[(size_t)e * ng + k] = link_id[i] >= 0 ? mg + link_id[i] : local_row[i];
+                I.colval[(size_t)e * ng + k] = tval[q];
+            }
+        }
+        H.max_c = std::max(H.max_c, I.wc * ng);
+        for (int i : rows[g]) {
+            I.rowptr.push_back((int32_t)I.rowidx.size());
+            I.nlong += (indptr[i + 1] - indptr[i] > 4) ? 1 : 0;   // rows are sorted by length
+            for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) { I.rowidx.push_back(local_col[indices[q]]); I.rowval.push_back(values[q]); }
+        }
+        I.rowptr.push_back((int32_t)I.rowidx.size());
+        H.max_r = std::max(H.max_r, (int)I.rowidx.size());
+        I.lptr.reserve((size_t)nlink + 1);
+    }
+    // linking rows restricted to every group (column order of the original row)
+    for (int r = 0; r < nlink; ++r) {
+        for (int g = 0; g < G; ++g) H.img[g].lptr.push_back((int32_t)H.img[g].lidx.size());
+        const int i = H.link_rows[r];
+        for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) {
+            const int j = indices[q], g = col_group[j];
+            H.img[g].lidx.push_back(local_col[j]); H.img[g].lval.push_back(values[q]);
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        H.img[g].lptr.push_back((int32_t)H.img[g].lidx.size());
+        H.max_l = std::max(H.max_l, (int)H.img[g].lidx.size());
+    }
+    return true;
+}
 
+static size_t blocks_smem_bytes(const HostGroups& H)
+{
+    return align16(8 * (3 * (size_t)H.max_n + 2 * (size_t)H.max_m + (size_t)H.nlink + (size_t)H.max_c + (size_t)H.max_r + (size_t)H.max_l) +
+                   4 * ((size_t)H.max_m + (size_t)H.nlink + 2 + (size_t)H.max_c + (size_t)H.max_r + (size_t)H.max_l));
+}
+
+// Returns 0 with *out == nullptr when the matrix has no usable block structure (not an error).
+int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, const int32_t* posX,
+                  const int32_t* posY, int device, int G, BlockPlan** out)
+{
+    *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin - 2048;
-
-    BlockPlan* bp = new (std::nothrow) BlockPlan();
-    if (!bp) { set_last_error("blocks_create: out of host memory"); return MLLP_E_NOMEM; }
-    bp->device = device; bp->ncomp = ncomp; bp->nlink = nlink; bp->link_nnz = link_nnz;
+    BlockPlan* bp = nullptr;
     int rc = 0;
     auto fail_cuda = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && rc == 0) { set_last_error(std::string("blocks_create: ") + what + ": " + cudaGetErrorString(e)); rc = (int)e; }
     };
-    auto up = [&](auto** dst, const auto& h) { up_vec(bp, dst, h, fail_cuda); };
     try {
-        // per group: column lists (block rows and linking rows, original row order), row lists, linking rows' lists
-        struct GroupOff { size_t ce, rp, re, lp, le, xp, yp; int wc; };
+        HostGroups H;
+        if (!build_groups(m, n, indptr, indices, values, G, H)) return 0;
+        const size_t smem = blocks_smem_bytes(H);
+        if (smem > smem_cap) return 0;   // a group's iterates and matrix share do not fit in shared memory
+        bp = new (std::nothrow) BlockPlan();
+        if (!bp) { set_last_error("blocks_create: out of host memory"); return MLLP_E_NOMEM; }
+        bp->device = device; bp->ncomp = H.ncomp; bp->nlink = H.nlink; bp->link_nnz = H.link_nnz;
+        auto up = [&](auto** dst, const auto& h) { up_vec(bp, dst, h, fail_cuda); };
+        // all groups' lists in a few pools
+        struct GroupOff { size_t ce, rp, re, lp, le, xp, yp; };
         std::vector<GroupOff> GO((size_t)G);
         std::vector<int32_t> P_ci, P_rp, P_ri, P_lp, P_li, P_pos;
         std::vector<double> P_cv, P_rv, P_lv;
-        int max_c = 0, max_r = 0, max_l = 0;
-        // transpose once: entries of every column in original row order
-        std::vector<int64_t> tptr((size_t)n + 1, 0);
-        for (int64_t q = 0; q < nnz; ++q) ++tptr[indices[q] + 1];
-        for (int j = 0; j < n; ++j) tptr[j + 1] += tptr[j];
-        std::vector<int32_t> trow((size_t)nnz);
-        std::vector<double> tval((size_t)nnz);
-        {
-            std::vector<int64_t> cur(tptr.begin(), tptr.end() - 1);
-            for (int i = 0; i < m; ++i)
-                for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) { const int64_t at = cur[indices[q]]++; trow[at] = i; tval[at] = values[q]; }
-        }
-        std::vector<std::vector<std::pair<int32_t, double>>> link_in((size_t)G);   // scratch per group, filled per linking row
         for (int g = 0; g < G; ++g) {
+            const HostGroups::Img& I = H.img[g];
             GroupOff& o = GO[g];
-            const int mg = (int)rows[g].size(), ng = (int)cols[g].size();
-            o.ce = P_ci.size();
-            int wc = 0;
-            for (int j : cols[g]) wc = std::max<int>(wc, (int)(tptr[j + 1] - tptr[j]));
-            o.wc = wc;
-            P_ci.resize(o.ce + (size_t)wc * ng, 0);
-            P_cv.resize(o.ce + (size_t)wc * ng, 0.0);
-            for (int k = 0; k < ng; ++k) {
-                const int j = cols[g][k];
-                int e = 0;
-                for (int64_t q = tptr[j]; q < tptr[j + 1]; ++q, ++e) {
-                    const int i = trow[q];
-                    P_ci[o.ce + (size_t)e * ng + k] = link_id[i] >= 0 ? mg + link_id[i] : local_row[i];
-                    P_cv[o.ce + (size_t)e * ng + k] = tval[q];
-                }
-            }
-            int32_t cnt = wc * ng;
-            max_c = std::max(max_c, (int)cnt);
-            o.rp = P_rp.size(); o.re = P_ri.size();
-            cnt = 0;
-            for (int i : rows[g]) {
-                P_rp.push_back(cnt);
-                for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) { P_ri.push_back(local_col[indices[q]]); P_rv.push_back(values[q]); ++cnt; }
-            }
-            P_rp.push_back(cnt);
-            max_r = std::max(max_r, (int)cnt);
-            o.xp = P_pos.size(); for (int j : cols[g]) P_pos.push_back(posX[j]);
-            o.yp = P_pos.size(); for (int i : rows[g]) P_pos.push_back(posY[i]);
+            o.ce = P_ci.size(); P_ci.insert(P_ci.end(), I.colidx.begin(), I.colidx.end()); P_cv.insert(P_cv.end(), I.colval.begin(), I.colval.end());
+            o.rp = P_rp.size(); P_rp.insert(P_rp.end(), I.rowptr.begin(), I.rowptr.end());
+            o.re = P_ri.size(); P_ri.insert(P_ri.end(), I.rowidx.begin(), I.rowidx.end()); P_rv.insert(P_rv.end(), I.rowval.begin(), I.rowval.end());
+            o.lp = P_lp.size(); P_lp.insert(P_lp.end(), I.lptr.begin(), I.lptr.end());
+            o.le = P_li.size(); P_li.insert(P_li.end(), I.lidx.begin(), I.lidx.end()); P_lv.insert(P_lv.end(), I.lval.begin(), I.lval.end());
+            o.xp = P_pos.size(); for (int j : H.cols[g]) P_pos.push_back(posX[j]);
+            o.yp = P_pos.size(); for (int i : H.rows[g]) P_pos.push_back(posY[i]);
         }
-        // linking rows restricted to every group (column order of the original row)
-        {
-            std::vector<std::vector<int32_t>> lp((size_t)G), li((size_t)G);
-            std::vector<std::vector<double>> lv((size_t)G);
-            for (int g = 0; g < G; ++g) lp[g].reserve((size_t)nlink + 1);
-            for (int r = 0; r < nlink; ++r) {
-                for (int g = 0; g < G; ++g) lp[g].push_back((int32_t)li[g].size());
-                const int i = link_rows[r];
-                for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) {
-                    const int j = indices[q], g = col_group[j];
-                    li[g].push_back(local_col[j]); lv[g].push_back(values[q]);
-                }
-            }
-            for (int g = 0; g < G; ++g) {
-                lp[g].push_back((int32_t)li[g].size());
-                GO[g].lp = P_lp.size(); GO[g].le = P_li.size();
-                P_lp.insert(P_lp.end(), lp[g].begin(), lp[g].end());
-                P_li.insert(P_li.end(), li[g].begin(), li[g].end());
-                P_lv.insert(P_lv.end(), lv[g].begin(), lv[g].end());
-                max_l = std::max(max_l, (int)li[g].size());
-            }
-        }
-        const size_t smem = align16(8 * (3 * (size_t)max_n + 2 * (size_t)max_m + (size_t)nlink + (size_t)max_c + (size_t)max_r + (size_t)max_l) +
-                                    4 * ((size_t)max_m + (size_t)nlink + 2 + (size_t)max_c + (size_t)max_r + (size_t)max_l));
-        if (smem > smem_cap) rc = -1;   // a group's iterates and matrix share do not fit in shared memory
-        int32_t *d_ci = nullptr, *d_rp = nullptr, *d_ri = nullptr, *d_lp = nullptr, *d_li = nullptr, *d_pos = nullptr,
-                *d_link_pos = nullptr;
+        int32_t *d_ci = nullptr, *d_rp = nullptr, *d_ri = nullptr, *d_lp = nullptr, *d_li = nullptr, *d_pos = nullptr, *d_link_pos = nullptr;
         double *d_cv = nullptr, *d_rv = nullptr, *d_lv = nullptr;
         unsigned long long *d_partial = nullptr, *d_ylink = nullptr;
         unsigned* d_abort = nullptr;
         BlockGroup* d_groups = nullptr;
-        if (rc == 0) {
-            up(&d_ci, P_ci); up(&d_cv, P_cv); up(&d_rp, P_rp); up(&d_ri, P_ri); up(&d_rv, P_rv);
-            up(&d_lp, P_lp); up(&d_li, P_li); up(&d_lv, P_lv); up(&d_pos, P_pos);
-            std::vector<int32_t> link_pos((size_t)nlink);
-            for (int r = 0; r < nlink; ++r) link_pos[r] = posY[link_rows[r]];
-            up(&d_link_pos, link_pos);
-            up(&d_partial, std::vector<unsigned long long>(2 * (size_t)std::max(nlink, 1) * G, 0ull));
-            up(&d_ylink, std::vector<unsigned long long>(2 * (size_t)std::max(nlink, 1) * G, 0ull));
-            up(&d_abort, std::vector<unsigned>(4, 0u));
-        }
+        up(&d_ci, P_ci); up(&d_cv, P_cv); up(&d_rp, P_rp); up(&d_ri, P_ri); up(&d_rv, P_rv);
+        up(&d_lp, P_lp); up(&d_li, P_li); up(&d_lv, P_lv); up(&d_pos, P_pos);
+        std::vector<int32_t> link_pos((size_t)H.nlink);
+        for (int r = 0; r < H.nlink; ++r) link_pos[r] = posY[H.link_rows[r]];
+        up(&d_link_pos, link_pos);
+        up(&d_partial, std::vector<unsigned long long>(2 * (size_t)std::max(H.nlink, 1) * G, 0ull));
+        up(&d_ylink, std::vector<unsigned long long>(2 * (size_t)std::max(H.nlink, 1) * G, 0ull));
+        up(&d_abort, std::vector<unsigned>(4, 0u));
         if (rc == 0) {
             std::vector<BlockGroup> groups((size_t)G);
             for (int g = 0; g < G; ++g) {
                 BlockGroup& Q = groups[g];
                 const GroupOff& o = GO[g];
-                Q.colidx = d_ci + o.ce; Q.colval = d_cv + o.ce; Q.wc = o.wc;
+                Q.colidx = d_ci + o.ce; Q.colval = d_cv + o.ce; Q.wc = H.img[g].wc;
                 Q.rowptr = d_rp + o.rp; Q.rowidx = d_ri + o.re; Q.rowval = d_rv + o.re;
                 Q.lptr = d_lp + o.lp; Q.lidx = d_li + o.le; Q.lval = d_lv + o.le;
                 Q.xpos = d_pos + o.xp; Q.ypos = d_pos + o.yp;
-                Q.m = (int)rows[g].size(); Q.n = (int)cols[g].size();
-                Q.nlong = 0; Q.nlc = 0;
-                for (int j : cols[g]) Q.nlc += col_link[j] ? 1 : 0;   // sorted to the front
-                for (int i : rows[g]) Q.nlong += (indptr[i + 1] - indptr[i] > 4) ? 1 : 0;   // rows are sorted by length
+                Q.m = (int)H.rows[g].size(); Q.n = (int)H.cols[g].size();
+                Q.nlong = H.img[g].nlong; Q.nlc = H.img[g].nlc;
             }
             up(&d_groups, groups);
         }
         if (rc == 0) {
             BlocksDev& D = bp->dev;
             D.groups = d_groups; D.link_pos = d_link_pos; D.partial = d_partial; D.ylink = d_ylink; D.abort_flag = d_abort;
-            D.nlink = nlink; D.G = G; D.max_m = max_m; D.max_n = max_n;
-            D.max_col_nnz = max_c; D.max_row_nnz = max_r; D.max_link_nnz = max_l;
+            D.nlink = H.nlink; D.G = G; D.max_m = H.max_m; D.max_n = H.max_n;
+            D.max_col_nnz = H.max_c; D.max_row_nnz = H.max_r; D.max_link_nnz = H.max_l;
             D.trace = nullptr;
             D.dbg = env_i("MLLP_BLOCKS_DEBUG", 0);
             D.poll_gap = env_i("MLLP_BLOCKS_POLL_NS", 0);
@@ -577,6 +593,71 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
         return rc == -1 ? 0 : rc;   // -1: does not fit -- not an error, the caller keeps the grid kernel
     }
     *out = bp;
+    return 0;
+}
+
+// Host-only check of the block images (no GPU): every row and column is placed exactly once, and the products A xbar
+// and A'y replayed from the groups' lists -- block rows per group, linking rows as the sum of the groups' parts, columns
+// from the padded column lists over (block duals | linking duals) -- equal the plain CSR products.
+// out8: [0] 1 if the matrix has a usable block structure for G groups, [1] components, [2] linking rows, [3] their
+// nonzeros, [4] worst relative error of A xbar, [5] of A'y, [6] shared memory per CTA (bytes), [7] largest group's columns.
+extern "C" int mllp_blocks_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                                     const double* values, int32_t G, double* out8)
+{
+    if (!out8 || !indptr || m < 0 || n < 0 || nnz < 0 || (nnz > 0 && (!indices || !values)) || G < 2) {
+        set_last_error("mllp_blocks_selfcheck: bad argument");
+        return MLLP_E_INVALID;
+    }
+    for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+    try {
+        HostGroups H;
+        if (!build_groups(m, n, indptr, indices, values, G, H)) return 0;
+        out8[0] = 1.0; out8[1] = H.ncomp; out8[2] = H.nlink; out8[3] = (double)H.link_nnz;
+        out8[6] = (double)blocks_smem_bytes(H); out8[7] = H.max_n;
+        std::vector<int> seen_row((size_t)m, 0), seen_col((size_t)n, 0);
+        for (int i : H.link_rows) ++seen_row[i];
+        for (int g = 0; g < G; ++g) {
+            for (int i : H.rows[g]) ++seen_row[i];
+            for (int j : H.cols[g]) ++seen_col[j];
+        }
+        for (int i = 0; i < m; ++i) if (seen_row[i] != 1) { set_last_error("mllp_blocks_selfcheck: a row is placed " + std::to_string(seen_row[i]) + " times"); return MLLP_E_STATE; }
+        for (int j = 0; j < n; ++j) if (seen_col[j] != 1) { set_last_error("mllp_blocks_selfcheck: a column is placed " + std::to_string(seen_col[j]) + " times"); return MLLP_E_STATE; }
+        // deterministic pseudo-random vectors
+        std::vector<double> xb((size_t)n), y((size_t)m), ax((size_t)m, 0.0), aty((size_t)n, 0.0), ax2((size_t)m, 0.0), aty2((size_t)n, 0.0);
+        unsigned long long st = 88172645463325252ull;
+        auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0 - 0.5; };
+        for (double& v : xb) v = rnd();
+        for (double& v : y) v = rnd();
+        for (int i = 0; i < m; ++i)
+            for (int32_t q = indptr[i]; q < indptr[i + 1]; ++q) { ax[i] += values[q] * xb[indices[q]]; aty[indices[q]] += values[q] * y[i]; }
+        for (int g = 0; g < G; ++g) {
+            const HostGroups::Img& I = H.img[g];
+            const int mg = (int)H.rows[g].size(), ng = (int)H.cols[g].size();
+            std::vector<double> yy((size_t)mg + H.nlink);
+            for (int k = 0; k < mg; ++k) yy[k] = y[H.rows[g][k]];
+            for (int r = 0; r < H.nlink; ++r) yy[(size_t)mg + r] = y[H.link_rows[r]];
+            for (int k = 0; k < ng; ++k) {
+                double d = 0.0;
+                for (int e = 0; e < I.wc; ++e) d += I.colval[(size_t)e * ng + k] * yy[I.colidx[(size_t)e * ng + k]];
+                aty2[H.cols[g][k]] = d;
+            }
+            for (int k = 0; k < mg; ++k) {
+                double d = 0.0;
+                for (int32_t e = I.rowptr[k]; e < I.rowptr[k + 1]; ++e) d += I.rowval[e] * xb[H.cols[g][I.rowidx[e]]];
+                ax2[H.rows[g][k]] = d;
+            }
+            for (int r = 0; r < H.nlink; ++r)
+                for (int32_t e = I.lptr[r]; e < I.lptr[r + 1]; ++e) ax2[H.link_rows[r]] += I.lval[e] * xb[H.cols[g][I.lidx[e]]];
+            if (I.nlc > ng || I.nlong > mg) { set_last_error("mllp_blocks_selfcheck: bad counts"); return MLLP_E_STATE; }
+        }
+        double ea = 0.0, et = 0.0;
+        for (int i = 0; i < m; ++i) ea = std::max(ea, std::fabs(ax[i] - ax2[i]) / (1.0 + std::fabs(ax[i])));
+        for (int j = 0; j < n; ++j) et = std::max(et, std::fabs(aty[j] - aty2[j]) / (1.0 + std::fabs(aty[j])));
+        out8[4] = ea; out8[5] = et;
+    } catch (const std::bad_alloc&) {
+        set_last_error("mllp_blocks_selfcheck: out of host memory");
+        return MLLP_E_NOMEM;
+    }
     return 0;
 }
 

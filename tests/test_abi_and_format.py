@@ -118,3 +118,43 @@ def test_host_argument_errors():
         M.pdhg_linear_program(constrs, A.data, b, c, num_iters=-1)
     with pytest.raises(ValueError):
         M.DeviceLP(constrs, A.data, 27, 51, device="cpu")
+
+
+def _blocks_selfcheck(A, G):
+    import ctypes
+    A = A.tocsr()
+    A.sort_indices()
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ii = np.ascontiguousarray(A.indices, dtype=np.int32)
+    vv = np.ascontiguousarray(A.data, dtype=np.float64)
+    out = (ctypes.c_double * 8)()
+    rc = _cabi.lib().mllp_blocks_selfcheck(A.shape[0], A.shape[1], int(A.nnz), ip.ctypes.data, ii.ctypes.data, vv.ctypes.data, G, out)
+    assert rc == 0, _cabi.last_error()
+    return list(out)
+
+
+def test_block_angular_structure_detection_and_images_on_the_host():
+    """blocks.cu, host side (no GPU): linking rows, connected components, groups; the groups' lists reproduce A xbar and A'y"""
+    import scipy.sparse as sp
+    import mllp_b200.linear_program_data as D
+    A, b, c = D.load_csr("ken-18")                      # 475 blocks of <= 801 nodes + 151 linking rows
+    found, ncomp, nlink, link_nnz, ea, et, smem, max_n = _blocks_selfcheck(A, 148)
+    assert found == 1 and ncomp == 475 and nlink == 151 and link_nnz == 49075
+    assert ea < 1e-13 and et < 1e-13 and smem < 227 * 1024 and 154699 / 148 <= max_n < 1600
+    for name in ("pds-20", "osa-60", "25fv47"):         # one giant component / too few pieces: keep the grid kernel
+        A, b, c = D.load_csr(name)
+        assert _blocks_selfcheck(A, 148)[0] == 0
+    # synthetic: 120 blocks, 5 dense linking rows, columns seen by linking rows only, an all-zero row, 16 groups
+    rng = np.random.default_rng(3)
+    blocks = []
+    for k in range(120):
+        Bk = sp.random(4, 6, density=0.5, random_state=k, format="csr")
+        Bk.data[:] = rng.standard_normal(Bk.nnz)
+        blocks.append(Bk)
+    top = sp.hstack([sp.block_diag(blocks, format="csr"), sp.csr_matrix((480, 9))]).tocsr()
+    link = sp.random(5, top.shape[1], density=0.15, random_state=77, format="csr")   # (linking rows may hold at most half of the nonzeros)
+    link.data[:] = rng.standard_normal(link.nnz)
+    A = sp.vstack([top[:100], link[:2], sp.csr_matrix((1, top.shape[1])), top[100:], link[2:]]).tocsr()
+    found, ncomp, nlink, link_nnz, ea, et, smem, max_n = _blocks_selfcheck(A, 16)
+    assert found == 1 and nlink == 5 and link_nnz == link.nnz and ncomp >= 120 and ea < 1e-13 and et < 1e-13
+    assert _blocks_selfcheck(A, 148)[0] == 0            # fewer than 2 x 148 pieces
