@@ -135,7 +135,7 @@ int mllp_lp_geometry(mllp_lp_t lp, double *out12);
  * components of the rest) and, when there are enough blocks to fill the grid, builds a second image of the LP in which
  * whole blocks are dealt to CTAs.  The parity kernel then keeps every CTA's blocks and iterates in shared memory, meets
  * with __syncthreads() only, and exchanges the linking rows' partial products and dual values as tagged 16-byte words
- * (two L2 hops per iteration instead of two grid barriers).  Both kernels are timed at create time, the faster is
+ * (two L2 hops per iteration instead of two grid barriers); standard and general form.  Both kernels are timed at create time, the faster is
  * used by mllp_pdhg_run (MLLP_BLOCKS=0 / 1 disables / forces it); iterates agree with the grid kernel to rounding.
  * out8: [0] 1 if mllp_pdhg_run uses the block kernel, [1] blocks (components), [2] linking rows, [3] their nonzeros,
  * [4] shared memory per CTA, [5] / [6] measured ns per iteration of the grid kernel / of the block kernel,

@@ -22,7 +22,7 @@
 //
 // Same arithmetic as the frozen spec (oracle/pdhg_oracle.c); rows and columns are summed in CSR order (the oracle's),
 // the linking rows per group and then over the groups, so iterates agree with the other kernels to rounding (1e-15),
-// not bitwise.  Standard form only (l = 0, u = inf, equality rows); parity mode only.
+// not bitwise.  Standard and general form (boxes on x, sign cones on y); parity mode only.
 // The reference has no counterpart.
 #include <cuda_runtime.h>
 
@@ -68,6 +68,7 @@ struct BlocksDev {
     unsigned* abort_flag;
     int nlink, G;
     int max_m, max_n, max_col_nnz, max_row_nnz, max_link_nnz;   // shared memory is sized for the largest group
+    const double *lb, *ub, *ylo, *yhi;   // general form: boxes in the handle's internal order (all four or none)
     unsigned long long* trace;      // dev tool (MLLP_BLOCKS_DEBUG & 2): [iter][cta][4] globaltimer stamps, else null
     int poll_gap;                   // ns between two reads of a polled word (MLLP_BLOCKS_POLL_NS)
     int dbg;                        // dev knob (MLLP_BLOCKS_DEBUG): 1 = no cross-CTA waits (timing of the local work only)
@@ -116,12 +117,13 @@ constexpr int FIN_BATCH = 8;  // parts per lane in flight together (8 x 32 = 256
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1)
 k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const double* gc, double tau, double sigma, int iters,
               unsigned long long tag0)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
-    __shared__ double fin_y[MAX_FIN], fin_b[MAX_FIN];
+    __shared__ double fin_y[MAX_FIN], fin_b[MAX_FIN], fin_lo[MAX_FIN], fin_hi[MAX_FIN];
     const BlockGroup G = B.groups[blockIdx.x];
     const int n = G.n, m = G.m, nlong = G.nlong, nlink = B.nlink, nctas = (int)gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -137,6 +139,8 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
     double* sc = p; p += B.max_n;
     double* syy = p; p += B.max_m + nlink;
     double* sb = p; p += B.max_m;
+    double *slb = nullptr, *sub = nullptr, *sylo = nullptr, *syhi = nullptr;
+    if (BOUNDS) { slb = p; p += B.max_n; sub = p; p += B.max_n; sylo = p; p += B.max_m; syhi = p; p += B.max_m; }
     double* colval = p; p += B.max_col_nnz;
     double* rowval = p; p += B.max_row_nnz;
     double* lval = p; p += B.max_link_nnz;
@@ -152,11 +156,13 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
         sx[k] = __ldcg(gx + pos);
         sc[k] = __ldg(gc + pos);
         sxbar[k] = 0.0;
+        if (BOUNDS) { slb[k] = __ldg(B.lb + pos); sub[k] = __ldg(B.ub + pos); }
     }
     for (int k = threadIdx.x; k < m; k += blockDim.x) {
         const int pos = __ldg(G.ypos + k);
         syy[k] = __ldcg(gy + pos);
         sb[k] = __ldg(gb + pos);
+        if (BOUNDS) { sylo[k] = __ldg(B.ylo + pos); syhi[k] = __ldg(B.yhi + pos); }
     }
     for (int r = threadIdx.x; r < nlink; r += blockDim.x) syy[m + r] = __ldcg(gy + __ldg(B.link_pos + r));
     for (int k = threadIdx.x; k <= m; k += blockDim.x) rowptr[k] = __ldg(G.rowptr + k);
@@ -172,6 +178,7 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
             const int pos = __ldg(B.link_pos + r);
             fin_y[threadIdx.x] = __ldcg(gy + pos);
             fin_b[threadIdx.x] = __ldg(gb + pos);
+            if (BOUNDS) { fin_lo[threadIdx.x] = __ldg(B.ylo + pos); fin_hi[threadIdx.x] = __ldg(B.yhi + pos); }
         }
     }
     __syncthreads();
@@ -188,7 +195,8 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
             double dot = 0.0;
             for (int e = 0; e < wc; ++e) dot = fma(colval[e * n + k], syy[colidx[e * n + k]], dot);
             const double g = sc[k] - dot, xk = sx[k];
-            const double xn = fmax(xk - tau * g, 0.0);
+            double xn = xk - tau * g;
+            if (BOUNDS) xn = fmin(fmax(xn, slb[k]), sub[k]); else xn = fmax(xn, 0.0);
             sxbar[k] = 2.0 * xn - xk;
             sx[k] = xn;
         };
@@ -246,7 +254,12 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
                 // the row's new dual value goes into every CTA's mailbox (one word per CTA and linking row: a CTA polls
                 // only its own copy -- a single copy polled by the whole grid made its L2 lines a hot spot that also
                 // delayed the store everybody was waiting for)
-                const double yn = __shfl_sync(FULL, lane == 0 ? fin_y[w] + sigma * (fin_b[w] - s) : 0.0, 0);
+                double yf = 0.0;
+                if (lane == 0) {
+                    yf = fin_y[w] + sigma * (fin_b[w] - s);
+                    if (BOUNDS) yf = fmin(fmax(yf, fin_lo[w]), fin_hi[w]);
+                }
+                const double yn = __shfl_sync(FULL, yf, 0);
                 if (lane == 0) fin_y[w] = yn;
                 for (int k = lane; k < nctas; k += 32) st_tagged(B.ylink + 2 * MAIL_AT(r, k), yn, tag);
                 if (tr && w == 0 && lane == 0) tr[2] = global_ns();   // this CTA's first linking row is finished and sent
@@ -272,13 +285,19 @@ k_pdhg_blocks(BlocksDev B, double* gx, double* gy, const double* gb, const doubl
                         for (int e = rowptr[k] + qq; e < rowptr[k + 1]; e += 4) dot = fma(rowval[e], sxbar[rowidx[e]], dot);
                     dot += __shfl_xor_sync(FULL, dot, 1);
                     dot += __shfl_xor_sync(FULL, dot, 2);
-                    if (k < nlong && qq == 0) syy[k] = syy[k] + sigma * (sb[k] - dot);
+                    if (k < nlong && qq == 0) {
+                        double yn = syy[k] + sigma * (sb[k] - dot);
+                        if (BOUNDS) yn = fmin(fmax(yn, sylo[k]), syhi[k]);
+                        syy[k] = yn;
+                    }
                 } else {
                     const int k = nlong + (u - ulong);
                     if (k < m) {
                         double dot = 0.0;
                         for (int e = rowptr[k]; e < rowptr[k + 1]; ++e) dot = fma(rowval[e], sxbar[rowidx[e]], dot);
-                        syy[k] = syy[k] + sigma * (sb[k] - dot);
+                        double yn = syy[k] + sigma * (sb[k] - dot);
+                        if (BOUNDS) yn = fmin(fmax(yn, sylo[k]), syhi[k]);
+                        syy[k] = yn;
                     }
                 }
             }
@@ -321,6 +340,7 @@ struct BlockPlan {
     BlocksDev dev{};
     int threads = 1024;
     size_t smem = 0;
+    const void* fn = nullptr;     // k_pdhg_blocks<false> (standard form) or <true> (boxes on x and y)
     std::vector<void*> allocs;
     int ncomp = 0, nlink = 0;
     int64_t link_nnz = 0;
@@ -495,17 +515,19 @@ static bool build_groups(int m, int n, const int32_t* indptr, const int32_t* ind
     return true;
 }
 
-static size_t blocks_smem_bytes(const HostGroups& H)
+static size_t blocks_smem_bytes(const HostGroups& H, bool bounds = false)
 {
-    return align16(8 * (3 * (size_t)H.max_n + 2 * (size_t)H.max_m + (size_t)H.nlink + (size_t)H.max_c + (size_t)H.max_r + (size_t)H.max_l) +
+    return align16(8 * ((bounds ? 5 : 3) * (size_t)H.max_n + (bounds ? 4 : 2) * (size_t)H.max_m + (size_t)H.nlink + (size_t)H.max_c + (size_t)H.max_r + (size_t)H.max_l) +
                    4 * ((size_t)H.max_m + (size_t)H.nlink + 2 + (size_t)H.max_c + (size_t)H.max_r + (size_t)H.max_l));
 }
 
 // Returns 0 with *out == nullptr when the matrix has no usable block structure (not an error).
 int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, const int32_t* posX,
-                  const int32_t* posY, int device, int G, BlockPlan** out)
+                  const int32_t* posY, const double* d_lb, const double* d_ub, const double* d_ylo, const double* d_yhi, int device,
+                  int G, BlockPlan** out)
 {
     *out = nullptr;
+    const bool bounds = d_lb != nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return 0;
     cudaDeviceProp prop;
@@ -519,7 +541,7 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
     try {
         HostGroups H;
         if (!build_groups(m, n, indptr, indices, values, G, H)) return 0;
-        const size_t smem = blocks_smem_bytes(H);
+        const size_t smem = blocks_smem_bytes(H, bounds);
         if (smem > smem_cap) return 0;   // a group's iterates and matrix share do not fit in shared memory
         bp = new (std::nothrow) BlockPlan();
         if (!bp) { set_last_error("blocks_create: out of host memory"); return MLLP_E_NOMEM; }
@@ -573,15 +595,17 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
             D.groups = d_groups; D.link_pos = d_link_pos; D.partial = d_partial; D.ylink = d_ylink; D.abort_flag = d_abort;
             D.nlink = H.nlink; D.G = G; D.max_m = H.max_m; D.max_n = H.max_n;
             D.max_col_nnz = H.max_c; D.max_row_nnz = H.max_r; D.max_link_nnz = H.max_l;
+            D.lb = d_lb; D.ub = d_ub; D.ylo = d_ylo; D.yhi = d_yhi;
             D.trace = nullptr;
             D.dbg = env_i("MLLP_BLOCKS_DEBUG", 0);
             D.poll_gap = env_i("MLLP_BLOCKS_POLL_NS", 0);
             bp->smem = smem;
             bp->threads = env_i("MLLP_BLOCKS_THREADS", 1024);
             if (bp->threads < 64 || bp->threads > 1024 || (bp->threads & 31)) bp->threads = 1024;
-            fail_cuda(cudaFuncSetAttribute((const void*)k_pdhg_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp->smem), "cudaFuncSetAttribute");
+            bp->fn = bounds ? (const void*)k_pdhg_blocks<true> : (const void*)k_pdhg_blocks<false>;
+            fail_cuda(cudaFuncSetAttribute(bp->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp->smem), "cudaFuncSetAttribute");
             int nb = 0;
-            fail_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_pdhg_blocks, bp->threads, bp->smem), "occupancy");
+            fail_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bp->fn, bp->threads, bp->smem), "occupancy");
             if (rc == 0 && nb * prop.multiProcessorCount < G) rc = -1;   // the whole grid must be resident
         }
     } catch (const std::bad_alloc&) {
@@ -684,7 +708,7 @@ int blocks_run(BlockPlan* bp, double* gx, double* gy, const double* gb, const do
         D.trace = d_tr;
         cudaMemsetAsync(D.abort_flag, 0, sizeof(unsigned), s);
         void* args[] = {&D, &gx, &gy, &gb, &gc, &tau, &sigma, &iters, &tag0};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_pdhg_blocks, dim3(D.G), dim3(bp->threads), args, bp->smem, s);
+        cudaError_t e = cudaLaunchCooperativeKernel(bp->fn, dim3(D.G), dim3(bp->threads), args, bp->smem, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         g_blocks_trace.assign(cnt, 0ull);
         if (e == cudaSuccess) e = cudaMemcpy(g_blocks_trace.data(), d_tr, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -696,7 +720,7 @@ int blocks_run(BlockPlan* bp, double* gx, double* gy, const double* gb, const do
     if (e != cudaSuccess) return (int)e;
     BlocksDev D = bp->dev;
     void* args[] = {&D, &gx, &gy, &gb, &gc, &tau, &sigma, &iters, &tag0};
-    e = cudaLaunchCooperativeKernel((const void*)k_pdhg_blocks, dim3(D.G), dim3(bp->threads), args, bp->smem, s);
+    e = cudaLaunchCooperativeKernel(bp->fn, dim3(D.G), dim3(bp->threads), args, bp->smem, s);
     return (int)e;
 }
 

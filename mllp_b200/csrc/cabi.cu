@@ -724,14 +724,14 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
         }
 
         // Block-angular LPs (ken-18: 475 independent blocks + 151 linking rows): the block kernel of blocks.cu keeps every
-        // CTA's blocks in shared memory and needs no grid barrier.  Built when the structure is there (standard form,
-        // single GPU, cooperative grid), timed against the grid kernel on the zero state, kept when faster.
+        // CTA's blocks in shared memory and needs no grid barrier.  Built when the structure is there (single GPU,
+        // cooperative grid), timed against the grid kernel on the zero state, kept when faster.
         // MLLP_BLOCKS = 0 / 1 disables / forces it.
-        if (rc == 0 && nranks == 1 && resident && !lp->bounds && lp->d.sync_mode == SYNC_GRID && m > 0 && n > 0 &&
+        if (rc == 0 && nranks == 1 && resident && lp->d.sync_mode == SYNC_GRID && m > 0 && n > 0 &&
             env_int("MLLP_BLOCKS", tune > 0 ? -1 : 0) != 0) {
             auto pick = [&]() -> int {
-                RC_OK(blocks_create(m, n, h_indptr, h_indices, h_values, posX.data(), posY.data(), device, prop.multiProcessorCount,
-                                    &lp->blocks));
+                RC_OK(blocks_create(m, n, h_indptr, h_indices, h_values, posX.data(), posY.data(), lp->d.lb, lp->d.ub, lp->d.ylo, lp->d.yhi,
+                                    device, prop.multiProcessorCount, &lp->blocks));
                 if (!lp->blocks) return 0;
                 if (env_int("MLLP_BLOCKS", -1) == 1) { lp->use_blocks = true; return 0; }
                 double t_grid = 0, t_blk = 0;

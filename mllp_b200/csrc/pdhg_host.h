@@ -35,7 +35,8 @@ int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, si
 // blocks.cu: block-angular LPs (components dealt to CTAs, linking rows through tagged words; no grid barrier)
 struct BlockPlan;
 int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, const int32_t* posX,
-                  const int32_t* posY, int device, int G, BlockPlan** out);   // *out == nullptr: no usable structure
+                  const int32_t* posY, const double* d_lb, const double* d_ub, const double* d_ylo, const double* d_yhi, int device,
+                  int G, BlockPlan** out);   // *out == nullptr: no usable structure; d_lb .. d_yhi: internal-order boxes or null
 int blocks_run(BlockPlan* bp, double* gx, double* gy, const double* gb, const double* gc, double tau, double sigma, int iters,
                unsigned long long tag0, cudaStream_t s);
 void blocks_info(const BlockPlan* bp, int64_t* out4);   // components, linking rows, linking nonzeros, shared memory | threads << 32

@@ -391,3 +391,27 @@ def test_block_angular_kernel_is_chosen_by_measurement_and_only_where_it_applies
     lp = M.DeviceLP(A, A.data, *A.shape, lb=np.zeros(A.shape[1]), ub=np.ones(A.shape[1]))
     assert not lp.blocks_info()["used"]
     lp.close()
+
+
+def test_block_angular_kernel_general_form(monkeypatch):
+    """boxes on x and sign cones on y (linking rows included) on the block kernel, warm start, against the oracle"""
+    monkeypatch.setenv("MLLP_BLOCKS", "1")
+    monkeypatch.setenv("MLLP_GEOM", "0")
+    A, b, c = _block_angular(seed=8)
+    m, n = A.shape
+    rng = np.random.default_rng(7)
+    lb = np.where(rng.random(n) < 0.3, -np.inf, rng.uniform(-1, 0, n))
+    ub = np.where(rng.random(n) < 0.3, np.inf, rng.uniform(0.5, 2, n))
+    kind = rng.integers(0, 3, m)
+    ylo, yhi = np.where(kind == 1, 0.0, -np.inf), np.where(kind == 2, 0.0, np.inf)
+    x0, y0 = rng.uniform(0, 0.4, n), np.clip(rng.standard_normal(m), ylo, yhi)
+    eta = 0.9 / O.power_iteration(A, 50)
+    lp = M.DeviceLP(A, A.data, m, n, lb=lb, ub=ub, ylo=ylo, yhi=yhi)
+    assert lp.blocks_info()["used"]
+    obj, x, y, info = M.pdhg_linear_program(A, A.data, b, c, num_iters=300, tau=eta, sigma=0.5 * eta, lb=lb, ub=ub,
+                                            ylo=ylo, yhi=yhi, x0=x0, y0=y0, handle=lp)
+    xo, yo = O.pdhg_run(A, b, c, x0, y0, eta, 0.5 * eta, 300, lb, ub, ylo, yhi)
+    assert rel(x, xo) < ITER_TOL and rel(y, yo) < ITER_TOL
+    scal_close(info, O.kkt(A, b, c, xo, yo, lb, ub, ylo, yhi))
+    assert np.all(x >= lb) and np.all(x <= ub) and np.all(y >= ylo) and np.all(y <= yhi)
+    lp.close()
