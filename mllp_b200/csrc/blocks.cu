@@ -5,8 +5,8 @@
 // nodes.  The fused iteration of pdhg_kernels.cu pays two grid barriers (~0.95 us each) per iteration for such a
 // matrix although almost no data has to cross SMs.  Here whole components are dealt to the CTAs of a cooperative
 // grid: a CTA keeps its components' iterates (x, xbar, c, y, b) AND its share of the matrix (plain CSR by rows and by
-// columns: a group holds ~2 000 nonzeros) in shared memory for the whole launch, one thread per row / column, and
-// synchronises with __syncthreads() only (two per iteration).
+// columns: a group holds ~2 000 nonzeros) in shared memory for the whole launch, one thread per row / column (four lanes
+// for rows above four entries), and synchronises with __syncthreads() only.
 // What does cross CTAs travels as tagged 16-byte words {value, value ^ tag} (tag = iteration number, so value and
 // validity arrive in one 128-bit access and no fence is needed; ld_tagged / st_tagged in pdhg_kernels.cuh):
 //   * every CTA publishes its part of every linking row's product  p[r][g] = sum_{j in g} a_rj xbar_j;
@@ -14,8 +14,11 @@
 //     dual value y_r and stores it into every CTA's mailbox;
 //   * every CTA polls the nlink dual values in its mailbox into the tail of its y vector, where the column lists of
 //     its A' point for their linking entries.
-// Two polled L2 hops per iteration (~0.9 us each, measured: scripts/blocks_trace.py) -- the cost of the two grid barriers
-// they replace -- but the phases between them run out of shared memory instead of gathering from L2.
+// Two polled L2 hops per iteration (scripts/blocks_trace.py) -- about the cost of the two grid barriers they replace -- but
+// only the columns that occur in linking rows stand between them: they are updated first, the last warps then serve the
+// linking rows while the other warps update the remaining columns and the block rows, all out of shared memory.  Both
+// hops STORE contiguously (a CTA's nlink parts, a finisher's G copies of a dual) and poll scattered words: scattered
+// 16-byte stores arrive over more than a microsecond.
 // A word is overwritten only after every reader has consumed it: a CTA publishes its next parts only after it has
 // read all dual values of this iteration, and a finisher publishes its next dual value only after it has read all
 // parts of the next iteration.
