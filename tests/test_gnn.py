@@ -170,3 +170,28 @@ def test_gpu_forward_plan_replays_bitwise(name):
     torch.cuda.synchronize()
     assert close(m1(g).cpu().numpy(), G.gnn_forward(m1.state, A, 0.5 * b, c))
     g.close()
+
+
+GOLD = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "gnn_forward_seed5.npz")
+
+
+@pytest.mark.parametrize("name", ["afiro", "sc105"])
+def test_oracle_reproduces_committed_fixture(name):
+    """tests/golden/gnn_forward_seed5.npz (make_golden.py gnn): the oracle's logits and a plain-torch fp32 run, committed"""
+    g = np.load(GOLD)
+    A, b, c = D.load_csr(name)
+    out = G.gnn_forward(G.init_state(5), A, b, c)
+    assert np.allclose(out, g[name + "_oracle"], rtol=0, atol=1e-12)
+    assert close(g[name + "_torch_fp32"], out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["afiro", "sc105"])
+def test_gpu_forward_matches_committed_fixture(name):
+    import mllp_b200.gnn as GN
+    g = np.load(GOLD)
+    A, b, c = D.load_csr(name)
+    gr = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c)
+    out = GN.GNNModel(G.init_state(5))(gr).cpu().numpy()
+    assert close(out, g[name + "_oracle"]) and close(out, g[name + "_torch_fp32"].astype(np.float64))
+    gr.close()
