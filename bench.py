@@ -326,11 +326,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no implementation of this path (SURVEY.md section 0); this arm times the repo's CPU oracle",
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints
+    its version there when a process group is created) are sent to stderr; the JSON line goes to the saved descriptor."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -472,7 +491,7 @@ def main():
             rate, its, dt, cores = cpu_oracle_rate(A, b, c, eta, args.cpu_baseline_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": "iterations/s", "cores": cores, "kind": "port",
                                     "sample": "%d iterations of %s on the CPU oracle (OpenMP, %d threads, %.1f s)" % (its, args.workload, cores, dt)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
