@@ -288,6 +288,115 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
     return out
 
 
+def measure_rowpart(M, torch, dist, dev, local, rank, world, names=("osa-60", "ken-18", "pds-20"), K=1000, parity_K=100,
+                    nccl_K=200, trace=False):
+    """BASELINE.json configs[3]: ONE large LP row-partitioned over all `world` GPUs (A by rows, A' phase replicated, one
+    exchange of the y slices per iteration).  Per instance: in-run parity against the CPU oracle (K=100, 1e-9, asserted
+    on every rank), us/iteration of the in-kernel NVLink exchange and of the NCCL all-gather variant (device time, max
+    over ranks), and the same run's one-GPU time of the same instance (best rank) for the speed-up."""
+    from mllp_b200 import _cabi
+    from mllp_b200.distributed import RowPartLP, pdhg_linear_program_rowpart
+    from oracle import pdhg_oracle as O   # the checker of the in-run parity assert
+    L = _cabi.lib()
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    out = {}
+
+    def timed(fn, reps=3):
+        fn(); torch.cuda.synchronize(dev); dist.barrier()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t[0]))
+        return best * 1e-3
+
+    for name in names:
+        A, b, c = M.load_csr(name)
+        m, n = A.shape
+        bt, ct = torch.tensor(b, device=dev), torch.tensor(c, device=dev)
+        xt, yt = torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(m, dtype=torch.float64, device=dev)
+
+        def run_on(handle, iters):
+            xt.zero_(); yt.zero_()
+            _cabi.check(L.mllp_pdhg_run(handle, xt.data_ptr(), yt.data_ptr(), bt.data_ptr(), ct.data_ptr(), eta, eta, iters,
+                                        None, sp), "mllp_pdhg_run")
+
+        one = M.DeviceLP(A, A.data, m, n, device=local)
+        eta = 0.9 / one.sigma_max()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        run_on(one.handle, K); torch.cuda.synchronize(dev)
+        e0.record(); run_on(one.handle, K); e1.record(); torch.cuda.synchronize(dev)
+        t1 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t1, op=dist.ReduceOp.MIN)
+        us_one = float(t1[0]) * 1e3 / K
+        one_kernel = "k_pdhg_blocks" if one.blocks_info()["used"] else "k_pdhg_persistent (%s)" % one.geometry()["mode"]
+        one.close()
+
+        lp = RowPartLP(A, A.data, m, n, device=local)
+        # in-run parity: K=100 against the oracle (computed on rank 0, broadcast), asserted on every rank
+        obj, x, y, info = pdhg_linear_program_rowpart(lp, b, c, num_iters=parity_K, tau=eta, sigma=eta)
+        ref = torch.zeros(n + m, dtype=torch.float64, device=dev)
+        if rank == 0:
+            xo, yo = O.pdhg_run(O.CSR(A), b, c, np.zeros(n), np.zeros(m), eta, eta, parity_K, nthreads=host_threads())
+            ref.copy_(torch.tensor(np.concatenate([xo, yo])))
+        dist.broadcast(ref, src=0)
+        refh = ref.cpu().numpy()
+        ex = float(np.linalg.norm(x - refh[:n]) / max(np.linalg.norm(refh[:n]), 1e-300))
+        ey = float(np.linalg.norm(y - refh[n:]) / max(np.linalg.norm(refh[n:]), 1e-300))
+        assert ex < 1e-9 and ey < 1e-9, "row-partitioned %s on rank %d: iterates differ from the oracle (%.2e, %.2e)" % (name, rank, ex, ey)
+        perr = torch.tensor([ex, ey], dtype=torch.float64, device=dev)
+        dist.all_reduce(perr, op=dist.ReduceOp.MAX)
+
+        sec = timed(lambda: run_on(lp.handle, K))
+        os.environ["MLLP_ROWPART_NCCL"] = "1"
+        try:
+            sec_nccl = timed(lambda: run_on(lp.handle, nccl_K), reps=2)
+        finally:
+            os.environ.pop("MLLP_ROWPART_NCCL", None)
+        assert lp.exchange_error() == 0
+        rec = {"n_gpus": world, "us_per_iteration": sec * 1e6 / K, "iterations_per_sec": K / sec,
+               "us_per_iteration_nccl_allgather": sec_nccl * 1e6 / nccl_K,
+               "us_per_iteration_one_gpu": us_one, "one_gpu_kernel": one_kernel, "speedup_vs_one_gpu": us_one / (sec * 1e6 / K),
+               "iters_timed": K, "parity_vs_oracle_K%d" % parity_K: {"x": float(perr[0]), "y": float(perr[1]), "tol": 1e-9},
+               "exchange": "tagged 16-byte words through peer mailboxes over NVLink inside one cooperative launch; A' phase replicated, one exchange per iteration"}
+        if trace:
+            rec["timeline_us"] = rowpart_timeline(lp, eta, dist, torch, dev)
+        out[name] = rec
+        lp.close()
+    return out
+
+
+def rowpart_timeline(lp, eta, dist, torch, dev, iters=64, skip=8):
+    """Per-phase split of one row-partitioned iteration from in-kernel timestamps (mllp_debug_trace_rowpart, dev tool):
+    mean over iterations of the per-rank maximum over CTAs, then max over ranks."""
+    import ctypes
+    from mllp_b200 import _cabi
+    L = ctypes.CDLL(_cabi.SO_PATH)
+    G = lp.info()["grid_ctas"]
+    buf = np.zeros(iters * G * 6, dtype=np.uint64)
+    dist.barrier()
+    rc = L.mllp_debug_trace_rowpart(ctypes.c_void_p(lp.handle.value), ctypes.c_double(eta), ctypes.c_double(eta),
+                                    ctypes.c_int32(iters), ctypes.c_void_p(buf.ctypes.data))
+    assert rc == 0, _cabi.last_error()
+    t = buf.reshape(iters, G, 6).astype(np.int64)
+    prev_rel = t[skip - 1:-1, :, 4].max(axis=1)            # previous iteration's release (last CTA)
+    cur = t[skip:]
+    seg = {
+        "At_phase": (cur[:, :, 0].max(axis=1) - prev_rel),                              # slowest CTA done with A'
+        "barrier_1": (cur[:, :, 1].max(axis=1) - cur[:, :, 0].max(axis=1)),
+        "A_phase": (cur[:, :, 2].max(axis=1) - cur[:, :, 1].max(axis=1)),               # slowest CTA done with its rows of A
+        "unpack_wait": (cur[:, :, 3].max(axis=1) - cur[:, :, 2].max(axis=1)),           # peers' words arrived and unpacked
+        "barrier_2": (cur[:, :, 4].max(axis=1) - cur[:, :, 3].max(axis=1)),
+        "iteration": (cur[:, :, 4].max(axis=1) - prev_rel),
+    }
+    vals = torch.tensor([float(v.mean()) * 1e-3 for v in seg.values()], dtype=torch.float64, device=dev)
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    return {k: round(float(v), 3) for k, v in zip(seg.keys(), vals)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU oracle timed on the host cores (rank 0 only)."""
     if rank != 0:
@@ -454,6 +563,8 @@ def main():
     extras = None
     if not args.no_extras:
         extras = measure_extras(M, torch, dev, local, rank, world, dist)
+        if world > 1:
+            extras["rowpart"] = measure_rowpart(M, torch, dist, dev, local, rank, world)
 
     if rank == 0:
         peak, peak_src = peaks()

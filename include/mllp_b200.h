@@ -74,9 +74,9 @@ int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indp
                           int32_t pref_steps, int32_t max_steps, double *out8);
 
 /* Host-only self check of the row-partitioned build: emulates all `nranks` ranks on the CPU
- * (tile walk + all-gather of the slices) against the plain CSR products.  out4: [0] worst
- * relative row error, [1]/[2] padded internal lengths of y / x, [3] largest nonzeros per rank
- * over the mean. */
+ * (tile walk of every rank's rows of A + exchange of the slices; the whole of A' against the padded y)
+ * against the plain CSR products.  out4: [0] worst relative row error, [1] padded internal length of y,
+ * [2] length of x, [3] largest nonzeros of A per rank over the mean. */
 int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr,
                            const int32_t *indices, const double *values, int32_t num_ctas,
                            int32_t nranks, double *out4);
@@ -192,15 +192,34 @@ int mllp_graph_edges(int32_t m, int64_t nnz, const int32_t *d_indptr, const int3
                      const double *d_values, int64_t *d_edge_index, float *d_edge_attr, void *stream);
 
 /*
+ * The rule behind the reference's `_norm` arrays (dataset/netlib_mps_norm/<name>_{constrs.npz,rhs.npy,coefs.npy}, loaded at
+ * linear_program_data.py:66-77; the generating script is not in the reference, the rule is restated and pinned against
+ * the data in oracle/norm_rule.py): from the raw arrays (device CSR, m x n) and the row senses d_sense[m]
+ * (0 = equality, +1 = "L": slack +1, -1 = "G": slack -1) build the standard form [A | S] -- one slack column per
+ * inequality row, appended in row order, `nslack` of them (the caller counts the non-zero senses and sizes the outputs) --
+ * scale row i by 1 / r_i, r_i = ||(a_i, slack_i)||_2 (squares added left to right in column order), or by 5 / b_i when
+ * |b_i| / r_i > 5, and c by 1 / ||c||_2.  Outputs (device): CSR of m x (n + nslack) with nnz + nslack entries,
+ * d_out_rhs[m], d_out_coefs[n + nslack], d_row_scale[m] (the factor of every row: y_raw = d_row_scale * y_norm) and
+ * d_cnorm[1] = ||c||_2 (objective in the file's units = objective of the `_norm` LP x ||c||_2 + offset).  d_work:
+ * mllp_norm_scale_work_bytes(m) bytes, 8-byte aligned.  Asynchronous on `stream`.
+ */
+int64_t mllp_norm_scale_work_bytes(int32_t m);
+int mllp_norm_scale(int32_t m, int32_t n, int64_t nnz, int32_t nslack, const int32_t *d_indptr, const int32_t *d_indices,
+                    const double *d_values, const int8_t *d_sense, const double *d_rhs, const double *d_coefs,
+                    int32_t *d_out_indptr, int32_t *d_out_indices, double *d_out_values, double *d_out_rhs,
+                    double *d_out_coefs, double *d_row_scale, double *d_cnorm, void *d_work, void *stream);
+
+/*
  * Row partition of ONE large LP over `nranks` GPUs (one process per GPU; BASELINE.json
  * configs[3]: ken-18, osa-60, pds-20).  Every rank passes the whole matrix; rank p keeps the
- * rows of A (entries of y) and the rows of A' (entries of x) assigned to it (balanced by nonzeros)
- * and the ranks exchange their slices of xbar and y with two NCCL all-gathers per iteration on
- * the caller's stream.  mllp_nccl_unique_id() is called on rank 0 and its 128 bytes are sent to
- * the other ranks by the host (e.g. torch.distributed.broadcast) before the collective
+ * rows of A assigned to it (balanced by nonzeros) -- its slice of y -- and ALL of A': the cheap
+ * A' phase is replicated (every rank updates the whole of x from the whole of y), so only the y
+ * slices cross GPUs, ONCE per iteration (the "all-gather once per iteration" of the north star; both A and
+ * A' are stored, so no reduce-scatter is needed).  mllp_nccl_unique_id() is called on rank 0 and its 128
+ * bytes are sent to the other ranks by the host (e.g. torch.distributed.broadcast) before the collective
  * mllp_lp_create_rowpart().  mllp_pdhg_run() on such a handle is a collective call: all ranks
- * pass the same full-length x, y, b, c (caller order) and all receive the full result.
- * mllp_pdhg_solve / mllp_spmv / mllp_estimate_norm are not available on these handles.
+ * pass the same full-length x, y, b, c (caller order) and the same num_iters, and all receive the full
+ * result.  mllp_pdhg_solve / mllp_spmv / mllp_estimate_norm are not available on these handles.
  */
 #define MLLP_NCCL_UNIQUE_ID_BYTES 128
 int mllp_nccl_unique_id(unsigned char *out128);
@@ -210,14 +229,17 @@ int mllp_lp_create_rowpart(int32_t m, int32_t n, int64_t nnz, const int32_t *h_i
                            uint32_t flags, int32_t rank, int32_t nranks,
                            const unsigned char *uid128, mllp_lp_t *out);
 
-/* In-kernel exchange for a row-partitioned handle: export this rank's three CUDA IPC handles
- * (xbar, y, flags; 3 x 64 bytes), let the host all-gather them (nranks x 192 bytes, rank order)
- * and import.  Afterwards mllp_pdhg_run() runs ALL iterations in one cooperative launch per rank:
- * each rank stores its slice of xbar / y straight into every peer's vector over NVLink as part of the
- * row update, and the two exchanges per iteration are cross-GPU flag barriers in peer memory (no NCCL
- * call, no kernel launch inside the loop).  Waits time out (status via mllp_rowpart_error) instead of
- * hanging.  Without import the handle uses two NCCL all-gathers per iteration. */
-int mllp_rowpart_ipc_export(mllp_lp_t lp, unsigned char *out192);
+/* In-kernel exchange for a row-partitioned handle: export the CUDA IPC handle of this rank's mailbox
+ * (MLLP_IPC_HANDLE_BYTES), let the host all-gather them (nranks x 64 bytes, rank order) and import.
+ * Afterwards mllp_pdhg_run() runs ALL iterations in one cooperative launch per rank: a row update stores
+ * its new dual value straight into every peer's mailbox over NVLink as one tagged 16-byte word
+ * {bits(y), bits(y) ^ tag} (value and validity in one access: no fence, no flag, no acknowledgement), and every
+ * rank unpacks the peers' words into its own y before the local grid barrier that ends the iteration
+ * (no NCCL call, no kernel launch inside the loop).  Waits time out (status via mllp_rowpart_error)
+ * instead of hanging.  Without import the handle uses one NCCL all-gather per iteration between the
+ * two launches of the iteration (environment MLLP_ROWPART_NCCL=1 forces that variant). */
+#define MLLP_IPC_HANDLE_BYTES 64
+int mllp_rowpart_ipc_export(mllp_lp_t lp, unsigned char *out64);
 int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char *all_ranks);
 /* 0 = no exchange wait has timed out on this rank (synchronises the device). */
 int mllp_rowpart_error(mllp_lp_t lp, int32_t *out_flag);

@@ -28,6 +28,8 @@ SIGNATURES = {
     "mllp_lp_create": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                       ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "mllp_graph_edges": (ctypes.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mllp_norm_scale_work_bytes": (ctypes.c_int64, [_i32]),
+    "mllp_norm_scale": (ctypes.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 15),
     "mllp_nccl_unique_id": (ctypes.c_int, [_vp]),
     "mllp_lp_create_rowpart": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                               ctypes.c_uint32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),

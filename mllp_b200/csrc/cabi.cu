@@ -94,20 +94,21 @@ struct mllp_lp {
     double* d_norm2 = nullptr;
     int64_t info[16] = {0};
     cudaGraphExec_t graph = nullptr;  // graph mode: GRAPH_UNROLL iterations
-    // row partition over GPUs (nranks > 1): this rank owns a slice of the rows of A (y) and of the
-    // rows of A' (x); internal vectors have nranks * Ly (Lx) entries, slices are exchanged with
-    // NCCL all-gathers between the half-iterations
+    // row partition over GPUs (nranks > 1): this rank owns a slice of the rows of A (its entries of y); the A' phase is
+    // replicated (every rank holds all of A' and of x), so the internal y has nranks * Ly entries (equal padded slices)
+    // and ONE exchange per iteration moves the slices: tagged words through peer mailboxes inside the persistent
+    // kernel, or one NCCL all-gather between the two launches of an iteration
     int rank = 0, nranks = 1;
-    int mi = 0, ni = 0;               // internal (padded) vector lengths
-    int Ly = 0, Lx = 0;               // slice lengths
+    int mi = 0, ni = 0;               // internal vector lengths (mi padded)
+    int Ly = 0;                       // slice length of y
     void* comm = nullptr;             // ncclComm_t
     // in-kernel exchange over NVLink peer memory (mllp_rowpart_ipc_export / _import)
     PeerInfo peers{};
-    unsigned* d_flags = nullptr;      // [MAX_RANKS] flags written by the peers
+    unsigned long long* d_mail = nullptr;   // this rank's mailbox: 2 buffers x mi tagged 16-byte words, written by the peers
     unsigned* d_err = nullptr;
     unsigned long long join_epoch = 0;   // last tag used by the polled split-row join
     bool p2p_ready = false;
-    unsigned epoch = 0;               // flag value of the last completed exchange
+    unsigned long long xseq = 0;      // exchanges done on this handle (tag / buffer of the next one; same on all ranks)
     std::vector<void*> ipc_opened;
 };
 constexpr int GRAPH_UNROLL = 32;
@@ -485,7 +486,6 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
     lp->m = m; lp->n = n; lp->nnz = nnz;
     lp->bounds = (h_lb != nullptr) || (h_ylo != nullptr);
     lp->rank = rank; lp->nranks = nranks;
-    if (nranks > 1) flags |= MLLP_F_GRAPH_MODE;   // half-iterations are separate launches around the all-gathers
     lp->flags = flags;
 
     // launch geometry of the persistent grid.  Resident mode (default): one 1024-thread CTA per
@@ -541,24 +541,21 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             build_host_mat(m, n, h_indptr, h_indices, h_values, orderY, posX, bp, HA);
             build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
         } else {
-            // Row partition: rank p owns the rows of A (entries of y) and the rows of A' (entries of x)
-            // that LPT-by-nnz gives it.  The global internal order is [rank 0's rows | rank 1's | ...],
-            // each slice padded to the same even length so one in-place all-gather moves it.
+            // Row partition: rank p owns the rows of A (entries of y) that LPT-by-nnz gives it; A' is built whole on every
+            // rank (replicated A' phase).  The internal order of y is [rank 0's rows | rank 1's | ...], each slice padded
+            // to the same even length (one in-place all-gather moves it in the NCCL variant); x keeps the single-GPU order.
             const BuildParams bpA = effective_params(m, h_indptr, bp), bpAT = effective_params(n, tptr.data(), bp);
-            RowPartition PY, PX;
+            RowPartition PY;
             partition_rows(m, h_indptr, orderY, nranks, PY);
-            partition_rows(n, tptr.data(), orderX, nranks, PX);
-            lp->Ly = PY.L; lp->Lx = PX.L;
-            posY = PY.pos; posX = PX.pos;
+            lp->Ly = PY.L;
+            posY = PY.pos;
             const std::vector<int32_t>& mineY = PY.lists[rank];
-            const std::vector<int32_t>& mineX = PX.lists[rank];
-            std::vector<int32_t> oY = PY.order_pad, oX = PX.order_pad;
-            mi = lp->Ly * nranks; ni = lp->Lx * nranks;
+            mi = lp->Ly * nranks;
             build_host_mat((int)mineY.size(), ni, h_indptr, h_indices, h_values, mineY, posX, bpA, HA, (uint32_t)(rank * lp->Ly));
-            build_host_mat((int)mineX.size(), mi, tptr.data(), tind.data(), tval.data(), mineX, posY, bpAT, HAT,
-                           (uint32_t)(rank * lp->Lx));
-            orderY.swap(oY);
-            orderX.swap(oX);
+            build_host_mat(n, mi, tptr.data(), tind.data(), tval.data(), orderX, posY, bpAT, HAT);
+            orderY = PY.order_pad;
+            lp->peers.rank = rank; lp->peers.nranks = nranks; lp->peers.Ly = lp->Ly; lp->peers.mi = mi;
+            for (int q = 0; q < nranks && q < MAX_RANKS; ++q) lp->peers.cnt[q] = (int)PY.lists[q].size();
         }
         lp->mi = mi; lp->ni = ni;
         auto permuted_pad = [](const double* src, const std::vector<int32_t>& order, double fill) {
@@ -607,7 +604,7 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             RC_OK(dev_zeros(lp, &lp->d_norm2, 2 + 256));
             if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
             if (nranks > 1) {
-                RC_OK(dev_zeros(lp, &lp->d_flags, (size_t)MAX_RANKS));
+                RC_OK(dev_zeros(lp, &lp->d_mail, (size_t)4 * mi + 2));
                 RC_OK(dev_zeros(lp, &lp->d_err, 4));
                 NcclApi* api = nccl_api();
                 if (!api) return fail(MLLP_E_STATE, "mllp_lp_create_rowpart: libnccl.so.2 could not be loaded");
@@ -808,16 +805,14 @@ int mllp_lp_create_rowpart(int32_t m, int32_t n, int64_t nnz, const int32_t* h_i
                        uid128, out);
 }
 
-int mllp_rowpart_ipc_export(mllp_lp_t lp, unsigned char* out192)
+int mllp_rowpart_ipc_export(mllp_lp_t lp, unsigned char* out64)
 {
-    if (!lp || !out192 || lp->nranks < 2) return fail(MLLP_E_INVALID, "mllp_rowpart_ipc_export: not a row-partitioned handle");
+    if (!lp || !out64 || lp->nranks < 2) return fail(MLLP_E_INVALID, "mllp_rowpart_ipc_export: not a row-partitioned handle");
     DeviceGuard guard(lp->device);
-    cudaIpcMemHandle_t h[3];
-    CUDA_OK(cudaIpcGetMemHandle(&h[0], lp->d.xbar));
-    CUDA_OK(cudaIpcGetMemHandle(&h[1], lp->d.y));
-    CUDA_OK(cudaIpcGetMemHandle(&h[2], lp->d_flags));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    memcpy(out192, h, sizeof(h));
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, lp->d_mail));
+    static_assert(sizeof(cudaIpcMemHandle_t) == MLLP_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(out64, &h, sizeof(h));
     return 0;
 }
 
@@ -827,22 +822,20 @@ int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char* all)
     if (lp->nranks > MAX_RANKS) return fail(MLLP_E_STATE, "mllp_rowpart_ipc_import: at most 8 ranks");
     DeviceGuard guard(lp->device);
     PeerInfo& P = lp->peers;
-    P.rank = lp->rank; P.nranks = lp->nranks; P.err = lp->d_err;
+    P.err = lp->d_err;
     for (int q = 0; q < lp->nranks; ++q) {
         if (q == lp->rank) {
-            P.xbar[q] = lp->d.xbar; P.y[q] = lp->d.y; P.flags[q] = lp->d_flags;
+            P.mail[q] = lp->d_mail;
             continue;
         }
-        cudaIpcMemHandle_t h[3];
-        memcpy(h, all + (size_t)q * 192, sizeof(h));
-        void* ptr[3] = {nullptr, nullptr, nullptr};
-        for (int k = 0; k < 3; ++k) {
-            CUDA_OK(cudaIpcOpenMemHandle(&ptr[k], h[k], cudaIpcMemLazyEnablePeerAccess));
-            lp->ipc_opened.push_back(ptr[k]);
-        }
-        P.xbar[q] = (double*)ptr[0]; P.y[q] = (double*)ptr[1]; P.flags[q] = (unsigned*)ptr[2];
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all + (size_t)q * MLLP_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        lp->ipc_opened.push_back(ptr);
+        P.mail[q] = (unsigned long long*)ptr;
     }
-    if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(xchg_set_smem(lp->bounds, lp->dyn_smem));
+    if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(rowpart_set_smem(lp->bounds, lp->dyn_smem));
     lp->p2p_ready = true;
     return 0;
 }
@@ -979,31 +972,29 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
     cudaStream_t s = (cudaStream_t)stream;
     RC_OK(load_problem(lp, d_x, d_y, d_b, d_c, s));
     if (lp->nranks > 1) {
-        // row partition: x-slice update | all-gather xbar | y-slice update | all-gather y, all on `s`
+        // row partition: whole-x update (replicated) | y-slice update | exchange of the y slices, all on `s`
         NcclApi* api = nccl_api();
         const double ts[2] = {tau, sigma};
         CUDA_OK(cudaMemcpyAsync(lp->d.ctrl, ts, sizeof(ts), cudaMemcpyHostToDevice, s));
         const bool p2p = lp->p2p_ready && env_int("MLLP_ROWPART_NCCL", 0) == 0;
         if (p2p && num_iters > 0) {
-            // all iterations in ONE cooperative launch per rank; exchange = peer stores + flag barriers
+            // all iterations in ONE cooperative launch per rank; exchange = tagged words through peer mailboxes
             lp->d.join_base = lp->join_epoch;
             lp->join_epoch += 2ull * (unsigned long long)num_iters + 2ull;
-            RC_OK(launch_pdhg_persistent_xchg(lp->d, lp->peers, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma,
-                                              num_iters, lp->epoch, s));
-            lp->epoch += 2u * (unsigned)num_iters;
+            RC_OK(launch_pdhg_rowpart(lp->d, lp->peers, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, num_iters,
+                                      lp->xseq, s));
+            lp->xseq += (unsigned long long)num_iters;
         }
         for (int it = 0; it < (p2p ? 0 : num_iters); ++it) {
             RC_OK(launch_primal(lp->d, lp->bounds, lp->G, lp->threads, s));
-            NCCL_OK(api->all_gather(lp->d.xbar + (size_t)lp->rank * lp->Lx, lp->d.xbar, (size_t)lp->Lx, NCCL_FLOAT64, lp->comm, s));
             RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));
             NCCL_OK(api->all_gather(lp->d.y + (size_t)lp->rank * lp->Ly, lp->d.y, (size_t)lp->Ly, NCCL_FLOAT64, lp->comm, s));
         }
-        if (num_iters > 0)
-            NCCL_OK(api->all_gather(lp->d.x + (size_t)lp->rank * lp->Lx, lp->d.x, (size_t)lp->Lx, NCCL_FLOAT64, lp->comm, s));
         if (d_scalars) {
+            // the A' side sums are complete on every rank (replicated phase); the A side sums are per rank
             RC_OK(launch_eval_partial(lp->d, lp->bounds, lp->G, lp->threads, s));
-            double* red = lp->d.red + (size_t)RED_EVALP * lp->G * NRED;   // EVALP and EVALD buffers are adjacent
-            NCCL_OK(api->all_reduce(red, red, (size_t)2 * lp->G * NRED, NCCL_FLOAT64, NCCL_SUM, lp->comm, s));
+            double* red = lp->d.red + (size_t)RED_EVALD * lp->G * NRED;
+            NCCL_OK(api->all_reduce(red, red, (size_t)lp->G * NRED, NCCL_FLOAT64, NCCL_SUM, lp->comm, s));
             RC_OK(launch_eval_finalize(lp->d, lp->G, d_scalars, (double)num_iters, s));
         }
         RC_OK(store_solution(lp, d_x, d_y, s));
@@ -1039,6 +1030,30 @@ int mllp_debug_trace(mllp_lp_t lp, double tau, double sigma, int32_t iters, unsi
         memcpy(h_out, tr.data(), tr.size() * sizeof(unsigned long long));
         return 0;
     }
+}
+
+// Dev tool (not in the public header), collective: `iters` traced iterations of the row-partitioned kernel on the current
+// internal state; h_out receives iters*G*6 timestamps (ns) per CTA: [A' phase done, barrier released, A phase done,
+// unpack done, barrier released, unused].
+int mllp_debug_trace_rowpart(mllp_lp_t lp, double tau, double sigma, int32_t iters, unsigned long long* h_out)
+{
+    if (!lp || !h_out || iters < 1 || lp->nranks < 2 || !lp->p2p_ready) return fail(MLLP_E_INVALID, "mllp_debug_trace_rowpart: bad argument");
+    DeviceGuard guard(lp->device);
+    unsigned long long* d_tr = nullptr;
+    const size_t cnt = (size_t)iters * lp->G * 6;
+    CUDA_OK(cudaMalloc(&d_tr, cnt * sizeof(unsigned long long)));
+    int rc = (int)cudaMemset(d_tr, 0, cnt * sizeof(unsigned long long));
+    lp->d.join_base = lp->join_epoch;
+    lp->join_epoch += 2ull * (unsigned long long)iters + 2ull;
+    DevLP d = lp->d;
+    d.trace = d_tr;
+    if (rc == 0) rc = launch_pdhg_rowpart(d, lp->peers, lp->bounds, lp->G, lp->threads, lp->dyn_smem, tau, sigma, iters, lp->xseq, 0);
+    lp->xseq += (unsigned long long)iters;
+    if (rc == 0) rc = (int)cudaDeviceSynchronize();
+    if (rc == 0) rc = (int)cudaMemcpy(h_out, d_tr, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_tr);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "traced row-partitioned run");
+    return 0;
 }
 
 int mllp_pdhg_run_host(mllp_lp_t lp, double* h_x, double* h_y, const double* h_b, const double* h_c, double tau,

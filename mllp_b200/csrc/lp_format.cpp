@@ -654,10 +654,11 @@ extern "C" int mllp_format_gather_lines(int32_t m, int32_t n, int64_t nnz, const
     return 0;
 }
 
-// Host-only self check of the ROW-PARTITIONED build: emulates all `nranks` ranks on the CPU --
-// each rank's tiles produce its slice of A v and A' w, slices are "all-gathered" by writing
-// into the shared padded vector -- and compares with the plain CSR products.  out4: [0] worst
-// relative row error, [1] padded y length, [2] padded x length, [3] largest / mean nonzeros per rank.
+// Host-only self check of the ROW-PARTITIONED build: emulates all `nranks` ranks on the CPU.  A is partitioned by rows
+// (each rank's tiles produce its slice of A v; slices are "exchanged" by writing into the shared padded vector), A' is
+// built whole on every rank with its column ids renamed to the padded positions of y (replicated A' phase); both are
+// compared with the plain CSR products.  out4: [0] worst relative row error, [1] padded y length, [2] x length,
+// [3] largest / mean nonzeros of A per rank.
 extern "C" int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr,
                                       const int32_t* indices, const double* values, int32_t num_ctas,
                                       int32_t nranks, double* out4)
@@ -674,91 +675,109 @@ extern "C" int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const i
     std::vector<int32_t> orderY, posY, orderX, posX;
     plan_orders(m, n, indptr, indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
     const BuildParams bpA = effective_params(m, indptr, bp), bpAT = effective_params(n, tptr.data(), bp);
-    RowPartition PY, PX;
+    RowPartition PY;
     partition_rows(m, indptr, orderY, nranks, PY);
-    partition_rows(n, tptr.data(), orderX, nranks, PX);
-    const int mi = PY.L * nranks, ni = PX.L * nranks;
+    const int mi = PY.L * nranks, ni = n;
     double worst = 0.0, max_nnz = 0.0;
-    for (int which = 0; which < 2; ++which) {
-        const int nr = which ? n : m, nc = which ? m : n, nci = which ? mi : ni, nri = which ? ni : mi;
-        const int32_t* ptr = which ? tptr.data() : indptr;
-        const int32_t* ind = which ? tind.data() : indices;
-        const double* val = which ? tval.data() : values;
-        const RowPartition& PR = which ? PX : PY;
-        const RowPartition& PC = which ? PY : PX;
-        std::vector<double> v_user((size_t)nc), v_int((size_t)nci, 0.0), out_int((size_t)nri, NAN);
-        for (int j = 0; j < nc; ++j) v_user[j] = 0.25 + (double)((j * 2654435761u) % 1000u) / 997.0;
-        for (int k = 0; k < nci; ++k) if (PC.order_pad[k] >= 0) v_int[k] = v_user[PC.order_pad[k]];
+    auto butterfly = [](double* ls, int L) {
+        for (int o = L >> 1; o > 0; o >>= 1) {
+            double nxt[32];
+            for (int lane = 0; lane < 32; ++lane) nxt[lane] = ls[lane] + ls[lane ^ o];
+            for (int lane = 0; lane < 32; ++lane) ls[lane] = nxt[lane];
+        }
+    };
+    // replay of one rank's tile walk of M on v_int; rows land in out_int (must be NaN before), inside [lo, hi)
+    auto replay = [&](const HostMat& M, const std::vector<double>& v_int, int nci, std::vector<double>& out_int, uint32_t lo,
+                      uint32_t hi) -> int {
+        std::vector<double> partial(M.num_partials, 0.0);
+        std::vector<uint32_t> arrived(M.splits.size(), 0);
+        for (int g = 0; g < bp.num_ctas; ++g) {
+            double spart[SPLIT_SLOTS];
+            for (uint32_t ti = M.cta_begin[g]; ti < M.cta_begin[g + 1]; ++ti) {
+                const Tile& t = M.tiles[ti];
+                const int L = 1 << t.logL;
+                double lane_sum[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    double s = 0.0;
+                    for (int st = 0; st < t.nsteps; ++st) {
+                        const size_t at = ((size_t)(t.off + st) * 32 + lane) * 2;
+                        if (M.idx[at] < 0 || M.idx[at] >= nci || M.idx[at + 1] < 0 || M.idx[at + 1] >= nci) return 3;
+                        s = std::fma(M.vals[at], v_int[M.idx[at]], s);
+                        s = std::fma(M.vals[at + 1], v_int[M.idx[at + 1]], s);
+                    }
+                    lane_sum[lane] = s;
+                }
+                butterfly(lane_sum, L);
+                if (t.split < 0) {
+                    for (int rr = 0; rr < t.nrows; ++rr) {
+                        const uint32_t r = t.row_base + rr;
+                        if (r < lo || r >= hi || !std::isnan(out_int[r])) return 5;
+                        out_int[r] = lane_sum[rr * L];
+                    }
+                } else {
+                    spart[t.split] = lane_sum[0];
+                }
+            }
+            for (uint32_t li = M.cta_lsplit_begin[g]; li < M.cta_lsplit_begin[g + 1]; ++li) {
+                const LocalSplit& ls = M.lsplits[li];
+                const SplitRow& sr = M.splits[ls.split_id];
+                double pl[32] = {0};
+                for (int k = 0; k < ls.count; ++k) pl[k % 32] += spart[ls.first + k];
+                butterfly(pl, 32);
+                partial[ls.gslot] = pl[0];
+                if (++arrived[ls.split_id] == sr.nparts) {
+                    double ls32[32] = {0};
+                    for (uint32_t k = 0; k < sr.nparts; ++k) ls32[k % 32] += partial[sr.first_slot + k];
+                    butterfly(ls32, 32);
+                    if (sr.row < lo || sr.row >= hi || !std::isnan(out_int[sr.row])) return 7;
+                    out_int[sr.row] = ls32[0];
+                }
+            }
+        }
+        return 0;
+    };
+    auto row_err = [&](const int32_t* ptr, const int32_t* ind, const double* val, const std::vector<double>& v_user, int r,
+                       double got) {
+        double ref = 0.0, mag = 0.0;
+        for (int32_t q = ptr[r]; q < ptr[r + 1]; ++q) {
+            ref += val[q] * v_user[ind[q]];
+            mag += std::fabs(val[q] * v_user[ind[q]]);
+        }
+        return std::fabs(ref - got) / (mag > 0.0 ? mag : 1.0);
+    };
+    {   // A v: every rank produces its slice of the padded result
+        std::vector<double> v_user((size_t)n), v_int((size_t)ni), out_int((size_t)mi, NAN);
+        for (int j = 0; j < n; ++j) v_user[j] = 0.25 + (double)((j * 2654435761u) % 1000u) / 997.0;
+        for (int k = 0; k < ni; ++k) v_int[k] = v_user[orderX[k]];
         for (int rank = 0; rank < nranks; ++rank) {
             HostMat M;
-            build_host_mat((int)PR.lists[rank].size(), nci, ptr, ind, val, PR.lists[rank], PC.pos, which ? bpAT : bpA, M,
-                           (uint32_t)(rank * PR.L));
+            build_host_mat((int)PY.lists[rank].size(), ni, indptr, indices, values, PY.lists[rank], posX, bpA, M,
+                           (uint32_t)(rank * PY.L));
             max_nnz = std::max(max_nnz, (double)M.nnz_emitted);
-            std::vector<double> partial(M.num_partials, 0.0);
-            std::vector<uint32_t> arrived(M.splits.size(), 0);
-            auto butterfly = [](double* ls, int L) {
-                for (int o = L >> 1; o > 0; o >>= 1) {
-                    double nxt[32];
-                    for (int lane = 0; lane < 32; ++lane) nxt[lane] = ls[lane] + ls[lane ^ o];
-                    for (int lane = 0; lane < 32; ++lane) ls[lane] = nxt[lane];
-                }
-            };
-            for (int g = 0; g < bp.num_ctas; ++g) {
-                double spart[SPLIT_SLOTS];
-                for (uint32_t ti = M.cta_begin[g]; ti < M.cta_begin[g + 1]; ++ti) {
-                    const Tile& t = M.tiles[ti];
-                    const int L = 1 << t.logL;
-                    double lane_sum[32];
-                    for (int lane = 0; lane < 32; ++lane) {
-                        double s = 0.0;
-                        for (int st = 0; st < t.nsteps; ++st) {
-                            const size_t at = ((size_t)(t.off + st) * 32 + lane) * 2;
-                            if (M.idx[at] < 0 || M.idx[at] >= nci || M.idx[at + 1] < 0 || M.idx[at + 1] >= nci) return 3;
-                            s = std::fma(M.vals[at], v_int[M.idx[at]], s);
-                            s = std::fma(M.vals[at + 1], v_int[M.idx[at + 1]], s);
-                        }
-                        lane_sum[lane] = s;
-                    }
-                    butterfly(lane_sum, L);
-                    if (t.split < 0) {
-                        for (int rr = 0; rr < t.nrows; ++rr) {
-                            const uint32_t r = t.row_base + rr;
-                            if (r < (uint32_t)(rank * PR.L) || r >= (uint32_t)((rank + 1) * PR.L) || !std::isnan(out_int[r])) return 5;
-                            out_int[r] = lane_sum[rr * L];
-                        }
-                    } else {
-                        spart[t.split] = lane_sum[0];
-                    }
-                }
-                for (uint32_t li = M.cta_lsplit_begin[g]; li < M.cta_lsplit_begin[g + 1]; ++li) {
-                    const LocalSplit& ls = M.lsplits[li];
-                    const SplitRow& sr = M.splits[ls.split_id];
-                    double pl[32] = {0};
-                    for (int k = 0; k < ls.count; ++k) pl[k % 32] += spart[ls.first + k];
-                    butterfly(pl, 32);
-                    partial[ls.gslot] = pl[0];
-                    if (++arrived[ls.split_id] == sr.nparts) {
-                        double ls32[32] = {0};
-                        for (uint32_t k = 0; k < sr.nparts; ++k) ls32[k % 32] += partial[sr.first_slot + k];
-                        butterfly(ls32, 32);
-                        if (sr.row >= (uint32_t)nri || !std::isnan(out_int[sr.row])) return 7;
-                        out_int[sr.row] = ls32[0];
-                    }
-                }
-            }
+            const int rc = replay(M, v_int, ni, out_int, (uint32_t)(rank * PY.L), (uint32_t)((rank + 1) * PY.L));
+            if (rc != 0) return rc;
         }
-        for (int r = 0; r < nr; ++r) {
-            const double got = out_int[PR.pos[r]];
+        for (int r = 0; r < m; ++r) {
+            const double got = out_int[PY.pos[r]];
             if (std::isnan(got)) return 8;
-            double ref = 0.0, mag = 0.0;
-            for (int32_t q = ptr[r]; q < ptr[r + 1]; ++q) {
-                ref += val[q] * v_user[ind[q]];
-                mag += std::fabs(val[q] * v_user[ind[q]]);
-            }
-            worst = std::max(worst, std::fabs(ref - got) / (mag > 0.0 ? mag : 1.0));
+            worst = std::max(worst, row_err(indptr, indices, values, v_user, r, got));
         }
-        for (int k = 0; k < nri; ++k)
-            if (PR.order_pad[k] < 0 && !std::isnan(out_int[k])) return 9;  // padding must stay untouched
+        for (int k = 0; k < mi; ++k)
+            if (PY.order_pad[k] < 0 && !std::isnan(out_int[k])) return 9;  // padding must stay untouched
+    }
+    {   // A' w: the whole product on every rank, gathering from the padded y
+        std::vector<double> w_user((size_t)m), w_int((size_t)mi, 0.0), out_int((size_t)n, NAN);
+        for (int j = 0; j < m; ++j) w_user[j] = 0.25 + (double)((j * 2654435761u) % 1000u) / 997.0;
+        for (int k = 0; k < mi; ++k) if (PY.order_pad[k] >= 0) w_int[k] = w_user[PY.order_pad[k]];
+        HostMat M;
+        build_host_mat(n, mi, tptr.data(), tind.data(), tval.data(), orderX, PY.pos, bpAT, M);
+        const int rc = replay(M, w_int, mi, out_int, 0u, (uint32_t)n);
+        if (rc != 0) return rc;
+        for (int r = 0; r < n; ++r) {
+            const double got = out_int[posX[r]];
+            if (std::isnan(got)) return 8;
+            worst = std::max(worst, row_err(tptr.data(), tind.data(), tval.data(), w_user, r, got));
+        }
     }
     out4[0] = worst;
     out4[1] = mi;

@@ -26,9 +26,9 @@ int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem);
 int persistent_cluster_fits(int ctas, int threads, bool bounds, size_t dyn_smem);
 int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double tau, double sigma,
                            int iters, cudaStream_t s);
-int xchg_set_smem(bool bounds, size_t dyn_smem);
-int launch_pdhg_persistent_xchg(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
-                                double tau, double sigma, int iters, unsigned epoch, cudaStream_t s);
+int rowpart_set_smem(bool bounds, size_t dyn_smem);
+int launch_pdhg_rowpart(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
+                        double tau, double sigma, int iters, unsigned long long seq, cudaStream_t s);
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
                             int max_iters, int check_every, double tol, double* out, cudaStream_t s);
 

@@ -285,24 +285,35 @@ __global__ void __launch_bounds__(1024, 1) k_pdhg_persistent(DevLP lp, double ta
     }
 }
 
-// Row-partitioned persistent kernel: the same loop, but the row updates also store into the peers'
-// vectors and the grid barriers are cross-GPU barriers (see PeerInfo / xchg_barrier).
+// Row-partitioned persistent kernel (see PeerInfo): replicated A' phase, local grid barrier, A phase on this rank's rows
+// with the new duals also mailed to the peers, unpack of the peers' duals, local grid barrier.  One cross-GPU exchange
+// per iteration, no NCCL call and no kernel launch inside the loop.  `seq` = exchanges done on this handle so far (the
+// same on every rank: the calls are collective); it selects the mailbox buffer and makes the tags unique.
 template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1)
-k_pdhg_persistent_xchg(DevLP lp, PeerInfo pi, double tau, double sigma, int iters, unsigned epoch)
+k_pdhg_rowpart(DevLP lp, PeerInfo pi, double tau, double sigma, int iters, unsigned long long seq)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     PersistentSmem P;
     persistent_setup(lp, dsm, P);
     unsigned target = 0;
-    PrimalXchgOp<BOUNDS> pop{lp, pi, tau};
-    DualXchgOp<BOUNDS> dop{lp, pi, sigma};
+    PrimalOp<BOUNDS> pop{lp, tau};
     double acc[NRED];
     for (int it = 0; it < iters; ++it) {
+        // dev trace, 6 slots per (iteration, CTA): A' phase done, barrier released, A phase done, unpack done, barrier released
+        unsigned long long* tr = lp.trace ? lp.trace + ((size_t)it * gridDim.x + blockIdx.x) * 6 : nullptr;
+        const unsigned long long s = seq + (unsigned long long)it + 1ull;
+        const size_t buf = (size_t)(s & 1ull) * 2 * (size_t)pi.mi;
         phase_AT(lp, P, pop, acc);
-        if (!xchg_barrier(lp.barrier, target, epoch + 2u * (unsigned)it + 1u, pi)) return;
+        grid_barrier(lp.barrier, target, tr);
+        DualMailOp<BOUNDS> dop{lp, pi, sigma, s, buf};
         phase_A(lp, P, dop, acc);
-        if (!xchg_barrier(lp.barrier, target, epoch + 2u * (unsigned)it + 2u, pi)) return;
+        if (tr) {
+            __syncthreads();
+            if (threadIdx.x == 0) tr[2] = global_ns();
+        }
+        unpack_mail(lp, pi, s, buf);
+        grid_barrier(lp.barrier, target, tr ? tr + 3 : nullptr);
     }
 }
 
@@ -756,21 +767,23 @@ int launch_pdhg_persistent(const DevLP& lp, bool bounds, int G, int threads, siz
     return launch_persistent_fn(persistent_fn(false, bounds, lp.sync_mode == SYNC_BCAST), lp.sync_mode, G, threads, dyn_smem, args, s);
 }
 
-int xchg_set_smem(bool bounds, size_t dyn_smem)
+static const void* rowpart_fn(bool bounds)
 {
-    const void* fn = bounds ? (const void*)k_pdhg_persistent_xchg<true> : (const void*)k_pdhg_persistent_xchg<false>;
-    return (int)cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    return bounds ? (const void*)k_pdhg_rowpart<true> : (const void*)k_pdhg_rowpart<false>;
+}
+int rowpart_set_smem(bool bounds, size_t dyn_smem)
+{
+    return (int)cudaFuncSetAttribute(rowpart_fn(bounds), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
 }
 
-int launch_pdhg_persistent_xchg(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
-                                double tau, double sigma, int iters, unsigned epoch, cudaStream_t s)
+int launch_pdhg_rowpart(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
+                        double tau, double sigma, int iters, unsigned long long seq, cudaStream_t s)
 {
     CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
     DevLP lpv = lp;
     PeerInfo piv = pi;
-    void* args[] = {&lpv, &piv, &tau, &sigma, &iters, &epoch};
-    const void* fn = bounds ? (const void*)k_pdhg_persistent_xchg<true> : (const void*)k_pdhg_persistent_xchg<false>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, dyn_smem, s));
+    void* args[] = {&lpv, &piv, &tau, &sigma, &iters, &seq};
+    CK(cudaLaunchCooperativeKernel(rowpart_fn(bounds), dim3(G), dim3(threads), args, dyn_smem, s));
     return 0;
 }
 

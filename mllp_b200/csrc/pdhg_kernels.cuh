@@ -545,48 +545,42 @@ struct SpmvOp {
 };
 
 // ---------------------------------------------------------------------------------------
-// Row partition over GPUs with the exchange INSIDE the persistent kernel: every rank writes its
-// slice of xbar (resp. y) straight into all peers' vectors with NVLink peer stores as part of the
-// row update, and the two all-gathers per iteration become two cross-GPU barriers on flags in
-// peer memory.  No NCCL call and no kernel launch inside the iteration loop.
+// Row partition of ONE large LP over GPUs (BASELINE.json configs[3]) with the exchange INSIDE the persistent kernel.
+// Rank p owns a slice of the rows of A (its entries of y); the cheap A' phase is replicated (every rank updates the
+// whole of x from the whole of y), so only y crosses GPUs: ONE exchange per iteration.  The exchange has no fence, no
+// flag and no acknowledgement: a row update stores its new dual value into every peer's MAILBOX over NVLink as one
+// tagged 16-byte word {bits(y), bits(y) ^ tag} (value and validity travel in one access; a word whose halves do not xor
+// to this iteration's tag is stale or torn and is read again), and every rank unpacks the words of the other ranks'
+// slices into its own y (coalesced polls of its local memory) before the local grid barrier that ends the iteration.
+// Two mailbox buffers alternate: rank p overwrites a word of iteration k only in iteration k + 2, which it starts after
+// it has received q's words of iteration k + 1, which q sent after unpacking iteration k.
 constexpr int MAX_RANKS = 8;
 struct PeerInfo {
-    double* xbar[MAX_RANKS];      // every rank's xbar vector (own entry = local pointer)
-    double* y[MAX_RANKS];
-    unsigned* flags[MAX_RANKS];   // every rank's flag array [MAX_RANKS]: slot q is written by rank q
-    unsigned* err;                // local: set to 1 when a wait timed out
-    int rank, nranks;
+    unsigned long long* mail[MAX_RANKS];   // every rank's mailbox [2][mi][2] (own entry = local pointer)
+    int cnt[MAX_RANKS];                    // valid rows at the head of every rank's slice of y
+    unsigned* err;                         // local: set to 1 when a wait timed out
+    int rank, nranks, Ly, mi;              // slice length, padded length of y (= nranks * Ly)
 };
 
-template <bool BOUNDS>
-struct PrimalXchgOp {
-    using Mem = GlobalMem;
-    const DevLP& lp;
-    const PeerInfo& pi;
-    double tau;
-    struct Pre { double c, x; };
-    __device__ __forceinline__ const double* vec() const { return lp.y; }
-    __device__ __forceinline__ Pre prefetch(int r) const { return {Mem::ld_ro(lp.c + r), Mem::ld_mut(lp.x + r)}; }
-    __device__ __forceinline__ void row(int r, double dot, const Pre& p, double*) const
-    {
-        const double g = p.c - dot;
-        double xn = p.x - tau * g;
-        if (BOUNDS) xn = fmin(fmax(xn, Mem::ld_ro(lp.lb + r)), Mem::ld_ro(lp.ub + r));
-        else xn = fmax(xn, 0.0);
-        const double xb = 2.0 * xn - p.x;
-        lp.x[r] = xn;
-#pragma unroll
-        for (int q = 0; q < MAX_RANKS; ++q)
-            if (q < pi.nranks) pi.xbar[q][r] = xb;   // own copy and every peer's, over NVLink
-    }
-};
+__device__ __forceinline__ void st_mail(unsigned long long* p, double v, unsigned long long tag)
+{
+    const unsigned long long a = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");
+}
+__device__ __forceinline__ void ld_mail(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
+{
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 
+// Dual update of this rank's rows: y goes to the local vector and, tagged, to every peer's mailbox.
 template <bool BOUNDS>
-struct DualXchgOp {
+struct DualMailOp {
     using Mem = GlobalMem;
     const DevLP& lp;
     const PeerInfo& pi;
     double sigma;
+    unsigned long long tag;
+    size_t buf;            // word offset of this iteration's mailbox buffer
     struct Pre { double b, y; };
     __device__ __forceinline__ const double* vec() const { return lp.xbar; }
     __device__ __forceinline__ Pre prefetch(int r) const { return {Mem::ld_ro(lp.b + r), Mem::ld_mut(lp.y + r)}; }
@@ -594,53 +588,42 @@ struct DualXchgOp {
     {
         double yn = p.y + sigma * (p.b - dot);
         if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
+        lp.y[r] = yn;
 #pragma unroll
         for (int q = 0; q < MAX_RANKS; ++q)
-            if (q < pi.nranks) pi.y[q][r] = yn;
+            if (q < pi.nranks && q != pi.rank) st_mail(pi.mail[q] + buf + 2 * (size_t)r, yn, tag);
     }
 };
 
-// Cross-GPU barrier: local arrivals on the grid counter (system-scope release, because the phase's
-// peer stores must be visible on the other GPUs); the CTA that completes the local count raises this
-// rank's flag on every GPU; every CTA then waits until all ranks' flags on ITS OWN GPU carry `tag`.
-// Waits time out (~2 s) and raise pi.err instead of hanging the GPU.  Returns false on error.
-__device__ __forceinline__ bool xchg_barrier(unsigned* counter, unsigned& target, unsigned tag, const PeerInfo& pi)
+// Unpack the peers' slices of y from this rank's mailbox (all threads of the grid, coalesced).  Waits give up after
+// ~10 s and raise pi.err instead of hanging the GPU; once it is raised every later wait gives up after one more look,
+// so the launch runs out quickly (with meaningless iterates) and the host reports the error (mllp_rowpart_error).
+__device__ __forceinline__ void unpack_mail(const DevLP& lp, const PeerInfo& pi, unsigned long long tag, size_t buf)
 {
-    __shared__ int s_ok;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int ok = 1;
-        __threadfence_system();        // this CTA's peer stores are performed (acknowledged) before it arrives
-        target += gridDim.x;
-        const unsigned old = atomicAdd(counter, 1u);
-        if (old + 1u == target) {
-            // every CTA of this GPU fenced at system scope before its arrival, so all of this rank's
-            // peer stores are performed: raise the flag everywhere (own GPU included)
-            __threadfence();
-            for (int q = 0; q < pi.nranks; ++q) {
-                volatile unsigned* f = pi.flags[q] + pi.rank;
-                *f = tag;
-            }
-        }
-        const long long t0 = clock64();
-        for (int q = 0; q < pi.nranks && ok; ++q) {
-            const volatile unsigned* f = pi.flags[pi.rank] + q;
-            for (;;) {
-                const unsigned v = *f;
-                if ((int)(v - tag) >= 0) break;
-                if (*(volatile unsigned*)pi.err != 0u || clock64() - t0 > 4000000000LL) {
-                    atomicExch(pi.err, 1u);
-                    ok = 0;
-                    break;
+    const unsigned long long* box = pi.mail[pi.rank] + buf;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int q = 0; q < pi.nranks; ++q) {
+        if (q == pi.rank) continue;
+        const int base = q * pi.Ly;
+        for (int k = gtid; k < pi.cnt[q]; k += gsz) {
+            const unsigned long long* w = box + 2 * (size_t)(base + k);
+            unsigned long long a, b;
+            ld_mail(w, a, b);
+            if ((a ^ b) != tag) {
+                const unsigned long long t0 = global_ns();
+                for (;;) {
+                    __nanosleep(MLLP_BARRIER_BACKOFF);
+                    ld_mail(w, a, b);
+                    if ((a ^ b) == tag) break;
+                    if (global_ns() - t0 > 10000000000ull || *(volatile unsigned*)pi.err != 0u) {
+                        atomicExch(pi.err, 1u);
+                        break;
+                    }
                 }
-                __nanosleep(MLLP_BARRIER_BACKOFF);
             }
+            lp.y[base + k] = __longlong_as_double((long long)a);
         }
-        __threadfence();               // acquire: invalidates this SM's L1 before the next phase gathers
-        s_ok = ok;
     }
-    __syncthreads();
-    return s_ok != 0;
 }
 
 // ---------------------------------------------------------------------------------------

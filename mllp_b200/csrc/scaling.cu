@@ -1,0 +1,159 @@
+// scaling.cu -- device-side scaling of LPs.
+//
+// (1) mllp_norm_scale: the rule behind the reference's `_norm` arrays (dataset/netlib_mps_norm/*, consumed at
+//     linear_program_data.py:66-77; rule reverse-engineered from the data, SURVEY App. A.3, restated and pinned in
+//     oracle/norm_rule.py): raw CSR + row senses -> standard form (one slack column per inequality row) with every row
+//     scaled by 1 / ||row||_2, or by 5 / b_i when that would leave |b_i| above 5, and c / ||c||_2.
+// (2) mllp_precondition: Ruiz equilibration + one Pock-Chambolle pass (the PDLP recipe) of a CSR matrix, in place on the
+//     values, returning the row / column scaling vectors (used by mllp_lp_create with MLLP_F_PRECONDITION).
+//
+// All of it is streaming integer / fp64 work on a few MB: HBM-(L2-)bound, one pass per quantity, coalesced.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <string>
+
+#include "../../include/mllp_b200.h"
+#include "pdhg_host.h"
+
+namespace mllp {
+void set_last_error(const std::string& msg);
+
+// ---- (1) the reference's `_norm` rule ------------------------------------------------------------------------------
+// Exclusive prefix count of the rows that own a slack column (sense != 0): one CTA, chunks of 1024 rows.
+__global__ void __launch_bounds__(1024, 1) k_slack_scan(int m, const signed char* __restrict__ sense, int* __restrict__ rank)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int f = (i < m && sense[i] != 0) ? 1 : 0;
+        int v = f;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int before = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + v - f;
+        if (i < m) rank[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rank[m] = carry_s;
+}
+
+// One warp per row.  The squares are added one by one in ascending column order (the order that reproduces the
+// reference's numbers to the bit): the lanes load 32 consecutive entries (coalesced) and every lane replays the same
+// left-to-right sum over the 32 shuffled squares; __dmul_rn / __dadd_rn keep the compiler from fusing them.
+__global__ void __launch_bounds__(256) k_norm_rows(int m, int n, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                   const double* __restrict__ values, const signed char* __restrict__ sense,
+                                                   const double* __restrict__ rhs, const int* __restrict__ rank,
+                                                   int* __restrict__ out_indptr, int* __restrict__ out_indices,
+                                                   double* __restrict__ out_values, double* __restrict__ out_rhs,
+                                                   double* __restrict__ row_scale)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < m; i += warps) {
+        const int a = indptr[i], e = indptr[i + 1];
+        const int s = sense[i];
+        double acc = 0.0;
+        for (int k0 = a; k0 < e; k0 += 32) {
+            const int k = k0 + lane;
+            const double v = k < e ? values[k] : 0.0;
+            const double sq = __dmul_rn(v, v);
+            const int cnt = min(32, e - k0);
+            for (int l = 0; l < cnt; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, sq, l));
+        }
+        if (s != 0) acc = __dadd_rn(acc, 1.0);
+        const double r = sqrt(acc);
+        const double b = rhs[i];
+        const bool nonempty = r > 0.0;
+        const bool divided = nonempty && (fabs(b) / r <= 5.0);
+        const double d5 = 5.0 / b;
+        const int o = a + rank[i];
+        for (int k = a + lane; k < e; k += 32) {
+            const double v = values[k];
+            out_values[o + (k - a)] = divided ? v / r : (nonempty ? __dmul_rn(v, d5) : v);
+            out_indices[o + (k - a)] = indices[k];
+        }
+        if (lane == 0) {
+            if (s != 0) {
+                const double v = s > 0 ? 1.0 : -1.0;
+                out_values[o + (e - a)] = divided ? v / r : __dmul_rn(v, d5);
+                out_indices[o + (e - a)] = n + rank[i];
+            }
+            out_rhs[i] = divided ? b / r : (nonempty ? __dmul_rn(b, d5) : b);
+            row_scale[i] = divided ? 1.0 / r : (nonempty ? d5 : 1.0);
+            out_indptr[i] = o;
+            if (i == m - 1) out_indptr[m] = e + rank[m];
+        }
+    }
+}
+
+__global__ void k_norm_coefs_tail(double* out_coefs, int n, int nslack, const double* norm2, double* cnorm)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nslack; k += gridDim.x * blockDim.x) out_coefs[n + k] = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cnorm) cnorm[0] = sqrt(norm2[0]);
+}
+
+}  // namespace mllp
+
+using namespace mllp;
+
+extern "C" {
+
+int64_t mllp_norm_scale_work_bytes(int32_t m) { return (int64_t)sizeof(int) * ((int64_t)m + 2) + 8 * (2 + 160); }
+
+int mllp_norm_scale(int32_t m, int32_t n, int64_t nnz, int32_t nslack, const int32_t* d_indptr, const int32_t* d_indices,
+                    const double* d_values, const int8_t* d_sense, const double* d_rhs, const double* d_coefs,
+                    int32_t* d_out_indptr, int32_t* d_out_indices, double* d_out_values, double* d_out_rhs,
+                    double* d_out_coefs, double* d_row_scale, double* d_cnorm, void* d_work, void* stream)
+{
+    if (m < 0 || n < 0 || nnz < 0 || nslack < 0 || nslack > m || !d_indptr || !d_sense || !d_rhs || !d_coefs || !d_out_indptr || !d_out_rhs || !d_out_coefs ||
+        !d_row_scale || !d_work || (nnz > 0 && (!d_indices || !d_values || !d_out_indices || !d_out_values))) {
+        set_last_error("mllp_norm_scale: null argument or bad shape");
+        return MLLP_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // work: [m + 1] slack ranks (padded to 8 bytes) | norm2 (1 double) + the partial sums of the two-stage sum
+    int* rank = (int*)d_work;
+    double* norm2 = (double*)((char*)d_work + sizeof(int) * (((size_t)m + 2) & ~(size_t)1));
+    k_slack_scan<<<1, 1024, 0, s>>>(m, (const signed char*)d_sense, rank);
+    if (m > 0) {
+        const int blocks = (m + 7) / 8 > 148 * 8 ? 148 * 8 : (m + 7) / 8;
+        k_norm_rows<<<blocks, 256, 0, s>>>(m, n, d_indptr, d_indices, d_values, (const signed char*)d_sense, d_rhs, rank,
+                                           d_out_indptr, d_out_indices, d_out_values, d_out_rhs, d_row_scale);
+    } else {
+        cudaMemsetAsync(d_out_indptr, 0, sizeof(int), s);
+    }
+    int rc = launch_sumsq(d_coefs, n, norm2, norm2 + 2, s);
+    if (rc == 0) rc = launch_scale_by_invnorm(d_out_coefs, d_coefs, norm2, n, s);
+    if (rc == 0) {
+        k_norm_coefs_tail<<<nslack > 0 ? (nslack + 255) / 256 : 1, 256, 0, s>>>(d_out_coefs, n, nslack, norm2, d_cnorm);   // slack costs are 0
+        rc = (int)cudaGetLastError();
+    }
+    if (rc != 0) {
+        set_last_error(std::string("mllp_norm_scale: ") + cudaGetErrorString((cudaError_t)rc));
+        return rc;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -5,9 +5,11 @@ Two ways the path shards:
 * independent LP instances (batches): contiguous blocks of instances per rank, NO data-path
   collective; one gather of the per-instance results at the end
   (``shard_range`` / ``solve_batch_data_parallel``);
-* ONE large LP (ken-18, osa-60, pds-20): row partition inside the C library with two NCCL
-  all-gathers per iteration (``RowPartLP`` / ``pdhg_linear_program_rowpart``).  Both ranks'
-  results are identical to the single-GPU path up to summation order.
+* ONE large LP (ken-18, osa-60, pds-20): row partition of A inside the C library, the A' phase
+  replicated, ONE exchange of the y slices per iteration -- tagged words through peer mailboxes
+  over NVLink inside the persistent kernel, or one NCCL all-gather per iteration
+  (``RowPartLP`` / ``pdhg_linear_program_rowpart``).  All ranks' results are identical to the
+  single-GPU path up to summation order.
 """
 import ctypes
 
@@ -110,8 +112,8 @@ class RowPartLP(DeviceLP):
         self._sigma_max = None
         self.p2p = False
         if p2p and 1 < self.world <= 8:
-            # in-kernel exchange over NVLink peer memory: swap CUDA IPC handles of xbar / y / flags
-            mine = np.zeros(192, dtype=np.uint8)
+            # in-kernel exchange over NVLink peer memory: swap the CUDA IPC handles of the ranks' mailboxes
+            mine = np.zeros(64, dtype=np.uint8)
             _cabi.check(L.mllp_rowpart_ipc_export(h, mine.ctypes.data), "mllp_rowpart_ipc_export")
             parts = [None] * self.world
             dist.all_gather_object(parts, (self.rank, mine.tobytes()))

@@ -7,8 +7,11 @@ makes 18 instances unbounded and 2 infeasible.  This reader re
     min c'x + offset   s.t.   A x - b in K_row (ylo <= y <= yhi),   lb <= x <= ub
 
 Rows: ``E`` -> dual free, ``G`` (a'x >= b) -> y in [0, inf), ``L`` (a'x <= b) -> y in (-inf, 0].
-RANGES rows become equality rows with one extra slack column boxed by the range
-(a'x - s = 0, lo <= s <= hi), the representation the reference's dataset uses.
+RANGES rows become equality rows with one extra slack column boxed by the range: by default
+a'x - s = 0, lo <= s <= hi; with ``range_form="dataset"`` exactly the representation of the
+reference's raw arrays ``dataset/netlib_mps/*`` (SURVEY App. A.2; Gurobi's): a'x + s = b,
+0 <= s <= |R| on an ``L`` row, a'x - s = b on a ``G`` row, the extra columns appended in row order --
+``A``, ``c`` and ``b`` then equal the reference's arrays bit for bit on all 97 files.
 Dialect handled: fixed/free format with whitespace-separated fields, ``*``
 comments, OBJSENSE (MAX is turned into MIN of -c), objective-row RHS = -offset, bound types
 UP / LO / FX / FR / MI / PL / BV, negative UP with untouched lower bound -> lower = -inf.
@@ -21,7 +24,9 @@ import scipy.sparse as sp
 INF = float("inf")
 
 
-def read_mps(path):
+def read_mps(path, range_form="boxed"):
+    if range_form not in ("boxed", "dataset"):
+        raise ValueError("range_form must be 'boxed' or 'dataset'")
     rows, row_sense, obj_row = {}, [], None
     cols, col_names = {}, []
     entries = []                 # (row, col, value)
@@ -136,8 +141,16 @@ def read_mps(path):
         extra_cols.append((i, lo, hi))
     ri = [e[0] for e in entries]; ci = [e[1] for e in entries]; vv = [e[2] for e in entries]
     for k, (i, lo, hi) in enumerate(extra_cols):
-        ri.append(i); ci.append(n + k); vv.append(-1.0)        # a'x - s = 0
-        b[i] = 0.0; ylo[i] = -INF; yhi[i] = INF
+        ri.append(i); ci.append(n + k)
+        if range_form == "dataset":
+            # the row keeps its right-hand side; the slack (0 <= s <= hi - lo) closes the gap to it from the row's side
+            upper = (row_sense[i] == "L") or (row_sense[i] == "E" and ranges[i] < 0)
+            vv.append(1.0 if upper else -1.0)
+            extra_cols[k] = (i, 0.0, hi - lo)
+        else:
+            vv.append(-1.0)        # a'x - s = 0
+            b[i] = 0.0
+        ylo[i] = -INF; yhi[i] = INF
     n2 = n + len(extra_cols)
     A = sp.csr_matrix((vv, (ri, ci)), shape=(m, n2))
     A.eliminate_zeros()   # explicit zeros in the file (standgub has one) are not entries; HiGHS drops them too
@@ -149,8 +162,11 @@ def read_mps(path):
         col_names = col_names + ["__range_%s" % k for k in range(len(extra_cols))]
     if maximize:
         c, offset = -c, -offset
+    # row_sense of a range row is reported as "E" (it is an equality row now); "row_sense_mps" keeps the file's letters
+    sense_out = ["E" if i in ranges else s_ for i, s_ in enumerate(row_sense)]
     return {"A": A, "b": b, "c": c, "lb": xl, "ub": xu, "ylo": ylo, "yhi": yhi, "offset": offset,
-            "maximize": maximize, "row_sense": row_sense, "col_names": col_names, "num_range_cols": len(extra_cols)}
+            "maximize": maximize, "row_sense": sense_out, "row_sense_mps": row_sense, "col_names": col_names,
+            "num_range_cols": len(extra_cols)}
 
 
 def to_loader_tuple(lp):
