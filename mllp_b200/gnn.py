@@ -181,7 +181,10 @@ class GNNModel:
         import ctypes
         import torch
         if not isinstance(g, BipartiteGraph):
-            raise TypeError("GNNModel.forward expects a BipartiteGraph")   # the reference asserts its type too (:239)
+            from .graph import BipartiteData
+            if not isinstance(g, BipartiteData):   # the reference asserts the type too (:239)
+                raise TypeError("GNNModel.forward expects the BipartiteData of build_graph_from_weights_sets or a BipartiteGraph")
+            g = g.bipartite_graph()
         if g.device != self.device:
             raise ValueError("graph and model live on different devices")
         dev = g.x1.device

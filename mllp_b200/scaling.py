@@ -8,8 +8,77 @@ one Pock-Chambolle (alpha = 1) pass, the PDLP recipe.  The scaled LP
 has the same optimal objective; row senses (dual boxes) are unchanged because Dr > 0.
 The reference's own `_norm` arrays are a different, one-sided row scaling.
 """
+import ctypes
+
 import numpy as np
 import scipy.sparse as sp
+
+from . import _cabi
+
+SENSE_CODE = {"E": 0, "L": 1, "G": -1}
+
+
+def netlib_norm(A, b, c, sense, device=0, return_device=False):
+    """The reference's `_norm` form of a raw LP, computed on the device (``mllp_norm_scale``): standard form with one
+    slack column per inequality row (``sense`` = 'E' / 'L' / 'G' per row, RANGES rows already equalities), rows scaled
+    by 1 / ||row||_2 or 5 / b_i, c by 1 / ||c||_2 -- the arrays ``dataset/netlib_mps_norm/<name>_{constrs,rhs,coefs}``
+    hold for the same file (reference linear_program_data.py:66-77; rule: oracle/norm_rule.py).
+
+    Returns ``(A_norm, rhs_norm, coefs_norm, info)`` with ``A_norm`` a scipy CSR matrix; ``info`` carries
+    ``row_scale`` (y_raw = row_scale * y_norm), ``c_norm2`` (objective in the file's units = objective of the `_norm`
+    LP * c_norm2 + offset) and ``num_slack``.  ``return_device=True`` adds the device tensors under ``info['device']``."""
+    import torch
+    from .linear_program_methods import _device_index, _torch_stream
+    A = sp.csr_matrix(A, dtype=np.float64)
+    A.sort_indices()
+    m, n = A.shape
+    codes = np.asarray([SENSE_CODE[s] for s in sense], dtype=np.int8) if len(sense) and isinstance(sense[0], str) \
+        else np.ascontiguousarray(sense, dtype=np.int8)
+    if codes.shape[0] != m or np.shape(b)[0] != m or np.shape(c)[0] != n:
+        raise ValueError("sense / rhs must have one entry per row and coefs one per column")
+    nslack = int(np.count_nonzero(codes))
+    dev = torch.device("cuda", _device_index(device))
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=dev)
+    d_ip, d_ii, d_vv = t(A.indptr, np.int32), t(A.indices, np.int32), t(A.data, np.float64)
+    d_se, d_b, d_c = t(codes, np.int8), t(b, np.float64), t(c, np.float64)
+    o_ip = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    o_ii = torch.empty(A.nnz + nslack, dtype=torch.int32, device=dev)
+    o_vv = torch.empty(A.nnz + nslack, dtype=torch.float64, device=dev)
+    o_b = torch.empty(m, dtype=torch.float64, device=dev)
+    o_c = torch.empty(n + nslack, dtype=torch.float64, device=dev)
+    o_d = torch.empty(m, dtype=torch.float64, device=dev)
+    o_cn = torch.zeros(1, dtype=torch.float64, device=dev)
+    L = _cabi.lib()
+    work = torch.empty(int(L.mllp_norm_scale_work_bytes(m)) // 8 + 1, dtype=torch.float64, device=dev)
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    _cabi.check(L.mllp_norm_scale(m, n, A.nnz, nslack, p(d_ip), p(d_ii), p(d_vv), p(d_se), p(d_b), p(d_c), p(o_ip), p(o_ii),
+                                  p(o_vv), p(o_b), p(o_c), p(o_d), p(o_cn), p(work), _torch_stream(dev)), "mllp_norm_scale")
+    An = sp.csr_matrix((o_vv.cpu().numpy(), o_ii.cpu().numpy(), o_ip.cpu().numpy()), shape=(m, n + nslack))
+    info = {"row_scale": o_d.cpu().numpy(), "c_norm2": float(o_cn.cpu()[0]), "num_slack": nslack}
+    if return_device:
+        info["device"] = {"indptr": o_ip, "indices": o_ii, "values": o_vv, "rhs": o_b, "coefs": o_c, "row_scale": o_d}
+    return An, o_b.cpu().numpy(), o_c.cpu().numpy(), info
+
+
+def netlib_norm_from_mps(path, device=0):
+    """MPS text -> the reference's loader tuple ``(file, constrs, constrs_weights, coefs, rhs, None)`` in `_norm` form
+    (what ``get_netlib_dataset(normalize=True)`` hands out for the same file, without the pre-converted arrays) plus
+    ``info`` (``c_norm2``, ``offset``, ``maximize``, ``row_scale``)."""
+    import os
+    from .mps import read_mps
+    lp = read_mps(path, range_form="dataset")
+    An, rhs, coefs, info = netlib_norm(lp["A"], lp["b"], lp["c"], lp["row_sense"], device=device)
+    info.update(offset=lp["offset"], maximize=lp["maximize"])
+    name = os.path.basename(str(path))
+    name = name[:-3] if name.endswith(".gz") else name
+    constrs = np.split(An.indices, An.indptr)[1:-1]
+    return (name, constrs, An.data, coefs, rhs, None), info
+
+
+def netlib_objective(objective_norm, info):
+    """Objective of the `_norm` LP in the MPS file's units: x ||c_raw||_2 + offset, sign restored."""
+    v = objective_norm * info["c_norm2"] + info.get("offset", 0.0)
+    return -v if info.get("maximize") else v
 
 
 def ruiz_pock_chambolle(A, ruiz_iters=10):

@@ -60,8 +60,9 @@ def norm_rule(A, b, c, sense):
         divided = (np.abs(b) / r <= 5.0) & (r > 0.0)
         d5 = 5.0 / b
     rows = np.repeat(np.arange(m), np.diff(As.indptr))
-    data = np.where(divided[rows], As.data / np.where(r > 0, r, 1.0)[rows], As.data * d5[rows])
-    rhs = np.where(divided, b / np.where(r > 0, r, 1.0), b * d5)
+    with np.errstate(invalid="ignore"):       # 5 / 0 on rows that are divided anyway
+        data = np.where(divided[rows], As.data / np.where(r > 0, r, 1.0)[rows], As.data * d5[rows])
+        rhs = np.where(divided, b / np.where(r > 0, r, 1.0), b * d5)
     rhs = np.where(r > 0.0, rhs, b)            # an empty row keeps its right-hand side
     An = sp.csr_matrix((data, As.indices.copy(), As.indptr.copy()), shape=As.shape)
     cn = float(np.linalg.norm(c))

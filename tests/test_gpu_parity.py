@@ -224,10 +224,20 @@ def test_device_graph_builder_matches_reference_loop(torch_cuda):
                 index_1.append(var_index)
                 index_2.append(constr_idx)
         ref_edge = torch.tensor([index_1, index_2])
-        assert torch.equal(g["edge_index"].cpu(), ref_edge)
-        assert torch.equal(g["edge_attr"].cpu(), torch.tensor(A.data, dtype=torch.float).unsqueeze(-1))
-        assert torch.equal(g["x_src"].cpu(), torch.tensor(c, dtype=torch.float).unsqueeze(-1))
-        assert torch.equal(g["x_tgt"].cpu(), torch.tensor(b, dtype=torch.float).unsqueeze(-1))
+        # the reference's BipartiteData attributes (:60-66)
+        assert torch.equal(g.edge_index.cpu(), ref_edge)
+        assert torch.equal(g.edge_attr.cpu(), torch.tensor(A.data, dtype=torch.float).unsqueeze(-1))
+        assert torch.equal(g.x1.cpu(), torch.tensor(c, dtype=torch.float).unsqueeze(-1))
+        assert torch.equal(g.x2.cpu(), torch.tensor(b, dtype=torch.float).unsqueeze(-1))
+        assert g["x_src"] is g.x1 and g["x_tgt"] is g.x2
+        assert torch.equal(g.__inc__("edge_index", None), torch.tensor([[c.shape[0]], [b.shape[0]]]))
+        # and the message-passing forward takes it as the reference's model takes its graph (:238-239)
+        import mllp_b200.gnn as GN
+        from oracle import gnn_numpy as GO
+        st = GO.init_state(3)
+        logits = GN.GNNModel(st, device=0)(g).cpu().numpy()
+        ref = GO.gnn_forward(st, A, b, c)
+        assert np.max(np.abs(logits - ref)) <= 2e-4 * max(1.0, np.max(np.abs(ref)))
 
 
 # Launch geometries of the persistent kernels (mllp_lp_geometry): cooperative grid, one cluster (hardware cluster
