@@ -63,6 +63,9 @@ typedef struct mllp_batch *mllp_batch_t;
 
 const char *mllp_last_error(void);
 int mllp_version(void);
+/* Statistics: number of kernel (or captured-graph) launches this library has issued in the calling process so far --
+ * the difference around a region is the count of the library's own launches inside it (bench.py: gpu_launches). */
+long long mllp_launch_count(void);
 
 /* Host-only self check of the format builder (no GPU needed): builds the tiled images of A
  * and A' for a grid of `num_ctas` CTAs and replays the kernel's tile walk on the CPU against

@@ -21,6 +21,7 @@ _dbl = ctypes.c_double
 SIGNATURES = {
     "mllp_last_error": (ctypes.c_char_p, []),
     "mllp_version": (ctypes.c_int, []),
+    "mllp_launch_count": (ctypes.c_longlong, []),
     "mllp_format_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "mllp_rowpart_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mllp_format_gather_lines": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

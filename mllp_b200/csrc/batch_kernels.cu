@@ -32,6 +32,8 @@ struct BatchInst {          // device-side descriptor of one instance
     DevMat A, AT;
     const int32_t* orderX;  // internal position k holds original column orderX[k]
     const int32_t* orderY;
+    const double* dr;       // preconditioned batch (MLLP_F_PRECONDITION): the matrix held is Dr A Dc; internal order; else null
+    const double* dc;
     int m, n;
     long long x_off, y_off; // offsets into the concatenated user vectors
 };
@@ -61,6 +63,7 @@ __device__ __forceinline__ DevLP smem_lp(const BatchInst& I, const BatchSmem& S)
     DevLP lp{};
     lp.A = I.A; lp.AT = I.AT; lp.m = I.m; lp.n = I.n;
     lp.b = S.b; lp.c = S.c; lp.x = S.x; lp.y = S.y; lp.xbar = S.xbar; lp.x0 = S.x0; lp.y0 = S.y0;
+    lp.dr = I.dr; lp.dc = I.dc;
     return lp;
 }
 
@@ -115,23 +118,26 @@ __device__ __forceinline__ void cta_allreduce(double* acc, const BatchSmem& S)
 __device__ __forceinline__ void load_instance(const BatchInst& I, const BatchSmem& S, const double* x, const double* y,
                                               const double* b, const double* c)
 {
+    // preconditioned batch: the caller's vectors are those of the ORIGINAL LP (x~ = x / dc, c~ = dc c, y~ = y / dr, b~ = dr b)
     for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
         const int j = __ldg(I.orderX + k);
-        S.x[k] = x[I.x_off + j];
-        S.c[k] = c[I.x_off + j];
+        const double sc = I.dc ? __ldg(I.dc + k) : 1.0;
+        S.x[k] = x[I.x_off + j] / sc;
+        S.c[k] = c[I.x_off + j] * sc;
         S.xbar[k] = 0.0;
     }
     for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
         const int i = __ldg(I.orderY + k);
-        S.y[k] = y[I.y_off + i];
-        S.b[k] = b[I.y_off + i];
+        const double sc = I.dr ? __ldg(I.dr + k) : 1.0;
+        S.y[k] = y[I.y_off + i] / sc;
+        S.b[k] = b[I.y_off + i] * sc;
     }
     __syncthreads();
 }
 __device__ __forceinline__ void store_instance(const BatchInst& I, const BatchSmem& S, double* x, double* y)
 {
-    for (int k = threadIdx.x; k < I.n; k += blockDim.x) x[I.x_off + __ldg(I.orderX + k)] = S.x[k];
-    for (int k = threadIdx.x; k < I.m; k += blockDim.x) y[I.y_off + __ldg(I.orderY + k)] = S.y[k];
+    for (int k = threadIdx.x; k < I.n; k += blockDim.x) x[I.x_off + __ldg(I.orderX + k)] = S.x[k] * (I.dc ? __ldg(I.dc + k) : 1.0);
+    for (int k = threadIdx.x; k < I.m; k += blockDim.x) y[I.y_off + __ldg(I.orderY + k)] = S.y[k] * (I.dr ? __ldg(I.dr + k) : 1.0);
     __syncthreads();
 }
 
@@ -150,10 +156,10 @@ __device__ __forceinline__ void batch_kkt(const DevLP& lp, const MatView& VA, co
         EvalDualOp<false, SmemMem> op{lp};
         run_phase(lp.A, VA, op, ad);
     }
-    cta_allreduce<6>(ap, S);
-    cta_allreduce<5>(ad, S);
+    cta_allreduce<7>(ap, S);
+    cta_allreduce<6>(ad, S);
     const double pobj = ap[0], dobj = ad[0] + ap[1];
-    s[0] = pobj; s[1] = dobj; s[2] = sqrt(ad[1]); s[3] = sqrt(ap[2]);
+    s[0] = pobj; s[1] = dobj; s[2] = sqrt(ad[1] + ap[6]); s[3] = sqrt(ap[2] + ad[5]);
     s[4] = sqrt(ad[2]); s[5] = sqrt(ap[3]); s[6] = sqrt(ap[4]); s[7] = sqrt(ad[3]);
     const double gap = fabs(pobj - dobj);
     double e = s[2] / (1.0 + s[4]);
@@ -504,42 +510,53 @@ struct DualHalpernR {
         }
     }
 };
-// acc[r * 6 + k]: 0 pobj, 1 dobj bound terms (0 here: l = 0, u = inf), 2 dual residual^2, 3 ||c||^2, 4 ||x||^2, 5 ||x-x0||^2
+// Same sums as EvalPrimalOp / EvalDualOp (ORIGINAL LP on a preconditioned batch: dc / dr are the matrix's scaling
+// vectors in internal order, or null).
+// acc[r * 7 + k]: 0 pobj, 1 dobj bound terms (0 here: l = 0, u = inf), 2 dual residual^2, 3 ||c||^2, 4 ||x||^2,
+//                 5 ||x~ - x~0||^2 (scaled), 6 distance^2 of x from x >= 0
 template <int R>
 struct EvalPrimalR {
     const SmemR<R>& S;
+    const double* dc;
     __device__ __forceinline__ const double* vec() const { return S.y; }
     __device__ __forceinline__ void row(int i, const double* dot, double* acc) const
     {
+        const double sc = dc ? __ldg(dc + i) : 1.0;
+        const double inv = 1.0 / sc;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double cc = S.c[(size_t)i * R + r], xx = S.x[(size_t)i * R + r], x0 = S.x0 ? S.x0[(size_t)i * R + r] : 0.0;
             const double rc = cc - dot[r];
             const double rn = rc < 0.0 ? rc : 0.0;
-            acc[r * 6 + 0] += cc * xx;
-            acc[r * 6 + 2] += rn * rn;
-            acc[r * 6 + 3] += cc * cc;
-            acc[r * 6 + 4] += xx * xx;
-            acc[r * 6 + 5] += (xx - x0) * (xx - x0);
+            const double xv = xx < 0.0 ? xx : 0.0;
+            acc[r * 7 + 0] += cc * xx;
+            acc[r * 7 + 2] += (rn * rn) * (inv * inv);
+            acc[r * 7 + 3] += (cc * inv) * (cc * inv);
+            acc[r * 7 + 4] += (xx * sc) * (xx * sc);
+            acc[r * 7 + 5] += (xx - x0) * (xx - x0);
+            acc[r * 7 + 6] += (xv * sc) * (xv * sc);
         }
     }
 };
-// acc[r * 6 + k]: 0 b'y, 1 primal residual^2, 2 ||b||^2, 3 ||y||^2, 4 ||y-y0||^2
+// acc[r * 7 + k]: 0 b'y, 1 primal residual^2, 2 ||b||^2, 3 ||y||^2, 4 ||y~ - y~0||^2 (scaled)
 template <int R>
 struct EvalDualR {
     const SmemR<R>& S;
+    const double* dr;
     __device__ __forceinline__ const double* vec() const { return S.x; }
     __device__ __forceinline__ void row(int i, const double* dot, double* acc) const
     {
+        const double sc = dr ? __ldg(dr + i) : 1.0;
+        const double inv = 1.0 / sc;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double bb = S.b[(size_t)i * R + r], yy = S.y[(size_t)i * R + r], y0 = S.y0 ? S.y0[(size_t)i * R + r] : 0.0;
             const double res = dot[r] - bb;
-            acc[r * 6 + 0] += bb * yy;
-            acc[r * 6 + 1] += res * res;
-            acc[r * 6 + 2] += bb * bb;
-            acc[r * 6 + 3] += yy * yy;
-            acc[r * 6 + 4] += (yy - y0) * (yy - y0);
+            acc[r * 7 + 0] += bb * yy;
+            acc[r * 7 + 1] += (res * inv) * (res * inv);
+            acc[r * 7 + 2] += (bb * inv) * (bb * inv);
+            acc[r * 7 + 3] += (yy * sc) * (yy * sc);
+            acc[r * 7 + 4] += (yy - y0) * (yy - y0);
         }
     }
 };
@@ -575,21 +592,21 @@ template <int R>
 __device__ __forceinline__ void batch_kkt_r(const BatchInst& I, const MatView& VA, const MatView& VAT, const SmemR<R>& S,
                                             double* s, double* dd)
 {
-    double ap[R * 6], ad[R * 6];
+    double ap[R * 7], ad[R * 7];
 #pragma unroll
-    for (int k = 0; k < R * 6; ++k) { ap[k] = 0.0; ad[k] = 0.0; }
-    { EvalPrimalR<R> op{S}; run_phase_r<R>(I.AT, VAT, op, S.spart, ap); }
+    for (int k = 0; k < R * 7; ++k) { ap[k] = 0.0; ad[k] = 0.0; }
+    { EvalPrimalR<R> op{S, I.dc}; run_phase_r<R>(I.AT, VAT, op, S.spart, ap); }
     __syncthreads();
-    { EvalDualR<R> op{S}; run_phase_r<R>(I.A, VA, op, S.spart, ad); }
-    cta_allreduce_r<R * 6, R>(ap, S);
-    cta_allreduce_r<R * 6, R>(ad, S);
+    { EvalDualR<R> op{S, I.dr}; run_phase_r<R>(I.A, VA, op, S.spart, ad); }
+    cta_allreduce_r<R * 7, R>(ap, S);
+    cta_allreduce_r<R * 7, R>(ad, S);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const double* p = ap + r * 6;
-        const double* d = ad + r * 6;
+        const double* p = ap + r * 7;
+        const double* d = ad + r * 7;
         double* o = s + r * 10;
         const double pobj = p[0], dobj = d[0] + p[1];
-        o[0] = pobj; o[1] = dobj; o[2] = sqrt(d[1]); o[3] = sqrt(p[2]);
+        o[0] = pobj; o[1] = dobj; o[2] = sqrt(d[1] + p[6]); o[3] = sqrt(p[2]);
         o[4] = sqrt(d[2]); o[5] = sqrt(p[3]); o[6] = sqrt(p[4]); o[7] = sqrt(d[3]);
         const double gap = fabs(pobj - dobj);
         double e = o[2] / (1.0 + o[4]);
@@ -606,23 +623,25 @@ __device__ __forceinline__ void load_group(const BatchInst& I, const SmemR<R>& S
 {
     for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
         const int j = __ldg(I.orderX + k);
+        const double sc = I.dc ? __ldg(I.dc + k) : 1.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool ok = inst0 + r < count;
             const size_t at = (size_t)(inst0 + r) * I.n + j;
-            S.x[(size_t)k * R + r] = ok ? x[at] : 0.0;
-            S.c[(size_t)k * R + r] = ok ? c[at] : 0.0;
+            S.x[(size_t)k * R + r] = ok ? x[at] / sc : 0.0;
+            S.c[(size_t)k * R + r] = ok ? c[at] * sc : 0.0;
             S.xbar[(size_t)k * R + r] = 0.0;
         }
     }
     for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
         const int i = __ldg(I.orderY + k);
+        const double sc = I.dr ? __ldg(I.dr + k) : 1.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool ok = inst0 + r < count;
             const size_t at = (size_t)(inst0 + r) * I.m + i;
-            S.y[(size_t)k * R + r] = ok ? y[at] : 0.0;
-            S.b[(size_t)k * R + r] = ok ? b[at] : 0.0;
+            S.y[(size_t)k * R + r] = ok ? y[at] / sc : 0.0;
+            S.b[(size_t)k * R + r] = ok ? b[at] * sc : 0.0;
         }
     }
     __syncthreads();
@@ -632,15 +651,17 @@ __device__ __forceinline__ void store_group(const BatchInst& I, const SmemR<R>& 
 {
     for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
         const int j = __ldg(I.orderX + k);
+        const double sc = I.dc ? __ldg(I.dc + k) : 1.0;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (inst0 + r < count) x[(size_t)(inst0 + r) * I.n + j] = S.x[(size_t)k * R + r];
+            if (inst0 + r < count) x[(size_t)(inst0 + r) * I.n + j] = S.x[(size_t)k * R + r] * sc;
     }
     for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
         const int i = __ldg(I.orderY + k);
+        const double sc = I.dr ? __ldg(I.dr + k) : 1.0;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (inst0 + r < count) y[(size_t)(inst0 + r) * I.m + i] = S.y[(size_t)k * R + r];
+            if (inst0 + r < count) y[(size_t)(inst0 + r) * I.m + i] = S.y[(size_t)k * R + r] * sc;
     }
     __syncthreads();
 }
@@ -696,23 +717,27 @@ __device__ __forceinline__ void load_slot(const BatchInst& I, const SmemR<R>& S,
 {
     for (int k = threadIdx.x; k < I.n; k += blockDim.x) {
         const size_t at = (size_t)inst * I.n + __ldg(I.orderX + k);
-        const double xv = x[at];
+        const double sc = I.dc ? __ldg(I.dc + k) : 1.0;
+        const double xv = x[at] / sc;
         S.x[(size_t)k * R + r] = xv; S.x0[(size_t)k * R + r] = xv;
-        S.c[(size_t)k * R + r] = c[at];
+        S.c[(size_t)k * R + r] = c[at] * sc;
         S.xbar[(size_t)k * R + r] = 0.0;
     }
     for (int k = threadIdx.x; k < I.m; k += blockDim.x) {
         const size_t at = (size_t)inst * I.m + __ldg(I.orderY + k);
-        const double yv = y[at];
+        const double sc = I.dr ? __ldg(I.dr + k) : 1.0;
+        const double yv = y[at] / sc;
         S.y[(size_t)k * R + r] = yv; S.y0[(size_t)k * R + r] = yv;
-        S.b[(size_t)k * R + r] = b[at];
+        S.b[(size_t)k * R + r] = b[at] * sc;
     }
 }
 template <int R>
 __device__ __forceinline__ void store_slot(const BatchInst& I, const SmemR<R>& S, int r, int inst, double* x, double* y)
 {
-    for (int k = threadIdx.x; k < I.n; k += blockDim.x) x[(size_t)inst * I.n + __ldg(I.orderX + k)] = S.x[(size_t)k * R + r];
-    for (int k = threadIdx.x; k < I.m; k += blockDim.x) y[(size_t)inst * I.m + __ldg(I.orderY + k)] = S.y[(size_t)k * R + r];
+    for (int k = threadIdx.x; k < I.n; k += blockDim.x)
+        x[(size_t)inst * I.n + __ldg(I.orderX + k)] = S.x[(size_t)k * R + r] * (I.dc ? __ldg(I.dc + k) : 1.0);
+    for (int k = threadIdx.x; k < I.m; k += blockDim.x)
+        y[(size_t)inst * I.m + __ldg(I.orderY + k)] = S.y[(size_t)k * R + r] * (I.dr ? __ldg(I.dr + k) : 1.0);
 }
 
 // Solve mode for a shared matrix, R instances per CTA: every slot runs its own instance with its own primal
@@ -914,6 +939,7 @@ k_batch_norm(const BatchInst* __restrict__ insts, int count, int shared, int ite
 // host side
 namespace mllp {
 void set_last_error(const std::string& msg);  // cabi.cu: the message mllp_last_error() returns
+void count_launch(int n);                       // cabi.cu: launch statistics (mllp_launch_count)
 }
 namespace {
 int bfail(int code, const std::string& msg) { mllp::set_last_error(msg); return code; }
@@ -1225,6 +1251,7 @@ int mllp_batch_estimate_norm(mllp_batch_t bt, int32_t iters, double* d_sigma_max
     if (!bt || !d_sigma_max || iters < 1) return bfail(MLLP_E_INVALID, "mllp_batch_estimate_norm: bad argument");
     DevGuard guard(bt->device);
     const int grid = bt->shared ? 1 : bt->grid;
+    mllp::count_launch(1);
     k_batch_norm<<<grid, bt->threads, bt->dyn_smem, (cudaStream_t)stream>>>(bt->d_insts, bt->count, bt->shared, iters, d_sigma_max);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bfail((int)e, std::string("mllp_batch_estimate_norm: ") + cudaGetErrorString(e));
@@ -1238,6 +1265,7 @@ int mllp_batch_run(mllp_batch_t bt, double* d_x, double* d_y, const double* d_b,
         return bfail(MLLP_E_INVALID, "mllp_batch_run: null argument or negative iteration count");
     DevGuard guard(bt->device);
     cudaStream_t st = (cudaStream_t)stream;
+    mllp::count_launch(1);
 #define MLLP_RUN_R(RR) k_batch_run_r<RR><<<bt->grid_run, bt->threads, bt->smem_run, st>>>(bt->d_insts, bt->count, bt->g_run, d_x, d_y, d_b, d_c, d_tau, d_sigma, num_iters, d_scalars)
     switch (bt->R_run) {
         case 4: MLLP_RUN_R(4); break;
@@ -1262,6 +1290,7 @@ int mllp_batch_solve(mllp_batch_t bt, double* d_x, double* d_y, const double* d_
     cudaError_t e0 = cudaMemsetAsync(bt->d_next, 0, sizeof(int), (cudaStream_t)stream);
     if (e0 != cudaSuccess) return bfail((int)e0, std::string("mllp_batch_solve: ") + cudaGetErrorString(e0));
     cudaStream_t st = (cudaStream_t)stream;
+    mllp::count_launch(1);
 #define MLLP_SOLVE_R(RR) k_batch_solve_r<RR><<<bt->grid_solve, bt->threads, bt->smem_solve, st>>>(bt->d_insts, bt->count, bt->g_solve, d_x, d_y, d_b, d_c, d_eta, w0, max_iters, check_every, tol, d_scalars, bt->d_next)
     switch (max_iters > 0 ? bt->R_solve : 1) {   // max_iters == 0 (scalars of the starting point): one-instance kernel
         case 4: MLLP_SOLVE_R(4); break;

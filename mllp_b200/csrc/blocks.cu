@@ -74,7 +74,8 @@ struct BlocksDev {
     const double *lb, *ub, *ylo, *yhi;   // general form: boxes in the handle's internal order (all four or none)
     unsigned long long* trace;      // dev tool (MLLP_BLOCKS_DEBUG & 2): [iter][cta][4] globaltimer stamps, else null
     int poll_gap;                   // ns between two reads of a polled word (MLLP_BLOCKS_POLL_NS)
-    int dbg;                        // dev knob (MLLP_BLOCKS_DEBUG): 1 = no cross-CTA waits (timing of the local work only)
+    int dbg;                        // dev knob (MLLP_BLOCKS_DEBUG): bit 1 = timeline stamps; bit 0 (builds with -DMLLP_DEV only) = no
+                                    // cross-CTA waits (timing of the local work only, results are wrong)
 };
 
 namespace {
@@ -600,7 +601,11 @@ int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, c
             D.max_col_nnz = H.max_c; D.max_row_nnz = H.max_r; D.max_link_nnz = H.max_l;
             D.lb = d_lb; D.ub = d_ub; D.ylo = d_ylo; D.yhi = d_yhi;
             D.trace = nullptr;
-            D.dbg = env_i("MLLP_BLOCKS_DEBUG", 0);
+#ifdef MLLP_DEV
+            D.dbg = env_i("MLLP_BLOCKS_DEBUG", 0);   // dev builds only (-DMLLP_DEV): bit 0 skips the cross-CTA waits (WRONG results)
+#else
+            D.dbg = env_i("MLLP_BLOCKS_DEBUG", 0) & 2;   // release builds: only the timeline stamps; nothing can skip work
+#endif
             D.poll_gap = env_i("MLLP_BLOCKS_POLL_NS", 0);
             bp->smem = smem;
             bp->threads = env_i("MLLP_BLOCKS_THREADS", 1024);
@@ -711,6 +716,7 @@ int blocks_run(BlockPlan* bp, double* gx, double* gy, const double* gb, const do
         D.trace = d_tr;
         cudaMemsetAsync(D.abort_flag, 0, sizeof(unsigned), s);
         void* args[] = {&D, &gx, &gy, &gb, &gc, &tau, &sigma, &iters, &tag0};
+        count_launch(1);
         cudaError_t e = cudaLaunchCooperativeKernel(bp->fn, dim3(D.G), dim3(bp->threads), args, bp->smem, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         g_blocks_trace.assign(cnt, 0ull);
@@ -723,6 +729,7 @@ int blocks_run(BlockPlan* bp, double* gx, double* gy, const double* gb, const do
     if (e != cudaSuccess) return (int)e;
     BlocksDev D = bp->dev;
     void* args[] = {&D, &gx, &gy, &gb, &gc, &tau, &sigma, &iters, &tag0};
+    count_launch(1);
     e = cudaLaunchCooperativeKernel(bp->fn, dim3(D.G), dim3(bp->threads), args, bp->smem, s);
     return (int)e;
 }

@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +40,8 @@ int env_int(const char* name, int dflt)
 
 namespace mllp {
 void set_last_error(const std::string& msg) { g_err = msg; }  // used by batch_kernels.cu
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }
 
 #define CUDA_OK(call)                                           \
@@ -441,7 +444,8 @@ static void update_feedback(const HostMat& H, const std::vector<double>& t, bool
 extern "C" {
 
 const char* mllp_last_error(void) { return g_err.c_str(); }
-int mllp_version(void) { return 100; }
+int mllp_version(void) { return 200; }
+long long mllp_launch_count(void) { return mllp::g_launches.load(std::memory_order_relaxed); }
 
 int mllp_device_info(int device, int64_t* out3)
 {
@@ -1004,7 +1008,7 @@ int mllp_pdhg_run(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, con
         const double ts[2] = {tau, sigma};
         CUDA_OK(cudaMemcpyAsync(lp->d.ctrl, ts, sizeof(ts), cudaMemcpyHostToDevice, s));
         int left = num_iters;
-        for (; left >= GRAPH_UNROLL; left -= GRAPH_UNROLL) CUDA_OK(cudaGraphLaunch(lp->graph, s));
+        for (; left >= GRAPH_UNROLL; left -= GRAPH_UNROLL) { count_launch(2 * GRAPH_UNROLL); CUDA_OK(cudaGraphLaunch(lp->graph, s)); }
         for (; left > 0; --left) {
             RC_OK(launch_primal(lp->d, lp->bounds, lp->G, lp->threads, s));
             RC_OK(launch_dual(lp->d, lp->bounds, lp->G, lp->threads, s));

@@ -41,6 +41,7 @@
 
 namespace mllp {
 void set_last_error(const std::string& msg);
+void count_launch(int n);   // cabi.cu: launch statistics (mllp_launch_count)
 
 namespace {
 constexpr int C = 16;              // channels
@@ -437,6 +438,7 @@ int launch_conv_din(const mllp_gnn_side& g, const float* hdst, const float* hsrc
 {
     // one wave of resident CTAs (the kernel walks its rows with a grid stride)
     const long long want = (((long long)g.nd * g.group + 31) / 32 + 7) / 8;
+    count_launch(g.nlong > 0 ? 3 : 1);
 #define MLLP_CONV_ROWS(SS)                                                                                                   \
     do {                                                                                                                     \
         static int per_sm = 0;                                                                                               \
@@ -595,6 +597,7 @@ int mllp_gnn_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_side* to_co
 int mllp_gnn_plan_run(mllp_gnn_plan_t plan, void* stream)
 {
     if (!plan || !plan->exec) return gfail(MLLP_E_INVALID, "mllp_gnn_plan_run: null plan");
+    mllp::count_launch(1);   // one graph launch (the kernels inside were counted when the plan was captured)
     const cudaError_t e = cudaGraphLaunch(plan->exec, (cudaStream_t)stream);
     if (e != cudaSuccess) return gfail((int)e, std::string("mllp_gnn_plan_run: ") + cudaGetErrorString(e));
     return 0;

@@ -8,6 +8,9 @@ struct DevMat;
 struct DevLP;
 struct PeerInfo;
 
+// statistics: every kernel (or captured graph) launch the library issues is counted (mllp_launch_count)
+void count_launch(int n);
+
 int launch_gather(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
 int launch_scatter(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s);
 int launch_fill(double* dst, double v, int n, cudaStream_t s);
@@ -31,6 +34,13 @@ int launch_pdhg_rowpart(const DevLP& lp, const PeerInfo& pi, bool bounds, int G,
                         double tau, double sigma, int iters, unsigned long long seq, cudaStream_t s);
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
                             int max_iters, int check_every, double tol, double* out, cudaStream_t s);
+
+// scaling.cu: Ruiz + Pock-Chambolle preconditioning on the device (creation time); h_values becomes Dr A Dc
+int precondition_device(int m, int n, long long nnz, const int* h_ptr, const int* h_ind, double* h_values, const int* h_tptr,
+                        const int* h_tind, const double* h_tval, int ruiz_iters, double* h_dr, double* h_dc);
+// dst[k] = src[order[k]] * s[k] (div = 0) or / s[k] (div = 1); dst[order[k]] = src[k] * s[k] or / s[k]; s = null: plain
+int launch_gather_scaled(double* dst, const double* src, const int32_t* order, const double* s, int div, int n, cudaStream_t st);
+int launch_scatter_scaled(double* dst, const double* src, const int32_t* order, const double* s, int div, int n, cudaStream_t st);
 
 // blocks.cu: block-angular LPs (components dealt to CTAs, linking rows through tagged words; no grid barrier)
 struct BlockPlan;

@@ -18,6 +18,19 @@ __global__ void k_scatter(double* __restrict__ dst, const double* __restrict__ s
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
         if (order[k] >= 0) dst[order[k]] = src[k];
 }
+// the same with a diagonal scaling in internal order (preconditioned handles: the caller's vectors are the ORIGINAL LP's)
+__global__ void k_gather_scaled(double* __restrict__ dst, const double* __restrict__ src, const int32_t* __restrict__ order,
+                                const double* __restrict__ s, int div, int n)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        dst[k] = order[k] >= 0 ? (div ? src[order[k]] / s[k] : src[order[k]] * s[k]) : 0.0;
+}
+__global__ void k_scatter_scaled(double* __restrict__ dst, const double* __restrict__ src, const int32_t* __restrict__ order,
+                                 const double* __restrict__ s, int div, int n)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        if (order[k] >= 0) dst[order[k]] = div ? src[k] / s[k] : src[k] * s[k];
+}
 __global__ void k_fill(double* dst, double v, int n)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[k] = v;
@@ -84,6 +97,7 @@ int launch_graph_edges(int m, long long nnz, const int32_t* indptr, const int32_
 {
     if (m <= 0 || nnz <= 0) return 0;
     const int blocks = (m + 7) / 8 > 2368 ? 2368 : (m + 7) / 8;
+    count_launch(1);
     k_graph_edges<<<blocks, 256, 0, s>>>(m, nnz, indptr, indices, values, edge_index, edge_attr);
     return (int)cudaGetLastError();
 }
@@ -125,7 +139,7 @@ __device__ __forceinline__ void eval_phases(const DevLP& lp, const MatView& VA, 
 #pragma unroll
         for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
         run_phase(lp.AT, VAT, op, acc);
-        cta_reduce_store<6>(acc, red_p + (size_t)blockIdx.x * NRED, smem);
+        cta_reduce_store<7>(acc, red_p + (size_t)blockIdx.x * NRED, smem);
     }
     {
         EvalDualOp<BOUNDS> op{lp};
@@ -133,7 +147,7 @@ __device__ __forceinline__ void eval_phases(const DevLP& lp, const MatView& VA, 
 #pragma unroll
         for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
         run_phase(lp.A, VA, op, acc);
-        cta_reduce_store<5>(acc, red_d + (size_t)blockIdx.x * NRED, smem);
+        cta_reduce_store<6>(acc, red_d + (size_t)blockIdx.x * NRED, smem);
     }
 }
 
@@ -150,11 +164,11 @@ __device__ __forceinline__ void kkt_from_sums(const double* red_p, const double*
 {
     const double pobj = grid_sum(red_p, G, 0);
     const double dbnd = grid_sum(red_p, G, 1);
-    const double dr2 = grid_sum(red_p, G, 2);
+    const double dr2 = grid_sum(red_p, G, 2) + grid_sum(red_d, G, 5);   // + distance of y from its cone
     const double nc2 = grid_sum(red_p, G, 3);
     const double nx2 = grid_sum(red_p, G, 4);
     const double by = grid_sum(red_d, G, 0);
-    const double pr2 = grid_sum(red_d, G, 1);
+    const double pr2 = grid_sum(red_d, G, 1) + grid_sum(red_p, G, 6);   // + distance of x from its box
     const double nb2 = grid_sum(red_d, G, 2);
     const double ny2 = grid_sum(red_d, G, 3);
     const double dobj = by + dbnd;
@@ -608,23 +622,43 @@ static inline int blocks_for(int n) { return n <= 0 ? 1 : (n + 255) / 256 > 1184
 int launch_gather(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s)
 {
     if (n <= 0) return 0;
+    count_launch(1);
     k_gather<<<blocks_for(n), 256, 0, s>>>(dst, src, order, n);
     return (int)cudaGetLastError();
 }
 int launch_scatter(double* dst, const double* src, const int32_t* order, int n, cudaStream_t s)
 {
     if (n <= 0) return 0;
+    count_launch(1);
     k_scatter<<<blocks_for(n), 256, 0, s>>>(dst, src, order, n);
+    return (int)cudaGetLastError();
+}
+int launch_gather_scaled(double* dst, const double* src, const int32_t* order, const double* sc, int div, int n, cudaStream_t s)
+{
+    if (!sc) return launch_gather(dst, src, order, n, s);
+    if (n <= 0) return 0;
+    count_launch(1);
+    k_gather_scaled<<<blocks_for(n), 256, 0, s>>>(dst, src, order, sc, div, n);
+    return (int)cudaGetLastError();
+}
+int launch_scatter_scaled(double* dst, const double* src, const int32_t* order, const double* sc, int div, int n, cudaStream_t s)
+{
+    if (!sc) return launch_scatter(dst, src, order, n, s);
+    if (n <= 0) return 0;
+    count_launch(1);
+    k_scatter_scaled<<<blocks_for(n), 256, 0, s>>>(dst, src, order, sc, div, n);
     return (int)cudaGetLastError();
 }
 int launch_fill(double* dst, double v, int n, cudaStream_t s)
 {
     if (n <= 0) return 0;
+    count_launch(1);
     k_fill<<<blocks_for(n), 256, 0, s>>>(dst, v, n);
     return (int)cudaGetLastError();
 }
 int launch_sumsq(const double* v, int n, double* out, double* scratch /* >= SUMSQ_BLOCKS doubles */, cudaStream_t s)
 {
+    count_launch(2);
     k_sumsq_partial<<<SUMSQ_BLOCKS, 256, 0, s>>>(v, n, scratch);
     k_sumsq_final<<<1, 256, 0, s>>>(scratch, SUMSQ_BLOCKS, out);
     return (int)cudaGetLastError();
@@ -632,41 +666,48 @@ int launch_sumsq(const double* v, int n, double* out, double* scratch /* >= SUMS
 int launch_scale_by_invnorm(double* dst, const double* src, const double* norm2, int n, cudaStream_t s)
 {
     if (n <= 0) return 0;
+    count_launch(1);
     k_scale_by_invnorm<<<blocks_for(n), 256, 0, s>>>(dst, src, norm2, n);
     return (int)cudaGetLastError();
 }
 
 int launch_spmv(const DevMat& M, const double* in, double* out, int G, int threads, cudaStream_t s)
 {
+    count_launch(1);
     k_spmv<<<G, threads, 0, s>>>(M, in, out);
     return (int)cudaGetLastError();
 }
 
 int launch_primal(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s)
 {
+    count_launch(1);
     if (bounds) k_primal<true><<<G, threads, 0, s>>>(lp);
     else k_primal<false><<<G, threads, 0, s>>>(lp);
     return (int)cudaGetLastError();
 }
 int launch_dual(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s)
 {
+    count_launch(1);
     if (bounds) k_dual<true><<<G, threads, 0, s>>>(lp);
     else k_dual<false><<<G, threads, 0, s>>>(lp);
     return (int)cudaGetLastError();
 }
 int launch_eval_partial(const DevLP& lp, bool bounds, int G, int threads, cudaStream_t s)
 {
+    count_launch(1);
     if (bounds) k_eval<true><<<G, threads, 0, s>>>(lp, G);
     else k_eval<false><<<G, threads, 0, s>>>(lp, G);
     return (int)cudaGetLastError();
 }
 int launch_eval_finalize(const DevLP& lp, int G, double* out, double iters, cudaStream_t s)
 {
+    count_launch(1);
     k_eval_finalize<<<1, 32, 0, s>>>(lp, G, out, iters);
     return (int)cudaGetLastError();
 }
 int launch_eval(const DevLP& lp, bool bounds, int G, int threads, double* out, double iters, cudaStream_t s)
 {
+    count_launch(2);
     if (bounds) k_eval<true><<<G, threads, 0, s>>>(lp, G);
     else k_eval<false><<<G, threads, 0, s>>>(lp, G);
     CK(cudaGetLastError());
@@ -709,6 +750,7 @@ int persistent_max_blocks_per_sm(int threads, bool bounds, size_t dyn_smem)
 // one CTA.
 static int launch_persistent_fn(const void* fn, int sync_mode, int G, int threads, size_t dyn_smem, void** args, cudaStream_t s)
 {
+    count_launch(1);
     if (sync_mode == SYNC_GRID) {
         CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, dyn_smem, s));
         return 0;
@@ -783,6 +825,7 @@ int launch_pdhg_rowpart(const DevLP& lp, const PeerInfo& pi, bool bounds, int G,
     DevLP lpv = lp;
     PeerInfo piv = pi;
     void* args[] = {&lpv, &piv, &tau, &sigma, &iters, &seq};
+    count_launch(1);
     CK(cudaLaunchCooperativeKernel(rowpart_fn(bounds), dim3(G), dim3(threads), args, dyn_smem, s));
     return 0;
 }

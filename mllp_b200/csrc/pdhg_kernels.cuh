@@ -52,6 +52,10 @@ struct DevLP {
     const double* ub;   // null => +inf
     const double* ylo;  // null => -inf
     const double* yhi;  // null => +inf
+    // Preconditioned handles (MLLP_F_PRECONDITION): the matrix held is Dr A Dc and the iteration runs on the scaled LP
+    // (x~ = x / dc, y~ = y / dr, b~ = dr b, c~ = dc c, box / dc); the KKT scalars are evaluated on the ORIGINAL LP.
+    const double* dr;   // null => 1
+    const double* dc;   // null => 1
     double* x;
     double* y;
     double* xbar;
@@ -475,8 +479,10 @@ struct DualHalpernOp {
     }
 };
 
-// KKT scalars, A' side: r = c - A'y.
-// acc: 0 pobj, 1 dobj bound terms, 2 dual residual^2, 3 ||c||^2, 4 ||x||^2, 5 ||x - x0||^2
+// KKT scalars, A' side: r = c - A'y.  All sums refer to the ORIGINAL LP: on a preconditioned handle the column's scale
+// s = dc_j turns the scaled quantities back (r = r~ / s, x = s x~, c = c~ / s; c'x and the bound terms u r^- are invariant).
+// acc: 0 pobj, 1 dobj bound terms, 2 dual residual^2, 3 ||c||^2, 4 ||x||^2, 5 ||x~ - x~0||^2 (scaled: feeds the primal
+// weight), 6 distance^2 of x from its box (part of the primal residual: the Halpern combinations can leave the box)
 template <bool BOUNDS, class MEM = GlobalMem>
 struct EvalPrimalOp {
     using Mem = MEM;
@@ -496,17 +502,21 @@ struct EvalPrimalOp {
         double viol = 0.0, dob = 0.0;
         if (isinf(hi)) viol += rn * rn; else dob += hi * rn;
         if (isinf(lo)) viol += rp * rp; else dob += lo * rp;
+        const double xv = p.x - fmin(fmax(p.x, lo), hi);
+        const double s = lp.dc ? __ldg(lp.dc + r) : 1.0;
+        const double inv = 1.0 / s;
         acc[0] += p.c * p.x;
         acc[1] += dob;
-        acc[2] += viol;
-        acc[3] += p.c * p.c;
-        acc[4] += p.x * p.x;
+        acc[2] += viol * (inv * inv);
+        acc[3] += (p.c * inv) * (p.c * inv);
+        acc[4] += (p.x * s) * (p.x * s);
         acc[5] += (p.x - p.x0) * (p.x - p.x0);
+        acc[6] += (xv * s) * (xv * s);
     }
 };
 
-// KKT scalars, A side: res = Ax - b.
-// acc: 0 b'y, 1 primal residual^2, 2 ||b||^2, 3 ||y||^2, 4 ||y - y0||^2
+// KKT scalars, A side: res = Ax - b (original LP: res = res~ / s, b = b~ / s, y = s y~ with s = dr_i).
+// acc: 0 b'y, 1 primal residual^2, 2 ||b||^2, 3 ||y||^2, 4 ||y~ - y~0||^2 (scaled), 5 distance^2 of y from its cone
 template <bool BOUNDS, class MEM = GlobalMem>
 struct EvalDualOp {
     using Mem = MEM;
@@ -520,16 +530,21 @@ struct EvalDualOp {
     __device__ __forceinline__ void row(int r, double dot, const Pre& p, double* acc) const
     {
         double res = dot - p.b;
+        double yv = 0.0;
         if (BOUNDS) {
             const double lo = MEM::ld_ro(lp.ylo + r), hi = MEM::ld_ro(lp.yhi + r);
             if (res > 0.0 && isinf(hi) && lo == 0.0) res = 0.0;
             if (res < 0.0 && isinf(lo) && hi == 0.0) res = 0.0;
+            yv = p.y - fmin(fmax(p.y, lo), hi);
         }
+        const double s = lp.dr ? __ldg(lp.dr + r) : 1.0;
+        const double inv = 1.0 / s;
         acc[0] += p.b * p.y;
-        acc[1] += res * res;
-        acc[2] += p.b * p.b;
-        acc[3] += p.y * p.y;
+        acc[1] += (res * inv) * (res * inv);
+        acc[2] += (p.b * inv) * (p.b * inv);
+        acc[3] += (p.y * s) * (p.y * s);
         acc[4] += (p.y - p.y0) * (p.y - p.y0);
+        acc[5] += (yv * s) * (yv * s);
     }
 };
 

@@ -113,6 +113,106 @@ __global__ void k_norm_coefs_tail(double* out_coefs, int n, int nslack, const do
     if (blockIdx.x == 0 && threadIdx.x == 0 && cnorm) cnorm[0] = sqrt(norm2[0]);
 }
 
+// ---- (2) Ruiz + Pock-Chambolle preconditioning ---------------------------------------------------------------------
+// out[r] = max (SUM = false) or sum (SUM = true) over the entries of row r of |a| * srow[r] * scol[col]: one warp per row,
+// lanes stride the row (coalesced), lane-strided partials then a butterfly -- a fixed order, no atomics.  The same kernel
+// walks A (row statistics) and A' (column statistics), so nothing is accumulated across rows.
+template <bool SUM>
+__global__ void __launch_bounds__(256) k_scaled_row_stat(int nrows, const int* __restrict__ ptr, const int* __restrict__ ind,
+                                                         const double* __restrict__ val, const double* __restrict__ srow,
+                                                         const double* __restrict__ scol, double* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += warps) {
+        const int a = ptr[r], e = ptr[r + 1];
+        const double sr = srow[r];
+        double acc = 0.0;
+        for (int k = a + lane; k < e; k += 32) {
+            const double v = (sr * fabs(val[k])) * scol[ind[k]];
+            acc = SUM ? acc + v : fmax(acc, v);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, acc, o);
+            acc = SUM ? acc + t : fmax(acc, t);
+        }
+        if (lane == 0) out[r] = acc;
+    }
+}
+// s[k] /= sqrt(stat[k])  (stat = 0: an empty row / column keeps its scale)
+__global__ void k_div_sqrt(double* __restrict__ s, const double* __restrict__ stat, int n)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double t = sqrt(stat[k]);
+        if (t > 0.0) s[k] = s[k] / t;
+    }
+}
+// a_ij <- (dr_i * a_ij) * dc_j
+__global__ void __launch_bounds__(256) k_scale_values(int nrows, const int* __restrict__ ptr, const int* __restrict__ ind,
+                                                      double* __restrict__ val, const double* __restrict__ dr,
+                                                      const double* __restrict__ dc)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += warps) {
+        const int a = ptr[r], e = ptr[r + 1];
+        const double sr = dr[r];
+        for (int k = a + lane; k < e; k += 32) val[k] = (sr * val[k]) * dc[ind[k]];
+    }
+}
+
+static inline int row_blocks(int nrows) { return nrows <= 0 ? 1 : ((nrows + 7) / 8 > 148 * 8 ? 148 * 8 : (nrows + 7) / 8); }
+
+// Diagonal preconditioning of A (m x n CSR; its transpose is passed as well so that column statistics are row walks):
+// `ruiz_iters` rounds of Ruiz equilibration (rows and columns divided by the square root of their largest scaled
+// magnitude, both from the same scaled matrix) and one Pock-Chambolle pass with alpha = 1 (square root of the scaled
+// absolute row / column sums) -- the PDLP recipe, computed ON THE DEVICE.  On return h_values holds Dr A Dc and
+// h_dr[m] / h_dc[n] the scaling vectors (x = Dc x~, y = Dr y~).  Synchronous (creation time, not the iteration path).
+int precondition_device(int m, int n, long long nnz, const int* h_ptr, const int* h_ind, double* h_values, const int* h_tptr,
+                        const int* h_tind, const double* h_tval, int ruiz_iters, double* h_dr, double* h_dc)
+{
+    int *ptr = nullptr, *ind = nullptr, *tptr = nullptr, *tind = nullptr;
+    double *val = nullptr, *tval = nullptr, *dr = nullptr, *dc = nullptr, *sr = nullptr, *scn = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8); };
+    auto up = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); };
+    const size_t z = (size_t)(nnz > 0 ? nnz : 0);
+    al((void**)&ptr, sizeof(int) * ((size_t)m + 1)); al((void**)&ind, sizeof(int) * z); al((void**)&val, 8 * z);
+    al((void**)&tptr, sizeof(int) * ((size_t)n + 1)); al((void**)&tind, sizeof(int) * z); al((void**)&tval, 8 * z);
+    al((void**)&dr, 8 * (size_t)m); al((void**)&dc, 8 * (size_t)n); al((void**)&sr, 8 * (size_t)m); al((void**)&scn, 8 * (size_t)n);
+    up(ptr, h_ptr, sizeof(int) * ((size_t)m + 1)); up(ind, h_ind, sizeof(int) * z); up(val, h_values, 8 * z);
+    up(tptr, h_tptr, sizeof(int) * ((size_t)n + 1)); up(tind, h_tind, sizeof(int) * z); up(tval, h_tval, 8 * z);
+    int rc = (int)e;
+    if (rc == 0) rc = launch_fill(dr, 1.0, m, 0);
+    if (rc == 0) rc = launch_fill(dc, 1.0, n, 0);
+    for (int it = 0; it <= ruiz_iters && rc == 0; ++it) {
+        const bool pc = it == ruiz_iters;   // the last round is the Pock-Chambolle pass (sums instead of maxima)
+        count_launch(4);
+        if (pc) {
+            k_scaled_row_stat<true><<<row_blocks(m), 256>>>(m, ptr, ind, val, dr, dc, sr);
+            k_scaled_row_stat<true><<<row_blocks(n), 256>>>(n, tptr, tind, tval, dc, dr, scn);
+        } else {
+            k_scaled_row_stat<false><<<row_blocks(m), 256>>>(m, ptr, ind, val, dr, dc, sr);
+            k_scaled_row_stat<false><<<row_blocks(n), 256>>>(n, tptr, tind, tval, dc, dr, scn);
+        }
+        k_div_sqrt<<<row_blocks(m), 256>>>(dr, sr, m);
+        k_div_sqrt<<<row_blocks(n), 256>>>(dc, scn, n);
+        rc = (int)cudaGetLastError();
+    }
+    if (rc == 0) {
+        count_launch(1);
+        k_scale_values<<<row_blocks(m), 256>>>(m, ptr, ind, val, dr, dc);
+        rc = (int)cudaGetLastError();
+    }
+    if (rc == 0) rc = (int)cudaMemcpy(h_values, val, 8 * z, cudaMemcpyDeviceToHost);
+    if (rc == 0) rc = (int)cudaMemcpy(h_dr, dr, 8 * (size_t)m, cudaMemcpyDeviceToHost);
+    if (rc == 0) rc = (int)cudaMemcpy(h_dc, dc, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    for (void* p : {(void*)ptr, (void*)ind, (void*)val, (void*)tptr, (void*)tind, (void*)tval, (void*)dr, (void*)dc, (void*)sr, (void*)scn})
+        cudaFree(p);
+    if (rc != 0) set_last_error(std::string("preconditioning on the device: ") + cudaGetErrorString((cudaError_t)rc));
+    return rc;
+}
+
 }  // namespace mllp
 
 using namespace mllp;
@@ -135,6 +235,7 @@ int mllp_norm_scale(int32_t m, int32_t n, int64_t nnz, int32_t nslack, const int
     // work: [m + 1] slack ranks (padded to 8 bytes) | norm2 (1 double) + the partial sums of the two-stage sum
     int* rank = (int*)d_work;
     double* norm2 = (double*)((char*)d_work + sizeof(int) * (((size_t)m + 2) & ~(size_t)1));
+    count_launch(m > 0 ? 3 : 2);   // scan, rows, coefficient tail (the two-stage sum and the scaling count themselves)
     k_slack_scan<<<1, 1024, 0, s>>>(m, (const signed char*)d_sense, rank);
     if (m > 0) {
         const int blocks = (m + 7) / 8 > 148 * 8 ? 148 * 8 : (m + 7) / 8;

@@ -110,6 +110,8 @@ class RowPartLP(DeviceLP):
         self._h = h
         self._finalizer = weakref.finalize(self, L.mllp_lp_destroy, h)
         self._sigma_max = None
+        self._sigma_robust = None
+        self.norm_upper = 0.0
         self.p2p = False
         if p2p and 1 < self.world <= 8:
             # in-kernel exchange over NVLink peer memory: swap the CUDA IPC handles of the ranks' mailboxes
@@ -121,6 +123,12 @@ class RowPartLP(DeviceLP):
             _cabi.check(L.mllp_rowpart_ipc_import(h, blob.ctypes.data), "mllp_rowpart_ipc_import")
             dist.barrier()
             self.p2p = True
+
+    def sigma_max(self, iters=50, stream=None):
+        raise RuntimeError("the power iteration is not available on a row-partitioned handle (mllp_estimate_norm); "
+                           "estimate the step size on a single-GPU DeviceLP of the same matrix and pass tau / sigma")
+
+    sigma_max_robust = sigma_max
 
     def exchange_error(self):
         f = ctypes.c_int32(0)

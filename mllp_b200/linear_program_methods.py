@@ -188,6 +188,17 @@ class DeviceLP:
             self._sigma_robust = min(est, self.norm_upper) if self.norm_upper > 0 else est
         return self._sigma_robust
 
+    def _host_staging(self):
+        """page-locked numpy views (x[n], y[m], scalars) for the host-buffer entry, allocated once per handle"""
+        st = getattr(self, "_staging", None)
+        if st is None:
+            import torch
+            pin = torch.cuda.is_available()
+            mk = lambda k: (torch.empty(k, dtype=torch.float64).pin_memory() if pin else torch.empty(k, dtype=torch.float64))
+            keep = (mk(max(self.n, 1)), mk(max(self.m, 1)), mk(_cabi.NUM_SCALARS))
+            st = self._staging = (keep, (keep[0].numpy()[:self.n], keep[1].numpy()[:self.m], keep[2].numpy()))
+        return st[1]
+
     # -- torch-tensor level helpers (device pointers, caller's stream) --------------------------
     def spmv(self, v, trans=False):
         import torch
@@ -217,8 +228,12 @@ _HANDLES = {}
 def device_lp(constrs, constr_weights, rhs, coefs, lb=None, ub=None, ylo=None, yhi=None, device=0,
               flags=_cabi.F_DEFAULT, cache=True):
     """Return the DeviceLP of this instance, building (and caching) it on first use.  The cache
-    is keyed on the identity of ``constr_weights`` -- the loader's tuple keeps that array alive."""
-    key = (id(constr_weights), _device_index(device), int(flags), lb is not None, ylo is not None)
+    is keyed on the identity of ``constr_weights`` -- the loader's tuple keeps that array alive.
+    Bounds and row senses are baked into the handle when it is built, so an LP that passes any of them is
+    never served from (or put into) the cache: two calls with the same matrix and different boxes get two handles."""
+    key = (id(constr_weights), _device_index(device), int(flags))
+    if lb is not None or ub is not None or ylo is not None or yhi is not None:
+        cache = False
     if cache:
         hit = _HANDLES.get(key)
         if hit is not None and hit[0]() is constr_weights:
@@ -281,8 +296,9 @@ def pdhg_linear_program(constrs, constr_weights, rhs, coefs, *, num_iters, lb=No
         c = coefs if _is_tensor(coefs) else torch.as_tensor(np.asarray(coefs, dtype=np.float64), device=dev)
         lp._check_tensor(b, lp.m, "rhs")
         lp._check_tensor(c, lp.n, "coefs")
-        x = torch.zeros(lp.n, dtype=torch.float64, device=dev) if x0 is None else x0.clone()
-        y = torch.zeros(lp.m, dtype=torch.float64, device=dev) if y0 is None else y0.clone()
+        start = lambda v, k, nm: (torch.zeros(k, dtype=torch.float64, device=dev) if v is None else
+                                  v.clone() if _is_tensor(v) else torch.as_tensor(_np_f64(v, k, nm), device=dev))
+        x, y = start(x0, lp.n, "x0"), start(y0, lp.m, "y0")
         lp._check_tensor(x, lp.n, "x0")
         lp._check_tensor(y, lp.m, "y0")
         scal = torch.empty(_cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
@@ -293,16 +309,18 @@ def pdhg_linear_program(constrs, constr_weights, rhs, coefs, *, num_iters, lb=No
         return scal[0], x, y, info
     b = _np_f64(rhs, lp.m, "rhs")
     c = _np_f64(coefs, lp.n, "coefs")
-    x = np.zeros(lp.n) if x0 is None else _np_f64(x0, lp.n, "x0").copy()
-    y = np.zeros(lp.m) if y0 is None else _np_f64(y0, lp.m, "y0").copy()
-    scal = np.zeros(_cabi.NUM_SCALARS)
+    # x / y are in-out for the C entry: the caller's x0 / y0 are never written, the results land in page-locked staging
+    # arrays of the handle (allocated once), so both directions of the copy run at the pinned rate
+    x, y, scal = lp._host_staging()
+    x[:] = 0.0 if x0 is None else _np_f64(x0, lp.n, "x0")
+    y[:] = 0.0 if y0 is None else _np_f64(y0, lp.m, "y0")
     _cabi.check(L.mllp_pdhg_run_host(lp.handle, _ptr(x), _ptr(y), _ptr(b), _ptr(c), float(tau), float(sigma),
                                      int(num_iters), _ptr(scal), None), "mllp_pdhg_run_host")
     info = _info_dict(scal)
     info.update(tau=float(tau), sigma=float(sigma), handle=lp)
     if verbose:
         print("pdhg: %d iters  pobj %.9g  dobj %.9g  rel_kkt %.3e" % (num_iters, scal[0], scal[1], scal[8]))
-    return float(scal[0]), x, y, info
+    return float(scal[0]), x.copy(), y.copy(), info
 
 
 def solve_linear_program(constrs, constr_weights, rhs, coefs, *, tol=1e-6, max_iters=200000, check_every=64,
@@ -385,6 +403,18 @@ class BatchLP:
         self.x_off = np.concatenate([[0], np.cumsum(self.n)])
         self.y_off = np.concatenate([[0], np.cumsum(self.m)])
         self._sigma = None
+        self._sigma_robust = None
+        # sqrt(||A||_1 ||A||_inf) >= ||A||_2 per distinct matrix: the guaranteed side of the step-size estimate
+        ups = []
+        for ip, ii, vv, m_, n_ in zip(ips, iis, vvs, ms, ns):
+            if vv.shape[0] == 0:
+                ups.append(0.0)
+                continue
+            av = np.abs(vv)
+            rs = np.bincount(np.repeat(np.arange(m_), np.diff(ip)), weights=av, minlength=m_).max()
+            cs = np.bincount(ii, weights=av, minlength=n_).max()
+            ups.append(float(np.sqrt(rs * cs)))
+        self.norm_upper = np.array(ups * (self.count if self.shared else 1), dtype=np.float64)
 
     @property
     def handle(self):
@@ -415,9 +445,26 @@ class BatchLP:
             self._sigma[iters] = s
         return self._sigma[iters]
 
-    def sigma_max_robust(self):
-        """solve mode: 400 power-iteration steps, inflated by 2 % (see DeviceLP.sigma_max_robust)."""
-        return 1.02 * self.sigma_max(400)
+    def sigma_max_robust(self, rel_change=1e-4, max_iters=3200):
+        """solve mode, where an underestimate of ||A_k||_2 makes an instance diverge: power iteration with doubling step
+        counts until no instance's estimate moves by more than ``rel_change`` (as DeviceLP.sigma_max_robust), inflated by
+        2 % and capped by sqrt(||A_k||_1 ||A_k||_inf) where that bound is known (``norm_upper``, per instance)."""
+        import torch
+        if getattr(self, "_sigma_robust", None) is None:
+            prev, iters = None, 100
+            while True:
+                cur = self.sigma_max(iters)
+                if prev is not None and bool(((cur - prev).abs() <= rel_change * cur).all()):
+                    break
+                if iters >= max_iters:
+                    break
+                prev, iters = cur, iters * 2
+            est = 1.02 * cur
+            if self.norm_upper is not None:
+                ub = torch.as_tensor(self.norm_upper, device=est.device)
+                est = torch.where(ub > 0, torch.minimum(est, ub), est)
+            self._sigma_robust = est
+        return self._sigma_robust
 
     # device-tensor level entries (concatenated vectors, caller's stream, no host sync)
     def run(self, x, y, b, c, tau, sigma, num_iters, scalars=None):

@@ -46,17 +46,19 @@ def kkt(A, b, c, x, y, lb=None, ub=None, ylo=None, yhi=None):
     fin_hi, fin_lo = np.isfinite(hi), np.isfinite(lo)
     dobj = b @ y + np.sum(np.where(fin_hi, hi, 0.0) * np.where(fin_hi, rn, 0.0)) \
         + np.sum(np.where(fin_lo, lo, 0.0) * np.where(fin_lo, rp, 0.0))
-    dres = np.sqrt(np.sum(np.where(fin_hi, 0.0, rn) ** 2) + np.sum(np.where(fin_lo, 0.0, rp) ** 2))
+    dres2 = np.sum(np.where(fin_hi, 0.0, rn) ** 2) + np.sum(np.where(fin_lo, 0.0, rp) ** 2)
     res = A @ x - b
     if ylo is not None:
         ge = np.isinf(yhi) & (ylo == 0.0)
         le = np.isinf(ylo) & (yhi == 0.0)
         res = np.where(ge & (res > 0), 0.0, res)
         res = np.where(le & (res < 0), 0.0, res)
+        dres2 += np.sum((y - np.clip(y, ylo, yhi)) ** 2)      # distance of y from its cone
+    pres2 = np.sum(res ** 2) + np.sum((x - np.clip(x, lo, hi)) ** 2)   # + distance of x from its box
     pobj = c @ x
     out = np.zeros(10)
     out[0], out[1] = pobj, dobj
-    out[2], out[3] = np.linalg.norm(res), dres
+    out[2], out[3] = np.sqrt(pres2), np.sqrt(dres2)
     out[4], out[5] = np.linalg.norm(b), np.linalg.norm(c)
     out[6], out[7] = np.linalg.norm(x), np.linalg.norm(y)
     gap = abs(pobj - dobj)

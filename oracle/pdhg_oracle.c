@@ -166,8 +166,11 @@ int oracle_pdhg_run(int m, int n, const int32_t *indptr, const int32_t *indices,
  *  0 pobj = c'x
  *  1 dobj = b'y + sum_j (l_j r_j^+ + u_j r_j^-)  over finite bounds, r = c - A'y
  *  2 ||primal residual||_2 : row i contributes (Ax-b)_i unless its sign is allowed
- *       (equality: always; ">=" row [ylo=0]: only if (Ax-b)_i < 0; "<=" row: only if > 0)
- *  3 ||dual residual||_2   : r_j^- if u_j = +inf (must be >= 0 there) and r_j^+ if l_j = -inf
+ *       (equality: always; ">=" row [ylo=0]: only if (Ax-b)_i < 0; "<=" row: only if > 0),
+ *       and column j contributes x_j - clip(x_j, l_j, u_j): the distance of x from its box (zero at
+ *       every projected point; the Halpern combinations of solve mode can leave the box slightly)
+ *  3 ||dual residual||_2   : r_j^- if u_j = +inf (must be >= 0 there) and r_j^+ if l_j = -inf,
+ *       and row i contributes y_i - clip(y_i, ylo_i, yhi_i): the distance of y from its cone
  *  4 ||b||_2   5 ||c||_2   6 ||x||_2   7 ||y||_2
  *  8 relative KKT error = max(out2/(1+out4), out3/(1+out5), |pobj-dobj|/(1+|pobj|+|dobj|))
  *  9 |pobj - dobj|
@@ -177,8 +180,8 @@ static void kkt_eval(const csr_pair *P, const double *b, const double *c,
                      const double *x, const double *y, double *out)
 {
     const int m = P->m, n = P->n;
-    double pobj = 0, dobj = 0, pr2 = 0, dr2 = 0, nb2 = 0, nc2 = 0, nx2 = 0, ny2 = 0;
-#pragma omp parallel for schedule(static) reduction(+ : pobj, dobj, dr2, nc2, nx2)
+    double pobj = 0, dobj = 0, pr2 = 0, dr2 = 0, nb2 = 0, nc2 = 0, nx2 = 0, ny2 = 0, pr2x = 0, dr2y = 0;
+#pragma omp parallel for schedule(static) reduction(+ : pobj, dobj, dr2, nc2, nx2, pr2x)
     for (int j = 0; j < n; ++j) {
         double r = c[j] - row_dot(P->tptr, P->tidx, P->tval, j, y);
         double lo = lb ? lb[j] : 0.0, hi = ub ? ub[j] : INFINITY;
@@ -186,22 +189,27 @@ static void kkt_eval(const csr_pair *P, const double *b, const double *c,
         if (isinf(hi)) viol += rn * rn; else dobj += hi * rn;
         if (isinf(lo)) viol += rp * rp; else dobj += lo * rp;
         dr2 += viol;
+        double xv = x[j] - clip(x[j], lo, hi);
+        pr2x += xv * xv;
         pobj += c[j] * x[j];
         nc2 += c[j] * c[j];
         nx2 += x[j] * x[j];
     }
-#pragma omp parallel for schedule(static) reduction(+ : dobj, pr2, nb2, ny2)
+#pragma omp parallel for schedule(static) reduction(+ : dobj, pr2, nb2, ny2, dr2y)
     for (int i = 0; i < m; ++i) {
         double res = row_dot(P->indptr, P->indices, P->values, i, x) - b[i];
         if (ylo) {
             if (res > 0 && isinf(yhi[i]) && ylo[i] == 0.0) res = 0.0; /* ">=" row satisfied */
             if (res < 0 && isinf(ylo[i]) && yhi[i] == 0.0) res = 0.0; /* "<=" row satisfied */
+            double yv = y[i] - clip(y[i], ylo[i], yhi[i]);
+            dr2y += yv * yv;
         }
         pr2 += res * res;
         dobj += b[i] * y[i];
         nb2 += b[i] * b[i];
         ny2 += y[i] * y[i];
     }
+    pr2 += pr2x; dr2 += dr2y;
     out[0] = pobj; out[1] = dobj; out[2] = sqrt(pr2); out[3] = sqrt(dr2);
     out[4] = sqrt(nb2); out[5] = sqrt(nc2); out[6] = sqrt(nx2); out[7] = sqrt(ny2);
     double gap = fabs(pobj - dobj);
