@@ -60,6 +60,13 @@ typedef struct mllp_batch *mllp_batch_t;
                                       of the persistent cooperative kernel */
 #define MLLP_F_NO_TUNE 4u          /* skip the tuning rounds of mllp_lp_create (measured re-dealing of the
                                       tiles to the CTAs; results never depend on it, only speed) */
+#define MLLP_F_PRECONDITION 8u     /* diagonal preconditioning computed ON THE DEVICE at create time (10 rounds of Ruiz
+                                      equilibration + one Pock-Chambolle pass, the PDLP recipe): the handle holds Dr A Dc and
+                                      iterates on the scaled LP.  Nothing changes for the caller: b, c, x, y, the boxes and
+                                      mllp_spmv are those of the ORIGINAL LP (scaled / un-scaled at the boundary) and the KKT
+                                      scalars -- also the termination test of mllp_pdhg_solve -- are evaluated on the
+                                      ORIGINAL LP.  mllp_estimate_norm returns ||Dr A Dc||_2 (what the step size needs).
+                                      Also accepted by mllp_batch_create (every distinct matrix is preconditioned). */
 
 const char *mllp_last_error(void);
 int mllp_version(void);
@@ -152,6 +159,10 @@ int mllp_lp_blocks_info(mllp_lp_t lp, double *out8);
  * columns. */
 int mllp_blocks_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices,
                           const double *values, int32_t G, double *out8);
+
+/* The diagonal preconditioner of a handle created with MLLP_F_PRECONDITION, in the caller's row / column order:
+ * d_dr[m], d_dc[n] with the handle holding Dr A Dc (all ones on a handle without preconditioning). */
+int mllp_lp_scaling(mllp_lp_t lp, double *d_dr, double *d_dc, void *stream);
 
 /* d_out = A d_in (trans = 0; d_in has n, d_out m entries) or A' d_in (trans = 1). */
 int mllp_spmv(mllp_lp_t lp, int trans, const double *d_in, double *d_out, void *stream);

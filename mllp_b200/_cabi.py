@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libmllp_b200.so")
 
 NUM_SCALARS = 16
-F_DEFAULT, F_NO_SMEM_RESIDENT, F_GRAPH_MODE, F_NO_TUNE = 0, 1, 2, 4
+F_DEFAULT, F_NO_SMEM_RESIDENT, F_GRAPH_MODE, F_NO_TUNE, F_PRECONDITION = 0, 1, 2, 4, 8
 
 _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32
@@ -43,6 +43,7 @@ SIGNATURES = {
     "mllp_lp_geometry": (ctypes.c_int, [_vp, _vp]),
     "mllp_lp_blocks_info": (ctypes.c_int, [_vp, _vp]),
     "mllp_blocks_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "mllp_lp_scaling": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "mllp_spmv": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
     "mllp_estimate_norm": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_dbl), _vp]),
     "mllp_pdhg_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _i32, _vp, _vp]),

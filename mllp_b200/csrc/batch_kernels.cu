@@ -940,6 +940,8 @@ k_batch_norm(const BatchInst* __restrict__ insts, int count, int shared, int ite
 namespace mllp {
 void set_last_error(const std::string& msg);  // cabi.cu: the message mllp_last_error() returns
 void count_launch(int n);                       // cabi.cu: launch statistics (mllp_launch_count)
+int precondition_device(int m, int n, long long nnz, const int* h_ptr, const int* h_ind, double* h_values, const int* h_tptr,
+                        const int* h_tind, const double* h_tval, int ruiz_iters, double* h_dr, double* h_dc);   // scaling.cu
 }
 namespace {
 int bfail(int code, const std::string& msg) { mllp::set_last_error(msg); return code; }
@@ -992,6 +994,7 @@ struct Pools {
     std::vector<SplitRow> splits;
     std::vector<LocalSplit> lsplits;
     std::vector<int32_t> order;
+    std::vector<double> scale;       // preconditioned batch: dr | dc of every matrix, internal order
 };
 struct MatOff { size_t vals, idx, tiles, cb, csb, clb, cns, splits, lsplits; int nrows, ncols; };
 
@@ -1020,7 +1023,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                       const int64_t* h_indptr_off, const int64_t* h_nnz_off, const int32_t* h_indptr,
                       const int32_t* h_indices, const double* h_values, int device, uint32_t flags, mllp_batch_t* out)
 {
-    (void)flags;
+    const bool precondition = (flags & MLLP_F_PRECONDITION) != 0;
     if (!out) return bfail(MLLP_E_INVALID, "mllp_batch_create: null output handle");
     *out = nullptr;
     if (count < 1 || !h_m || !h_n || !h_indptr || !h_indptr_off || !h_nnz_off)
@@ -1052,7 +1055,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
     try {
         Pools P;
         std::vector<MatOff> offA((size_t)nmat), offAT((size_t)nmat);
-        std::vector<size_t> offOX((size_t)nmat), offOY((size_t)nmat);
+        std::vector<size_t> offOX((size_t)nmat), offOY((size_t)nmat), offDR((size_t)nmat), offDC((size_t)nmat);
         int max_tiles = 0, max_tiles_A = 0, max_tiles_AT = 0, max_steps_A = 0, max_steps_AT = 0;
         for (int k = 0; k < nmat && rc == 0; ++k) {
             const int m = h_m[k], n = h_n[k];
@@ -1068,8 +1071,27 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             std::vector<int32_t> tptr, tind;
             std::vector<double> tval;
             csr_transpose(m, n, ip, ii, vv, tptr, tind, tval);
+            // MLLP_F_PRECONDITION: Ruiz + Pock-Chambolle of every distinct matrix on the device; the kernels scale the caller's
+            // (original) vectors when they load / store an instance and evaluate the KKT scalars on the original LP
+            std::vector<double> scaled, h_dr, h_dc;
+            if (precondition) {
+                scaled.assign(vv, vv + nnz);
+                h_dr.assign((size_t)m, 1.0); h_dc.assign((size_t)n, 1.0);
+                const char* rz = getenv("MLLP_RUIZ_ITERS");
+                const int prc = precondition_device(m, n, nnz, ip, ii, scaled.data(), tptr.data(), tind.data(), tval.data(),
+                                                    rz && *rz ? atoi(rz) : 10, h_dr.data(), h_dc.data());
+                if (prc != 0) { rc = prc; break; }
+                vv = scaled.data();
+                csr_transpose(m, n, ip, ii, vv, tptr, tind, tval);
+            }
             std::vector<int32_t> orderY, posY, orderX, posX;
             plan_orders(m, n, ip, ii, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
+            if (precondition) {
+                offDR[k] = P.scale.size();
+                for (int q = 0; q < m; ++q) P.scale.push_back(h_dr[orderY[q]]);
+                offDC[k] = P.scale.size();
+                for (int q = 0; q < n; ++q) P.scale.push_back(h_dc[orderX[q]]);
+            }
             HostMat HA, HAT;
             build_host_mat(m, n, ip, ii, vv, orderY, posX, bp, HA);
             build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
@@ -1091,7 +1113,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                 bt->sum_n += h_n[bt->shared ? 0 : k];
             }
             double* d_vals; int32_t* d_idx; Tile* d_tiles; uint32_t* d_u32; SplitRow* d_splits; LocalSplit* d_ls; int32_t* d_order;
-            double* d_dummy_partials; unsigned* d_dummy_counters;
+            double* d_dummy_partials; unsigned* d_dummy_counters; double* d_scale = nullptr;
             auto ck = [&](cudaError_t ce, const char* what) { if (ce != cudaSuccess && rc == 0) rc = bfail((int)ce, std::string(what) + ": " + cudaGetErrorString(ce)); };
             ck(up(bt, &d_vals, P.vals), "upload vals");
             ck(up(bt, &d_idx, P.idx), "upload idx");
@@ -1100,6 +1122,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             ck(up(bt, &d_splits, P.splits), "upload splits");
             ck(up(bt, &d_ls, P.lsplits), "upload local splits");
             ck(up(bt, &d_order, P.order), "upload orders");
+            if (precondition) ck(up(bt, &d_scale, P.scale), "upload scaling vectors");
             ck(up(bt, &d_dummy_partials, std::vector<double>(P.splits.size() + 1, 0.0)), "alloc partials");
             ck(up(bt, &d_dummy_counters, std::vector<unsigned>(P.splits.size() + 1, 0u)), "alloc counters");
             ck(up(bt, &bt->d_next, std::vector<int>(4, 0)), "alloc work counter");
@@ -1122,6 +1145,8 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                     BatchInst& I = insts[k];
                     I.A = dev_mat(offA[k]); I.AT = dev_mat(offAT[k]);
                     I.orderX = d_order + offOX[k]; I.orderY = d_order + offOY[k];
+                    I.dr = precondition ? d_scale + offDR[k] : nullptr;
+                    I.dc = precondition ? d_scale + offDC[k] : nullptr;
                     I.m = h_m[k]; I.n = h_n[k];
                     I.x_off = xo; I.y_off = yo;
                     xo += h_n[k]; yo += h_m[k];

@@ -93,6 +93,9 @@ struct mllp_lp {
     double* u_y = nullptr;
     double* u_b = nullptr;
     double* u_c = nullptr;
+    double* d_box[4] = {nullptr, nullptr, nullptr, nullptr};   // lb, ub (ni), ylo, yhi (mi) in internal order (general form)
+    double* d_dr = nullptr;       // preconditioned handle: row / column scaling in internal order (d.dr / d.dc)
+    double* d_dc = nullptr;
     double* d_scal = nullptr;     // MLLP_NUM_SCALARS
     double* d_norm2 = nullptr;
     int64_t info[16] = {0};
@@ -459,14 +462,18 @@ int mllp_device_info(int device, int64_t* out3)
 }
 
 static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indptr, const int32_t* h_indices,
-                       const double* h_values, const double* h_lb, const double* h_ub, const double* h_ylo,
+                       const double* h_values_in, const double* h_lb_in, const double* h_ub_in, const double* h_ylo,
                        const double* h_yhi, int device, uint32_t flags, int rank, int nranks, const unsigned char* uid,
                        mllp_lp_t* out)
 {
     if (!out) return fail(MLLP_E_INVALID, "mllp_lp_create: null output handle");
     *out = nullptr;
+    const double* h_values = h_values_in;
+    const double *h_lb = h_lb_in, *h_ub = h_ub_in;
     if (m < 0 || n < 0 || nnz < 0 || !h_indptr || (nnz > 0 && (!h_indices || !h_values)))
         return fail(MLLP_E_INVALID, "mllp_lp_create: bad shape or null CSR arrays");
+    if ((flags & MLLP_F_PRECONDITION) && nranks > 1)
+        return fail(MLLP_E_STATE, "mllp_lp_create_rowpart: MLLP_F_PRECONDITION is not available on a row-partitioned handle");
     if (h_indptr[0] != 0 || (int64_t)h_indptr[m] != nnz)
         return fail(MLLP_E_INVALID, "mllp_lp_create: indptr[0] must be 0 and indptr[m] == nnz");
     for (int i = 0; i < m; ++i)
@@ -537,6 +544,25 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
         std::vector<int32_t> tptr, tind;
         std::vector<double> tval;
         csr_transpose(m, n, h_indptr, h_indices, h_values, tptr, tind, tval);
+        // MLLP_F_PRECONDITION: Ruiz + Pock-Chambolle on the device; from here on the matrix is Dr A Dc and the box is
+        // l / dc, u / dc.  The caller keeps speaking the ORIGINAL LP: vectors are scaled at the boundary
+        // (load_problem / store_solution) and the KKT scalars are evaluated on the original LP (Eval*Op).
+        std::vector<double> scaled_vals, h_dr, h_dc, lb_s, ub_s;
+        if (flags & MLLP_F_PRECONDITION) {
+            scaled_vals.assign(h_values_in, h_values_in + nnz);
+            h_dr.assign((size_t)m, 1.0); h_dc.assign((size_t)n, 1.0);
+            DeviceGuard pg(device);
+            int prc = precondition_device(m, n, nnz, h_indptr, h_indices, scaled_vals.data(), tptr.data(), tind.data(), tval.data(),
+                                          env_int("MLLP_RUIZ_ITERS", 10), h_dr.data(), h_dc.data());
+            if (prc != 0) { delete lp; return prc < 1000 ? cuda_fail((cudaError_t)prc, "mllp_lp_create: preconditioning") : prc; }
+            h_values = scaled_vals.data();
+            csr_transpose(m, n, h_indptr, h_indices, h_values, tptr, tind, tval);
+            if (h_lb) {
+                lb_s.resize((size_t)n); ub_s.resize((size_t)n);
+                for (int j = 0; j < n; ++j) { lb_s[j] = h_lb_in[j] / h_dc[j]; ub_s[j] = h_ub_in[j] / h_dc[j]; }
+                h_lb = lb_s.data(); h_ub = ub_s.data();
+            }
+        }
         std::vector<int32_t> orderY, posY, orderX, posX;
         plan_orders(m, n, h_indptr, h_indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
         HostMat HA, HAT;
@@ -568,6 +594,23 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             return outv;
         };
 
+        auto upload_scales = [&]() -> int {   // dr / dc in the CURRENT internal order (re-done when a geometry re-orders)
+            if (h_dr.empty()) return 0;
+            const std::vector<double> pr = permuted_pad(h_dr.data(), orderY, 1.0), pc = permuted_pad(h_dc.data(), orderX, 1.0);
+            CUDA_OK(cudaMemcpy(lp->d_dr, pr.data(), pr.size() * sizeof(double), cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMemcpy(lp->d_dc, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
+            return 0;
+        };
+        auto upload_boxes = [&]() -> int {   // general form: every box array is materialised (missing ones get +-inf / 0), in the
+                                             // CURRENT internal order (re-done when a geometry re-orders the rows / columns)
+            std::vector<double> lb(orderX.size(), 0.0), ub(orderX.size(), INFINITY), ylo(orderY.size(), -INFINITY), yhi(orderY.size(), INFINITY);
+            if (h_lb) { lb = permuted_pad(h_lb, orderX, 0.0); ub = permuted_pad(h_ub, orderX, 0.0); }
+            if (h_ylo) { ylo = permuted_pad(h_ylo, orderY, 0.0); yhi = permuted_pad(h_yhi, orderY, 0.0); }
+            const std::vector<double>* src[4] = {&lb, &ub, &ylo, &yhi};
+            for (int q = 0; q < 4; ++q)
+                CUDA_OK(cudaMemcpy(lp->d_box[q], src[q]->data(), src[q]->size() * sizeof(double), cudaMemcpyHostToDevice));
+            return 0;
+        };
         auto body = [&]() -> int {
             RC_OK(upload_mat(lp, HA, lp->d.A));
             RC_OK(upload_mat(lp, HAT, lp->d.AT));
@@ -578,16 +621,10 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             RC_OK(dev_zeros(lp, &lp->d_c, (size_t)ni));
             lp->d.b = lp->d_b; lp->d.c = lp->d_c;
             if (lp->bounds) {
-                // general form: every box array is materialised (missing ones get +-inf / 0)
-                std::vector<double> lb((size_t)ni, 0.0), ub((size_t)ni, INFINITY), ylo((size_t)mi, -INFINITY), yhi((size_t)mi, INFINITY);
-                if (h_lb) { lb = permuted_pad(h_lb, orderX, 0.0); ub = permuted_pad(h_ub, orderX, 0.0); }
-                if (h_ylo) { ylo = permuted_pad(h_ylo, orderY, 0.0); yhi = permuted_pad(h_yhi, orderY, 0.0); }
-                double *p1, *p2, *p3, *p4;
-                RC_OK(dev_upload(lp, &p1, lb.data(), lb.size()));
-                RC_OK(dev_upload(lp, &p2, ub.data(), ub.size()));
-                RC_OK(dev_upload(lp, &p3, ylo.data(), ylo.size()));
-                RC_OK(dev_upload(lp, &p4, yhi.data(), yhi.size()));
-                lp->d.lb = p1; lp->d.ub = p2; lp->d.ylo = p3; lp->d.yhi = p4;
+                for (double** q : {&lp->d_box[0], &lp->d_box[1]}) RC_OK(dev_zeros(lp, q, (size_t)ni));
+                for (double** q : {&lp->d_box[2], &lp->d_box[3]}) RC_OK(dev_zeros(lp, q, (size_t)mi));
+                lp->d.lb = lp->d_box[0]; lp->d.ub = lp->d_box[1]; lp->d.ylo = lp->d_box[2]; lp->d.yhi = lp->d_box[3];
+                RC_OK(upload_boxes());
             }
             RC_OK(dev_zeros(lp, &lp->d.x, (size_t)ni + 2));
             RC_OK(dev_zeros(lp, &lp->d.y, (size_t)mi + 2));
@@ -604,6 +641,12 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             RC_OK(dev_zeros(lp, &lp->u_y, (size_t)m));
             RC_OK(dev_zeros(lp, &lp->u_b, (size_t)m));
             RC_OK(dev_zeros(lp, &lp->u_c, (size_t)n));
+            if (!h_dr.empty()) {
+                RC_OK(dev_zeros(lp, &lp->d_dr, (size_t)mi));
+                RC_OK(dev_zeros(lp, &lp->d_dc, (size_t)ni));
+                lp->d.dr = lp->d_dr; lp->d.dc = lp->d_dc;
+                RC_OK(upload_scales());
+            }
             RC_OK(dev_zeros(lp, &lp->d_scal, MLLP_NUM_SCALARS));
             RC_OK(dev_zeros(lp, &lp->d_norm2, 2 + 256));
             if (flags & MLLP_F_GRAPH_MODE) RC_OK(build_graph(lp));
@@ -640,6 +683,8 @@ static int create_impl(int32_t m, int32_t n, int64_t nnz, const int32_t* h_indpt
             RC_OK(upload_mat(lp, HAT, lp->d.AT));
             CUDA_OK(cudaMemcpy(lp->d_orderX, orderX.data(), orderX.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
             CUDA_OK(cudaMemcpy(lp->d_orderY, orderY.data(), orderY.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            RC_OK(upload_scales());
+            if (lp->bounds) RC_OK(upload_boxes());
             RC_OK(configure_residency(lp, HA, HAT, prop, bpsm, resident));
             return 0;
         };
@@ -912,20 +957,36 @@ int mllp_lp_geometry(mllp_lp_t lp, double* out12)
     return 0;
 }
 
+int mllp_lp_scaling(mllp_lp_t lp, double* d_dr, double* d_dc, void* stream)
+{
+    if (!lp || !d_dr || !d_dc) return fail(MLLP_E_INVALID, "mllp_lp_scaling: null argument");
+    DeviceGuard guard(lp->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!lp->d_dr) {
+        RC_OK(launch_fill(d_dr, 1.0, lp->m, s));
+        RC_OK(launch_fill(d_dc, 1.0, lp->n, s));
+        return 0;
+    }
+    RC_OK(launch_scatter(d_dr, lp->d_dr, lp->d_orderY, lp->mi, s));
+    RC_OK(launch_scatter(d_dc, lp->d_dc, lp->d_orderX, lp->ni, s));
+    return 0;
+}
+
 int mllp_spmv(mllp_lp_t lp, int trans, const double* d_in, double* d_out, void* stream)
 {
     if (!lp || !d_in || !d_out) return fail(MLLP_E_INVALID, "mllp_spmv: null argument");
     if (lp->nranks > 1) return fail(MLLP_E_STATE, "mllp_spmv: not available on a row-partitioned handle");
     DeviceGuard guard(lp->device);
     cudaStream_t s = (cudaStream_t)stream;
+    // products with the ORIGINAL matrix also on a preconditioned handle: A = Dr^-1 (Dr A Dc) Dc^-1
     if (!trans) {
-        RC_OK(launch_gather(lp->tmp_n, d_in, lp->d_orderX, lp->n, s));
+        RC_OK(launch_gather_scaled(lp->tmp_n, d_in, lp->d_orderX, lp->d_dc, 1, lp->n, s));
         RC_OK(launch_spmv(lp->d.A, lp->tmp_n, lp->tmp_m, lp->G, lp->threads, s));
-        RC_OK(launch_scatter(d_out, lp->tmp_m, lp->d_orderY, lp->m, s));
+        RC_OK(launch_scatter_scaled(d_out, lp->tmp_m, lp->d_orderY, lp->d_dr, 1, lp->m, s));
     } else {
-        RC_OK(launch_gather(lp->tmp_m, d_in, lp->d_orderY, lp->m, s));
+        RC_OK(launch_gather_scaled(lp->tmp_m, d_in, lp->d_orderY, lp->d_dr, 1, lp->m, s));
         RC_OK(launch_spmv(lp->d.AT, lp->tmp_m, lp->tmp_n, lp->G, lp->threads, s));
-        RC_OK(launch_scatter(d_out, lp->tmp_n, lp->d_orderX, lp->n, s));
+        RC_OK(launch_scatter_scaled(d_out, lp->tmp_n, lp->d_orderX, lp->d_dc, 1, lp->n, s));
     }
     return 0;
 }
@@ -954,16 +1015,17 @@ int mllp_estimate_norm(mllp_lp_t lp, int iters, double* h_sigma_max, void* strea
 static int load_problem(mllp_lp* lp, const double* d_x, const double* d_y, const double* d_b, const double* d_c,
                         cudaStream_t s)
 {
-    RC_OK(launch_gather(lp->d.x, d_x, lp->d_orderX, lp->ni, s));
-    RC_OK(launch_gather(lp->d.y, d_y, lp->d_orderY, lp->mi, s));
-    RC_OK(launch_gather(lp->d_b, d_b, lp->d_orderY, lp->mi, s));
-    RC_OK(launch_gather(lp->d_c, d_c, lp->d_orderX, lp->ni, s));
+    // preconditioned handle: x~ = x / dc, y~ = y / dr, b~ = dr b, c~ = dc c (the caller's vectors are the original LP's)
+    RC_OK(launch_gather_scaled(lp->d.x, d_x, lp->d_orderX, lp->d_dc, 1, lp->ni, s));
+    RC_OK(launch_gather_scaled(lp->d.y, d_y, lp->d_orderY, lp->d_dr, 1, lp->mi, s));
+    RC_OK(launch_gather_scaled(lp->d_b, d_b, lp->d_orderY, lp->d_dr, 0, lp->mi, s));
+    RC_OK(launch_gather_scaled(lp->d_c, d_c, lp->d_orderX, lp->d_dc, 0, lp->ni, s));
     return 0;
 }
 static int store_solution(mllp_lp* lp, double* d_x, double* d_y, cudaStream_t s)
 {
-    RC_OK(launch_scatter(d_x, lp->d.x, lp->d_orderX, lp->ni, s));
-    RC_OK(launch_scatter(d_y, lp->d.y, lp->d_orderY, lp->mi, s));
+    RC_OK(launch_scatter_scaled(d_x, lp->d.x, lp->d_orderX, lp->d_dc, 0, lp->ni, s));   // x = dc x~
+    RC_OK(launch_scatter_scaled(d_y, lp->d.y, lp->d_orderY, lp->d_dr, 0, lp->mi, s));   // y = dr y~
     return 0;
 }
 

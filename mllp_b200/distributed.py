@@ -51,21 +51,41 @@ def gather_results(local_results, count):
     return out
 
 
-def solve_batch_data_parallel(instances, *, mode="solve", device=None, compute=None, **kwargs):
+def solve_batch_data_parallel(instances, *, mode="solve", device=None, compute=None, shared=False, rhs_batch=None,
+                              coefs_batch=None, single_process=False, count=None, **kwargs):
     """Shard independent LP instances over the ranks, run the batched kernel on each rank's
     block, gather.  ``mode`` = "solve" (to tolerance) or "run" (fixed ``num_iters``).
-    ``compute`` overrides the per-shard solver (used by the CPU tests of this host logic)."""
-    dist = _dist()
-    world, rank = dist.get_world_size(), dist.get_rank()
-    lo, hi = shard_range(len(instances), rank, world)
-    mine = instances[lo:hi]
+    ``shared=True``: ONE matrix ``instances[0]`` and (B, m) / (B, n) batches of right-hand sides and costs
+    (BASELINE.json configs[4]); the rows of the batches are what is sharded.
+    With ``count`` given, ``rhs_batch`` / ``coefs_batch`` hold only THIS rank's rows [lo, hi) of the ``count`` instances
+    (each rank generated or loaded its own shard); otherwise every rank passes the whole batches.
+    ``compute`` overrides the per-shard solver (used by the CPU tests of this host logic).
+    ``single_process=True``: no process group (one GPU): the whole batch is this process's shard."""
+    if single_process:
+        world, rank = 1, 0
+    else:
+        dist = _dist()
+        world, rank = dist.get_world_size(), dist.get_rank()
+    local_rows = shared and count is not None
+    count = int(count) if local_rows else (len(rhs_batch) if shared else len(instances))
+    lo, hi = shard_range(count, rank, world)
+    if local_rows and len(rhs_batch) != hi - lo:
+        raise ValueError("rank %d holds %d rows of the batches, its shard has %d" % (rank, len(rhs_batch), hi - lo))
     if compute is None:
         fn = solve_linear_program_batch if mode == "solve" else pdhg_linear_program_batch
-        compute = lambda shard: fn(shard, device=rank if device is None else device, **kwargs) if shard else []
-    local = compute(mine)
+        dev = rank if device is None else device
+        if shared:
+            pick = (lambda a, sl: np.asarray(a)) if local_rows else (lambda a, sl: np.asarray(a)[sl])
+            compute = lambda sl: fn(instances[:1], device=dev, shared=True, rhs_batch=pick(rhs_batch, sl),
+                                    coefs_batch=pick(coefs_batch, sl), **kwargs) if sl.stop > sl.start else []
+        else:
+            compute = lambda shard: fn(shard, device=dev, **kwargs) if shard else []
+    local = compute(slice(lo, hi) if shared else instances[lo:hi])
     # results carry numpy arrays only (picklable); drop handles
     local = [(o, x, y, {k: v for k, v in info.items() if k != "handle"}) for (o, x, y, info) in local]
-    return gather_results(local, len(instances))
+    if single_process:
+        return local
+    return gather_results(local, count)
 
 
 def broadcast_unique_id(src=0):

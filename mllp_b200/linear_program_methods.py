@@ -89,7 +89,14 @@ class DeviceLP:
     loader).  Wraps an ``mllp_lp_t`` handle."""
 
     def __init__(self, constrs, constr_weights, num_rows, num_cols, lb=None, ub=None, ylo=None, yhi=None,
-                 device=0, flags=_cabi.F_DEFAULT):
+                 device=0, flags=_cabi.F_DEFAULT, precondition=False):
+        """``precondition=True`` (flag MLLP_F_PRECONDITION): Ruiz + Pock-Chambolle scaling computed on the device at create
+        time; the handle iterates on the scaled LP, every vector the caller passes or receives and the KKT scalars
+        (incl. the termination test of solve mode) stay those of the ORIGINAL LP."""
+        import time
+        t_create = time.perf_counter()
+        if precondition:
+            flags = int(flags) | _cabi.F_PRECONDITION
         L = _cabi.lib()
         self.m, self.n = int(num_rows), int(num_cols)
         indptr, indices, values = csr_from_constrs(constrs, constr_weights, self.n)
@@ -121,6 +128,17 @@ class DeviceLP:
         else:
             col_sum = 0.0
         self.norm_upper = float(np.sqrt(row_sum * col_sum))
+        self.preconditioned = bool(self.flags & _cabi.F_PRECONDITION)
+        self.create_s = time.perf_counter() - t_create   # format build + geometry search + tuning rounds (synchronous)
+
+    def scaling(self):
+        """(dr, dc) of a preconditioned handle as numpy arrays in the caller's order (ones otherwise)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        dr = torch.empty(self.m, dtype=torch.float64, device=dev)
+        dc = torch.empty(self.n, dtype=torch.float64, device=dev)
+        _cabi.check(_cabi.lib().mllp_lp_scaling(self.handle, dr.data_ptr(), dc.data_ptr(), _torch_stream(dev)), "mllp_lp_scaling")
+        return dr.cpu().numpy(), dc.cpu().numpy()
 
     def close(self):
         self._finalizer()
@@ -185,7 +203,8 @@ class DeviceLP:
                     break
                 prev, iters = cur, iters * 2
             est = 1.02 * cur
-            self._sigma_robust = min(est, self.norm_upper) if self.norm_upper > 0 else est
+            # the cap is a bound on the ORIGINAL matrix's norm: it does not apply to Dr A Dc
+            self._sigma_robust = min(est, self.norm_upper) if (self.norm_upper > 0 and not self.preconditioned) else est
         return self._sigma_robust
 
     def _host_staging(self):
@@ -226,11 +245,13 @@ _HANDLES = {}
 
 
 def device_lp(constrs, constr_weights, rhs, coefs, lb=None, ub=None, ylo=None, yhi=None, device=0,
-              flags=_cabi.F_DEFAULT, cache=True):
+              flags=_cabi.F_DEFAULT, cache=True, precondition=False):
     """Return the DeviceLP of this instance, building (and caching) it on first use.  The cache
     is keyed on the identity of ``constr_weights`` -- the loader's tuple keeps that array alive.
     Bounds and row senses are baked into the handle when it is built, so an LP that passes any of them is
     never served from (or put into) the cache: two calls with the same matrix and different boxes get two handles."""
+    if precondition:
+        flags = int(flags) | _cabi.F_PRECONDITION
     key = (id(constr_weights), _device_index(device), int(flags))
     if lb is not None or ub is not None or ylo is not None or yhi is not None:
         cache = False
@@ -325,13 +346,15 @@ def pdhg_linear_program(constrs, constr_weights, rhs, coefs, *, num_iters, lb=No
 
 def solve_linear_program(constrs, constr_weights, rhs, coefs, *, tol=1e-6, max_iters=200000, check_every=64,
                          lb=None, ub=None, ylo=None, yhi=None, x0=None, y0=None, eta=None, primal_weight=1.0,
-                         device=0, handle=None, flags=_cabi.F_DEFAULT, verbose=False):
+                         device=0, handle=None, flags=_cabi.F_DEFAULT, verbose=False, precondition=False):
     """Solve mode: reflected restarted Halpern PDHG on the device until the relative KKT error is
     <= ``tol`` (spec: oracle_pdhg_solve).  Returns ``(objective, x, y, info)``; numpy in/out.
-    Non-convergence within ``max_iters`` is reported in ``info['converged']``, not raised."""
+    Non-convergence within ``max_iters`` is reported in ``info['converged']``, not raised.
+    ``precondition=True`` builds (and caches) a handle with the device-side Ruiz + Pock-Chambolle scaling: typically
+    2-4x fewer iterations; x, y, the objective and the KKT error -- hence termination -- refer to the ORIGINAL LP."""
     import torch
     lp = handle if handle is not None else device_lp(constrs, constr_weights, rhs, coefs, lb, ub, ylo, yhi,
-                                                     device, flags)
+                                                     device, flags, precondition=precondition)
     if eta is None:
         sm = lp.sigma_max_robust()
         eta = 0.99 / sm if sm > 0 else 1.0
@@ -371,9 +394,10 @@ class BatchLP:
     labels), or -- ``shared=True`` -- ONE such matrix used by ``count`` instances that differ
     only in b and c (BASELINE.json configs[4])."""
 
-    def __init__(self, instances, shared=False, count=None, device=0):
+    def __init__(self, instances, shared=False, count=None, device=0, precondition=False):
         L = _cabi.lib()
         self.device = _device_index(device)
+        self.preconditioned = bool(precondition)
         self.shared = bool(shared)
         mats = [instances[0]] if self.shared else list(instances)
         self.count = int(count if self.shared else len(mats))
@@ -396,7 +420,8 @@ class BatchLP:
         vv_all = np.ascontiguousarray(np.concatenate(vvs), dtype=np.float64) if sum(a.shape[0] for a in vvs) else np.zeros(1)
         h = ctypes.c_void_p()
         rc = L.mllp_batch_create(self.count, int(self.shared), _ptr(h_m), _ptr(h_n), _ptr(ip_off), _ptr(nz_off),
-                                 _ptr(ip_all), _ptr(ii_all), _ptr(vv_all), self.device, 0, ctypes.byref(h))
+                                 _ptr(ip_all), _ptr(ii_all), _ptr(vv_all), self.device,
+                                 _cabi.F_PRECONDITION if precondition else 0, ctypes.byref(h))
         _cabi.check(rc, "mllp_batch_create")
         self._h = h
         self._finalizer = weakref.finalize(self, L.mllp_batch_destroy, h)
@@ -460,7 +485,7 @@ class BatchLP:
                     break
                 prev, iters = cur, iters * 2
             est = 1.02 * cur
-            if self.norm_upper is not None:
+            if self.norm_upper is not None and not self.preconditioned:   # the bound is on the original matrices
                 ub = torch.as_tensor(self.norm_upper, device=est.device)
                 est = torch.where(ub > 0, torch.minimum(est, ub), est)
             self._sigma_robust = est
@@ -530,65 +555,23 @@ def pdhg_linear_program_batch(instances, *, num_iters, x0=None, y0=None, tau=Non
     return _batch_results(bt, x, y, scal, {"tau": tau_t.cpu().numpy(), "sigma": sigma_t.cpu().numpy()})
 
 
-def _scaled_batch(instances, shared, rhs_batch, coefs_batch):
-    """Ruiz + Pock-Chambolle scaling of every distinct matrix of a batch (mllp_b200/scaling.py): returns the scaled
-    instances / batches and the per-instance scaling vectors (dr, dc)."""
-    import scipy.sparse as sp
-    from .scaling import ruiz_pock_chambolle
-    cache, out, scal = {}, [], []
-    for constrs, weights, rhs, coefs in ([instances[0]] if shared else instances):
-        key = id(weights)
-        if key not in cache:
-            n = len(coefs) if np.ndim(coefs) == 1 else np.shape(coefs)[-1]
-            ip, ii, vv = csr_from_constrs(constrs, weights, n)
-            A = sp.csr_matrix((vv, ii, ip), shape=(ip.shape[0] - 1, n))
-            dr, dc = ruiz_pock_chambolle(A)
-            As = (sp.diags(dr) @ A @ sp.diags(dc)).tocsr()
-            As.sort_indices()
-            cache[key] = (As, dr, dc)
-        As, dr, dc = cache[key]
-        out.append((As, As.data, dr * np.asarray(rhs, dtype=np.float64), dc * np.asarray(coefs, dtype=np.float64)))
-        scal.append((dr, dc))
-    if shared:
-        dr, dc = scal[0]
-        rhs_batch = np.asarray(rhs_batch, dtype=np.float64) * dr
-        coefs_batch = np.asarray(coefs_batch, dtype=np.float64) * dc
-        scal = scal * len(rhs_batch)
-    return out, rhs_batch, coefs_batch, scal
-
-
 def solve_linear_program_batch(instances, *, tol=1e-6, max_iters=200000, check_every=64, x0=None, y0=None, eta=None,
                                primal_weight=1.0, device=0, handle=None, shared=False, rhs_batch=None, coefs_batch=None,
                                scale=False):
     """Solve mode on a whole batch in one launch; every instance restarts and terminates on
     its own.  Returns a list of ``(objective, x, y, info)``.  ``scale=True``: every distinct matrix is preconditioned
-    (Ruiz + Pock-Chambolle, on the host) before the solve -- typically 2-4x fewer iterations on the Netlib instances --;
-    termination is then decided on the scaled LP, the returned x, y, objective and info['rel_kkt_original'] (evaluated
-    on the device by a zero-iteration run of the unscaled batch) refer to the ORIGINAL LP."""
+    (Ruiz + Pock-Chambolle, computed on the device by mllp_batch_create with MLLP_F_PRECONDITION) -- typically 2-4x fewer
+    iterations on the Netlib instances; x, y, the objective and the KKT error, hence every instance's termination,
+    refer to the ORIGINAL LP (``info['rel_kkt_original']`` repeats ``info['rel_kkt']``)."""
     import torch
-    if scale:
-        if handle is not None or x0 is not None or y0 is not None:
-            raise ValueError("scale=True builds its own batch handle and starts from zero")
-        s_inst, s_rhs, s_coefs, scal = _scaled_batch(instances, shared, rhs_batch, coefs_batch)
-        res = solve_linear_program_batch(s_inst, tol=tol, max_iters=max_iters, check_every=check_every, eta=eta,
-                                         primal_weight=primal_weight, device=device, shared=shared, rhs_batch=s_rhs,
-                                         coefs_batch=s_coefs)
-        xs = [dc * r[1] for r, (dr, dc) in zip(res, scal)]
-        ys = [dr * r[2] for r, (dr, dc) in zip(res, scal)]
-        orig = pdhg_linear_program_batch(instances, num_iters=0, x0=xs, y0=ys, tau=1.0, sigma=1.0, device=device, shared=shared,
-                                         rhs_batch=rhs_batch, coefs_batch=coefs_batch)
-        out = []
-        for r, o, x, y in zip(res, orig, xs, ys):
-            info = dict(r[3])
-            info["rel_kkt_original"] = o[3]["rel_kkt"]
-            info["pobj"], info["dobj"] = o[3]["pobj"], o[3]["dobj"]
-            out.append((o[0], x, y, info))
-        return out
-    bt = handle if handle is not None else BatchLP(instances, shared=shared,
-                                                   count=None if not shared else len(rhs_batch), device=device)
+    bt = handle if handle is not None else BatchLP(instances, shared=shared, count=None if not shared else len(rhs_batch),
+                                                   device=device, precondition=scale)
     b, c, x, y, dev = _batch_vectors(bt, instances, rhs_batch, coefs_batch, x0, y0)
     eta_t = 0.99 / bt.sigma_max_robust() if eta is None else torch.as_tensor(
         np.broadcast_to(np.asarray(eta, dtype=np.float64), (bt.count,)).copy(), device=dev)
     scal = torch.zeros(bt.count * _cabi.NUM_SCALARS, dtype=torch.float64, device=dev)
     bt.solve(x, y, b, c, eta_t, scal, primal_weight, max_iters, check_every, tol)
-    return _batch_results(bt, x, y, scal, {"eta": eta_t.cpu().numpy()})
+    res = _batch_results(bt, x, y, scal, {"eta": eta_t.cpu().numpy()})
+    for r in res:
+        r[3]["rel_kkt_original"] = r[3]["rel_kkt"]
+    return res

@@ -64,6 +64,19 @@ def _worker(rank, world, port, q):
         res = solve_batch_data_parallel(instances, compute=fake_compute)
         ok = len(res) == 7 and all(r[0] == float(k) and r[1][0] == k and r[3]["iters"] == 10 * k for k, r in enumerate(res))
         ok = ok and [r[3]["rank"] for r in res] == [0, 0, 0, 0, 1, 1, 1] and all("handle" not in r[3] for r in res)
+        # shared matrix (BASELINE.json configs[4]): the rows of the (B, m) / (B, n) batches are what is sharded
+        bb, cb = np.arange(10, dtype=np.float64).reshape(5, 2), np.arange(15, dtype=np.float64).reshape(5, 3)
+
+        def fake_shared(sl):
+            return [(float(cb[i].sum()), cb[i].copy(), bb[i].copy(), {"iters": i}) for i in range(sl.start, sl.stop)]
+
+        res2 = solve_batch_data_parallel([("A", None, None, None)], compute=fake_shared, shared=True, rhs_batch=bb, coefs_batch=cb)
+        ok = ok and len(res2) == 5 and all(r[3]["iters"] == i and np.array_equal(r[1], cb[i]) for i, r in enumerate(res2))
+        # ... also when every rank passes only its own rows
+        lo, hi = (0, 3) if dist.get_rank() == 0 else (3, 5)
+        res3 = solve_batch_data_parallel([("A", None, None, None)], compute=fake_shared, shared=True, rhs_batch=bb[lo:hi],
+                                         coefs_batch=cb[lo:hi], count=5)
+        ok = ok and [r[3]["iters"] for r in res3] == [0, 1, 2, 3, 4]
         # a wrong shard size is detected
         try:
             gather_results([1, 2, 3] if rank == 0 else [1], 7)

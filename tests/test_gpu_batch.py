@@ -172,15 +172,15 @@ def test_batch_errors():
 
 
 def test_preconditioned_batch_solve_matches_highs_with_fewer_iterations():
-    """scale=True: Ruiz + Pock-Chambolle per distinct matrix on the host, one solve launch on the scaled batch, results and
-    KKT error reported for the ORIGINAL LPs"""
+    """scale=True: Ruiz + Pock-Chambolle per distinct matrix on the device (MLLP_F_PRECONDITION), one solve launch; results,
+    KKT error and termination refer to the ORIGINAL LPs"""
     names = ["sc50a", "sc105", "adlittle", "blend", "share2b"]
     insts, mats = load_batch(names)
     plain = M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000)
     res = M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000, scale=True)
     for nm, (A, b, c), (obj, x, y, inf) in zip(names, mats, res):
-        assert inf["converged"] and inf["rel_kkt"] <= 1e-6 and inf["rel_kkt_original"] <= 1e-4
-        assert abs(obj - HIGHS[nm]) <= 1e-4 * (1 + abs(HIGHS[nm]))
+        assert inf["converged"] and inf["rel_kkt"] <= 1e-6 and inf["rel_kkt_original"] <= 1e-6
+        assert abs(obj - HIGHS[nm]) <= 1e-5 * (1 + abs(HIGHS[nm]))
         kk = O.kkt(A, b, c, x, y)
         assert abs(kk[0] - obj) <= 1e-6 * (1 + abs(obj)) and abs(kk[8] - inf["rel_kkt_original"]) <= 1e-9
     assert sum(r[3]["iters"] for r in res) < sum(r[3]["iters"] for r in plain)
