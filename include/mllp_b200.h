@@ -188,7 +188,8 @@ int mllp_pdhg_run_host(mllp_lp_t lp, double *h_x, double *h_y, const double *h_b
 
 /*
  * Solve mode: reflected restarted Halpern PDHG with fixed step eta (tau = eta/w,
- * sigma = eta*w, w0 the initial primal weight), KKT check and restart test every
+ * sigma = eta*w, w0 > 0 the initial primal weight; w0 = 0 selects the PDLP default ||c||_2 / ||b||_2 of the LP the
+ * handle iterates on -- the scaled one when preconditioned --, computed on the device), KKT check and restart test every
  * `check_every` iterations, all decided on the device; stops at rel. KKT error <= tol or
  * max_iters.  Spec: oracle_pdhg_solve in oracle/pdhg_oracle.c.  No host sync.
  */

@@ -237,11 +237,19 @@ k_batch_solve(const BatchInst* __restrict__ insts, int count, int shared, BatchG
         for (int k = threadIdx.x; k < I.m; k += blockDim.x) S.y0[k] = S.y[k];
         const double eta = __ldg(eta_arr + inst);
         int pb = 0;
-        if (threadIdx.x == 0) { s_par[0][0] = eta / w0; s_par[0][1] = eta * w0; s_par[0][2] = 0.5; }
+        double w_init = w0;
+        if (!(w0 > 0.0)) {   // the PDLP default ||c~|| / ||b~|| of this instance (scaled data, as loaded)
+            double nn[2] = {0.0, 0.0};
+            for (int q = threadIdx.x; q < I.m; q += blockDim.x) nn[0] += S.b[q] * S.b[q];
+            for (int q = threadIdx.x; q < I.n; q += blockDim.x) nn[1] += S.c[q] * S.c[q];
+            cta_allreduce<2>(nn, S);
+            w_init = (nn[0] > 0.0 && nn[1] > 0.0) ? sqrt(nn[1] / nn[0]) : 1.0;
+        }
+        if (threadIdx.x == 0) { s_par[0][0] = eta / w_init; s_par[0][1] = eta * w_init; s_par[0][2] = 0.5; }
         __syncthreads();
         const DevLP lp = smem_lp(I, S);
         if (!have_views || !shared) { batch_views(I, geom, dsm, VA, VAT); have_views = true; }
-        double w = w0, fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
+        double w = w_init, fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
         int k = 0, it = 0, restarts = 0, converged = 0;
         double kk[10], dd[2];
         batch_kkt(lp, VA, VAT, S, kk, dd);
@@ -777,12 +785,12 @@ k_batch_solve_r(const BatchInst* __restrict__ insts, int count, BatchGeom geom, 
             const int nx = s_next[r];
             active[r] = nx < count;
             inst[r] = nx;
-            eta[r] = 1.0; w[r] = w0; fpe_restart[r] = -1.0; fpe_prev[r] = INFINITY; fpe[r] = 0.0;
+            eta[r] = 1.0; w[r] = w0 > 0.0 ? w0 : 1.0; fpe_restart[r] = -1.0; fpe_prev[r] = INFINITY; fpe[r] = 0.0;
             k[r] = 0; it[r] = 0; restarts[r] = 0;
             if (threadIdx.x == 0) s_act[r] = active[r];
             if (active[r]) {
                 eta[r] = __ldg(eta_arr + nx);
-                if (threadIdx.x == 0) { s_par[pb][0][r] = eta[r] / w0; s_par[pb][1][r] = eta[r] * w0; s_par[pb][2][r] = 0.5; }
+                if (threadIdx.x == 0) { s_par[pb][0][r] = eta[r] / w[r]; s_par[pb][1][r] = eta[r] * w[r]; s_par[pb][2][r] = 0.5; }
                 load_slot<R>(I, S, r, nx, x, y, b, c);
             } else {
                 // idle slot: zero vectors keep its (masked) lanes finite
@@ -795,6 +803,25 @@ k_batch_solve_r(const BatchInst* __restrict__ insts, int count, BatchGeom geom, 
             }
         }
         __syncthreads();
+        if (!(w0 > 0.0)) {   // the PDLP default ||c~|| / ||b~|| of every slot that was just filled (uniform control flow)
+            double nn[2 * R];
+#pragma unroll
+            for (int q = 0; q < 2 * R; ++q) nn[q] = 0.0;
+            for (int q = threadIdx.x; q < I.m; q += blockDim.x)
+#pragma unroll
+                for (int r = 0; r < R; ++r) nn[2 * r] += S.b[(size_t)q * R + r] * S.b[(size_t)q * R + r];
+            for (int q = threadIdx.x; q < I.n; q += blockDim.x)
+#pragma unroll
+                for (int r = 0; r < R; ++r) nn[2 * r + 1] += S.c[(size_t)q * R + r] * S.c[(size_t)q * R + r];
+            cta_allreduce_r<2 * R, R>(nn, S);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (!want[r] || !active[r]) continue;
+                w[r] = (nn[2 * r] > 0.0 && nn[2 * r + 1] > 0.0) ? sqrt(nn[2 * r + 1] / nn[2 * r]) : 1.0;
+                if (threadIdx.x == 0) { s_par[pb][0][r] = eta[r] / w[r]; s_par[pb][1][r] = eta[r] * w[r]; }
+            }
+            __syncthreads();
+        }
     };
     {
         bool all[R];
@@ -1045,7 +1072,11 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
 
     BuildParams bp;
     bp.num_ctas = 1;           // one CTA walks the whole instance
-    bp.pref_steps = 2;         // small LPs: favour lanes over steps (latency, not throughput)
+    // Lanes per row: a batch that fills the GPU several times over is bound by INSTRUCTION ISSUE (ncu, 4096 x 25fv47:
+    // issue slots 46 % busy, DFMA 6 % of the instructions, the rest is tile decoding, shuffle trees and row updates), so rows
+    // get few lanes and up to 6 steps -- fewer, longer tiles: 152 -> 105 us per batch iteration (measured 2 / 3 / 4 / 6 / 8
+    // steps: 152 / 129 / 126 / 105 / 109 us).  A small batch is latency bound: 2 steps, wide rows.
+    bp.pref_steps = count >= 4 * prop.multiProcessorCount ? 6 : 2;
     bp.max_steps = 4;
     const char* ev = getenv("MLLP_BATCH_PREF_STEPS");
     if (ev && *ev) bp.pref_steps = std::max(1, atoi(ev));
@@ -1309,7 +1340,7 @@ int mllp_batch_run(mllp_batch_t bt, double* d_x, double* d_y, const double* d_b,
 int mllp_batch_solve(mllp_batch_t bt, double* d_x, double* d_y, const double* d_b, const double* d_c, const double* d_eta,
                      double w0, int32_t max_iters, int32_t check_every, double tol, double* d_scalars, void* stream)
 {
-    if (!bt || !d_x || !d_y || !d_b || !d_c || !d_eta || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 > 0.0))
+    if (!bt || !d_x || !d_y || !d_b || !d_c || !d_eta || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 >= 0.0))
         return bfail(MLLP_E_INVALID, "mllp_batch_solve: bad argument");
     DevGuard guard(bt->device);
     cudaError_t e0 = cudaMemsetAsync(bt->d_next, 0, sizeof(int), (cudaStream_t)stream);

@@ -1145,7 +1145,7 @@ int mllp_pdhg_run_host(mllp_lp_t lp, double* h_x, double* h_y, const double* h_b
 int mllp_pdhg_solve(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, const double* d_c, double eta,
                     double w0, int32_t max_iters, int32_t check_every, double tol, double* d_scalars, void* stream)
 {
-    if (!lp || !d_x || !d_y || !d_b || !d_c || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 > 0.0) ||
+    if (!lp || !d_x || !d_y || !d_b || !d_c || !d_scalars || max_iters < 0 || check_every < 1 || !(w0 >= 0.0) ||
         !(eta > 0.0))
         return fail(MLLP_E_INVALID, "mllp_pdhg_solve: bad argument");
     if (lp->nranks > 1) return fail(MLLP_E_STATE, "mllp_pdhg_solve: not available on a row-partitioned handle");
@@ -1157,9 +1157,17 @@ int mllp_pdhg_solve(mllp_lp_t lp, double* d_x, double* d_y, const double* d_b, c
     RC_OK(launch_eval(lp->d, lp->bounds, lp->G, lp->threads, d_scalars, 0.0, s));
     lp->d.join_base = lp->join_epoch;
     lp->join_epoch += 2ull * (unsigned long long)max_iters + 2ull;
+    const double* w0_dev = nullptr;
+    if (w0 == 0.0 && max_iters > 0) {
+        // the PDLP default initial primal weight ||c~|| / ||b~|| of the LP the handle iterates on (scaled when preconditioned):
+        // squared norms by the fixed-order two-stage sum, read by the kernel (no host synchronisation)
+        RC_OK(launch_sumsq(lp->d_b, lp->mi, lp->d_norm2, lp->d_norm2 + 2, s));
+        RC_OK(launch_sumsq(lp->d_c, lp->ni, lp->d_norm2 + 1, lp->d_norm2 + 2, s));
+        w0_dev = lp->d_norm2;
+    }
     if (max_iters > 0)
-        RC_OK(launch_solve_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, eta, w0, max_iters, check_every, tol,
-                                      d_scalars, s));
+        RC_OK(launch_solve_persistent(lp->d, lp->bounds, lp->G, lp->threads, lp->dyn_smem, eta, w0 > 0.0 ? w0 : 1.0, max_iters,
+                                      check_every, tol, d_scalars, w0_dev, s));
     RC_OK(store_solution(lp, d_x, d_y, s));
     return 0;
 }

@@ -33,7 +33,7 @@ int rowpart_set_smem(bool bounds, size_t dyn_smem);
 int launch_pdhg_rowpart(const DevLP& lp, const PeerInfo& pi, bool bounds, int G, int threads, size_t dyn_smem,
                         double tau, double sigma, int iters, unsigned long long seq, cudaStream_t s);
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
-                            int max_iters, int check_every, double tol, double* out, cudaStream_t s);
+                            int max_iters, int check_every, double tol, double* out, const double* w0_dev, cudaStream_t s);
 
 // scaling.cu: Ruiz + Pock-Chambolle preconditioning on the device (creation time); h_values becomes Dr A Dc
 int precondition_device(int m, int n, long long nnz, const int* h_ptr, const int* h_ind, double* h_values, const int* h_tptr,

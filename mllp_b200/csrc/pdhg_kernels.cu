@@ -336,8 +336,13 @@ k_pdhg_rowpart(DevLP lp, PeerInfo pi, double tau, double sigma, int iters, unsig
 // the same arithmetic, so all CTAs take identical branches.
 template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1) k_solve_persistent(DevLP lp, int G, double eta, double w0, int max_iters,
-                                                              int check_every, double tol, double* out)
+                                                              int check_every, double tol, double* out, const double* w0_dev)
 {
+    // w0_dev != null: the PDLP default ||c~||_2 / ||b~||_2 from the squared norms {||b~||^2, ||c~||^2} left there by the host side
+    if (w0_dev) {
+        const double nb2 = __ldcg(w0_dev), nc2 = __ldcg(w0_dev + 1);
+        w0 = (nb2 > 0.0 && nc2 > 0.0) ? sqrt(nc2 / nb2) : 1.0;
+    }
     __shared__ double smem[32 * NRED];
     __shared__ double bc[16];
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -501,8 +506,12 @@ __global__ void __launch_bounds__(1024, 1) k_pdhg_cluster(DevLP lp, double tau, 
 // for the KKT checks (every check_every iterations), which run on the global-memory evaluation path.
 template <bool BOUNDS>
 __global__ void __launch_bounds__(1024, 1) k_solve_cluster(DevLP lp, int G, double eta, double w0, int max_iters,
-                                                           int check_every, double tol, double* out)
+                                                           int check_every, double tol, double* out, const double* w0_dev)
 {
+    if (w0_dev) {
+        const double nb2 = __ldcg(w0_dev), nc2 = __ldcg(w0_dev + 1);
+        w0 = (nb2 > 0.0 && nc2 > 0.0) ? sqrt(nc2 / nb2) : 1.0;
+    }
     __shared__ double smem[32 * NRED];
     __shared__ double bc[16];
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -831,11 +840,11 @@ int launch_pdhg_rowpart(const DevLP& lp, const PeerInfo& pi, bool bounds, int G,
 }
 
 int launch_solve_persistent(const DevLP& lp, bool bounds, int G, int threads, size_t dyn_smem, double eta, double w0,
-                            int max_iters, int check_every, double tol, double* out, cudaStream_t s)
+                            int max_iters, int check_every, double tol, double* out, const double* w0_dev, cudaStream_t s)
 {
     if (lp.sync_mode == SYNC_GRID) CK(cudaMemsetAsync(lp.barrier, 0, sizeof(unsigned), s));
     DevLP lpv = lp;
-    void* args[] = {&lpv, &G, &eta, &w0, &max_iters, &check_every, &tol, &out};
+    void* args[] = {&lpv, &G, &eta, &w0, &max_iters, &check_every, &tol, &out, &w0_dev};
     return launch_persistent_fn(persistent_fn(true, bounds, lp.sync_mode == SYNC_BCAST), lp.sync_mode, G, threads, dyn_smem, args, s);
 }
 

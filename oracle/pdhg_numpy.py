@@ -82,7 +82,7 @@ def power_iteration(A, iters=50):
     return np.sqrt(lam)
 
 
-def pdhg_solve(A, b, c, x, y, eta, w0=1.0, max_iters=100000, check_every=64, tol=1e-6,
+def pdhg_solve(A, b, c, x, y, eta, w0=0.0, max_iters=100000, check_every=64, tol=1e-6,
                lb=None, ub=None, ylo=None, yhi=None):
     """Solve mode: reflected restarted Halpern PDHG, spec in oracle_pdhg_solve's comment."""
     A = sp.csr_matrix(A)
@@ -92,6 +92,9 @@ def pdhg_solve(A, b, c, x, y, eta, w0=1.0, max_iters=100000, check_every=64, tol
     lo = np.zeros_like(x) if lb is None else lb
     hi = np.full_like(x, np.inf) if ub is None else ub
     x0, y0 = x.copy(), y.copy()
+    if w0 <= 0:   # the PDLP default
+        nb2, nc2 = float(np.dot(b, b)), float(np.dot(c, c))
+        w0 = np.sqrt(nc2 / nb2) if nb2 > 0 and nc2 > 0 else 1.0
     w, fpe_restart, fpe_prev = w0, -1.0, np.inf
     k = it = restarts = 0
     converged = False

@@ -288,6 +288,7 @@ int oracle_power_iteration(int m, int n, const int32_t *indptr, const int32_t *i
  *       on restart: w <- exp(0.5 log(dy/dx) + 0.5 log w) with dx = ||x - x0||, dy = ||y - y0||
  *                   (only if both > 1e-10), z0 <- z, k <- 0, and fpe_at_restart is the fpe
  *                   of the first step after the restart.
+ *   Initial primal weight: w0 > 0 as given; w0 <= 0 selects the PDLP default ||c||_2 / ||b||_2 (1 if either is zero).
  *   info[0] iterations done, info[1] restarts, info[2] converged flag, info[3] final w.
  */
 int oracle_pdhg_solve(int m, int n, const int32_t *indptr, const int32_t *indices,
@@ -306,6 +307,12 @@ int oracle_pdhg_solve(int m, int n, const int32_t *indptr, const int32_t *indice
     if (!xbar || !x0 || !y0) return -1;
     memcpy(x0, x, (size_t)n * sizeof(double));
     memcpy(y0, y, (size_t)m * sizeof(double));
+    if (w0 <= 0.0) {
+        double nb2 = 0.0, nc2 = 0.0;
+        for (int i = 0; i < m; ++i) nb2 += b[i] * b[i];
+        for (int j = 0; j < n; ++j) nc2 += c[j] * c[j];
+        w0 = (nb2 > 0.0 && nc2 > 0.0) ? sqrt(nc2 / nb2) : 1.0;
+    }
     double w = w0, fpe_restart = -1.0, fpe_prev = INFINITY;
     int k = 0, it = 0, restarts = 0, converged = 0;
     double kk[10];

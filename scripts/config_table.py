@@ -17,8 +17,8 @@ def main(out_path):
     except Exception:
         hbm = 6531.6
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    rows = ["| instance | m x n | nnz | geometry | us / iteration | iterations/s | bytes / iteration | algorithmic GB/s | of measured HBM %.1f GB/s | CPU oracle it/s (%d thr) | x rel. err vs oracle (K=200) |" % (hbm, os.cpu_count()),
-            "|---|---|---:|---|---:|---:|---:|---:|---:|---:|---:|"]
+    rows = ["| instance | m x n | nnz | geometry | us / iteration | iterations/s | bytes / iteration | algorithmic GB/s | of measured HBM %.1f GB/s | solve mode us / iteration (check every 64) | create s | CPU oracle it/s (%d thr) | x rel. err vs oracle (K=200) |" % (hbm, os.cpu_count()),
+            "|---|---|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     for name in NAMES:
         A, b, c = M.load_csr(name); m, n = A.shape
         lp = M.DeviceLP(A, A.data, m, n)
@@ -43,8 +43,18 @@ def main(out_path):
         err = np.linalg.norm(x - xo2) / max(np.linalg.norm(xo2), 1e-300)
         g = lp.geometry()
         bpi = lp.info()["bytes_per_iter"]
-        rows.append("| %s | %dx%d | %d | %s x%d | %.2f | %.3g | %d | %.0f | %.3f | %.3g | %.1e |" % (
-            name, m, n, A.nnz, "blocks" if lp.blocks_info()["used"] else g["mode"], g["ctas"], us, 1e6 / us, bpi, bpi / us / 1e3, bpi / us / 1e3 / hbm, cpu, err))
+        # solve mode (k_solve_persistent / k_solve_cluster: Halpern combination, fixed-point error, KKT check + restart test
+        # every 64 iterations, all on the device) at a tolerance that is never met: time per iteration of the solve loop
+        ss = []
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); M.solve_linear_program(A, A.data, bt, ct, tol=0.0, max_iters=K, check_every=64, eta=eta, handle=lp); e1.record()
+            torch.cuda.synchronize()
+            ss.append(e0.elapsed_time(e1))
+        us_solve = float(np.median(ss)) * 1e3 / K
+        rows.append("| %s | %dx%d | %d | %s x%d | %.2f | %.3g | %d | %.0f | %.3f | %.2f | %.2f | %.3g | %.1e |" % (
+            name, m, n, A.nnz, "blocks" if lp.blocks_info()["used"] else g["mode"], g["ctas"], us, 1e6 / us, bpi, bpi / us / 1e3, bpi / us / 1e3 / hbm, us_solve, lp.create_s, cpu, err))
         print(rows[-1], flush=True)
         lp.close()
     open(out_path, "w").write("\n".join(rows) + "\n")

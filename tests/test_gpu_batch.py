@@ -193,3 +193,28 @@ def test_preconditioned_batch_solve_matches_highs_with_fewer_iterations():
     ref = M.solve_linear_program_batch([insts[1]], tol=1e-6, max_iters=400000, shared=True, rhs_batch=bb, coefs_batch=cb)
     for (obj, x, y, inf), (obj0, _, _, inf0) in zip(res, ref):
         assert inf["converged"] and abs(obj - obj0) <= 1e-4 * (1 + abs(obj0)) and np.all(x >= -1e-12)
+
+
+def test_config5_shared_matrix_data_parallel_path_runs_the_real_kernels():
+    """BASELINE.json configs[4] through the public data-parallel call (one process = the whole batch is this rank's shard):
+    perturbed instances of one Netlib matrix, solve mode with the library preconditioner, HOST batches in, per-instance
+    results out; every instance is checked by the oracle's KKT evaluation on its ORIGINAL LP and against HiGHS-level
+    objectives of the unperturbed LP's neighbourhood (perturbation 10 %)."""
+    import sys
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    import bench
+    from mllp_b200.distributed import solve_batch_data_parallel
+    A, b, c = D.load_csr("sc105")
+    bb, cb = bench.config5_batches(A, b, c, 0, 24)
+    assert bench.slack_rows(A, c).size > 0 and np.array_equal(bb[:, np.setdiff1d(np.arange(A.shape[0]), bench.slack_rows(A, c))][0],
+                                                               b[np.setdiff1d(np.arange(A.shape[0]), bench.slack_rows(A, c))])
+    res = solve_batch_data_parallel([(A, A.data, b, c)], mode="solve", device=0, shared=True, rhs_batch=bb, coefs_batch=cb, count=24,
+                                    tol=1e-6, max_iters=400000, scale=True, single_process=True)
+    assert len(res) == 24
+    for i, (obj, x, y, info) in enumerate(res):
+        assert info["converged"] and info["rel_kkt"] <= 1e-6
+        kk = O.kkt(A, bb[i], cb[i], x, y)
+        assert kk[8] <= 1.001e-6 and abs(kk[8] - info["rel_kkt"]) <= 1e-9 and abs(kk[0] - obj) <= 1e-9 * (1 + abs(obj))
+    # the same instances one by one through the single-LP solve: same optimum
+    o1, _, _, i1 = M.solve_linear_program(A, A.data, bb[3], cb[3], tol=1e-6, max_iters=400000, precondition=True)
+    assert i1["converged"] and abs(o1 - res[3][0]) <= 2e-5 * (1 + abs(o1))
