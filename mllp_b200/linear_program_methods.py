@@ -345,13 +345,15 @@ def pdhg_linear_program(constrs, constr_weights, rhs, coefs, *, num_iters, lb=No
 
 
 def solve_linear_program(constrs, constr_weights, rhs, coefs, *, tol=1e-6, max_iters=200000, check_every=64,
-                         lb=None, ub=None, ylo=None, yhi=None, x0=None, y0=None, eta=None, primal_weight=None,
+                         lb=None, ub=None, ylo=None, yhi=None, x0=None, y0=None, eta=None, primal_weight=1.0,
                          device=0, handle=None, flags=_cabi.F_DEFAULT, verbose=False, precondition=False):
     """Solve mode: reflected restarted Halpern PDHG on the device until the relative KKT error is
     <= ``tol`` (spec: oracle_pdhg_solve).  Returns ``(objective, x, y, info)``; numpy in/out.
     Non-convergence within ``max_iters`` is reported in ``info['converged']``, not raised.
-    ``primal_weight=None``: the PDLP default initial weight ||c|| / ||b|| (of the scaled LP on a preconditioned handle),
-    computed on the device.  ``precondition=True`` builds (and caches) a handle with the device-side Ruiz + Pock-Chambolle scaling: typically
+    ``primal_weight=None`` selects PDLP's initial weight ||c|| / ||b|| (of the scaled LP on a preconditioned handle),
+    computed on the device -- measured: it brings 4 of the 7 first-order-hard Netlib files (bnl1, pilot4, pilot.we, greenbea)
+    to 1e-6 within 4e6 iterations where 1.0 brings 2, but it slows d2q06c and 25fv47 down several times, so 1.0 stays the
+    default.  ``precondition=True`` builds (and caches) a handle with the device-side Ruiz + Pock-Chambolle scaling: typically
     2-4x fewer iterations; x, y, the objective and the KKT error -- hence termination -- refer to the ORIGINAL LP."""
     import torch
     lp = handle if handle is not None else device_lp(constrs, constr_weights, rhs, coefs, lb, ub, ylo, yhi,
@@ -499,8 +501,8 @@ class BatchLP:
                                                None if scalars is None else scalars.data_ptr(),
                                                _torch_stream(x.device)), "mllp_batch_run")
 
-    def solve(self, x, y, b, c, eta, scalars, w0=0.0, max_iters=200000, check_every=64, tol=1e-6):
-        """w0 = 0: every instance starts from the PDLP default primal weight ||c|| / ||b|| (computed in the kernel)"""
+    def solve(self, x, y, b, c, eta, scalars, w0=1.0, max_iters=200000, check_every=64, tol=1e-6):
+        """w0 = 0: every instance starts from PDLP's initial primal weight ||c|| / ||b|| (computed in the kernel)"""
         _cabi.check(_cabi.lib().mllp_batch_solve(self.handle, x.data_ptr(), y.data_ptr(), b.data_ptr(), c.data_ptr(),
                                                  eta.data_ptr(), float(w0), int(max_iters), int(check_every), float(tol),
                                                  scalars.data_ptr(), _torch_stream(x.device)), "mllp_batch_solve")
@@ -558,7 +560,7 @@ def pdhg_linear_program_batch(instances, *, num_iters, x0=None, y0=None, tau=Non
 
 
 def solve_linear_program_batch(instances, *, tol=1e-6, max_iters=200000, check_every=64, x0=None, y0=None, eta=None,
-                               primal_weight=None, device=0, handle=None, shared=False, rhs_batch=None, coefs_batch=None,
+                               primal_weight=1.0, device=0, handle=None, shared=False, rhs_batch=None, coefs_batch=None,
                                scale=False):
     """Solve mode on a whole batch in one launch; every instance restarts and terminates on
     its own.  Returns a list of ``(objective, x, y, info)``.  ``scale=True``: every distinct matrix is preconditioned

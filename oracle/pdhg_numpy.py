@@ -82,7 +82,7 @@ def power_iteration(A, iters=50):
     return np.sqrt(lam)
 
 
-def pdhg_solve(A, b, c, x, y, eta, w0=0.0, max_iters=100000, check_every=64, tol=1e-6,
+def pdhg_solve(A, b, c, x, y, eta, w0=1.0, max_iters=100000, check_every=64, tol=1e-6,
                lb=None, ub=None, ylo=None, yhi=None):
     """Solve mode: reflected restarted Halpern PDHG, spec in oracle_pdhg_solve's comment."""
     A = sp.csr_matrix(A)

@@ -107,7 +107,7 @@ def power_iteration(A, iters=50, nthreads=0):
     return s.value
 
 
-def pdhg_solve(A, b, c, x, y, eta, w0=0.0, max_iters=100000, check_every=64, tol=1e-6,
+def pdhg_solve(A, b, c, x, y, eta, w0=1.0, max_iters=100000, check_every=64, tol=1e-6,
                lb=None, ub=None, ylo=None, yhi=None, nthreads=0):
     A = A if isinstance(A, CSR) else CSR(A)
     b, c, lb, ub, ylo, yhi = map(_f64, (b, c, lb, ub, ylo, yhi))

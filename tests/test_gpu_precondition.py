@@ -73,3 +73,18 @@ def test_handle_cache_does_not_mix_boxes():
     xo2, _ = O.pdhg_run(A, b, c, np.zeros(n), np.zeros(m), eta, eta, 400, lo, hi2)
     assert np.linalg.norm(x1 - xo1) <= 1e-9 * np.linalg.norm(xo1) and np.linalg.norm(x2 - xo2) <= 1e-9 * np.linalg.norm(xo2)
     assert x2.max() <= 1.0 and x1.max() > 1.0
+
+
+def test_pdlp_initial_primal_weight_option_follows_the_oracle():
+    """primal_weight=None (w0 = 0 in the C ABI): ||c|| / ||b|| computed on the device; same rule in the oracle"""
+    A, b, c = D.load_csr("sc50a")
+    m, n = A.shape
+    obj, x, y, info = M.solve_linear_program(A, A.data, b, c, tol=1e-30, max_iters=256, check_every=32, primal_weight=None)
+    xs, ys, ks, si = O.pdhg_solve(A, b, c, np.zeros(n), np.zeros(m), info["eta"], w0=0.0, max_iters=256, tol=1e-30, check_every=32)
+    rel = lambda a, r: np.linalg.norm(a - r) / max(np.linalg.norm(r), 1e-300)
+    assert rel(x, xs) < 1e-7 and rel(y, ys) < 1e-7
+    assert abs(info["primal_weight"] - si["w"]) <= 1e-9 * si["w"]
+    res = M.solve_linear_program_batch([(A, A.data, b, c)] * 3, tol=1e-30, max_iters=256, check_every=32, primal_weight=None,
+                                       eta=info["eta"])
+    for r in res:
+        assert rel(r[1], xs) < 1e-7 and rel(r[2], ys) < 1e-7
