@@ -237,7 +237,7 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
         _, xk, yk, _ = M.pdhg_linear_program(A, A.data, b, c, num_iters=100, tau=eta, sigma=eta, handle=lp)
         xo, yo = O.pdhg_run(O.CSR(A), b, c, np.zeros(n), np.zeros(m), eta, eta, 100, nthreads=host_threads())
         ex, ey = rel(xk, xo), rel(yk, yo)
-        assert ex < 1e-9 and ey < 1e-9, "%s: iterates differ from the oracle (%.2e, %.2e)" % (name, ex, ey)
+        parity_check(ex < 1e-9 and ey < 1e-9, "%s: iterates differ from the oracle (%.2e, %.2e)" % (name, ex, ey))
         bt, ct = torch.tensor(b, device=dev), torch.tensor(c, device=dev)
         xt, yt = torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(m, dtype=torch.float64, device=dev)
         sec = timed(lambda: _cabi.check(L.mllp_pdhg_run(lp.handle, xt.data_ptr(), yt.data_ptr(), bt.data_ptr(), ct.data_ptr(),
@@ -272,7 +272,7 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
         xo, yo = O.pdhg_run(O.CSR(A), bb[i * m:(i + 1) * m].cpu().numpy(), cb[i * n:(i + 1) * n].cpu().numpy(), np.zeros(n), np.zeros(m),
                             float(eh[i]), float(eh[i]), 50)
         perr = max(perr, rel(xb[i * n:(i + 1) * n].cpu().numpy(), xo), rel(yb[i * m:(i + 1) * m].cpu().numpy(), yo))
-    assert perr < 1e-9, "batch iterates differ from the oracle (%.2e)" % perr
+    parity_check(perr < 1e-9, "batch iterates differ from the oracle (%.2e)" % perr)
     xb.zero_(); yb.zero_()
     sec = timed(lambda: bs.run(xb, yb, bb, cb, etab, etab, K), reps=2)
     out["batch_4096x25fv47"] = {"lp_iterations_per_sec": world * B * K / sec, "instances_per_rank": B,
@@ -354,7 +354,7 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
         Ai, _, bi, ci = insts[i]
         kk = O.kkt(O.CSR(Ai), bi, ci, xh[bsol.x_off[i]:bsol.x_off[i + 1]], yh[bsol.y_off[i]:bsol.y_off[i + 1]])
         kerr = max(kerr, abs(kk[8] - sc[i, 8]))
-    assert kerr <= 1e-9, "KKT scalars of the preconditioned batch differ from the oracle's on the original LPs (%.2e)" % kerr
+    parity_check(kerr <= 1e-9, "KKT scalars of the preconditioned batch differ from the oracle's on the original LPs (%.2e)" % kerr)
     out["solve_3072_small_netlib_preconditioned"] = {
         "lps_solved_per_sec": world * len(insts) / sec, "instances_per_rank": len(insts), "converged_fraction": float(conv.mean()),
         "mean_iterations": float(sc[:, 10].mean()), "tol": 1e-6, "max_iters": 100000, "seconds": sec,
@@ -454,7 +454,7 @@ def measure_rowpart(M, torch, dist, dev, local, rank, world, names=("osa-60", "k
         refh = ref.cpu().numpy()
         ex = float(np.linalg.norm(x - refh[:n]) / max(np.linalg.norm(refh[:n]), 1e-300))
         ey = float(np.linalg.norm(y - refh[n:]) / max(np.linalg.norm(refh[n:]), 1e-300))
-        assert ex < 1e-9 and ey < 1e-9, "row-partitioned %s on rank %d: iterates differ from the oracle (%.2e, %.2e)" % (name, rank, ex, ey)
+        parity_check(ex < 1e-9 and ey < 1e-9, "row-partitioned %s on rank %d: iterates differ from the oracle (%.2e, %.2e)" % (name, rank, ex, ey))
         perr = torch.tensor([ex, ey], dtype=torch.float64, device=dev)
         dist.all_reduce(perr, op=dist.ReduceOp.MAX)
 
@@ -464,7 +464,7 @@ def measure_rowpart(M, torch, dist, dev, local, rank, world, names=("osa-60", "k
             sec_nccl = timed(lambda: run_on(lp.handle, nccl_K), reps=2)
         finally:
             os.environ.pop("MLLP_ROWPART_NCCL", None)
-        assert lp.exchange_error() == 0
+        parity_check(lp.exchange_error() == 0, "row-partitioned %s on rank %d: an exchange wait timed out" % (name, rank))
         rec = {"n_gpus": world, "us_per_iteration": sec * 1e6 / K, "iterations_per_sec": K / sec,
                "us_per_iteration_nccl_allgather": sec_nccl * 1e6 / nccl_K,
                "us_per_iteration_one_gpu": us_one, "one_gpu_kernel": one_kernel, "speedup_vs_one_gpu": us_one / (sec * 1e6 / K),
@@ -547,6 +547,15 @@ def run_reference(args, rank, world):
 
 
 _JSON_OUT = None
+# in-run parity checks that failed: the JSON line is still printed (with "parity_failures"), then the process exits non-zero
+PARITY_FAILURES = []
+
+
+def parity_check(ok, msg):
+    if not ok:
+        PARITY_FAILURES.append(msg)
+        sys.stderr.write("PARITY FAILURE: " + msg + "\n")
+    return bool(ok)
 
 
 def quiet_stdout():
@@ -669,7 +678,8 @@ def main():
                "ms_per_step": 1e3 * float(te[0]) / args.steps,
                "call": "mllp_b200.pdhg_linear_program(constrs, constr_weights, rhs, coefs, num_iters=%d) with numpy (pinned) arrays; device formats cached by the loader" % KI}
         # the end-to-end call starts from the same point with the same data as the device-timed step: same scalars
-        assert abs(inf["pobj"] - final_scal[0]) <= 1e-9 * (1 + abs(final_scal[0])), (inf["pobj"], final_scal[0])
+        parity_check(abs(inf["pobj"] - final_scal[0]) <= 1e-9 * (1 + abs(final_scal[0])),
+                     "end-to-end call and device-timed step disagree on the objective (%r vs %r)" % (inf["pobj"], final_scal[0]))
 
     extras = None
     if not args.no_extras:
@@ -720,9 +730,16 @@ def main():
                                     "sample": "%d iterations of %s on the CPU oracle (OpenMP, %d threads, %.1f s)" % (its, args.workload, cores, dt),
                                     "scipy_csr_1_thread": {"value": r1, "unit": "iterations/s", "cores": 1,
                                                            "sample": "%d iterations of the same update with scipy.sparse CSR products on one thread" % k1}}
+        line["parity_checks"] = "in-run asserts against the CPU oracle: ken-18 / pds-20 K=100, batch K=50, preconditioned batch KKT scalars, row partition K=100 on every rank (N > 1), e2e vs device objective"
+        if PARITY_FAILURES:
+            line["parity_failures"] = PARITY_FAILURES
         emit(line)
+    nfail = torch.tensor([len(PARITY_FAILURES)], dtype=torch.int64, device=dev)
     if world > 1:
+        dist.all_reduce(nfail)
         dist.destroy_process_group()
+    if int(nfail[0]) > 0:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -872,6 +872,8 @@ int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char* all)
     DeviceGuard guard(lp->device);
     PeerInfo& P = lp->peers;
     P.err = lp->d_err;
+    P.backoff_ns = env_int("MLLP_MAIL_BACKOFF", 100);
+    P.backoff_max_ns = env_int("MLLP_MAIL_BACKOFF_MAX", 400);
     for (int q = 0; q < lp->nranks; ++q) {
         if (q == lp->rank) {
             P.mail[q] = lp->d_mail;

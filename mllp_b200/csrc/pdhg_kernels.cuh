@@ -575,6 +575,7 @@ struct PeerInfo {
     int cnt[MAX_RANKS];                    // valid rows at the head of every rank's slice of y
     unsigned* err;                         // local: set to 1 when a wait timed out
     int rank, nranks, Ly, mi;              // slice length, padded length of y (= nranks * Ly)
+    int backoff_ns, backoff_max_ns;        // sleep between two looks at a word that has not arrived (doubles up to the cap)
 };
 
 __device__ __forceinline__ void st_mail(unsigned long long* p, double v, unsigned long long tag)
@@ -625,9 +626,13 @@ __device__ __forceinline__ void unpack_mail(const DevLP& lp, const PeerInfo& pi,
             unsigned long long a, b;
             ld_mail(w, a, b);
             if ((a ^ b) != tag) {
+                // every thread of the grid may be waiting here: back off, or the polls crowd the L2 that the CTAs still in
+                // their A phase (split-row joins, gathers) and the peers' incoming words need
                 const unsigned long long t0 = global_ns();
+                unsigned ns = (unsigned)pi.backoff_ns;
                 for (;;) {
-                    __nanosleep(MLLP_BARRIER_BACKOFF);
+                    __nanosleep(ns);
+                    if (ns < (unsigned)pi.backoff_max_ns) ns *= 2;
                     ld_mail(w, a, b);
                     if ((a ^ b) == tag) break;
                     if (global_ns() - t0 > 10000000000ull || *(volatile unsigned*)pi.err != 0u) {

@@ -83,33 +83,54 @@ def netlib_objective(objective_norm, info):
     return -v if info.get("maximize") else v
 
 
+# Solve-mode settings tried in turn by ``portfolio=True`` (each from the zero start, on the same preconditioned handle):
+# (check_every, initial primal weight, iteration cap).  Measured on the 97 Netlib MPS files (profiles/r02_netlib_all.md,
+# r02_hard_instances.md): the first setting brings 90 to 1e-6 within 2e6 iterations; the restart test every 512
+# iterations adds bnl1, pilot4, pilot (93); PDLP's initial weight ||c|| / ||b|| adds greenbea and pilot.we (95).
+# perold and pilot.ja reach 7e-5 / 2e-4 at best.
+PORTFOLIO = ((64, 1.0, 2000000), (512, 1.0, 4000000), (64, None, 4000000))
+
+
 def solve_scaled(A, b, c, *, lb=None, ub=None, ylo=None, yhi=None, tol=1e-6, max_iters=400000, check_every=64, device=0,
-                 scale=True):
+                 scale=True, primal_weight=1.0, portfolio=False):
     """Solve mode on a handle preconditioned by the library (``MLLP_F_PRECONDITION``: Ruiz + Pock-Chambolle computed on
     the device at create time).  Returns (objective, x, y, info) of the ORIGINAL LP; the in-kernel termination test is
-    the KKT error of the original LP, ``info['rel_kkt_original']`` repeats it (kept for round-1 callers)."""
+    the KKT error of the original LP, ``info['rel_kkt_original']`` repeats it (kept for round-1 callers).
+    ``portfolio=True``: the settings of ``PORTFOLIO`` are tried in turn until one converges (``info['attempt']``,
+    ``info['iters_all_attempts']``); ``max_iters`` / ``check_every`` / ``primal_weight`` are then ignored."""
     from .linear_program_methods import DeviceLP, solve_linear_program
     A = sp.csr_matrix(A)
     m, n = A.shape
     h = DeviceLP(A, A.data, m, n, lb=lb, ub=ub, ylo=ylo, yhi=yhi, device=device, precondition=bool(scale))
+    settings = PORTFOLIO if portfolio else ((check_every, primal_weight, max_iters),)
+    total = 0
     try:
-        obj, x, y, info = solve_linear_program(A, A.data, b, c, tol=tol, max_iters=max_iters, check_every=check_every, handle=h)
+        for k, (ce, w0, cap) in enumerate(settings):
+            obj, x, y, info = solve_linear_program(A, A.data, b, c, tol=tol, max_iters=int(cap), check_every=int(ce),
+                                                   primal_weight=w0, handle=h)
+            total += info["iters"]
+            if info["converged"]:
+                break
     finally:
         h.close()
     info = dict(info)
     info.pop("handle", None)
     info["rel_kkt_original"] = info["rel_kkt"]
+    info["attempt"] = k
+    info["iters_all_attempts"] = total
+    info["setting"] = {"check_every": int(ce), "primal_weight": w0, "max_iters": int(cap)}
     return obj, x, y, info
 
 
-def solve_mps(path, *, tol=1e-6, max_iters=400000, check_every=64, device=0, scale=True):
+def solve_mps(path, *, tol=1e-6, max_iters=400000, check_every=64, device=0, scale=True, primal_weight=1.0, portfolio=False):
     """Read an MPS file (with row senses, bounds, ranges), precondition, solve on the GPU in
     solve mode and return (objective incl. offset, x, y, info) in the ORIGINAL variables.
     info['rel_kkt_original'] is the KKT error re-evaluated on the unscaled LP on the device."""
     from .mps import read_mps
     lp = read_mps(path)
     pobj, x, y, info = solve_scaled(lp["A"], lp["b"], lp["c"], lb=lp["lb"], ub=lp["ub"], ylo=lp["ylo"], yhi=lp["yhi"], tol=tol,
-                                    max_iters=max_iters, check_every=check_every, device=device, scale=scale)
+                                    max_iters=max_iters, check_every=check_every, device=device, scale=scale,
+                                    primal_weight=primal_weight, portfolio=portfolio)
     info["offset"] = lp["offset"]
     objective = pobj + lp["offset"]
     if lp["maximize"]:

@@ -20,6 +20,7 @@ dist.init_process_group("nccl", device_id=dev)
 names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["afiro", "pilot87", "osa-60", "ken-18", "pds-20"]
 K = 1000 if "--quick" not in sys.argv else 300
 res = bench.measure_rowpart(M, torch, dist, dev, local, rank, world, names=names, K=K, trace=True)
+assert not bench.PARITY_FAILURES, bench.PARITY_FAILURES      # every rank holds the oracle's iterates to 1e-9
 for nm in names:
     print("rank %d %s rowpart parity x %.2e y %.2e" % (rank, nm, res[nm]["parity_vs_oracle_K100"]["x"], res[nm]["parity_vs_oracle_K100"]["y"]), flush=True)
 if rank == 0:

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--check-every", type=int, default=64)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "netlib_all"))
     ap.add_argument("--budget", type=float, default=1e9, help="stop starting new instances after this many seconds")
+    ap.add_argument("--portfolio", action="store_true", help="try the settings of mllp_b200.scaling.PORTFOLIO in turn")
     a = ap.parse_args()
     from mllp_b200.scaling import solve_mps
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "mps_models_all.json")))
@@ -36,7 +37,7 @@ def main():
         t = time.time()
         try:
             obj, x, y, info = solve_mps(os.path.join(d, nm + ".mps.gz"), tol=a.tol, max_iters=a.max_iters,
-                                        check_every=a.check_every)
+                                        check_every=a.check_every, portfolio=a.portfolio)
         except Exception as e:  # keep going: the table must show failures too
             print(nm, "FAILED", repr(e), flush=True)
             rows.append({"name": nm, "error": repr(e)})
@@ -46,7 +47,8 @@ def main():
         r = {"name": nm, "m": g["m"], "n": g["n"], "nnz": g["nnz"], "objective": obj, "highs": ref,
              "rel_err": abs(obj - ref) / (1 + abs(ref)), "iters": int(info["iters"]), "restarts": int(info["restarts"]),
              "converged": bool(info["converged"]), "rel_kkt": float(info["rel_kkt"]),
-             "rel_kkt_original": float(info["rel_kkt_original"]), "seconds": dt}
+             "rel_kkt_original": float(info["rel_kkt_original"]), "seconds": dt, "attempt": int(info.get("attempt", 0)),
+             "iters_all_attempts": int(info.get("iters_all_attempts", info["iters"]))}
         rows.append(r)
         print("%-10s obj %.9g ref %.9g relerr %.2e iters %d conv %s kkt %.1e/%.1e %.2fs" % (
             nm, obj, ref, r["rel_err"], r["iters"], r["converged"], r["rel_kkt"], r["rel_kkt_original"], dt), flush=True)

@@ -88,3 +88,14 @@ def test_pdlp_initial_primal_weight_option_follows_the_oracle():
                                        eta=info["eta"])
     for r in res:
         assert rel(r[1], xs) < 1e-7 and rel(r[2], ys) < 1e-7
+
+
+def test_portfolio_walks_the_settings_until_one_converges(monkeypatch):
+    import os
+    import mllp_b200.scaling as S
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "netlib_mps_gz", "afiro.mps.gz")
+    monkeypatch.setattr(S, "PORTFOLIO", ((64, 1.0, 128), (512, 1.0, 100000), (64, None, 100000)))   # the first cap is too small
+    obj, x, y, info = S.solve_mps(path, portfolio=True)
+    assert info["converged"] and info["attempt"] == 1 and info["setting"]["check_every"] == 512
+    assert info["iters_all_attempts"] == 128 + info["iters"]
+    assert abs(obj - (-464.7531429)) <= 1e-5 * 465
