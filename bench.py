@@ -469,7 +469,10 @@ def measure_rowpart(M, torch, dist, dev, local, rank, world, names=("osa-60", "k
                "us_per_iteration_nccl_allgather": sec_nccl * 1e6 / nccl_K,
                "us_per_iteration_one_gpu": us_one, "one_gpu_kernel": one_kernel, "speedup_vs_one_gpu": us_one / (sec * 1e6 / K),
                "iters_timed": K, "parity_vs_oracle_K%d" % parity_K: {"x": float(perr[0]), "y": float(perr[1]), "tol": 1e-9},
-               "exchange": "tagged 16-byte words through peer mailboxes over NVLink inside one cooperative launch; A' phase replicated, one exchange per iteration"}
+               "multicast": bool(lp.multicast),
+               "exchange": ("tagged 16-byte words, ONE multimem.st per dual replicated by NVSwitch multicast into every rank's mailbox" if lp.multicast else
+                            "tagged 16-byte words stored into every peer's mailbox over NVLink (world - 1 stores per dual)") +
+                           ", inside one cooperative launch; A' phase replicated, one exchange per iteration"}
         if trace:
             rec["timeline_us"] = rowpart_timeline(lp, eta, dist, torch, dev)
         out[name] = rec

@@ -259,6 +259,21 @@ int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char *all_ranks);
 /* 0 = no exchange wait has timed out on this rank (synchronises the device). */
 int mllp_rowpart_error(mllp_lp_t lp, int32_t *out_flag);
 
+/* NVSwitch multicast for the in-kernel exchange (instead of mllp_rowpart_ipc_*): the mailboxes of all ranks are bound into
+ * ONE multicast object, so a row update issues a single `multimem.st` that the switch replicates into every GPU's mailbox
+ * (with peer pointers every dual value is stored nranks - 1 times as a 16-byte NVLink write).  Collective protocol, driven by
+ * the host (mllp_b200/distributed.py):
+ *   1. every rank: mllp_rowpart_mc_supported (CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED); continue only if all say 1;
+ *   2. rank 0: mllp_rowpart_mc_create -> a POSIX file descriptor of the multicast object; the other ranks duplicate it into
+ *      their process (pidfd_getfd on rank 0's pid, or SCM_RIGHTS);
+ *   3. every rank: mllp_rowpart_mc_attach(fd) (imports the object, adds this rank's device); barrier;
+ *   4. every rank: mllp_rowpart_mc_bind (allocates the mailbox with the VMM API, binds it, maps it unicast for the local
+ *      polls and multicast for the stores); barrier.  mllp_pdhg_run then uses the multicast exchange. */
+int mllp_rowpart_mc_supported(mllp_lp_t lp, int32_t *out);
+int mllp_rowpart_mc_create(mllp_lp_t lp, int32_t *out_fd);
+int mllp_rowpart_mc_attach(mllp_lp_t lp, int32_t fd);
+int mllp_rowpart_mc_bind(mllp_lp_t lp);
+
 /*
  * Batched mode: `count` independent LPs in one launch (one CTA per LP, the whole LP held
  * in shared memory).  Instance k has shape m[k] x n[k]; its CSR arrays are the slices

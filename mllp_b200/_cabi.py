@@ -37,6 +37,10 @@ SIGNATURES = {
     "mllp_rowpart_ipc_export": (ctypes.c_int, [_vp, _vp]),
     "mllp_rowpart_ipc_import": (ctypes.c_int, [_vp, _vp]),
     "mllp_rowpart_error": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32)]),
+    "mllp_rowpart_mc_supported": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32)]),
+    "mllp_rowpart_mc_create": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32)]),
+    "mllp_rowpart_mc_attach": (ctypes.c_int, [_vp, ctypes.c_int32]),
+    "mllp_rowpart_mc_bind": (ctypes.c_int, [_vp]),
     "mllp_lp_destroy": (ctypes.c_int, [_vp]),
     "mllp_lp_info": (ctypes.c_int, [_vp, _vp]),
     "mllp_lp_tune_info": (ctypes.c_int, [_vp, _vp]),

@@ -115,6 +115,7 @@ struct mllp_lp {
     unsigned long long join_epoch = 0;   // last tag used by the polled split-row join
     bool p2p_ready = false;
     unsigned long long xseq = 0;      // exchanges done on this handle (tag / buffer of the next one; same on all ranks)
+    McState mcs{};                    // NVSwitch multicast mailbox (mllp_rowpart_mc_*), replaces d_mail + peer pointers
     std::vector<void*> ipc_opened;
 };
 constexpr int GRAPH_UNROLL = 32;
@@ -872,8 +873,10 @@ int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char* all)
     DeviceGuard guard(lp->device);
     PeerInfo& P = lp->peers;
     P.err = lp->d_err;
-    P.backoff_ns = env_int("MLLP_MAIL_BACKOFF", 100);
-    P.backoff_max_ns = env_int("MLLP_MAIL_BACKOFF_MAX", 400);
+    P.backoff_ns = env_int("MLLP_MAIL_BACKOFF", 40);       // measured on 4 GPUs: 40 / 100..400 / 250..2000 ns make no difference
+    P.backoff_max_ns = env_int("MLLP_MAIL_BACKOFF_MAX", 40);
+    P.st_mode = env_int("MLLP_MAIL_ST", 0);                // dev knob; relaxed.sys / weak / .cg / volatile stores: no difference either
+    P.mc = nullptr;
     for (int q = 0; q < lp->nranks; ++q) {
         if (q == lp->rank) {
             P.mail[q] = lp->d_mail;
@@ -886,6 +889,57 @@ int mllp_rowpart_ipc_import(mllp_lp_t lp, const unsigned char* all)
         lp->ipc_opened.push_back(ptr);
         P.mail[q] = (unsigned long long*)ptr;
     }
+    if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(rowpart_set_smem(lp->bounds, lp->dyn_smem));
+    lp->p2p_ready = true;
+    return 0;
+}
+
+// NVSwitch multicast for the in-kernel exchange (see include/mllp_b200.h)
+static size_t mailbox_bytes(const mllp_lp* lp) { return sizeof(unsigned long long) * ((size_t)4 * lp->mi + 2); }
+
+int mllp_rowpart_mc_supported(mllp_lp_t lp, int32_t* out)
+{
+    if (!lp || !out || lp->nranks < 2) return fail(MLLP_E_INVALID, "mllp_rowpart_mc_supported: not a row-partitioned handle");
+    DeviceGuard guard(lp->device);
+    int sup = 0;
+    RC_OK(mc_supported(lp->device, &sup));
+    *out = sup;
+    return 0;
+}
+
+int mllp_rowpart_mc_create(mllp_lp_t lp, int32_t* out_fd)
+{
+    if (!lp || !out_fd || lp->nranks < 2 || lp->rank != 0) return fail(MLLP_E_INVALID, "mllp_rowpart_mc_create: rank 0 of a row-partitioned handle only");
+    DeviceGuard guard(lp->device);
+    int fd = -1;
+    RC_OK(mc_create(&lp->mcs, lp->nranks, mailbox_bytes(lp), &fd));
+    *out_fd = fd;
+    return 0;
+}
+
+int mllp_rowpart_mc_attach(mllp_lp_t lp, int32_t fd)
+{
+    if (!lp || lp->nranks < 2) return fail(MLLP_E_INVALID, "mllp_rowpart_mc_attach: not a row-partitioned handle");
+    DeviceGuard guard(lp->device);
+    if (lp->rank != 0) RC_OK(mc_import(&lp->mcs, lp->nranks, mailbox_bytes(lp), fd));
+    if (!lp->mcs.have_mc) return fail(MLLP_E_STATE, "mllp_rowpart_mc_attach: no multicast object (mllp_rowpart_mc_create first on rank 0)");
+    RC_OK(mc_add_device(&lp->mcs, lp->device));
+    return 0;
+}
+
+int mllp_rowpart_mc_bind(mllp_lp_t lp)
+{
+    if (!lp || lp->nranks < 2 || !lp->mcs.have_mc) return fail(MLLP_E_INVALID, "mllp_rowpart_mc_bind: attach first");
+    DeviceGuard guard(lp->device);
+    RC_OK(mc_bind_map(&lp->mcs));
+    PeerInfo& P = lp->peers;
+    P.err = lp->d_err;
+    P.backoff_ns = env_int("MLLP_MAIL_BACKOFF", 40);
+    P.backoff_max_ns = env_int("MLLP_MAIL_BACKOFF_MAX", 40);
+    P.st_mode = 0;
+    for (int q = 0; q < MAX_RANKS; ++q) P.mail[q] = nullptr;
+    P.mail[lp->rank] = (unsigned long long*)lp->mcs.uc;     // the local polls read this rank's own (unicast) mapping
+    P.mc = (unsigned long long*)lp->mcs.mcva;
     if (lp->dyn_smem > 48 * 1024 - 4096) RC_OK(rowpart_set_smem(lp->bounds, lp->dyn_smem));
     lp->p2p_ready = true;
     return 0;
@@ -917,6 +971,7 @@ int mllp_lp_destroy(mllp_lp_t lp)
     if (!lp) return 0;
     DeviceGuard guard(lp->device);
     for (void* p : lp->ipc_opened) cudaIpcCloseMemHandle(p);
+    mc_destroy(&lp->mcs);
     if (lp->comm) { NcclApi* api = nccl_api(); if (api) api->comm_destroy(lp->comm); }
     if (lp->graph) cudaGraphExecDestroy(lp->graph);
     blocks_destroy(lp->blocks);

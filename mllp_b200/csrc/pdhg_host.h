@@ -42,6 +42,21 @@ int precondition_device(int m, int n, long long nnz, const int* h_ptr, const int
 int launch_gather_scaled(double* dst, const double* src, const int32_t* order, const double* s, int div, int n, cudaStream_t st);
 int launch_scatter_scaled(double* dst, const double* src, const int32_t* order, const double* s, int div, int n, cudaStream_t st);
 
+// multicast.cu: NVSwitch multicast mailbox of the row-partitioned exchange (driver API, bound at run time)
+struct McState {
+    unsigned long long mc = 0, mem = 0;      // CUmemGenericAllocationHandle of the multicast object / of this rank's mailbox
+    unsigned long long uc = 0, mcva = 0;     // unicast and multicast mappings (CUdeviceptr)
+    size_t size = 0, gran = 0;
+    int device = 0;
+    bool have_mc = false, have_mem = false, bound = false, uc_mapped = false, mc_mapped = false;
+};
+int mc_supported(int device, int* out);
+int mc_create(McState* S, int nranks, size_t bytes, int* fd);       // rank 0
+int mc_import(McState* S, int nranks, size_t bytes, int fd);        // the other ranks (fd already duplicated into this process)
+int mc_add_device(McState* S, int device);                          // every rank
+int mc_bind_map(McState* S);                                        // every rank, after all have added their device
+void mc_destroy(McState* S);
+
 // blocks.cu: block-angular LPs (components dealt to CTAs, linking rows through tagged words; no grid barrier)
 struct BlockPlan;
 int blocks_create(int m, int n, const int32_t* indptr, const int32_t* indices, const double* values, const int32_t* posX,

@@ -572,16 +572,21 @@ struct SpmvOp {
 constexpr int MAX_RANKS = 8;
 struct PeerInfo {
     unsigned long long* mail[MAX_RANKS];   // every rank's mailbox [2][mi][2] (own entry = local pointer)
+    unsigned long long* mc;                // multicast address of all mailboxes (one store reaches every rank), or null
     int cnt[MAX_RANKS];                    // valid rows at the head of every rank's slice of y
     unsigned* err;                         // local: set to 1 when a wait timed out
     int rank, nranks, Ly, mi;              // slice length, padded length of y (= nranks * Ly)
     int backoff_ns, backoff_max_ns;        // sleep between two looks at a word that has not arrived (doubles up to the cap)
+    int st_mode;                           // dev knob: how a word is stored into a peer's mailbox (see st_mail)
 };
 
-__device__ __forceinline__ void st_mail(unsigned long long* p, double v, unsigned long long tag)
+__device__ __forceinline__ void st_mail(unsigned long long* p, double v, unsigned long long tag, int mode = 0)
 {
     const unsigned long long a = (unsigned long long)__double_as_longlong(v);
-    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");
+    if (mode == 1) asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");              // weak
+    else if (mode == 2) asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");      // weak, L2 only
+    else if (mode == 3) asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");
+    else asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(a ^ tag) : "memory");
 }
 __device__ __forceinline__ void ld_mail(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
 {
@@ -605,9 +610,15 @@ struct DualMailOp {
         double yn = p.y + sigma * (p.b - dot);
         if (BOUNDS) yn = fmin(fmax(yn, Mem::ld_ro(lp.ylo + r)), Mem::ld_ro(lp.yhi + r));
         lp.y[r] = yn;
+        if (pi.mc) {   // NVSwitch multicast: ONE 16-byte store, replicated by the switch into every rank's mailbox
+            const unsigned long long a = (unsigned long long)__double_as_longlong(yn), b = a ^ tag;
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pi.mc + buf + 2 * (size_t)r),
+                         "r"((unsigned)a), "r"((unsigned)(a >> 32)), "r"((unsigned)b), "r"((unsigned)(b >> 32)) : "memory");
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < MAX_RANKS; ++q)
-            if (q < pi.nranks && q != pi.rank) st_mail(pi.mail[q] + buf + 2 * (size_t)r, yn, tag);
+            if (q < pi.nranks && q != pi.rank) st_mail(pi.mail[q] + buf + 2 * (size_t)r, yn, tag, pi.st_mode);
     }
 };
 
@@ -618,31 +629,40 @@ __device__ __forceinline__ void unpack_mail(const DevLP& lp, const PeerInfo& pi,
 {
     const unsigned long long* box = pi.mail[pi.rank] + buf;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (int q = 0; q < pi.nranks; ++q) {
-        if (q == pi.rank) continue;
-        const int base = q * pi.Ly;
-        for (int k = gtid; k < pi.cnt[q]; k += gsz) {
-            const unsigned long long* w = box + 2 * (size_t)(base + k);
-            unsigned long long a, b;
-            ld_mail(w, a, b);
-            if ((a ^ b) != tag) {
-                // every thread of the grid may be waiting here: back off, or the polls crowd the L2 that the CTAs still in
-                // their A phase (split-row joins, gathers) and the peers' incoming words need
-                const unsigned long long t0 = global_ns();
-                unsigned ns = (unsigned)pi.backoff_ns;
-                for (;;) {
-                    __nanosleep(ns);
-                    if (ns < (unsigned)pi.backoff_max_ns) ns *= 2;
-                    ld_mail(w, a, b);
-                    if ((a ^ b) == tag) break;
-                    if (global_ns() - t0 > 10000000000ull || *(volatile unsigned*)pi.err != 0u) {
-                        atomicExch(pi.err, 1u);
-                        break;
-                    }
+    // ONE flat index space over the words of all peers, so that the whole grid shares them: with a loop over the peers
+    // inside every thread the first cnt threads polled world - 1 words one after the other (a dependent L2 round trip each)
+    // while the rest of the grid idled -- the wait grew with the rank count (ken-18: 2.5 / 5.2 / 9.9 us on 2 / 4 / 8 GPUs)
+    int total = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_RANKS; ++q)
+        if (q < pi.nranks && q != pi.rank) total += pi.cnt[q];
+    for (int f = gtid; f < total; f += gsz) {
+        int k = f, q = 0;
+#pragma unroll
+        for (int p = 0; p < MAX_RANKS; ++p) {       // flat index -> (peer q, row k within its slice)
+            const int c = (p < pi.nranks && p != pi.rank) ? pi.cnt[p] : 0;
+            if (k < c) { q = p; break; }
+            k -= c;
+        }
+        const int at = q * pi.Ly + k;
+        const unsigned long long* w = box + 2 * (size_t)at;
+        unsigned long long a, b;
+        ld_mail(w, a, b);
+        if ((a ^ b) != tag) {
+            const unsigned long long t0 = global_ns();
+            unsigned ns = (unsigned)pi.backoff_ns;
+            for (;;) {
+                __nanosleep(ns);
+                if (ns < (unsigned)pi.backoff_max_ns) ns *= 2;
+                ld_mail(w, a, b);
+                if ((a ^ b) == tag) break;
+                if (global_ns() - t0 > 10000000000ull || *(volatile unsigned*)pi.err != 0u) {
+                    atomicExch(pi.err, 1u);
+                    break;
                 }
             }
-            lp.y[base + k] = __longlong_as_double((long long)a);
         }
+        lp.y[at] = __longlong_as_double((long long)a);
     }
 }
 

@@ -12,12 +12,27 @@ Two ways the path shards:
   single-GPU path up to summation order.
 """
 import ctypes
+import os
 
 import numpy as np
 
 from . import _cabi
 from .linear_program_methods import (DeviceLP, _device_index, _info_dict, _np_f64, _ptr, _torch_stream,
                                      csr_from_constrs, pdhg_linear_program_batch, solve_linear_program_batch)
+
+
+def _dup_fd_from(pid, fd):
+    """Duplicate file descriptor `fd` of process `pid` into this process (pidfd_open + pidfd_getfd, Linux >= 5.6; the
+    ranks of one node run under one user).  Returns -1 if the kernel refuses."""
+    libc = ctypes.CDLL(None, use_errno=True)
+    SYS_pidfd_open, SYS_pidfd_getfd = 434, 438        # x86-64 and aarch64 share these numbers
+    pfd = libc.syscall(SYS_pidfd_open, int(pid), 0)
+    if pfd < 0:
+        return -1
+    try:
+        return int(libc.syscall(SYS_pidfd_getfd, pfd, int(fd), 0))
+    finally:
+        os.close(pfd)
 
 
 def shard_range(count, rank, world):
@@ -133,7 +148,13 @@ class RowPartLP(DeviceLP):
         self._sigma_robust = None
         self.norm_upper = 0.0
         self.p2p = False
-        if p2p and 1 < self.world <= 8:
+        self.multicast = False
+        # NVSwitch multicast pays from 4 ranks on (8 GPUs: ken-18 15.7 -> 14.0 us, osa-60 15.2 -> 14.6); on 2 it only adds a
+        # second copy of every word (ken-18 8.1 -> 8.5 us).  MLLP_ROWPART_MC = 0 / 1 forces it off / on.
+        if p2p and 1 < self.world <= 8 and os.environ.get("MLLP_ROWPART_MC", "1" if self.world >= 4 else "0") != "0":
+            self.multicast = self._setup_multicast(dist, L, h)
+            self.p2p = self.multicast
+        if p2p and 1 < self.world <= 8 and not self.multicast:
             # in-kernel exchange over NVLink peer memory: swap the CUDA IPC handles of the ranks' mailboxes
             mine = np.zeros(64, dtype=np.uint8)
             _cabi.check(L.mllp_rowpart_ipc_export(h, mine.ctypes.data), "mllp_rowpart_ipc_export")
@@ -143,6 +164,42 @@ class RowPartLP(DeviceLP):
             _cabi.check(L.mllp_rowpart_ipc_import(h, blob.ctypes.data), "mllp_rowpart_ipc_import")
             dist.barrier()
             self.p2p = True
+
+    def _setup_multicast(self, dist, L, h):
+        """NVSwitch multicast mailbox (mllp_rowpart_mc_*): one multimem.st per dual value instead of world - 1 peer stores.
+        Collective; returns False (on every rank) when any rank cannot do it -- the caller then swaps IPC handles instead."""
+        import torch
+        dev = torch.device("cuda", self.device)
+
+        def all_ok(flag):
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(int(t[0]))
+
+        sup = ctypes.c_int32(0)
+        ok = L.mllp_rowpart_mc_supported(h, ctypes.byref(sup)) == 0 and sup.value == 1
+        if not all_ok(ok):
+            return False
+        fd = ctypes.c_int32(-1)
+        ok = True
+        if self.rank == 0:
+            ok = L.mllp_rowpart_mc_create(h, ctypes.byref(fd)) == 0
+        box = [(os.getpid(), int(fd.value)) if ok else None]
+        dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            return False
+        my_fd = int(fd.value)
+        if self.rank != 0:
+            my_fd = _dup_fd_from(box[0][0], box[0][1])
+        ok = my_fd >= 0 and L.mllp_rowpart_mc_attach(h, my_fd) == 0
+        if not all_ok(ok):          # also the barrier "every device has been added"
+            return False
+        ok = L.mllp_rowpart_mc_bind(h) == 0
+        if not all_ok(ok):          # ... and "every mailbox is bound"
+            raise RuntimeError("mllp_b200: binding the multicast mailbox failed on some rank: %s" % _cabi.last_error())
+        if my_fd >= 0:
+            os.close(my_fd)         # the driver holds its own reference to the object
+        return True
 
     def sigma_max(self, iters=50, stream=None):
         raise RuntimeError("the power iteration is not available on a row-partitioned handle (mllp_estimate_norm); "
