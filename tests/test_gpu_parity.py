@@ -27,7 +27,7 @@ SCAL_TOL = 1e-6
 # (instance, iterations): every BASELINE.json config instance
 CASES = [("afiro", 5000), ("sc50a", 1000), ("sc105", 1000), ("adlittle", 1000), ("blend", 1000), ("share2b", 1000),
          ("kb2", 1000), ("25fv47", 1000), ("pilot87", 1000), ("d2q06c", 1000), ("dfl001", 1000), ("ken-18", 1000),
-         ("osa-60", 300), ("pds-20", 1000)]
+         ("osa-60", 1000), ("pds-20", 1000)]
 
 
 def rel(a, b):
