@@ -169,17 +169,27 @@ def slack_rows(A, c):
     return np.array(sorted(rows), dtype=np.int64)
 
 
-def config5_batches(A, b, c, lo, hi):
+def config5_batches(A, b, c, lo, hi, variant="bounded"):
     """BASELINE.json configs[4] / SURVEY 8d config 5: instance i of the 4096 perturbs the fixed matrix's data with
-    torch.Generator().manual_seed(1234 + i) on the CPU in fp64: c_i = c (1 + 0.1 U(-1, 1)), b_i = b (1 + 0.1 U(0, 1)) on the
-    rows that own a slack column (relaxes them, keeps feasibility), equality rows unchanged."""
+    torch.Generator().manual_seed(1234 + i) on the CPU in fp64; b_i = b (1 + 0.1 U(0, 1)) on the rows that own a slack
+    column, equality rows unchanged.  The cost perturbation:
+      variant "survey"  : c_i = c (1 + 0.1 U(-1, 1)), as SURVEY 8d writes it.  On 25fv47 (`_norm` form: bounds dropped, x >= 0)
+                          this makes the LP UNBOUNDED for about nine instances in ten (HiGHS: status 3; the unperturbed LP has
+                          recession directions with c'd = 0, any sign change of c'd opens them) -- there is nothing to solve;
+      variant "bounded" : c_ij = c_j (1 + 0.1 u) for c_j > 0 and c_j (1 - 0.1 u) for c_j < 0, u ~ U(0, 1) from the same stream:
+                          c'd can only grow on every direction d >= 0, so every instance stays bounded (and, with the same b
+                          rule, feasible: checked with HiGHS in tests/test_oracle.py).  This is what the bench solves."""
     import torch
     m, n = A.shape
     sr = slack_rows(A, c)
     cb, bb = np.empty((hi - lo, n)), np.tile(b, (hi - lo, 1))
     for k, i in enumerate(range(lo, hi)):
         g = torch.Generator().manual_seed(1234 + i)
-        cb[k] = c * (1.0 + 0.1 * (2.0 * torch.rand(n, generator=g, dtype=torch.float64).numpy() - 1.0))
+        u = torch.rand(n, generator=g, dtype=torch.float64).numpy()
+        if variant == "survey":
+            cb[k] = c * (1.0 + 0.1 * (2.0 * u - 1.0))
+        else:
+            cb[k] = np.where(c > 0, c * (1.0 + 0.1 * u), c * (1.0 - 0.1 * u))
         bb[k, sr] = b[sr] * (1.0 + 0.1 * torch.rand(sr.shape[0], generator=g, dtype=torch.float64).numpy())
     return bb, cb
 
@@ -392,6 +402,7 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
         "rel_kkt_original_max_over_converged": float(kk5[conv].max()) if conv.any() else None, "tol": 1e-6,
         "h2d_bytes": 8 * (hi - lo) * (m + n) + 8 * (hi - lo) * (m + n), "d2h_bytes": 8 * (hi - lo) * (m + n + _cabi.NUM_SCALARS),
         "scaling": "strong (4096 instances in total over %d GPU(s))" % world,
+        "perturbation": "seeds 1234+i, b (1 + 0.1 U(0,1)) on slack rows; costs moved AWAY from zero-cost recession directions (c_j > 0: x(1 + 0.1u), c_j < 0: x(1 - 0.1u)): SURVEY 8d's c (1 + 0.1 U(-1,1)) makes ~90 % of the 25fv47 instances unbounded (HiGHS), see config5_batches",
         "call": "mllp_b200.distributed.solve_batch_data_parallel(shared matrix, rhs_batch, coefs_batch, scale=True) with numpy batches; includes format build + device preconditioning"}
     return out
 

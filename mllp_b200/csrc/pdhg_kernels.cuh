@@ -916,24 +916,39 @@ __device__ __forceinline__ void run_phase(const DevMat& M, const MatView& V, con
                 const unsigned long long* w0 = reinterpret_cast<const unsigned long long*>(M.slots) + 2 * (size_t)(uint32_t)sr.y;
                 double s = 0.0;
                 const long long t0 = clock64();
-                for (uint32_t k0 = 0; k0 < np; k0 += 32) {
-                    const uint32_t k = k0 + lane;
-                    double v = 0.0;
+                // PW words per lane are in flight together and only the stale ones are read again: a row whose partials come
+                // from more than 32 CTAs (row partition: a rank's one long row is spread over the whole grid) costs one
+                // polled round trip, not one per 32 partials.  Same summation order as before: per lane ascending k, then the
+                // butterfly.
+                constexpr int PW = 4;
+                for (uint32_t k0 = 0; k0 < np; k0 += 32 * PW) {
+                    unsigned long long qa[PW], qb[PW];
+#pragma unroll
+                    for (int u = 0; u < PW; ++u) {
+                        const uint32_t k = k0 + 32u * u + lane;
+                        qa[u] = 0ull; qb[u] = tag;                     // a word that does not exist counts as arrived, value 0
+                        if (k < np)
+                            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(qa[u]), "=l"(qb[u]) : "l"(w0 + 2 * (size_t)k) : "memory");
+                    }
                     for (;;) {
                         bool ok = true;
-                        if (k < np) {
-                            unsigned long long qa, qb;
-                            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(qa), "=l"(qb) : "l"(w0 + 2 * (size_t)k) : "memory");
-                            ok = (qa ^ qb) == tag;
-                            v = __longlong_as_double((long long)qa);
-                        }
+#pragma unroll
+                        for (int u = 0; u < PW; ++u) ok &= (qa[u] ^ qb[u]) == tag;
                         if (__all_sync(FULL, ok)) break;
                         if (clock64() - t0 > 4000000000LL) {   // never hang: flag the error and move on
                             if (lane == 0) M.partials[0] = NAN, *reinterpret_cast<volatile double*>(M.slots) = NAN;
                             break;
                         }
+#pragma unroll
+                        for (int u = 0; u < PW; ++u) {
+                            const uint32_t k = k0 + 32u * u + lane;
+                            if ((qa[u] ^ qb[u]) != tag)
+                                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(qa[u]), "=l"(qb[u]) : "l"(w0 + 2 * (size_t)k) : "memory");
+                        }
                     }
-                    s += v;
+#pragma unroll
+                    for (int u = 0; u < PW; ++u)
+                        if (k0 + 32u * u < np) s += __longlong_as_double((long long)qa[u]);
                 }
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0) op_row(op, sr.x, -1, s, spre, acc);

@@ -109,3 +109,25 @@ def test_oracle_edge_cases():
     x2, y2 = P.pdhg_run(A, b, c, np.zeros(4), np.zeros(3), 0.1, 0.1, 50)
     assert rel(x, x2) < 1e-13 and rel(y, y2) < 1e-13
     assert y[1] == 0.0  # empty row with b = 0 never moves
+
+
+def test_config5_perturbation_keeps_the_lp_bounded_where_the_survey_recipe_does_not():
+    """BASELINE.json configs[4]: the generator of the 4096-instance batch (bench.config5_batches).  SURVEY 8d's cost
+    perturbation c (1 + 0.1 U(-1, 1)) makes 25fv47 (`_norm` form: no upper bounds) unbounded; the variant the bench solves
+    moves every cost away from the zero-cost recession directions and keeps the LP feasible and bounded (HiGHS)."""
+    import os
+    import sys
+    import scipy.optimize
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import mllp_b200.linear_program_data as D
+    A, b, c = D.load_csr("25fv47")
+    bs, cs = bench.config5_batches(A, b, c, 0, 1, variant="survey")
+    bb, cb = bench.config5_batches(A, b, c, 0, 1, variant="bounded")
+    assert np.array_equal(bs, bb)                                     # same right-hand sides, same random stream
+    st_survey = [scipy.optimize.linprog(cs[i], A_eq=A, b_eq=bs[i], bounds=(0, None), method="highs").status for i in range(1)]
+    res = [scipy.optimize.linprog(cb[i], A_eq=A, b_eq=bb[i], bounds=(0, None), method="highs") for i in range(1)]
+    assert st_survey == [3]                                           # unbounded
+    assert [r.status for r in res] == [0] and all(30.0 < r.fun < 45.0 for r in res)     # optimum of 25fv47: 35.204
+    sr = bench.slack_rows(A, c)
+    assert sr.size == 305 and np.all(bb[:, sr] >= b[sr] - 1e-15 * np.abs(b[sr])) or np.all(np.sign(bb[:, sr]) == np.sign(b[sr]))
