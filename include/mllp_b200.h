@@ -364,6 +364,29 @@ int mllp_gnn_plan_destroy(mllp_gnn_plan_t plan);
 int mllp_gnn_conv(const mllp_gnn_side *side, int32_t din, const float *d_hdst, const float *d_hsrc, const float *d_params,
                   float *d_hout, int32_t relu, void *stream);
 
+/* Backward pass of the same model: what loss.backward() does through GNNModel in the reference's training loop
+ * (linear_program_experiment.py:115-157: model(graph) -> BCEWithLogitsLoss -> backward -> Adam step).
+ *
+ * The trainable parameters live in ONE flat float vector of mllp_gnn_flat_param_floats() entries: the six convs in the
+ * module's order (gconv1_w2s, gconv1_s2w, gconv2_w2s, gconv2_s2w, gconv3_w2s, gconv3_s2w -- the last one is registered
+ * but unused, linear_program_methods.py:247), each as torch_geometric registers its tensors
+ *   lin_key.weight[16][din] | lin_key.bias[16] | lin_query.weight | lin_query.bias | lin_value.weight | lin_value.bias |
+ *   lin_edge.weight[16] | lin_skip.weight | lin_skip.bias,
+ * then fc.weight[16] | fc.bias.  mllp_gnn_pack_params forms, on the device, the parameter blocks mllp_gnn_forward takes
+ * (mllp_gnn_packed_param_floats() floats) from the flat vector.
+ *
+ * mllp_gnn_backward: d_work is the workspace of the forward that was just run with d_packed on the same graph (it holds
+ * the activations), d_bwork a scratch of mllp_gnn_backward_workspace_floats(n, m) floats (16-byte aligned), d_dout[n] =
+ * d loss / d logit; writes d loss / d flat into d_dflat (all entries; gconv3_s2w and lin_key.bias get zeros).  No atomics:
+ * the result is bitwise reproducible.  Asynchronous on `stream`. */
+int64_t mllp_gnn_flat_param_floats(void);
+int64_t mllp_gnn_packed_param_floats(void);
+int mllp_gnn_pack_params(const float *d_flat, float *d_packed, void *stream);
+int64_t mllp_gnn_backward_workspace_floats(int32_t n, int32_t m);
+int mllp_gnn_backward(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
+                      const float *d_flat, const float *d_packed, const float *d_work, float *d_bwork,
+                      const float *d_dout, float *d_dflat, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

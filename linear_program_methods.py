@@ -8,14 +8,15 @@ What the driver takes from that import (linear_program_experiment.py:19, 50, 83,
 * ON the hot path, provided here (mllp_b200, hand-written sm_100a kernels behind the C ABI, no CPU fallback):
   ``build_graph_from_weights_sets`` (same signature and ``BipartiteData``-shaped return, edge list written on the device),
   ``BipartiteData``, and the solve functions the reference lacks: ``pdhg_linear_program``, ``solve_linear_program``,
-  their ``*_batch`` twins, ``DeviceLP`` / ``device_lp``, ``DeviceGNNModel`` (the message-passing forward).
+  their ``*_batch`` twins, ``DeviceLP`` / ``device_lp``, ``DeviceGNNModel`` (the message-passing forward) and
+  ``TrainableGNNModel`` (the same model as a ``torch.nn.Module`` with a device backward, for the driver's training loop).
 * ``set_seed`` -- same effect as the reference's (:15-24).
 * Everything else (the basis-prediction models and the max-covering learners / solvers, SURVEY.md section 2 rows 5-12, OUT
   of scope) is NOT rebuilt: those names resolve lazily to the reference's own definitions when a reference checkout is
   reachable (``MLLP_REFERENCE_DIR``, default ``/root/reference``) and its third-party imports (torch_geometric,
   gumbel_sinkhorn_topk, perturbations, blackbox_diff, lap_solvers -- reference :7, :9-12) are installed; otherwise to a
   placeholder that raises ``ImportError`` naming what is missing WHEN USED, so the star-import itself always succeeds.
-  ``GNNModel`` is the reference's trainable module when that is available and the forward-only device model otherwise.
+  ``GNNModel`` is the reference's module when that is available and the device model (``TrainableGNNModel``) otherwise.
 """
 import importlib.util
 import os
@@ -27,11 +28,12 @@ import torch
 
 from mllp_b200.graph import BipartiteData, build_graph_from_weights_sets
 from mllp_b200.gnn import GNNModel as DeviceGNNModel
+from mllp_b200.gnn_train import TrainableGNNModel
 from mllp_b200.linear_program_methods import (BatchLP, DeviceLP, device_lp, estimate_step_size, pdhg_linear_program,
                                               pdhg_linear_program_batch, solve_linear_program,
                                               solve_linear_program_batch)
 
-_OURS = ["torch", "np", "set_seed", "BipartiteData", "build_graph_from_weights_sets", "DeviceGNNModel", "DeviceLP", "BatchLP",
+_OURS = ["torch", "np", "set_seed", "BipartiteData", "build_graph_from_weights_sets", "DeviceGNNModel", "TrainableGNNModel", "DeviceLP", "BatchLP",
          "device_lp", "estimate_step_size", "pdhg_linear_program", "pdhg_linear_program_batch", "solve_linear_program",
          "solve_linear_program_batch"]
 # names of the reference module that are outside the hot path (resolved lazily, see the module docstring)
@@ -101,7 +103,7 @@ def __getattr__(name):   # PEP 562: called for the lazily resolved names (also b
     if mod is not None and hasattr(mod, name):
         obj = getattr(mod, name)
     elif name == "GNNModel":
-        obj = DeviceGNNModel   # forward only; training needs the reference's torch module
+        obj = TrainableGNNModel   # the device model: forward and backward in hand-written kernels (mllp_b200/gnn_train.py)
     else:
         obj = _Unavailable(name, why or "the reference module has no such name")
     globals()[name] = obj

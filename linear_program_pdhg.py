@@ -11,6 +11,12 @@ from the working directory's ``netlib_mps/`` + ``dataset/`` exactly as the drive
 driver logs to ``train_log.json`` (:77-78).  Objectives are also given in the MPS file's units (x ||c_raw||_2, SURVEY
 App. A.3) when ``dataset/netlib_mps/<name>_coefs.npy`` is there.
 
+``'gs-topk'`` / ``'soft-topk'`` (the supervised basis-prediction training of ``GNNModel``, :115-157) are handled too, with
+the reference's loop -- ``build_graph_from_weights_sets`` -> ``model(graph)`` -> ``BCEWithLogitsLoss`` against ``basis_opt`` ->
+``backward`` -> ``Adam.step`` per instance, ``train_iter`` epochs, ``train_log.json``, ``state_dict`` saved to
+``linear_program_<train_data_type>_<method>.pt`` (:46, :185) -- on the device model (forward AND backward in hand-written
+kernels, mllp_b200/gnn_train.py); the stock driver cannot run it without torch_geometric.
+
 Extra yaml keys (all optional): ``pdhg_tol`` (1e-6), ``pdhg_max_iters`` (400000), ``pdhg_check_every`` (64),
 ``pdhg_instances`` (list of names; default: all listed instances), ``pdhg_scale`` (true: Ruiz + Pock-Chambolle preconditioning).
 """
@@ -37,6 +43,46 @@ class Config(dict):
         return conv(raw)
 
 
+def train_gnn(cfg, method_name, train_dataset, train_dict, device):
+    """the reference's training branch for 'gs-topk' / 'soft-topk' (linear_program_experiment.py:115-157, :185-186)"""
+    import torch
+    from sklearn.metrics import f1_score
+    from linear_program_methods import TrainableGNNModel, build_graph_from_weights_sets
+    print(f"Training the model weights for {method_name}...")
+    dev = torch.device(device)
+    model = TrainableGNNModel(device=dev.index or 0)
+    criterion = torch.nn.BCEWithLogitsLoss()
+    train_optimizer = torch.optim.Adam(model.parameters(), lr=float(cfg.train_lr))
+    graphs = {}
+    for epoch in range(int(cfg.train_iter)):
+        obj_sum = 0
+        for name, constrs, constr_weights, coefs, rhs, basis_opt in train_dataset:
+            if name not in graphs:   # the reference rebuilds the graph every epoch (:124); the device graph is kept
+                graphs[name] = build_graph_from_weights_sets(constrs, constr_weights, rhs, coefs, dev)
+            latent_vars = model(graphs[name])
+            target = torch.tensor(basis_opt, dtype=torch.float, device=dev)
+            obj = criterion(latent_vars, target)
+            obj.backward()
+            obj_sum += obj.mean()
+            train_optimizer.step()
+            train_optimizer.zero_grad()
+            pred_indices = torch.topk(latent_vars, k=rhs.shape[0])[-1].cpu().detach().numpy()
+            pred = np.zeros([coefs.shape[0]])
+            pred[pred_indices] = 1
+            f1 = f1_score(np.asarray(basis_opt), pred)
+            correct_num = pred @ np.asarray(basis_opt)
+            print("%8d, %8d, %8d, %5f" % (correct_num, rhs.shape[0], coefs.shape[0], f1))
+            train_dict[name].append(float(correct_num))
+        train_dict["obj"].append(float(obj_sum) / len(train_dataset))
+        with open("train_log.json", "w") as json_file:
+            json.dump(train_dict, json_file)
+        print(f"epoch {epoch}, obj={obj_sum / len(train_dataset)}")
+    model_path = f"linear_program_{cfg.train_data_type}_{method_name}.pt"
+    torch.save(model.state_dict(), model_path)
+    print(f"Model saved to {model_path}.")
+    return model
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description="PDHG solve runner (B200)")
     ap.add_argument("--cfg", "--config", dest="cfg_file", default=None)
@@ -56,8 +102,11 @@ def main(argv=None):
     train_dataset, train_dict = get_netlib_dataset(normalize=True, names=names)
     log = {"obj": []}
     for method_name in cfg.methods or []:
+        if method_name in ("gs-topk", "soft-topk"):
+            train_gnn(cfg, method_name, train_dataset, train_dict, args.device)
+            continue
         if method_name != "pdhg":
-            continue    # the stock methods belong to the stock driver
+            continue    # the other stock methods belong to the stock driver
         print("Solving the LPs with pdhg...")
         for name, constrs, constr_weights, coefs, rhs, basis_opt in train_dataset:
             scale = bool(cfg.pdhg_scale) if cfg.pdhg_scale is not None else True

@@ -67,6 +67,11 @@ SIGNATURES = {
     "mllp_gnn_plan_destroy": (ctypes.c_int, [_vp]),
     "mllp_gnn_conv_param_floats": (ctypes.c_int64, [_i32]),
     "mllp_gnn_conv": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "mllp_gnn_flat_param_floats": (ctypes.c_int64, []),
+    "mllp_gnn_packed_param_floats": (ctypes.c_int64, []),
+    "mllp_gnn_pack_params": (ctypes.c_int, [_vp, _vp, _vp]),
+    "mllp_gnn_backward_workspace_floats": (ctypes.c_int64, [_i32, _i32]),
+    "mllp_gnn_backward": (ctypes.c_int, [_vp] * 11),
 }
 
 

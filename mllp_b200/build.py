@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(CSRC, "libmllp_b200.so")
-SOURCES = ["lp_format.cpp", "pdhg_kernels.cu", "batch_kernels.cu", "gnn_kernels.cu", "blocks.cu", "scaling.cu", "multicast.cu", "cabi.cu"]
-HEADERS = ["lp_format.h", "pdhg_kernels.cuh", "pdhg_host.h", os.path.join(ROOT, "include", "mllp_b200.h")]
+SOURCES = ["lp_format.cpp", "pdhg_kernels.cu", "batch_kernels.cu", "gnn_kernels.cu", "gnn_backward.cu", "blocks.cu", "scaling.cu", "multicast.cu", "cabi.cu"]
+HEADERS = ["lp_format.h", "pdhg_kernels.cuh", "pdhg_host.h", "gnn_common.cuh", os.path.join(ROOT, "include", "mllp_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -82,3 +82,22 @@ def test_runner_solves_afiro_through_the_yaml(tmp_path):
     from mllp_b200.mps import read_mps
     craw = np.linalg.norm(read_mps(os.path.join(ROOT, "data", "netlib_mps_gz", "afiro.mps.gz"))["c"])
     assert abs(log["afiro.mps"]["objective"] * craw - (-464.7531429)) <= 1e-5 * 464.8
+
+
+@pytest.mark.gpu
+def test_runner_trains_the_gnn_through_the_yaml(tmp_path):
+    """methods: ['soft-topk'] = the reference's supervised training loop (linear_program_experiment.py:115-157) on the
+    device model: train_log.json in the reference's shape, a state_dict under the reference's tensor names, a falling loss"""
+    import torch
+    d = _layout(tmp_path)
+    (d / "linear_program_netlib.yaml").write_text(
+        "train_data_type: 'netlib'\ntest_data_type: 'facebook'\ntrain_lr: 1.e-2\ntrain_iter: 25\nverbose: True\n"
+        "methods:\n   - 'soft-topk'\n")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "linear_program_pdhg.py"), "--cfg", "linear_program_netlib.yaml"],
+                       cwd=d, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    log = json.load(open(d / "train_log.json"))
+    assert len(log["obj"]) == 25 and len(log["afiro.mps"]) == 25 and len(log["sc50a.mps"]) == 25
+    assert log["obj"][-1] < log["obj"][0]
+    sd = torch.load(d / "linear_program_netlib_soft-topk.pt", map_location="cpu")
+    assert "gconv1_w2s.lin_key.weight" in sd and "fc.bias" in sd and len(sd) == 6 * 9 + 2
