@@ -72,7 +72,7 @@ def _device_grads(st, A, b, c, dout=None, target=None, groups=None):
         loss = torch.nn.BCEWithLogitsLoss()(out, torch.as_tensor(np.asarray(target, dtype=np.float32), device=out.device))
     loss.backward()
     grads = {k: v.detach().cpu().numpy() for k, v in model.named_gradients().items()}
-    return out.detach().cpu().numpy(), float(loss), grads, model, g
+    return out.detach().cpu().numpy(), float(loss.detach()), grads, model, g
 
 
 @pytest.mark.gpu
