@@ -36,7 +36,7 @@ struct Rec {
 // per-node vectors for the parameter gradients
 template <int DIN>
 struct NR {
-    static constexpr int xbar = 0, dqt = DIN, g = 2 * DIN, abar = g + C, dqe = abar + 1, any = abar + 2, total = (any + 1 + 3) & ~3;
+    static constexpr int g = 0, xbar = C, dqt = C + DIN, abar = C + 2 * DIN, dqe = abar + 1, any = abar + 2, total = (any + 1 + 3) & ~3;   // g first: float4 stores
 };
 // flat parameter vector of one conv, torch_geometric's registration order:
 //   lin_key.weight[16][din] | lin_key.bias[16] | lin_query.weight | lin_query.bias | lin_value.weight | lin_value.bias |
@@ -48,7 +48,7 @@ struct Flat {
 };
 constexpr int FLAT_TOTAL = 2 * Flat<1>::total + 4 * Flat<C>::total + C + 1;   // six convs (gconv3_s2w is unused) + fc
 constexpr int PACKED_TOTAL = 2 * Off<1>::total + 3 * Off<C>::total + C + 1;
-constexpr int PGRID = 148 * 2;   // CTAs of the parameter-gradient partial sums
+constexpr int PGRID = 148 * 4;   // CTAs of the parameter-gradient partial sums
 
 __host__ __device__ inline int flat_offset(int conv) { return conv < 2 ? conv * Flat<1>::total : 2 * Flat<1>::total + (conv - 2) * Flat<C>::total; }
 __host__ __device__ inline int packed_offset(int conv) { return conv < 2 ? conv * Off<1>::total : 2 * Off<1>::total + (conv - 2) * Off<C>::total; }
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) k_gnn_unpack_grads(const float* __restric
 
 // dxbar = Wv' g, dabar = We . g, dxs = Ws' g over the channels [c0, c0 + CNT) held by this lane
 template <int DIN, int CNT>
-__device__ __forceinline__ void g_products(const float* prm, int c0, const float* g, float* dxb, float* dxs, float& dab)
+__device__ __forceinline__ void g_products_xb(const float* prm, int c0, const float* g, float* dxb, float& dab)
 {
     using O = Off<DIN>;
 #pragma unroll
@@ -172,11 +172,25 @@ __device__ __forceinline__ void g_products(const float* prm, int c0, const float
         const float gc = g[k];
         dab = fmaf(prm[O::we + c0 + k], gc, dab);
 #pragma unroll
-        for (int d = 0; d < DIN; ++d) {
-            dxb[d] = fmaf(prm[O::wv + d * C + c0 + k], gc, dxb[d]);
-            dxs[d] = fmaf(prm[O::ws + d * C + c0 + k], gc, dxs[d]);
-        }
+        for (int d = 0; d < DIN; ++d) dxb[d] = fmaf(prm[O::wv + d * C + c0 + k], gc, dxb[d]);
     }
+}
+template <int DIN, int CNT>
+__device__ __forceinline__ void g_products_xs(const float* prm, int c0, const float* g, float* dxs)
+{
+    using O = Off<DIN>;
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) {
+        const float gc = g[k];
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) dxs[d] = fmaf(prm[O::ws + d * C + c0 + k], gc, dxs[d]);
+    }
+}
+template <int DIN, int CNT>
+__device__ __forceinline__ void g_products(const float* prm, int c0, const float* g, float* dxb, float* dxs, float& dab)
+{
+    g_products_xb<DIN, CNT>(prm, c0, g, dxb, dab);
+    g_products_xs<DIN, CNT>(prm, c0, g, dxs);
 }
 
 // one edge of the second sweep
@@ -224,35 +238,74 @@ __device__ __forceinline__ void store_dx_dst(const float* prm, const float* dxs,
     }
 }
 
+// the record of a destination node, in two parts: {qt, qe, lse} and {dxbar, dabar, D}
 template <int DIN>
-__device__ __forceinline__ void store_rec(float* r, const float* qt, const float* dxb, float qe, float lse, float dab, float D)
+__device__ __forceinline__ void store_rec_q(float* r, const float* qt, float qe, float lse)
 {
     using R = Rec<DIN>;
     if constexpr (DIN % 4 == 0) {
         float4* q = reinterpret_cast<float4*>(r);
 #pragma unroll
         for (int k = 0; k < DIN / 4; ++k) q[k] = make_float4(qt[4 * k], qt[4 * k + 1], qt[4 * k + 2], qt[4 * k + 3]);
-#pragma unroll
-        for (int k = 0; k < DIN / 4; ++k) q[DIN / 4 + k] = make_float4(dxb[4 * k], dxb[4 * k + 1], dxb[4 * k + 2], dxb[4 * k + 3]);
-        q[DIN / 2] = make_float4(qe, lse, dab, D);
+        *reinterpret_cast<float2*>(r + R::qe) = make_float2(qe, lse);
     } else {
 #pragma unroll
-        for (int d = 0; d < DIN; ++d) { r[R::qt + d] = qt[d]; r[R::dxb + d] = dxb[d]; }
-        r[R::qe] = qe; r[R::lse] = lse; r[R::dab] = dab; r[R::dd] = D;
+        for (int d = 0; d < DIN; ++d) r[R::qt + d] = qt[d];
+        r[R::qe] = qe; r[R::lse] = lse;
+    }
+}
+template <int DIN>
+__device__ __forceinline__ void store_rec_d(float* r, const float* dxb, float dab, float D)
+{
+    using R = Rec<DIN>;
+    if constexpr (DIN % 4 == 0) {
+        float4* q = reinterpret_cast<float4*>(r + R::dxb);
+#pragma unroll
+        for (int k = 0; k < DIN / 4; ++k) q[k] = make_float4(dxb[4 * k], dxb[4 * k + 1], dxb[4 * k + 2], dxb[4 * k + 3]);
+        *reinterpret_cast<float2*>(r + R::dab) = make_float2(dab, D);
+    } else {
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) r[R::dxb + d] = dxb[d];
+        r[R::dab] = dab; r[R::dd] = D;
+    }
+}
+template <int DIN>
+__device__ __forceinline__ void store_rec(float* r, const float* qt, const float* dxb, float qe, float lse, float dab, float D)
+{
+    store_rec_q<DIN>(r, qt, qe, lse);
+    store_rec_d<DIN>(r, dxb, dab, D);
+}
+
+template <int DIN>
+__device__ __forceinline__ void load_rec(const float* __restrict__ rec_i, float* qt, float* dxb, float& qe, float& lse, float& dab, float& D)
+{
+    using R = Rec<DIN>;
+    load_row<DIN>(rec_i + R::qt, qt);
+    load_row<DIN>(rec_i + R::dxb, dxb);
+    if constexpr (DIN % 4 == 0) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(rec_i + R::qe));
+        qe = t.x; lse = t.y; dab = t.z; D = t.w;
+    } else {
+        qe = __ldg(rec_i + R::qe); lse = __ldg(rec_i + R::lse); dab = __ldg(rec_i + R::dab); D = __ldg(rec_i + R::dd);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// destination pass, rows of at most `chunk` edges: S lanes per row.
+// destination pass, rows of at most `chunk` edges: S lanes per row, in two kernels (one kernel needed 255 registers and
+// ran one CTA per SM; the gathers want occupancy):
+//   k_gnn_bwd_dst_stats: the forward's row walk again: softmax statistics, pre-activation output -> g (ReLU mask applied), the
+//                        query-side part of the node's record and its per-node vectors;
+//   k_gnn_bwd_dst_dense: the dense maps dxbar = Wv' g, dabar, D (rest of the record), Ws' g parked in d x -- 16 lanes per node;
+//   k_gnn_bwd_dst_sweep: second sweep of the row's edges from the record -> dqt, dqe, d x.
 //   upstream gradient: gh[nd][16] (d loss / d relu(out)), or for the last conv dout[nd] and fcw[16] (the folded Linear(16, 1));
-//   rec / dxdst may be null (first layer: the inputs need no gradient); hfc[nd][16] = dout_i relu(out_i) for d fc.weight.
+//   dxdst may be null (first layer: the inputs need no gradient); hfc[nd][16] = dout_i relu(out_i) for d fc.weight.
 template <int S, int DIN>
-__global__ void __launch_bounds__(256, 1) k_gnn_bwd_dst(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+__global__ void __launch_bounds__(256, 3) k_gnn_bwd_dst_stats(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                      const double* __restrict__ values, const float* __restrict__ hdst,
                                                      const float* __restrict__ hsrc, const float* __restrict__ prm_g,
                                                      const float* __restrict__ gh, const float* __restrict__ dout,
                                                      const float* __restrict__ fcw_g, int chunk, float* __restrict__ rec,
-                                                     float* __restrict__ nr, float* __restrict__ dxdst, float* __restrict__ hfc)
+                                                     float* __restrict__ nr, float* __restrict__ hfc)
 {
     using O = Off<DIN>;
     using N = NR<DIN>;
@@ -284,67 +337,143 @@ __global__ void __launch_bounds__(256, 1) k_gnn_bwd_dst(int nd, const int32_t* _
         const bool any = st.l > 0.0f;
         const float inv = any ? 1.0f / st.l : 0.0f;
         const float lse = any ? st.m + __logf(st.l) : 0.0f;
-        // this lane's channels: pre-activation output, ReLU mask, upstream gradient
+        const bool writer = live && gl == 0;
+        float* rc = rec + (size_t)i * Rec<DIN>::total;
+        // the phases below are ordered so that few vectors are live at a time (S = 1: one lane holds all 16 channels):
+        // the query-side part of the record leaves the registers first
+        if (writer) store_rec_q<DIN>(rc, qt, qe, lse);
+        // xbar, abar in place of the unnormalised sums
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) st.acc[d] *= inv;
+        const float abar = st.pa * inv;
+        if (writer) {
+            float* r = nr + (size_t)i * N::total;
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) r[N::xbar + d] = st.acc[d];
+            r[N::abar] = abar;
+            r[N::any] = any ? 1.0f : 0.0f;
+        }
+        // this lane's channels: pre-activation output, ReLU mask, upstream gradient -> g (k_gnn_bwd_dst_dense goes on from it)
         const float di = (dout && live) ? __ldg(dout + i) : 0.0f;
-        float g[CNT];
         constexpr int STEP = CNT >= 4 ? 4 : CNT;
 #pragma unroll
         for (int k0 = 0; k0 < CNT; k0 += STEP) {
             float o[STEP];
-            out_channels<DIN, STEP>(prm, c0 + k0, x, st.acc, st.pa, inv, any, 0, o);
+            out_channels<DIN, STEP>(prm, c0 + k0, x, st.acc, abar, 1.0f, any, 0, o);
+            if (live && owner) {
+                float gk[STEP];
 #pragma unroll
-            for (int k = 0; k < STEP; ++k) {
-                const int c = c0 + k0 + k;
-                float up = 0.0f;
-                if (live && owner) up = gh ? __ldg(gh + (size_t)i * C + c) : di * prm[O::total + c];
-                g[k0 + k] = o[k] > 0.0f ? up : 0.0f;
-                if (live && owner) {
-                    nr[(size_t)i * N::total + N::g + c] = g[k0 + k];
+                for (int k = 0; k < STEP; ++k) {
+                    const int c = c0 + k0 + k;
+                    const float up = gh ? __ldg(gh + (size_t)i * C + c) : di * prm[O::total + c];
+                    gk[k] = o[k] > 0.0f ? up : 0.0f;
                     if (hfc) hfc[(size_t)i * C + c] = di * fmaxf(o[k], 0.0f);
                 }
+                float* gp = nr + (size_t)i * N::total + N::g + c0 + k0;
+                if constexpr (STEP == 4) *reinterpret_cast<float4*>(gp) = make_float4(gk[0], gk[1], gk[2], gk[3]);
+                else if constexpr (STEP == 2) *reinterpret_cast<float2*>(gp) = make_float2(gk[0], gk[1]);
+                else gp[0] = gk[0];
             }
         }
-        float dxb[DIN], dxs[DIN], dab = 0.0f;
+    }
+}
+
+// The dense maps of the destination pass for the rows of at most `chunk` edges, 16 lanes per node (lane q holds channel q of
+// g and produces entry q of dxbar = Wv' g and of Ws' g with its columns of the weights in registers):
+//   record {dxbar, dabar = We . g, D = dxbar . xbar + dabar abar}, and Ws' g parked in the row's d x.
+template <int DIN>
+__global__ void __launch_bounds__(256) k_gnn_bwd_dst_dense(int nd, const int32_t* __restrict__ indptr, const float* __restrict__ prm,
+                                                           int chunk, const float* __restrict__ nr, float* __restrict__ rec,
+                                                           float* __restrict__ dxdst)
+{
+    using O = Off<DIN>;
+    using N = NR<DIN>;
+    using R = Rec<DIN>;
+    const int lane = threadIdx.x & 31, q = lane & 15;
+    const bool has_d = q < DIN;
+    float wv[C], ws[C];
 #pragma unroll
-        for (int d = 0; d < DIN; ++d) { dxb[d] = 0.0f; dxs[d] = 0.0f; }
-        g_products<DIN, CNT>(prm, c0, g, dxb, dxs, dab);
+    for (int c = 0; c < C; ++c) {
+        wv[c] = has_d ? __ldg(prm + O::wv + q * C + c) : 0.0f;
+        ws[c] = has_d ? __ldg(prm + O::ws + q * C + c) : 0.0f;
+    }
+    const float we = __ldg(prm + O::we + q);
+    const int groups = (gridDim.x * blockDim.x) >> 4;
+    // trip count uniform over the warp (the shuffles below are warp-wide)
+    for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; base < nd; base += groups) {
+        const int i = base + (lane >> 4);
+        bool live = i < nd;
+        if (live) live = __ldg(indptr + i + 1) - __ldg(indptr + i) <= chunk;
+        const float* p = nr + (size_t)(live ? i : 0) * N::total;
+        const float gq = live ? p[N::g + q] : 0.0f;
+        const float xbq = (live && has_d) ? p[N::xbar + q] : 0.0f;
+        const float abar = live ? p[N::abar] : 0.0f;
+        float dxb = 0.0f, dxs = 0.0f;
+        float dab = we * gq;
+        const int src0 = lane & 16;
 #pragma unroll
-        for (int o = S / 2; o > 0; o >>= 1) {
+        for (int c = 0; c < C; ++c) {
+            const float gc = __shfl_sync(FULLM, gq, src0 + c);
+            dxb = fmaf(wv[c], gc, dxb);
+            dxs = fmaf(ws[c], gc, dxs);
+        }
+        float D = dxb * xbq;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
             dab += __shfl_xor_sync(FULLM, dab, o);
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) {
-                dxb[d] += __shfl_xor_sync(FULLM, dxb[d], o);
-                dxs[d] += __shfl_xor_sync(FULLM, dxs[d], o);
+            D += __shfl_xor_sync(FULLM, D, o);
+        }
+        D = fmaf(dab, abar, D);
+        if (live) {
+            float* r = rec + (size_t)i * R::total;
+            if (has_d) {
+                r[R::dxb + q] = dxb;
+                if (dxdst) dxdst[(size_t)i * DIN + q] = dxs;
             }
+            if (q == 0) { r[R::dab] = dab; r[R::dd] = D; }
         }
-        const float abar = st.pa * inv;
-        float D = dab * abar;
-#pragma unroll
-        for (int d = 0; d < DIN; ++d) D = fmaf(dxb[d], st.acc[d] * inv, D);
-        if (live && gl == 0) {
-            float* r = nr + (size_t)i * N::total;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) r[N::xbar + d] = st.acc[d] * inv;
-            r[N::abar] = abar;
-            r[N::any] = any ? 1.0f : 0.0f;
-            if (rec) store_rec<DIN>(rec + (size_t)i * Rec<DIN>::total, qt, dxb, qe, lse, dab, D);
-        }
-        // second sweep over the row's edges
+    }
+}
+
+template <int S, int DIN>
+__global__ void __launch_bounds__(256, 3) k_gnn_bwd_dst_sweep(int nd, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                           const double* __restrict__ values, const float* __restrict__ hsrc,
+                                                           const float* __restrict__ prm_g, int chunk, const float* __restrict__ rec,
+                                                           float* __restrict__ nr, float* __restrict__ dxdst)
+{
+    using O = Off<DIN>;
+    using N = NR<DIN>;
+    __shared__ __align__(16) float prm[O::wv];   // MQ, wq: the d x epilogue
+    for (int k = threadIdx.x; k < O::wv; k += blockDim.x) prm[k] = prm_g[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, gl = lane & (S - 1);
+    constexpr int RPW = 32 / S;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; base < nd; base += warps * RPW) {
+        const int i = base + lane / S;
+        int e0 = 0, e1 = 0;
+        if (i < nd) { e0 = __ldg(indptr + i); e1 = __ldg(indptr + i + 1); }
+        const bool live = i < nd && e1 - e0 <= chunk;
+        if (!live) e0 = e1 = 0;
         float dqt[DIN], dqe = 0.0f;
 #pragma unroll
         for (int d = 0; d < DIN; ++d) dqt[d] = 0.0f;
-        for (int e = e0 + gl; e < e1; e += 2 * S) {
-            const int eb = e + S;
-            const bool two = eb < e1;
-            const int ja = __ldg(indices + e);
-            const int jb = two ? __ldg(indices + eb) : ja;
-            const float aa = (float)__ldg(values + e);
-            const float ab = two ? (float)__ldg(values + eb) : 0.0f;
-            float xa[DIN], xb[DIN];
-            load_row<DIN>(hsrc + (size_t)ja * DIN, xa);
-            load_row<DIN>(hsrc + (size_t)jb * DIN, xb);
-            edge_ds<DIN>(aa, xa, qt, qe, lse, dxb, dab, D, dqt, dqe);
-            if (two) edge_ds<DIN>(ab, xb, qt, qe, lse, dxb, dab, D, dqt, dqe);
+        if (e1 > e0) {
+            float qt[DIN], dxb[DIN], qe, lse, dab, D;
+            load_rec<DIN>(rec + (size_t)i * Rec<DIN>::total, qt, dxb, qe, lse, dab, D);
+            for (int e = e0 + gl; e < e1; e += 2 * S) {
+                const int eb = e + S;
+                const bool two = eb < e1;
+                const int ja = __ldg(indices + e);
+                const int jb = two ? __ldg(indices + eb) : ja;
+                const float aa = (float)__ldg(values + e);
+                const float ab = two ? (float)__ldg(values + eb) : 0.0f;
+                float xa[DIN], xb[DIN];
+                load_row<DIN>(hsrc + (size_t)ja * DIN, xa);
+                load_row<DIN>(hsrc + (size_t)jb * DIN, xb);
+                edge_ds<DIN>(aa, xa, qt, qe, lse, dxb, dab, D, dqt, dqe);
+                if (two) edge_ds<DIN>(ab, xb, qt, qe, lse, dxb, dab, D, dqt, dqe);
+            }
         }
 #pragma unroll
         for (int o = S / 2; o > 0; o >>= 1) {
@@ -357,109 +486,117 @@ __global__ void __launch_bounds__(256, 1) k_gnn_bwd_dst(int nd, const int32_t* _
 #pragma unroll
             for (int d = 0; d < DIN; ++d) r[N::dqt + d] = dqt[d];
             r[N::dqe] = dqe;
-            if (dxdst) store_dx_dst<DIN>(prm, dxs, dqt, dqe, dxdst + (size_t)i * DIN);
+            if (dxdst) {
+                float park[DIN];
+#pragma unroll
+                for (int d = 0; d < DIN; ++d) park[d] = dxdst[(size_t)i * DIN + d];
+                store_dx_dst<DIN>(prm, park, dqt, dqe, dxdst + (size_t)i * DIN);
+            }
         }
     }
 }
 
-// destination pass, rows above `chunk` edges: one CTA per row, the warps' partial states / sums combined in shared
-// memory in a fixed order
+// destination pass, rows above `chunk` edges (osa-60: rows of 173 366 edges).  The row is cut into the forward's items
+// (one warp each, mllp_gnn_side.items):  k_gnn_conv_items leaves the items' partial softmax states in the scratch, then
+//   k_gnn_bwd_dst_long_stats  (one warp per row) merges them in a fixed order, forms g, dxbar, dabar, D, writes the node's
+//                             record and per-node vectors and parks Ws' g in the row's d x;
+//   k_gnn_bwd_dst_items       (one warp per item) sweeps the item's edges for its part of dqt, dqe -> scratch;
+//   k_gnn_bwd_dst_long_final  (one warp per row) adds the parts in a fixed order and finishes d x.
 template <int DIN>
-__global__ void __launch_bounds__(256) k_gnn_bwd_dst_long(int nlong, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ indptr,
-                                                          const int32_t* __restrict__ indices, const double* __restrict__ values,
-                                                          const float* __restrict__ hdst, const float* __restrict__ hsrc,
-                                                          const float* __restrict__ prm_g, const float* __restrict__ gh,
-                                                          const float* __restrict__ dout, const float* __restrict__ fcw_g,
-                                                          float* __restrict__ rec, float* __restrict__ nr, float* __restrict__ dxdst,
-                                                          float* __restrict__ hfc)
+__global__ void __launch_bounds__(256) k_gnn_bwd_dst_long_stats(int nlong, const int32_t* __restrict__ long_rows,
+                                                                const int32_t* __restrict__ first, const float* __restrict__ scratch,
+                                                                const float* __restrict__ hdst, const float* __restrict__ prm_g,
+                                                                const float* __restrict__ gh, const float* __restrict__ dout,
+                                                                const float* __restrict__ fcw_g, float* __restrict__ rec,
+                                                                float* __restrict__ nr, float* __restrict__ dxdst, float* __restrict__ hfc)
 {
     using O = Off<DIN>;
     using N = NR<DIN>;
     __shared__ __align__(16) float prm[O::total + C];
-    __shared__ float red[8][DIN + 4];
-    __shared__ float gsh[C];
     for (int k = threadIdx.x; k < O::total; k += blockDim.x) prm[k] = prm_g[k];
     if (fcw_g && threadIdx.x < C) prm[O::total + threadIdx.x] = fcw_g[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = blockIdx.x; r < nlong; r += gridDim.x) {
+    const int lane = threadIdx.x & 31, c = lane & 15;
+    const bool owner = lane < C;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nlong; r += warps) {
         const int i = __ldg(long_rows + r);
-        const int e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
-        float x[DIN], qt[DIN], qe;
-        load_row<DIN>(hdst + (size_t)i * DIN, x);
-        dst_prologue<1, DIN>(prm, x, 0, qt, qe);
         State<DIN> st;
-        state_init<DIN>(st);
-        for (int e = e0 + (int)threadIdx.x; e < e1; e += 256) {
-            const int j = __ldg(indices + e);
-            const float a = (float)__ldg(values + e);
-            float xj[DIN];
-            load_row<DIN>(hsrc + (size_t)j * DIN, xj);
-            float s = a * qe;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) s = fmaf(qt[d], xj[d], s);
-            fold<DIN>(st, s, a, xj);
-        }
-        merge_group<32, DIN>(st);
-        if (lane == 0) {
-            red[warp][0] = st.m; red[warp][1] = st.l; red[warp][2] = st.pa;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) red[warp][4 + d] = st.acc[d];
-        }
-        __syncthreads();
-        state_init<DIN>(st);
-        for (int w = 0; w < 8; ++w) {
-            const float mw = red[w][0];
-            const float mn = fmaxf(st.m, mw);
-            const float s1 = st.m == -INFINITY ? 0.0f : __expf(st.m - mn), s2 = mw == -INFINITY ? 0.0f : __expf(mw - mn);
-            st.l = st.l * s1 + red[w][1] * s2;
-            st.pa = st.pa * s1 + red[w][2] * s2;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) st.acc[d] = st.acc[d] * s1 + red[w][4 + d] * s2;
-            st.m = mn;
-        }
+        merge_items<DIN>(scratch, __ldg(first + r), __ldg(first + r + 1), lane, st);
         const bool any = st.l > 0.0f;
         const float inv = any ? 1.0f / st.l : 0.0f;
         const float lse = any ? st.m + __logf(st.l) : 0.0f;
+        float x[DIN], qt[DIN], qe;
+        load_row<DIN>(hdst + (size_t)i * DIN, x);
+        dst_prologue<1, DIN>(prm, x, 0, qt, qe);
         const float di = dout ? __ldg(dout + i) : 0.0f;
-        if (threadIdx.x < C) {
-            const int c = threadIdx.x;
-            float o1[1];
-            out_channels<DIN, 1>(prm, c, x, st.acc, st.pa, inv, any, 0, o1);
+        float o1[1];
+        out_channels<DIN, 1>(prm, c, x, st.acc, st.pa, inv, any, 0, o1);
+        float g[1] = {0.0f};
+        if (owner) {
             const float up = gh ? __ldg(gh + (size_t)i * C + c) : di * prm[O::total + c];
-            const float gc = o1[0] > 0.0f ? up : 0.0f;
-            gsh[c] = gc;
-            nr[(size_t)i * N::total + N::g + c] = gc;
+            g[0] = o1[0] > 0.0f ? up : 0.0f;
+            nr[(size_t)i * N::total + N::g + c] = g[0];
             if (hfc) hfc[(size_t)i * C + c] = di * fmaxf(o1[0], 0.0f);
         }
-        __syncthreads();   // gsh ready; red free again
-        float g[C], dxb[DIN], dxs[DIN], dab = 0.0f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) g[c] = gsh[c];
+        float dxb[DIN], dxs[DIN], dab = 0.0f;
 #pragma unroll
         for (int d = 0; d < DIN; ++d) { dxb[d] = 0.0f; dxs[d] = 0.0f; }
-        g_products<DIN, C>(prm, 0, g, dxb, dxs, dab);
+        g_products<DIN, 1>(prm, c, g, dxb, dxs, dab);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dab += __shfl_xor_sync(FULLM, dab, o);
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) {
+                dxb[d] += __shfl_xor_sync(FULLM, dxb[d], o);
+                dxs[d] += __shfl_xor_sync(FULLM, dxs[d], o);
+            }
+        }
         const float abar = st.pa * inv;
         float D = dab * abar;
 #pragma unroll
         for (int d = 0; d < DIN; ++d) D = fmaf(dxb[d], st.acc[d] * inv, D);
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             float* q = nr + (size_t)i * N::total;
 #pragma unroll
             for (int d = 0; d < DIN; ++d) q[N::xbar + d] = st.acc[d] * inv;
             q[N::abar] = abar;
             q[N::any] = any ? 1.0f : 0.0f;
-            if (rec) store_rec<DIN>(rec + (size_t)i * Rec<DIN>::total, qt, dxb, qe, lse, dab, D);
+            store_rec<DIN>(rec + (size_t)i * Rec<DIN>::total, qt, dxb, qe, lse, dab, D);
+            if (dxdst) {
+#pragma unroll
+                for (int d = 0; d < DIN; ++d) dxdst[(size_t)i * DIN + d] = dxs[d];
+            }
         }
+    }
+}
+
+template <int DIN>
+__global__ void __launch_bounds__(256) k_gnn_bwd_dst_items(int nitems, const int32_t* __restrict__ items, const int32_t* __restrict__ indices,
+                                                           const double* __restrict__ values, const float* __restrict__ hsrc,
+                                                           const float* __restrict__ rec, float* __restrict__ scratch)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nitems; t += warps) {
+        const int i = __ldg(items + 3 * t), e0 = __ldg(items + 3 * t + 1), e1 = __ldg(items + 3 * t + 2);
+        float qt[DIN], dxb[DIN], qe, lse, dab, D;
+        load_rec<DIN>(rec + (size_t)i * Rec<DIN>::total, qt, dxb, qe, lse, dab, D);
         float dqt[DIN], dqe = 0.0f;
 #pragma unroll
         for (int d = 0; d < DIN; ++d) dqt[d] = 0.0f;
-        for (int e = e0 + (int)threadIdx.x; e < e1; e += 256) {
-            const int j = __ldg(indices + e);
-            const float a = (float)__ldg(values + e);
-            float xj[DIN];
-            load_row<DIN>(hsrc + (size_t)j * DIN, xj);
-            edge_ds<DIN>(a, xj, qt, qe, lse, dxb, dab, D, dqt, dqe);
+        for (int e = e0 + lane; e < e1; e += 64) {
+            const int eb = e + 32;
+            const bool two = eb < e1;
+            const int ja = __ldg(indices + e);
+            const int jb = two ? __ldg(indices + eb) : ja;
+            const float aa = (float)__ldg(values + e);
+            const float ab = two ? (float)__ldg(values + eb) : 0.0f;
+            float xa[DIN], xb[DIN];
+            load_row<DIN>(hsrc + (size_t)ja * DIN, xa);
+            load_row<DIN>(hsrc + (size_t)jb * DIN, xb);
+            edge_ds<DIN>(aa, xa, qt, qe, lse, dxb, dab, D, dqt, dqe);
+            if (two) edge_ds<DIN>(ab, xb, qt, qe, lse, dxb, dab, D, dqt, dqe);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -468,29 +605,60 @@ __global__ void __launch_bounds__(256) k_gnn_bwd_dst_long(int nlong, const int32
             for (int d = 0; d < DIN; ++d) dqt[d] += __shfl_xor_sync(FULLM, dqt[d], o);
         }
         if (lane == 0) {
-            red[warp][0] = dqe;
+            float* o = scratch + (size_t)t * ITEM_FLOATS;
 #pragma unroll
-            for (int d = 0; d < DIN; ++d) red[warp][4 + d] = dqt[d];
+            for (int d = 0; d < DIN; ++d) o[d] = dqt[d];
+            o[DIN] = dqe;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            dqe = 0.0f;
+    }
+}
+
+template <int DIN>
+__global__ void __launch_bounds__(256) k_gnn_bwd_dst_long_final(int nlong, const int32_t* __restrict__ long_rows,
+                                                                const int32_t* __restrict__ first, const float* __restrict__ scratch,
+                                                                const float* __restrict__ prm_g, float* __restrict__ nr,
+                                                                float* __restrict__ dxdst)
+{
+    using O = Off<DIN>;
+    using N = NR<DIN>;
+    __shared__ __align__(16) float prm[O::wv];
+    for (int k = threadIdx.x; k < O::wv; k += blockDim.x) prm[k] = prm_g[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nlong; r += warps) {
+        const int i = __ldg(long_rows + r);
+        const int t1 = __ldg(first + r + 1);
+        float dqt[DIN], dqe = 0.0f;
 #pragma unroll
-            for (int d = 0; d < DIN; ++d) dqt[d] = 0.0f;
-            for (int w = 0; w < 8; ++w) {
-                dqe += red[w][0];
+        for (int d = 0; d < DIN; ++d) dqt[d] = 0.0f;
+        for (int t = __ldg(first + r) + lane; t < t1; t += 32) {
+            const float* o = scratch + (size_t)t * ITEM_FLOATS;
 #pragma unroll
-                for (int d = 0; d < DIN; ++d) dqt[d] += red[w][4 + d];
-            }
+            for (int d = 0; d < DIN; ++d) dqt[d] += o[d];
+            dqe += o[DIN];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dqe += __shfl_xor_sync(FULLM, dqe, o);
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) dqt[d] += __shfl_xor_sync(FULLM, dqt[d], o);
+        }
+        if (lane == 0) {
             float* q = nr + (size_t)i * N::total;
 #pragma unroll
             for (int d = 0; d < DIN; ++d) q[N::dqt + d] = dqt[d];
             q[N::dqe] = dqe;
-            if (dxdst) store_dx_dst<DIN>(prm, dxs, dqt, dqe, dxdst + (size_t)i * DIN);
+            if (dxdst) {
+                float dxs[DIN];
+#pragma unroll
+                for (int d = 0; d < DIN; ++d) dxs[d] = dxdst[(size_t)i * DIN + d];   // Ws' g, parked by the stats kernel
+                store_dx_dst<DIN>(prm, dxs, dqt, dqe, dxdst + (size_t)i * DIN);
+            }
         }
-        __syncthreads();
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // source pass along the transposed structure (rows = source nodes j of the conv, indices = destination nodes i):
@@ -568,110 +736,153 @@ __global__ void __launch_bounds__(256) k_gnn_bwd_src(int ns, const int32_t* __re
     }
 }
 
+// source pass, rows of the transposed structure above its `chunk`: one warp per item, then one warp per row adds the items'
+// parts in a fixed order
 template <int DIN>
-__global__ void __launch_bounds__(256) k_gnn_bwd_src_long(int nlong, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ indptr,
-                                                          const int32_t* __restrict__ indices, const double* __restrict__ values,
-                                                          const float* __restrict__ hsrc, const float* __restrict__ rec,
-                                                          float* __restrict__ dxsrc, int accumulate)
+__global__ void __launch_bounds__(256) k_gnn_bwd_src_items(int nitems, const int32_t* __restrict__ items, const int32_t* __restrict__ indices,
+                                                           const double* __restrict__ values, const float* __restrict__ hsrc,
+                                                           const float* __restrict__ rec, float* __restrict__ scratch)
 {
-    __shared__ float red[8][DIN];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = blockIdx.x; r < nlong; r += gridDim.x) {
-        const int j = __ldg(long_rows + r);
-        const int e0 = __ldg(indptr + j), e1 = __ldg(indptr + j + 1);
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nitems; t += warps) {
+        const int j = __ldg(items + 3 * t), e0 = __ldg(items + 3 * t + 1), e1 = __ldg(items + 3 * t + 2);
         float xj[DIN], dx[DIN];
         load_row<DIN>(hsrc + (size_t)j * DIN, xj);
 #pragma unroll
         for (int d = 0; d < DIN; ++d) dx[d] = 0.0f;
-        for (int e = e0 + (int)threadIdx.x; e < e1; e += 256)
-            edge_src<DIN>((float)__ldg(values + e), rec + (size_t)__ldg(indices + e) * Rec<DIN>::total, xj, dx);
+        for (int e = e0 + lane; e < e1; e += 64) {
+            const int eb = e + 32;
+            const bool two = eb < e1;
+            const int ia = __ldg(indices + e);
+            const int ib = two ? __ldg(indices + eb) : ia;
+            const float aa = (float)__ldg(values + e);
+            const float ab = two ? (float)__ldg(values + eb) : 0.0f;
+            edge_src<DIN>(aa, rec + (size_t)ia * Rec<DIN>::total, xj, dx);
+            if (two) edge_src<DIN>(ab, rec + (size_t)ib * Rec<DIN>::total, xj, dx);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
             for (int d = 0; d < DIN; ++d) dx[d] += __shfl_xor_sync(FULLM, dx[d], o);
         }
         if (lane == 0) {
+            float4* o = reinterpret_cast<float4*>(scratch + (size_t)t * ITEM_FLOATS);
 #pragma unroll
-            for (int d = 0; d < DIN; ++d) red[warp][d] = dx[d];
+            for (int k = 0; k < DIN / 4; ++k) o[k] = make_float4(dx[4 * k], dx[4 * k + 1], dx[4 * k + 2], dx[4 * k + 3]);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) dx[d] = 0.0f;
-            for (int w = 0; w < 8; ++w) {
-#pragma unroll
-                for (int d = 0; d < DIN; ++d) dx[d] += red[w][d];
-            }
-            store_dx_src<DIN>(dxsrc + (size_t)j * DIN, dx, accumulate);
-        }
-        __syncthreads();
     }
 }
+
+template <int DIN>
+__global__ void __launch_bounds__(256) k_gnn_bwd_src_long_final(int nlong, const int32_t* __restrict__ long_rows,
+                                                                const int32_t* __restrict__ first, const float* __restrict__ scratch,
+                                                                float* __restrict__ dxsrc, int accumulate)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nlong; r += warps) {
+        const int j = __ldg(long_rows + r);
+        const int t1 = __ldg(first + r + 1);
+        float dx[DIN];
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) dx[d] = 0.0f;
+        for (int t = __ldg(first + r) + lane; t < t1; t += 32) {
+            const float4* o = reinterpret_cast<const float4*>(scratch + (size_t)t * ITEM_FLOATS);
+#pragma unroll
+            for (int k = 0; k < DIN / 4; ++k) {
+                const float4 v = o[k];
+                dx[4 * k] += v.x; dx[4 * k + 1] += v.y; dx[4 * k + 2] += v.z; dx[4 * k + 3] += v.w;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int d = 0; d < DIN; ++d) dx[d] += __shfl_xor_sync(FULLM, dx[d], o);
+        }
+        if (lane == 0) store_dx_src<DIN>(dxsrc + (size_t)j * DIN, dx, accumulate);
+    }
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // parameter gradients of one conv (layout of the fused block): every entry is sum_i U_i[a] V_i[b] with
 //   U_i = {x_i[DIN], xbar_i[DIN], abar_i, any_i, 1},  V_i = {dqt_i[DIN], dqe_i, g_i[16]}
+// A CTA walks tiles of 32 nodes: the nodes' rows {per-node vectors | x | 1} go to shared memory as float4 loads that are all
+// issued before the previous tile is consumed; a thread owns up to 4 entries of the block and keeps them in registers.
 template <int DIN>
 __global__ void __launch_bounds__(256) k_gnn_param_partial(int nd, const float* __restrict__ hdst, const float* __restrict__ nr,
                                                            float* __restrict__ partial)
 {
     using O = Off<DIN>;
     using N = NR<DIN>;
-    constexpr int UW = 2 * DIN + 3, VW = DIN + 1 + C, TN = 32;
+    constexpr int TN = 32, NT = N::total, NV = NT / 4, W = NT + DIN + 1, WS = W | 1;
+    constexpr int COL_X = NT, COL_ONE = NT + DIN;
     constexpr int EPT = (O::total + 255) / 256;
-    constexpr int U_ABAR = 2 * DIN, U_ANY = 2 * DIN + 1, U_ONE = 2 * DIN + 2, V_DQE = DIN, V_G = DIN + 1;
-    __shared__ float U[TN][UW + 1], V[TN][VW + 1];
+    constexpr int LOADS = (TN * NV + 255) / 256;
+    __shared__ float T[TN][WS];
     int ua[EPT], vb[EPT];
     float acc[EPT];
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
         const int e = threadIdx.x + 256 * k;
         int a = -1, b = 0;
-        if (e < O::vq) { a = e / DIN; b = e % DIN; }
-        else if (e < O::wq) { a = U_ONE; b = e - O::vq; }
-        else if (e < O::sq) { a = e - O::wq; b = V_DQE; }
-        else if (e == O::sq) { a = U_ONE; b = V_DQE; }
+        if (e < O::vq) { a = COL_X + e / DIN; b = N::dqt + e % DIN; }
+        else if (e < O::wq) { a = COL_ONE; b = N::dqt + e - O::vq; }
+        else if (e < O::sq) { a = COL_X + e - O::wq; b = N::dqe; }
+        else if (e == O::sq) { a = COL_ONE; b = N::dqe; }
         else if (e < O::wv) { a = -1; }
-        else if (e < O::bv) { a = DIN + (e - O::wv) / C; b = V_G + (e - O::wv) % C; }
-        else if (e < O::ws) { a = U_ANY; b = V_G + e - O::bv; }
-        else if (e < O::bs) { a = (e - O::ws) / C; b = V_G + (e - O::ws) % C; }
-        else if (e < O::we) { a = U_ONE; b = V_G + e - O::bs; }
-        else if (e < O::total) { a = U_ABAR; b = V_G + e - O::we; }
+        else if (e < O::bv) { a = N::xbar + (e - O::wv) / C; b = N::g + (e - O::wv) % C; }
+        else if (e < O::ws) { a = N::any; b = N::g + e - O::bv; }
+        else if (e < O::bs) { a = COL_X + (e - O::ws) / C; b = N::g + (e - O::ws) % C; }
+        else if (e < O::we) { a = COL_ONE; b = N::g + e - O::bs; }
+        else if (e < O::total) { a = N::abar; b = N::g + e - O::we; }
         ua[k] = a; vb[k] = b; acc[k] = 0.0f;
     }
     const int ntiles = (nd + TN - 1) / TN;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < TN * UW; idx += 256) {
-            const int r = idx / UW, q = idx % UW;
+    float4 buf[LOADS];
+    float4 xb = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int tile) {
+#pragma unroll
+        for (int u = 0; u < LOADS; ++u) {
+            const int idx = threadIdx.x + 256 * u;
+            const int r = idx / NV, q = idx % NV;
             const int node = tile * TN + r;
-            float v = 0.0f;
-            if (node < nd) {
-                const float* p = nr + (size_t)node * N::total;
-                if (q < DIN) v = __ldg(hdst + (size_t)node * DIN + q);
-                else if (q < 2 * DIN) v = p[N::xbar + q - DIN];
-                else if (q == U_ABAR) v = p[N::abar];
-                else if (q == U_ANY) v = p[N::any];
-                else v = 1.0f;
-            }
-            U[r][q] = v;
+            buf[u] = (idx < TN * NV && node < nd) ? __ldg(reinterpret_cast<const float4*>(nr + (size_t)node * NT) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int idx = threadIdx.x; idx < TN * VW; idx += 256) {
-            const int r = idx / VW, q = idx % VW;
+        if constexpr (DIN % 4 == 0) {
+            const int r = threadIdx.x / (DIN / 4), q = threadIdx.x % (DIN / 4);
             const int node = tile * TN + r;
-            float v = 0.0f;
-            if (node < nd) {
-                const float* p = nr + (size_t)node * N::total;
-                v = q < DIN ? p[N::dqt + q] : q == V_DQE ? p[N::dqe] : p[N::g + q - V_G];
-            }
-            V[r][q] = v;
+            xb = (r < TN && node < nd) ? __ldg(reinterpret_cast<const float4*>(hdst + (size_t)node * DIN) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int node = tile * TN + (int)threadIdx.x;
+            xb.x = (threadIdx.x < TN && node < nd) ? __ldg(hdst + (size_t)node * DIN) : 0.0f;
         }
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) fetch(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();   // the previous tile has been consumed
+#pragma unroll
+        for (int u = 0; u < LOADS; ++u) {
+            const int idx = threadIdx.x + 256 * u;
+            const int r = idx / NV, q = idx % NV;
+            if (idx < TN * NV) { T[r][4 * q] = buf[u].x; T[r][4 * q + 1] = buf[u].y; T[r][4 * q + 2] = buf[u].z; T[r][4 * q + 3] = buf[u].w; }
+        }
+        if constexpr (DIN % 4 == 0) {
+            const int r = threadIdx.x / (DIN / 4), q = threadIdx.x % (DIN / 4);
+            if (r < TN) { T[r][COL_X + 4 * q] = xb.x; T[r][COL_X + 4 * q + 1] = xb.y; T[r][COL_X + 4 * q + 2] = xb.z; T[r][COL_X + 4 * q + 3] = xb.w; }
+        } else {
+            if (threadIdx.x < TN) T[threadIdx.x][COL_X] = xb.x;
+        }
+        if (threadIdx.x < TN) T[threadIdx.x][COL_ONE] = (tile * TN + (int)threadIdx.x < nd) ? 1.0f : 0.0f;
         __syncthreads();
-#pragma unroll 4
+        if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);   // in flight while this tile is consumed
+#pragma unroll 8
         for (int r = 0; r < TN; ++r) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k)
-                if (ua[k] >= 0) acc[k] = fmaf(U[r][ua[k]], V[r][vb[k]], acc[k]);
+                if (ua[k] >= 0) acc[k] = fmaf(T[r][ua[k]], T[r][vb[k]], acc[k]);
         }
     }
 #pragma unroll
@@ -681,14 +892,31 @@ __global__ void __launch_bounds__(256) k_gnn_param_partial(int nd, const float* 
     }
 }
 
-// out[e] = sum over the parts, in order
-__global__ void k_gnn_sum_parts(int nparts, int width, const float* __restrict__ partial, float* __restrict__ out)
+// out[e] = sum over the parts: 32 strided sub-sums per entry (four loads in flight each), added in a fixed order
+__global__ void __launch_bounds__(256) k_gnn_sum_parts(int nparts, int width, const float* __restrict__ partial, float* __restrict__ out)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= width) return;
-    float s = 0.0f;
-    for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * width + e];
-    out[e] = s;
+    __shared__ float sm[32][9];
+    const int el = threadIdx.x & 7, pg = threadIdx.x >> 3;
+    const int e = blockIdx.x * 8 + el;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (e < width) {
+        int b = pg;
+        for (; b + 96 < nparts; b += 128) {
+            s0 += partial[(size_t)b * width + e];
+            s1 += partial[(size_t)(b + 32) * width + e];
+            s2 += partial[(size_t)(b + 64) * width + e];
+            s3 += partial[(size_t)(b + 96) * width + e];
+        }
+        for (; b < nparts; b += 32) s0 += partial[(size_t)b * width + e];
+    }
+    sm[pg][el] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (pg == 0 && e < width) {
+        float t = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) t += sm[q][el];
+        out[e] = t;
+    }
 }
 
 // d fc.weight[c] = sum_i hfc[i][c], d fc.bias = sum_i dout[i]: per-CTA partials (17 floats)
@@ -697,12 +925,21 @@ __global__ void __launch_bounds__(256) k_gnn_fc_partial(int n, const float* __re
 {
     __shared__ float sm[16][C + 1];
     const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
-    float a = 0.0f, b = 0.0f;
-    for (int i = blockIdx.x * 16 + r; i < n; i += gridDim.x * 16) {
-        a += hfc[(size_t)i * C + c];
+    const int stride = gridDim.x * 16;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, b = 0.0f;
+    int i = blockIdx.x * 16 + r;
+    for (; i + 3 * stride < n; i += 4 * stride) {   // four independent loads in flight
+        a0 += hfc[(size_t)i * C + c];
+        a1 += hfc[(size_t)(i + stride) * C + c];
+        a2 += hfc[(size_t)(i + 2 * stride) * C + c];
+        a3 += hfc[(size_t)(i + 3 * stride) * C + c];
+        if (c == 0) b += (dout[i] + dout[i + stride]) + (dout[i + 2 * stride] + dout[i + 3 * stride]);
+    }
+    for (; i < n; i += stride) {
+        a0 += hfc[(size_t)i * C + c];
         if (c == 0) b += dout[i];
     }
-    sm[r][c] = a;
+    sm[r][c] = (a0 + a1) + (a2 + a3);
     if (c == 0) sm[r][C] = b;
     __syncthreads();
     if (threadIdx.x <= C) {
@@ -711,6 +948,7 @@ __global__ void __launch_bounds__(256) k_gnn_fc_partial(int n, const float* __re
         partial[(size_t)blockIdx.x * (C + 1) + threadIdx.x] = s;
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
@@ -728,10 +966,16 @@ int launch_bwd_dst(const mllp_gnn_side& g, const float* hdst, const float* hsrc,
                    const float* fcw, float* rec, float* nr, float* dxdst, float* hfc, cudaStream_t s)
 {
     const long long want = (((long long)g.nd * g.group + 31) / 32 + 7) / 8;
-    count_launch(g.nlong > 0 ? 2 : 1);
+    count_launch(g.nlong > 0 ? 7 : 3);
 #define MLLP_BWD_DST(SS)                                                                                                              \
-    k_gnn_bwd_dst<SS, DIN><<<resident_grid(k_gnn_bwd_dst<SS, DIN>, want), 256, 0, s>>>(g.nd, g.indptr, g.indices, g.values, hdst, hsrc, prm, \
-                                                                                       gh, dout, fcw, g.chunk, rec, nr, dxdst, hfc)
+    do {                                                                                                                              \
+        k_gnn_bwd_dst_stats<SS, DIN><<<resident_grid(k_gnn_bwd_dst_stats<SS, DIN>, want), 256, 0, s>>>(                               \
+            g.nd, g.indptr, g.indices, g.values, hdst, hsrc, prm, gh, dout, fcw, g.chunk, rec, nr, hfc);                              \
+        k_gnn_bwd_dst_dense<DIN><<<resident_grid(k_gnn_bwd_dst_dense<DIN>, ((long long)g.nd + 15) / 16), 256, 0, s>>>(                \
+            g.nd, g.indptr, prm, g.chunk, nr, rec, dxdst);                                                                            \
+        k_gnn_bwd_dst_sweep<SS, DIN><<<resident_grid(k_gnn_bwd_dst_sweep<SS, DIN>, want), 256, 0, s>>>(                               \
+            g.nd, g.indptr, g.indices, g.values, hsrc, prm, g.chunk, rec, nr, dxdst);                                                 \
+    } while (0)
     switch (g.group) {
         case 1: MLLP_BWD_DST(1); break;
         case 2: MLLP_BWD_DST(2); break;
@@ -741,9 +985,13 @@ int launch_bwd_dst(const mllp_gnn_side& g, const float* hdst, const float* hsrc,
         default: MLLP_BWD_DST(32); break;
     }
 #undef MLLP_BWD_DST
-    if (g.nlong > 0)
-        k_gnn_bwd_dst_long<DIN><<<g.nlong < 148 * 4 ? g.nlong : 148 * 4, 256, 0, s>>>(g.nlong, g.long_rows, g.indptr, g.indices, g.values, hdst,
-                                                                                      hsrc, prm, gh, dout, fcw, rec, nr, dxdst, hfc);
+    if (g.nlong > 0) {   // cut rows: the forward's items
+        k_gnn_conv_items<DIN><<<grid_for_warps(g.nitems), 256, 0, s>>>(g.nitems, g.items, g.indices, g.values, hdst, hsrc, prm, g.scratch);
+        k_gnn_bwd_dst_long_stats<DIN><<<grid_for_warps(g.nlong), 256, 0, s>>>(g.nlong, g.long_rows, g.long_first, g.scratch, hdst, prm, gh, dout,
+                                                                            fcw, rec, nr, dxdst, hfc);
+        k_gnn_bwd_dst_items<DIN><<<grid_for_warps(g.nitems), 256, 0, s>>>(g.nitems, g.items, g.indices, g.values, hsrc, rec, g.scratch);
+        k_gnn_bwd_dst_long_final<DIN><<<grid_for_warps(g.nlong), 256, 0, s>>>(g.nlong, g.long_rows, g.long_first, g.scratch, prm, nr, dxdst);
+    }
     return cuda_status("mllp_gnn_backward: destination pass");
 }
 
@@ -751,7 +999,7 @@ int launch_bwd_dst(const mllp_gnn_side& g, const float* hdst, const float* hsrc,
 int launch_bwd_src(const mllp_gnn_side& t, const float* hsrc, const float* rec, float* dxsrc, int accumulate, cudaStream_t s)
 {
     const long long want = (((long long)t.nd * t.group + 31) / 32 + 7) / 8;
-    count_launch(t.nlong > 0 ? 2 : 1);
+    count_launch(t.nlong > 0 ? 3 : 1);
 #define MLLP_BWD_SRC(SS)                                                                                                              \
     k_gnn_bwd_src<SS, C><<<resident_grid(k_gnn_bwd_src<SS, C>, want), 256, 0, s>>>(t.nd, t.indptr, t.indices, t.values, hsrc, rec, t.chunk, \
                                                                                    dxsrc, accumulate)
@@ -764,9 +1012,10 @@ int launch_bwd_src(const mllp_gnn_side& t, const float* hsrc, const float* rec, 
         default: MLLP_BWD_SRC(32); break;
     }
 #undef MLLP_BWD_SRC
-    if (t.nlong > 0)
-        k_gnn_bwd_src_long<C><<<t.nlong < 148 * 4 ? t.nlong : 148 * 4, 256, 0, s>>>(t.nlong, t.long_rows, t.indptr, t.indices, t.values, hsrc, rec,
-                                                                                    dxsrc, accumulate);
+    if (t.nlong > 0) {
+        k_gnn_bwd_src_items<C><<<grid_for_warps(t.nitems), 256, 0, s>>>(t.nitems, t.items, t.indices, t.values, hsrc, rec, t.scratch);
+        k_gnn_bwd_src_long_final<C><<<grid_for_warps(t.nlong), 256, 0, s>>>(t.nlong, t.long_rows, t.long_first, t.scratch, dxsrc, accumulate);
+    }
     return cuda_status("mllp_gnn_backward: source pass");
 }
 
@@ -777,7 +1026,7 @@ int launch_param_grads(int nd, const float* hdst, const float* nr, float* partia
     const int grid = ntiles < 1 ? 1 : ntiles > PGRID ? PGRID : ntiles;
     count_launch(2);
     k_gnn_param_partial<DIN><<<grid, 256, 0, s>>>(nd, hdst, nr, partial);
-    k_gnn_sum_parts<<<(Off<DIN>::total + 255) / 256, 256, 0, s>>>(grid, Off<DIN>::total, partial, dpacked);
+    k_gnn_sum_parts<<<(Off<DIN>::total + 7) / 8, 256, 0, s>>>(grid, Off<DIN>::total, partial, dpacked);
     return cuda_status("mllp_gnn_backward: parameter gradients");
 }
 
@@ -855,7 +1104,7 @@ int mllp_gnn_backward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, 
         const int grid = (int)((n + 15) / 16 > PGRID ? PGRID : (n + 15) / 16);
         count_launch(2);
         k_gnn_fc_partial<<<grid, 256, 0, s>>>((int)n, w.hfc, d_dout, w.partial);
-        k_gnn_sum_parts<<<1, 32, 0, s>>>(grid, C + 1, w.partial, dfc);
+        k_gnn_sum_parts<<<(C + 1 + 7) / 8, 256, 0, s>>>(grid, C + 1, w.partial, dfc);
         rc = cuda_status("mllp_gnn_backward: fc");
     }
     if (rc == 0) rc = launch_bwd_src(*to_con, h2b, w.rec1, w.d2b, 0, s);
@@ -867,9 +1116,9 @@ int mllp_gnn_backward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, 
     if (rc == 0) rc = launch_bwd_src(*to_con, h2a, w.rec1, w.d2a, 1, s);
     if (rc == 0) rc = launch_bwd_src(*to_var, h1a, w.rec2, w.d1a, 1, s);
     // layer 1: the inputs need no gradient
-    if (rc == 0) rc = launch_bwd_dst<1>(*to_var, d_x1, d_x2, P[0], w.d1a, nullptr, nullptr, nullptr, w.nr, nullptr, nullptr, s);
+    if (rc == 0) rc = launch_bwd_dst<1>(*to_var, d_x1, d_x2, P[0], w.d1a, nullptr, nullptr, w.rec1, w.nr, nullptr, nullptr, s);
     if (rc == 0) rc = launch_param_grads<1>((int)n, d_x1, w.nr, w.partial, dP[0], s);
-    if (rc == 0) rc = launch_bwd_dst<1>(*to_con, d_x2, d_x1, P[1], w.d2a, nullptr, nullptr, nullptr, w.nr, nullptr, nullptr, s);
+    if (rc == 0) rc = launch_bwd_dst<1>(*to_con, d_x2, d_x1, P[1], w.d2a, nullptr, nullptr, w.rec2, w.nr, nullptr, nullptr, s);
     if (rc == 0) rc = launch_param_grads<1>((int)m, d_x2, w.nr, w.partial, dP[1], s);
     if (rc != 0) return rc;
     count_launch(1);

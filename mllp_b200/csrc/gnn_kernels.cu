@@ -104,40 +104,6 @@ __global__ void __launch_bounds__(256, 3) k_gnn_conv_rows(int nd, const int32_t*
     }
 }
 
-// long rows: item t = (row, first edge, end edge); one warp per item, merged partial state -> scratch[t][20]
-template <int DIN>
-__global__ void __launch_bounds__(256) k_gnn_conv_items(int nitems, const int32_t* __restrict__ items, const int32_t* __restrict__ indices,
-                                                        const double* __restrict__ values, const float* __restrict__ hdst,
-                                                        const float* __restrict__ hsrc, const float* __restrict__ prm_g,
-                                                        float* __restrict__ scratch)
-{
-    using O = Off<DIN>;
-    __shared__ __align__(16) float prm[O::wv];   // the prologue's part of the block
-    for (int k = threadIdx.x; k < O::wv; k += blockDim.x) prm[k] = prm_g[k];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nitems; t += warps) {
-        const int i = __ldg(items + 3 * t), e0 = __ldg(items + 3 * t + 1), e1 = __ldg(items + 3 * t + 2);
-        float x[DIN], qt[DIN], qe;
-        load_row<DIN>(hdst + (size_t)i * DIN, x);
-        dst_prologue<32, DIN>(prm, x, lane, qt, qe);
-        State<DIN> st;
-        state_init<DIN>(st);
-        edge_loop<32, DIN>(indices, values, hsrc, e0, e1, lane, qt, qe, st);
-        merge_group<32, DIN>(st);
-        if (lane == 0) {
-            float4* o = reinterpret_cast<float4*>(scratch + (size_t)t * ITEM_FLOATS);
-            o[0] = make_float4(st.m, st.l, st.pa, 0.0f);
-            float a[C];
-#pragma unroll
-            for (int d = 0; d < C; ++d) a[d] = d < DIN ? st.acc[d < DIN ? d : 0] : 0.0f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[1 + k] = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
-        }
-    }
-}
-
 // long rows: merge the partial states of row r's items [first[r], first[r+1]) -- lane k folds items k, k + 32, ... in
 // order, then the 32 lanes' states are merged by the butterfly (a fixed order: osa-60's longest row has 340 items, one
 // after the other they were a 140 us chain of dependent loads) -- then the epilogue (lane c < 16 finishes channel c)
@@ -154,31 +120,7 @@ __global__ void __launch_bounds__(256) k_gnn_conv_merge(int nlong, const int32_t
         const int i = __ldg(long_rows + r);
         const int t1 = __ldg(first + r + 1);
         State<DIN> st;
-        state_init<DIN>(st);
-#pragma unroll 2
-        for (int t = __ldg(first + r) + lane; t < t1; t += 32) {
-            const float4* o = reinterpret_cast<const float4*>(scratch + (size_t)t * ITEM_FLOATS);
-            const float4 h = o[0];   // m, l, pa
-            float a2[DIN];
-            if constexpr (DIN % 4 == 0) {
-#pragma unroll
-                for (int k = 0; k < DIN / 4; ++k) {
-                    const float4 q = o[1 + k];
-                    a2[4 * k] = q.x; a2[4 * k + 1] = q.y; a2[4 * k + 2] = q.z; a2[4 * k + 3] = q.w;
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < DIN; ++d) a2[d] = scratch[(size_t)t * ITEM_FLOATS + 4 + d];
-            }
-            const float mn = fmaxf(st.m, h.x);
-            const float s1 = st.m == -INFINITY ? 0.0f : __expf(st.m - mn), s2 = h.x == -INFINITY ? 0.0f : __expf(h.x - mn);
-            st.l = st.l * s1 + h.y * s2;
-            st.pa = st.pa * s1 + h.z * s2;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) st.acc[d] = st.acc[d] * s1 + a2[d] * s2;
-            st.m = mn;
-        }
-        merge_group<32, DIN>(st);
+        merge_items<DIN>(scratch, __ldg(first + r), t1, lane, st);
         const bool any = st.l > 0.0f;
         const float inv = any ? 1.0f / st.l : 0.0f;
         float x[DIN], o1[1];
