@@ -386,6 +386,15 @@ int64_t mllp_gnn_backward_workspace_floats(int32_t n, int32_t m);
 int mllp_gnn_backward(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
                       const float *d_flat, const float *d_packed, const float *d_work, float *d_bwork,
                       const float *d_dout, float *d_dflat, void *stream);
+/* The training step's two halves as replayable plans (CUDA graphs, run / destroyed with mllp_gnn_plan_run / _destroy; the
+ * small Netlib graphs are launch-bound: the backward is 32 - 44 launches): mllp_gnn_train_plan_create = pack + forward into
+ * d_out, mllp_gnn_backward_plan_create = pack + backward from d_dout into d_dflat.  The plans keep the POINTERS they were
+ * created with; the contents (parameters, d_dout) may change between runs. */
+int mllp_gnn_train_plan_create(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1, const float *d_x2,
+                               const float *d_flat, float *d_packed, float *d_work, float *d_out, mllp_gnn_plan_t *out);
+int mllp_gnn_backward_plan_create(const mllp_gnn_side *to_var, const mllp_gnn_side *to_con, const float *d_x1,
+                                  const float *d_x2, const float *d_flat, float *d_packed, const float *d_work,
+                                  float *d_bwork, const float *d_dout, float *d_dflat, mllp_gnn_plan_t *out);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,8 @@ SIGNATURES = {
     "mllp_gnn_pack_params": (ctypes.c_int, [_vp, _vp, _vp]),
     "mllp_gnn_backward_workspace_floats": (ctypes.c_int64, [_i32, _i32]),
     "mllp_gnn_backward": (ctypes.c_int, [_vp] * 11),
+    "mllp_gnn_train_plan_create": (ctypes.c_int, [_vp] * 8 + [ctypes.POINTER(_vp)]),
+    "mllp_gnn_backward_plan_create": (ctypes.c_int, [_vp] * 10 + [ctypes.POINTER(_vp)]),
 }
 
 

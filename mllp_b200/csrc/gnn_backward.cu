@@ -23,6 +23,9 @@
 //     formed on the device from the flat parameter vector (k_gnn_pack) so an optimiser step needs no host round trip.
 //
 // fp32 like the forward.  L2/HBM-bound gathers (hidden = 16): no tensor cores.
+#include <mutex>
+#include <unordered_map>
+
 #include "gnn_common.cuh"
 
 namespace mllp {
@@ -952,11 +955,23 @@ __global__ void __launch_bounds__(256) k_gnn_fc_partial(int n, const float* __re
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
+// one wave of resident CTAs of `kernel` (256 threads, no dynamic shared memory); the occupancy query is cached per kernel
 template <class K>
 int resident_grid(K kernel, long long want)
 {
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find((const void*)kernel);
+        if (it != cache.end()) per_sm = it->second;
+    }
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        std::lock_guard<std::mutex> lock(mu);
+        cache[(const void*)kernel] = per_sm;
+    }
     const long long cap = 148LL * per_sm;
     return (int)(want < 1 ? 1 : want > cap ? cap : want);
 }
@@ -1070,15 +1085,16 @@ int64_t mllp_gnn_backward_workspace_floats(int32_t n, int32_t m)
     return (int64_t)carve(w, nullptr, (size_t)n, (size_t)m) + 16;
 }
 
-int mllp_gnn_backward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
-                      const float* d_flat, const float* d_packed, const float* d_work, float* d_bwork, const float* d_dout,
-                      float* d_dflat, void* stream)
+}  // extern "C"
+
+static int backward_impl(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                         const float* d_flat, const float* d_packed, const float* d_work, float* d_bwork, const float* d_dout,
+                         float* d_dflat, cudaStream_t s, const char* who)
 {
     if (!side_ok(to_var) || !side_ok(to_con) || !d_x1 || !d_x2 || !d_flat || !d_packed || !d_work || !d_bwork || !d_dout || !d_dflat)
-        return gfail(MLLP_E_INVALID, "mllp_gnn_backward: bad argument");
+        return gfail(MLLP_E_INVALID, std::string(who) + ": bad argument");
     if (to_var->ns != to_con->nd || to_con->ns != to_var->nd)
-        return gfail(MLLP_E_INVALID, "mllp_gnn_backward: the two sides do not describe one graph");
-    cudaStream_t s = (cudaStream_t)stream;
+        return gfail(MLLP_E_INVALID, std::string(who) + ": the two sides do not describe one graph");
     const size_t n = (size_t)to_var->nd, m = (size_t)to_con->nd;
     BwdWork w;
     carve(w, d_bwork, n, m);
@@ -1124,6 +1140,31 @@ int mllp_gnn_backward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, 
     count_launch(1);
     k_gnn_unpack_grads<<<7, 256, 0, s>>>(d_flat, w.dpacked, d_dflat);
     return cuda_status("mllp_gnn_backward: unpack");
+}
+
+
+extern "C" {
+
+int mllp_gnn_backward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                      const float* d_flat, const float* d_packed, const float* d_work, float* d_bwork, const float* d_dout,
+                      float* d_dflat, void* stream)
+{
+    return backward_impl(to_var, to_con, d_x1, d_x2, d_flat, d_packed, d_work, d_bwork, d_dout, d_dflat, (cudaStream_t)stream,
+                         "mllp_gnn_backward");
+}
+
+int mllp_gnn_backward_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                                  const float* d_flat, float* d_packed, const float* d_work, float* d_bwork, const float* d_dout,
+                                  float* d_dflat, mllp_gnn_plan_t* out)
+{
+    if (!out) return gfail(MLLP_E_INVALID, "mllp_gnn_backward_plan_create: null output");
+    *out = nullptr;
+    return capture_plan("mllp_gnn_backward_plan_create", out, [&](cudaStream_t s, cudaStream_t, cudaEvent_t*) {
+        int rc = mllp_gnn_pack_params(d_flat, d_packed, s);
+        if (rc == 0) rc = backward_impl(to_var, to_con, d_x1, d_x2, d_flat, d_packed, d_work, d_bwork, d_dout, d_dflat, s,
+                                        "mllp_gnn_backward_plan_create");
+        return rc;
+    });
 }
 
 }  // extern "C"

@@ -315,3 +315,49 @@ bool side_ok(const mllp_gnn_side* g)
 
 }  // namespace
 }  // namespace mllp
+
+// A captured launch sequence (forward: mllp_gnn_plan_create, backward: mllp_gnn_backward_plan_create)
+struct mllp_gnn_plan {
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+};
+
+namespace mllp {
+namespace {
+// Capture what `body(stream, second stream, events[4])` launches into a CUDA graph and instantiate it.
+template <class F>
+int capture_plan(const char* who, mllp_gnn_plan_t* out, F body)
+{
+    cudaStream_t s = nullptr, s2 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph = nullptr;
+    mllp_gnn_plan* plan = new (std::nothrow) mllp_gnn_plan();
+    if (!plan) return gfail(MLLP_E_NOMEM, std::string(who) + ": out of host memory");
+    auto cleanup = [&]() {
+        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+        if (graph) cudaGraphDestroy(graph);
+        if (s2) cudaStreamDestroy(s2);
+        if (s) cudaStreamDestroy(s);
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cleanup(); delete plan; return gfail((int)e, std::string(who) + ": " + cudaGetErrorString(e)); }
+    int rc = body(s, s2, ev);
+    e = cudaStreamEndCapture(s, &graph);
+    if (rc == 0 && e != cudaSuccess) rc = gfail((int)e, std::string(who) + ": capture: " + cudaGetErrorString(e));
+    if (rc == 0) {
+        size_t nodes = 0;
+        cudaGraphGetNodes(graph, nullptr, &nodes);
+        plan->launches = (int)nodes;
+        e = cudaGraphInstantiate(&plan->exec, graph, 0);
+        if (e != cudaSuccess) rc = gfail((int)e, std::string(who) + ": instantiate: " + cudaGetErrorString(e));
+    }
+    cleanup();
+    if (rc != 0) { cudaGetLastError(); delete plan; return rc; }
+    *out = plan;
+    return 0;
+}
+}  // namespace
+}  // namespace mllp

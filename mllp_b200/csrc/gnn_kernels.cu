@@ -254,11 +254,6 @@ int mllp_gnn_forward(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, c
     return forward_impl(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, (cudaStream_t)stream, nullptr, nullptr);
 }
 
-struct mllp_gnn_plan {
-    cudaGraphExec_t exec = nullptr;
-    int launches = 0;
-};
-
 int mllp_gnn_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
                          const float* d_params, float* d_work, float* d_out, mllp_gnn_plan_t* out)
 {
@@ -266,36 +261,24 @@ int mllp_gnn_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_side* to_co
     *out = nullptr;
     int rc = forward_args_ok(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, "mllp_gnn_plan_create");
     if (rc != 0) return rc;
-    cudaStream_t s = nullptr, s2 = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaGraph_t graph = nullptr;
-    mllp_gnn_plan* plan = new (std::nothrow) mllp_gnn_plan();
-    if (!plan) return gfail(MLLP_E_NOMEM, "mllp_gnn_plan_create: out of host memory");
-    auto cleanup = [&]() {
-        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
-        if (graph) cudaGraphDestroy(graph);
-        if (s2) cudaStreamDestroy(s2);
-        if (s) cudaStreamDestroy(s);
-    };
-    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
-    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { cleanup(); delete plan; return gfail((int)e, std::string("mllp_gnn_plan_create: ") + cudaGetErrorString(e)); }
-    rc = forward_impl(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, s, s2, ev);
-    e = cudaStreamEndCapture(s, &graph);
-    if (rc == 0 && e != cudaSuccess) rc = gfail((int)e, std::string("mllp_gnn_plan_create: capture: ") + cudaGetErrorString(e));
-    if (rc == 0) {
-        size_t nodes = 0;
-        cudaGraphGetNodes(graph, nullptr, &nodes);
-        plan->launches = (int)nodes;
-        e = cudaGraphInstantiate(&plan->exec, graph, 0);
-        if (e != cudaSuccess) rc = gfail((int)e, std::string("mllp_gnn_plan_create: instantiate: ") + cudaGetErrorString(e));
-    }
-    cleanup();
-    if (rc != 0) { cudaGetLastError(); delete plan; return rc; }
-    *out = plan;
-    return 0;
+    return capture_plan("mllp_gnn_plan_create", out, [&](cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev) {
+        return forward_impl(to_var, to_con, d_x1, d_x2, d_params, d_work, d_out, s, s2, ev);
+    });
+}
+
+int mllp_gnn_train_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
+                               const float* d_flat, float* d_packed, float* d_work, float* d_out, mllp_gnn_plan_t* out)
+{
+    if (!out) return gfail(MLLP_E_INVALID, "mllp_gnn_train_plan_create: null output");
+    *out = nullptr;
+    int rc = forward_args_ok(to_var, to_con, d_x1, d_x2, d_packed, d_work, d_out, "mllp_gnn_train_plan_create");
+    if (rc != 0) return rc;
+    if (!d_flat) return gfail(MLLP_E_INVALID, "mllp_gnn_train_plan_create: null parameters");
+    return capture_plan("mllp_gnn_train_plan_create", out, [&](cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev) {
+        int r = mllp_gnn_pack_params(d_flat, d_packed, s);
+        if (r == 0) r = forward_impl(to_var, to_con, d_x1, d_x2, d_packed, d_work, d_out, s, s2, ev);
+        return r;
+    });
 }
 
 int mllp_gnn_plan_run(mllp_gnn_plan_t plan, void* stream)

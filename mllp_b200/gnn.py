@@ -114,8 +114,8 @@ class BipartiteGraph:
 
     def close(self):
         """release the captured forward plans (the device arrays go with the object)"""
-        for plan, _, _ in self._plans.values():
-            _cabi.lib().mllp_gnn_plan_destroy(plan)
+        for entry in self._plans.values():   # entry[0] is the mllp_gnn_plan_t, the rest keeps its buffers alive
+            _cabi.lib().mllp_gnn_plan_destroy(entry[0])
         self._plans = {}
 
     def __del__(self):

@@ -40,17 +40,52 @@ def flat_layout():
     return out, off + 1
 
 
+def _plans(g, model, flat_c):
+    """the (graph, parameter storage) pair's captured forward / backward (mllp_gnn_train_plan_create,
+    mllp_gnn_backward_plan_create) and the fixed buffers they read and write; kept on the graph, released by g.close()"""
+    key = ("train", flat_c.data_ptr(), model._packed.data_ptr())
+    entry = g._plans.get(key)
+    if entry is None:
+        L = _cabi.lib()
+        dev = flat_c.device
+        out = torch.empty(g.n, dtype=torch.float32, device=dev)
+        dout = torch.zeros(g.n, dtype=torch.float32, device=dev)
+        dflat = torch.empty_like(flat_c)
+        bwork = torch.empty(int(L.mllp_gnn_backward_workspace_floats(g.n, g.m)), dtype=torch.float32, device=dev)
+        fwd, bwd = ctypes.c_void_p(), ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(L.mllp_gnn_train_plan_create(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
+                                                     g.x2.data_ptr(), flat_c.data_ptr(), model._packed.data_ptr(),
+                                                     g.work.data_ptr(), out.data_ptr(), ctypes.byref(fwd)),
+                        "mllp_gnn_train_plan_create")
+            _cabi.check(L.mllp_gnn_backward_plan_create(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
+                                                        g.x2.data_ptr(), flat_c.data_ptr(), model._packed.data_ptr(),
+                                                        g.work.data_ptr(), bwork.data_ptr(), dout.data_ptr(), dflat.data_ptr(),
+                                                        ctypes.byref(bwd)), "mllp_gnn_backward_plan_create")
+        # the plans hold these pointers: the tensors stay alive with the entry
+        entry = g._plans[key] = (fwd, bwd, out, dout, dflat, bwork, flat_c, model._packed)
+        g._plans[key + ("bwd",)] = (bwd,)   # so that g.close() destroys it too
+    return entry
+
+
 class _Forward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flat, model, g):
         L = _cabi.lib()
         dev = flat.device
         stream = _torch_stream(dev)
-        flat_c = flat.detach().contiguous()
-        _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
-        out = torch.empty(g.n, dtype=torch.float32, device=dev)
-        _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
-                                       model._packed.data_ptr(), g.work.data_ptr(), out.data_ptr(), stream), "mllp_gnn_forward")
+        flat_c = flat.detach()
+        if not flat_c.is_contiguous():
+            raise ValueError("the flat parameter vector must be contiguous")
+        if model.use_plans:
+            entry = _plans(g, model, flat_c)
+            _cabi.check(L.mllp_gnn_plan_run(entry[0], stream), "mllp_gnn_plan_run")
+            out = entry[2].clone()
+        else:
+            _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
+            out = torch.empty(g.n, dtype=torch.float32, device=dev)
+            _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
+                                           model._packed.data_ptr(), g.work.data_ptr(), out.data_ptr(), stream), "mllp_gnn_forward")
         g._forward_serial = getattr(g, "_forward_serial", 0) + 1
         ctx.g, ctx.model, ctx.serial = g, model, g._forward_serial
         ctx.save_for_backward(flat_c)
@@ -65,26 +100,35 @@ class _Forward(torch.autograd.Function):
                                "forward live in the graph's workspace and are gone (call backward() first)")
         L = _cabi.lib()
         dev = flat_c.device
+        stream = _torch_stream(dev)
+        dout = dout.to(torch.float32).contiguous()
+        if model.use_plans:
+            entry = _plans(g, model, flat_c)
+            entry[3].copy_(dout)
+            _cabi.check(L.mllp_gnn_plan_run(entry[1], stream), "mllp_gnn_plan_run")
+            return entry[4].clone(), None, None
         # the fused blocks of THIS forward's parameters (the model may have packed others since)
-        _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), _torch_stream(dev)), "mllp_gnn_pack_params")
+        _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
         need = int(L.mllp_gnn_backward_workspace_floats(g.n, g.m))
         bw = getattr(g, "_bwork", None)
         if bw is None or bw.numel() < need:
             bw = g._bwork = torch.empty(need, dtype=torch.float32, device=dev)
         dflat = torch.empty_like(flat_c)
-        dout = dout.to(torch.float32).contiguous()
         _cabi.check(L.mllp_gnn_backward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
                                         flat_c.data_ptr(), model._packed.data_ptr(), g.work.data_ptr(), bw.data_ptr(),
-                                        dout.data_ptr(), dflat.data_ptr(), _torch_stream(dev)), "mllp_gnn_backward")
+                                        dout.data_ptr(), dflat.data_ptr(), stream), "mllp_gnn_backward")
         return dflat, None, None
 
 
 class TrainableGNNModel(torch.nn.Module):
     """``GNNModel`` with a backward pass.  ``TrainableGNNModel().to(device)``, ``model(graph)`` with the ``BipartiteData``
-    of ``build_graph_from_weights_sets`` (or a ``BipartiteGraph``), ``model.parameters()`` for the optimiser."""
+    of ``build_graph_from_weights_sets`` (or a ``BipartiteGraph``), ``model.parameters()`` for the optimiser.  With
+    ``use_plans`` (default) the two halves of a step are captured once per (graph, model) into CUDA graphs: the small Netlib
+    graphs are launch-bound (the backward is 32 - 44 kernels)."""
 
-    def __init__(self, state_dict=None, device=0, seed=0):
+    def __init__(self, state_dict=None, device=0, seed=0, use_plans=True):
         super().__init__()
+        self.use_plans = bool(use_plans)   # forward / backward replayed as CUDA graphs (one launch each) or launched kernel by kernel
         layout, total = flat_layout()
         if total != int(_cabi.lib().mllp_gnn_flat_param_floats()):
             raise RuntimeError("flat parameter layout of gnn_train.py and the library disagree")

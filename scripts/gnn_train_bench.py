@@ -74,9 +74,14 @@ def main(names, out=None):
     if out:
         with open(out, "w") as f:
             f.write("# r02 -- device GNNModel training step (forward + BCEWithLogitsLoss + mllp_gnn_backward + Adam), one B200\n\n"
-                    "`python scripts/gnn_train_bench.py`: CUDA events, median of 10, warm L2.  The forward here is the plain launch sequence\n"
-                    "(pack kernel + 5-11 conv launches, no CUDA-graph plan); the backward is 20-28 launches (destination / source passes,\n"
-                    "parameter-gradient partial sums, unpack).  The loss and Adam are torch ops on the (n,) logits / the 4721 parameters.\n\n"
+                    "`python scripts/gnn_train_bench.py`: CUDA events, median of 10, warm L2.  Forward and backward are each ONE CUDA-graph\n"
+                    "launch (`mllp_gnn_train_plan_create` = pack + 5-11 conv kernels, `mllp_gnn_backward_plan_create` = pack + 32-44 kernels:\n"
+                    "row walk / dense maps / second sweep per conv, source passes over the transposed structure, parameter-gradient partial\n"
+                    "sums, unpack) plus a copy in and a clone out.  The loss and Adam are torch ops on the (n,) logits / the 4721 parameters --\n"
+                    "on the small graphs they are most of the step.  History of the backward on ken-18 / osa-60 / pds-20 (us): first version\n"
+                    "1096 / 3647 / 738 (one CTA per cut row, one 255-register kernel per destination pass); cut rows through the forward's\n"
+                    "items 1153 / 1329 / 766; destination pass split into row walk (80 registers) + dense maps (16 lanes per node) + sweep,\n"
+                    "float4-prefetched parameter-gradient tiles, parallel partial sums 836 / 1010 / 593; as CUDA graphs: the table.\n\n"
                     "| instance | m | n | nnz | lanes per row (A' / A) | forward us | backward us | whole training step us | launches fwd / bwd |\n"
                     "|---|---:|---:|---:|---|---:|---:|---:|---|\n")
             for r in rows:

@@ -59,12 +59,12 @@ def test_flat_layout_matches_the_library():
     assert offs == sorted(offs) and offs[0] == 0
 
 
-def _device_grads(st, A, b, c, dout=None, target=None, groups=None):
+def _device_grads(st, A, b, c, dout=None, target=None, groups=None, use_plans=True):
     import torch
     import mllp_b200.gnn as GN
     from mllp_b200.gnn_train import TrainableGNNModel
     g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c, groups=groups)
-    model = TrainableGNNModel(st)
+    model = TrainableGNNModel(st, use_plans=use_plans)
     out = model(g)
     if dout is not None:
         loss = (out * torch.as_tensor(np.asarray(dout, dtype=np.float32), device=out.device)).sum()
@@ -116,12 +116,24 @@ def test_gpu_backward_edge_cases_determinism_and_errors():
     _, _, got, model, g = _device_grads(st, A, b, c, dout=dout)
     assert max(grad_errors(got, ref).values()) < GTOL
     assert not np.any(got["gconv3_s2w.lin_value.weight"]) and not np.any(got["gconv1_w2s.lin_key.bias"])
-    # no atomics: the same backward twice gives the same bits
+    # no atomics: the same backward twice gives the same bits, replayed as a CUDA graph or launched kernel by kernel
     A2, b2, c2 = D.load_csr("25fv47")
     d2 = np.random.default_rng(0).standard_normal(A2.shape[1])
     _, _, g1, _, _ = _device_grads(st, A2, b2, c2, dout=d2)
     _, _, g2, _, _ = _device_grads(st, A2, b2, c2, dout=d2)
-    assert all(np.array_equal(g1[k], g2[k]) for k in g1)
+    _, _, g3, _, _ = _device_grads(st, A2, b2, c2, dout=d2, use_plans=False)
+    assert all(np.array_equal(g1[k], g2[k]) and np.array_equal(g1[k], g3[k]) for k in g1)
+    # a plan is replayed with new parameters and a new upstream gradient (the pointers stay, the contents change)
+    import mllp_b200.gnn as GN
+    from mllp_b200.gnn_train import TrainableGNNModel
+    gg = GN.BipartiteGraph(np.split(A2.indices, A2.indptr)[1:-1], A2.data, b2, c2)
+    mm = TrainableGNNModel(G.init_state(8))
+    mm(gg).backward(torch.as_tensor(d2.astype(np.float32), device="cuda"))     # captures both plans with other contents
+    mm.flat.grad = None
+    mm.load_state_dict(st)
+    mm(gg).backward(torch.as_tensor(d2.astype(np.float32), device="cuda"))
+    assert all(np.array_equal(mm.named_gradients()[k].cpu().numpy(), g1[k]) for k in g1)
+    gg.close()
     # a second forward on the same graph overwrites the activations: backward of the first one must refuse
     o1 = model(g)
     model(g)
