@@ -404,7 +404,98 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
         "scaling": "strong (4096 instances in total over %d GPU(s))" % world,
         "perturbation": "seeds 1234+i, b (1 + 0.1 U(0,1)) on slack rows; costs moved AWAY from zero-cost recession directions (c_j > 0: x(1 + 0.1u), c_j < 0: x(1 - 0.1u)): SURVEY 8d's c (1 + 0.1 U(-1,1)) makes ~90 % of the 25fv47 instances unbounded (HiGHS), see config5_batches",
         "call": "mllp_b200.distributed.solve_batch_data_parallel(shared matrix, rhs_batch, coefs_batch, scale=True) with numpy batches; includes format build + device preconditioning"}
+    if world == 1:
+        out["solve_mode_large"] = measure_solve_large(M, torch, dev, local)
+        out["gnn_training_step"] = measure_gnn_training(torch, dev)
     return out
+
+
+def measure_solve_large(M, torch, dev, local, names=(("osa-60", 3.224480553), ("pds-20", 21985.28701))):
+    """Solve mode (k_solve_persistent: reflected restarted Halpern PDHG, KKT test of the ORIGINAL LP on the device) on the
+    large config-4 instances that are bounded in the dataset form: time per iteration of the solve kernel and the objective
+    against HiGHS on the same arrays."""
+    out = {}
+    for name, target in names:
+        A, b, c = M.load_csr(name)
+        m, n = A.shape
+        lp = M.DeviceLP(A, A.data, m, n, device=local, precondition=True)
+        eta = 0.99 / lp.sigma_max_robust()
+        bt, ct = torch.tensor(b, device=dev), torch.tensor(c, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        _, xt, yt, inf = M.solve_linear_program(A, A.data, bt, ct, tol=1e-6, max_iters=400000, check_every=64, handle=lp, eta=eta)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sec = e0.elapsed_time(e1) * 1e-3
+        from mllp_b200.linear_program_methods import _info_dict
+        info = _info_dict(inf["scalars"].cpu().numpy())
+        obj = float(inf["scalars"][0])
+        geo = lp.geometry()
+        out[name] = {"iterations": int(info["iters"]), "converged": bool(info["converged"]), "rel_kkt_original": float(info["rel_kkt"]),
+                     "objective": float(obj), "highs_on_the_same_arrays": target, "rel_error": abs(float(obj) - target) / (1 + abs(target)),
+                     "seconds_on_device": sec, "us_per_iteration": 1e6 * sec / max(int(info["iters"]), 1),
+                     "restarts": int(info.get("restarts", -1)), "geometry": geo["mode"], "create_s": lp.create_s,
+                     "kernel": "k_solve_persistent" if geo["mode"] == "grid" else "k_solve_cluster"}
+        parity_check(bool(info["converged"]) and out[name]["rel_error"] <= 1e-5,
+                     "%s: solve mode did not reach the HiGHS objective (%r vs %r)" % (name, float(obj), target))
+        lp.close()
+    return out
+
+
+def measure_gnn_training(torch, dev, name="ken-18"):
+    """One training step of the reference's GNNModel on the device kernels (mllp_gnn_backward; the reference trains it,
+    linear_program_experiment.py:115-157): times on `name`, and an in-run check of the device gradients against
+    torch.autograd through the plain-PyTorch float64 checker on afiro."""
+    import mllp_b200.gnn as GN
+    import mllp_b200.linear_program_data as D
+    from mllp_b200.gnn_train import TrainableGNNModel
+    from oracle import gnn_numpy as GO, gnn_torch as GT   # checker only
+    A, b, c = D.load_csr("afiro")
+    st = GO.init_state(5)
+    dout = np.random.default_rng(2).standard_normal(A.shape[1])
+    _, _, ref = GT.torch_model_loss_and_grads(st, A, b, c, dout=dout)
+    g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c)
+    model = TrainableGNNModel(st)
+    (model(g) * torch.as_tensor(dout.astype(np.float32), device=dev)).sum().backward()
+    got = {k: v.detach().cpu().numpy() for k, v in model.named_gradients().items()}
+    top = max(np.abs(v).max() for v in ref.values())
+    gerr = max(float(np.abs(got[k] - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-4 * top)) for k in ref)
+    parity_check(gerr < 2e-3, "device GNN gradients differ from autograd (%.2e)" % gerr)
+    g.close()
+
+    A, b, c = D.load_csr(name)
+    n = A.shape[1]
+    g = GN.BipartiteGraph(np.split(A.indices, A.indptr)[1:-1], A.data, b, c)
+    model = TrainableGNNModel(seed=1)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = torch.nn.BCEWithLogitsLoss()
+    target = torch.as_tensor((np.random.default_rng(0).random(n) < 0.4).astype(np.float32), device=dev)
+
+    def step():
+        loss = crit(model(g), target)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+
+    def timed(fn, reps=10):
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return float(np.median(ts))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    t_step = timed(step)
+    with torch.no_grad():
+        t_fwd = timed(lambda: model(g))
+    g.close()
+    return {"instance": name, "us_forward": t_fwd, "us_training_step": t_step,
+            "what": "forward + BCEWithLogitsLoss + backward (mllp_gnn_backward, one CUDA-graph launch) + Adam step",
+            "gradients_vs_autograd_afiro": {"max_rel": gerr, "tol": 2e-3}}
 
 
 def measure_rowpart(M, torch, dist, dev, local, rank, world, names=("osa-60", "ken-18", "pds-20"), K=1000, parity_K=100,
@@ -744,7 +835,7 @@ def main():
                                     "sample": "%d iterations of %s on the CPU oracle (OpenMP, %d threads, %.1f s)" % (its, args.workload, cores, dt),
                                     "scipy_csr_1_thread": {"value": r1, "unit": "iterations/s", "cores": 1,
                                                            "sample": "%d iterations of the same update with scipy.sparse CSR products on one thread" % k1}}
-        line["parity_checks"] = "in-run asserts against the CPU oracle: ken-18 / pds-20 K=100, batch K=50, preconditioned batch KKT scalars, row partition K=100 on every rank (N > 1), e2e vs device objective"
+        line["parity_checks"] = "in-run asserts against the CPU oracle: ken-18 / pds-20 K=100, batch K=50, preconditioned batch KKT scalars, row partition K=100 on every rank (N > 1), e2e vs device objective, solve mode on osa-60 / pds-20 vs HiGHS, GNN gradients vs autograd"
         if PARITY_FAILURES:
             line["parity_failures"] = PARITY_FAILURES
         emit(line)
