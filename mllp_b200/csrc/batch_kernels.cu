@@ -923,6 +923,276 @@ k_batch_solve_r(const BatchInst* __restrict__ insts, int count, BatchGeom geom, 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Small LPs in large batches: ONE WARP per instance.
+//
+// The CTA-per-instance kernels above spend most of their issue slots on what a CTA needs to cooperate (tile strides over
+// the warps, __syncthreads between the phases, block-wide reductions through shared memory): measured on 4096 x sc105
+// (340 nonzeros, a handful of tiles per phase) ~3 000 warp instructions per LP iteration, and the shared memory of a CTA
+// (split-row scratch, reduction scratch) caps the LPs in flight at 12 per SM.  Here a warp owns an instance: it walks
+// ALL tiles of A' and of A itself (two at a time), the phases are separated by __syncwarp(), every reduction is a
+// butterfly, and shared memory holds nothing but the instance's seven vectors, so ~30 instances are in flight per SM.
+// Chosen by the host (mllp_batch_create) for shared-matrix batches of >= WARP_MIN_COUNT instances without split rows whose
+// vectors fit WARP_MIN_PER_SM times into an SM's shared memory (MLLP_BATCH_WARP=1 forces it for any batch without split
+// rows: with one matrix per instance it measured slower, see there).  Per row the summation order is that of run_phase (same tiles, same
+// lanes), so parity-mode iterates are bitwise those of the CTA kernels; the sums over rows (KKT scalars, fixed-point
+// error) are added in another order (lane-wise, then the butterfly), still fixed.
+constexpr int WARP_LPS = 4;            // warps (instances) per CTA
+constexpr int WARP_MIN_COUNT = 1024;   // smaller batches are latency-bound: the CTA kernels serve them
+constexpr int WARP_MIN_PER_SM = 16;
+
+struct WarpSmem {
+    double *x, *xbar, *c, *y, *b, *x0, *y0;
+};
+__host__ __device__ inline size_t warp_lp_bytes(int m, int n) { return (8 * (4 * (size_t)n + 3 * (size_t)m) + 15) & ~(size_t)15; }
+__device__ __forceinline__ WarpSmem carve_warp(unsigned char* base, int m, int n)
+{
+    WarpSmem S;
+    double* p = reinterpret_cast<double*>(base);
+    S.x = p; p += n; S.xbar = p; p += n; S.c = p; p += n; S.x0 = p; p += n;
+    S.y = p; p += m; S.b = p; p += m; S.y0 = p;
+    return S;
+}
+__device__ __forceinline__ DevLP warp_lp(const BatchInst& I, const WarpSmem& S)
+{
+    DevLP lp{};
+    lp.A = I.A; lp.AT = I.AT; lp.m = I.m; lp.n = I.n;
+    lp.b = S.b; lp.c = S.c; lp.x = S.x; lp.y = S.y; lp.xbar = S.xbar; lp.x0 = S.x0; lp.y0 = S.y0;
+    lp.dr = I.dr; lp.dc = I.dc;
+    return lp;
+}
+
+// all tiles of one matrix by one warp, two tiles in flight (the regular-tile loop of run_phase with one warp)
+template <class Op>
+__device__ __forceinline__ void warp_tiles(const MatView& V, const Op& op, double* acc)
+{
+    const double* __restrict__ vec = op.vec();
+    const int lane = threadIdx.x & 31;
+    for (uint32_t t = 0; t < V.ntiles; t += 2) {
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(V.desc + t));
+        const int nsteps = raw.z & 0xffff, logL = (raw.z >> 16) & 0xff, nrows = (raw.z >> 24) & 0xff;
+        const int L = 1 << logL, rr = lane >> logL;
+        const bool owner = ((lane & (L - 1)) == 0) && (rr < nrows);
+        const int r = raw.y + rr;
+        typename Op::Pre pre{};
+        if (owner) pre = op.prefetch(r);
+        if (t + 1 < V.ntiles) {
+            const int4 raw2 = __ldg(reinterpret_cast<const int4*>(V.desc + t + 1));
+            const int nsteps2 = raw2.z & 0xffff, logL2 = (raw2.z >> 16) & 0xff, nrows2 = (raw2.z >> 24) & 0xff;
+            const int L2 = 1 << logL2, rr2 = lane >> logL2;
+            const bool owner2 = ((lane & (L2 - 1)) == 0) && (rr2 < nrows2);
+            const int r2 = raw2.y + rr2;
+            typename Op::Pre pre2{};
+            if (owner2) pre2 = op.prefetch(r2);
+            double dot, dot2;
+            if (nsteps == nsteps2 && nsteps >= 1 && nsteps <= 3) {
+                const double2* vpa = V.gvals + (size_t)(uint32_t)raw.x * 32 + lane;
+                const int2* ipa = V.gidx + (size_t)(uint32_t)raw.x * 32 + lane;
+                const double2* vpb = V.gvals + (size_t)(uint32_t)raw2.x * 32 + lane;
+                const int2* ipb = V.gidx + (size_t)(uint32_t)raw2.x * 32 + lane;
+                if (nsteps == 1) pair_dot<typename Op::Mem, 1>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                else if (nsteps == 2) pair_dot<typename Op::Mem, 2>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+                else pair_dot<typename Op::Mem, 3>(vpa, ipa, vpb, ipb, vec, dot, dot2);
+            } else {
+                dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
+                dot2 = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw2.x, nsteps2, lane);
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+            for (int o = L2 >> 1; o > 0; o >>= 1) dot2 += __shfl_xor_sync(FULL, dot2, o);
+            if (owner) op.row(r, dot, pre, acc);
+            if (owner2) op.row(r2, dot2, pre2, acc);
+        } else {
+            double dot = tile_dot<typename Op::Mem>(V, vec, (uint32_t)raw.x, nsteps, lane);
+            for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+            if (owner) op.row(r, dot, pre, acc);
+        }
+    }
+    __syncwarp();   // the rows this phase wrote are gathered by the next one
+}
+
+template <int N>
+__device__ __forceinline__ void warp_allreduce(double* acc)
+{
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(FULL, acc[k], o);
+}
+
+__device__ __forceinline__ void warp_load_instance(const BatchInst& I, const WarpSmem& S, const double* x, const double* y,
+                                                   const double* b, const double* c)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < I.n; k += 32) {
+        const int j = __ldg(I.orderX + k);
+        const double sc = I.dc ? __ldg(I.dc + k) : 1.0;
+        const double xv = x[I.x_off + j] / sc;
+        S.x[k] = xv; S.x0[k] = xv;
+        S.c[k] = c[I.x_off + j] * sc;
+        S.xbar[k] = 0.0;
+    }
+    for (int k = lane; k < I.m; k += 32) {
+        const int i = __ldg(I.orderY + k);
+        const double sc = I.dr ? __ldg(I.dr + k) : 1.0;
+        const double yv = y[I.y_off + i] / sc;
+        S.y[k] = yv; S.y0[k] = yv;
+        S.b[k] = b[I.y_off + i] * sc;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_store_instance(const BatchInst& I, const WarpSmem& S, double* x, double* y)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < I.n; k += 32) x[I.x_off + __ldg(I.orderX + k)] = S.x[k] * (I.dc ? __ldg(I.dc + k) : 1.0);
+    for (int k = lane; k < I.m; k += 32) y[I.y_off + __ldg(I.orderY + k)] = S.y[k] * (I.dr ? __ldg(I.dr + k) : 1.0);
+    __syncwarp();
+}
+
+// KKT scalars of (S.x, S.y) -> s[0..9] in every lane; also ||x-x0||^2, ||y-y0||^2 in dd[0..1]
+__device__ __forceinline__ void warp_kkt(const DevLP& lp, const MatView& VA, const MatView& VAT, double* s, double* dd)
+{
+    double ap[NRED], ad[NRED];
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) { ap[k] = 0.0; ad[k] = 0.0; }
+    { EvalPrimalOp<false, SmemMem> op{lp}; warp_tiles(VAT, op, ap); }
+    { EvalDualOp<false, SmemMem> op{lp}; warp_tiles(VA, op, ad); }
+    warp_allreduce<7>(ap);
+    warp_allreduce<6>(ad);
+    const double pobj = ap[0], dobj = ad[0] + ap[1];
+    s[0] = pobj; s[1] = dobj; s[2] = sqrt(ad[1] + ap[6]); s[3] = sqrt(ap[2] + ad[5]);
+    s[4] = sqrt(ad[2]); s[5] = sqrt(ap[3]); s[6] = sqrt(ap[4]); s[7] = sqrt(ad[3]);
+    const double gap = fabs(pobj - dobj);
+    double e = s[2] / (1.0 + s[4]);
+    e = fmax(e, s[3] / (1.0 + s[5]));
+    e = fmax(e, gap / (1.0 + fabs(pobj) + fabs(dobj)));
+    s[8] = e; s[9] = gap;
+    dd[0] = ap[5]; dd[1] = ad[4];
+}
+
+__global__ void __launch_bounds__(32 * WARP_LPS, 6)
+k_batch_run_warp(const BatchInst* __restrict__ insts, int count, int shared, uint32_t lp_bytes, double* x, double* y, const double* b,
+                 const double* c, const double* tau, const double* sigma, int iters, double* scalars)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* mine = dsm + (size_t)wid * lp_bytes;
+    const int nw = gridDim.x * WARP_LPS;
+    for (int inst = blockIdx.x * WARP_LPS + wid; inst < count; inst += nw) {
+        BatchInst I = insts[shared ? 0 : inst];
+        if (shared) { I.x_off = (long long)inst * I.n; I.y_off = (long long)inst * I.m; }
+        const WarpSmem S = carve_warp(mine, I.m, I.n);
+        warp_load_instance(I, S, x, y, b, c);
+        for (int k = lane; k < I.n; k += 32) S.x0[k] = 0.0;   // anchors unused here; keep the evaluation finite
+        for (int k = lane; k < I.m; k += 32) S.y0[k] = 0.0;
+        __syncwarp();
+        const DevLP lp = warp_lp(I, S);
+        const MatView VA = global_view(I.A, 0u), VAT = global_view(I.AT, 0u);
+        PrimalOp<false, SmemMem> pop{lp, __ldg(tau + inst)};
+        DualOp<false, SmemMem> dop{lp, __ldg(sigma + inst)};
+        double acc[NRED];
+        for (int it = 0; it < iters; ++it) {
+            warp_tiles(VAT, pop, acc);
+            warp_tiles(VA, dop, acc);
+        }
+        if (scalars) {
+            double s[10], dd[2];
+            warp_kkt(lp, VA, VAT, s, dd);
+            if (lane == 0) {
+                double* o = scalars + (size_t)inst * MLLP_NUM_SCALARS;
+                for (int k = 0; k < 10; ++k) o[k] = s[k];
+                o[10] = (double)iters; o[11] = 0.0; o[12] = 0.0; o[13] = 1.0; o[14] = 0.0; o[15] = 0.0;
+            }
+        }
+        warp_store_instance(I, S, x, y);
+    }
+}
+
+// Solve mode per warp: the control flow of k_batch_solve / oracle_pdhg_solve; all lanes hold the same scalars.
+__global__ void __launch_bounds__(32 * WARP_LPS, 6)
+k_batch_solve_warp(const BatchInst* __restrict__ insts, int count, int shared, uint32_t lp_bytes, double* x, double* y,
+                   const double* b, const double* c, const double* eta_arr, double w0, int max_iters, int check_every, double tol,
+                   double* scalars, int* next_inst)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* mine = dsm + (size_t)wid * lp_bytes;
+    for (;;) {
+        // instances converge after very different iteration counts: warps pull the next one from a device counter
+        int inst = 0;
+        if (lane == 0) inst = atomicAdd(next_inst, 1);
+        inst = __shfl_sync(FULL, inst, 0);
+        if (inst >= count) break;
+        BatchInst I = insts[shared ? 0 : inst];
+        if (shared) { I.x_off = (long long)inst * I.n; I.y_off = (long long)inst * I.m; }
+        const WarpSmem S = carve_warp(mine, I.m, I.n);
+        warp_load_instance(I, S, x, y, b, c);
+        const double eta = __ldg(eta_arr + inst);
+        double w = w0;
+        if (!(w0 > 0.0)) {   // the PDLP default ||c~|| / ||b~|| of this instance (scaled data, as loaded)
+            double nn[2] = {0.0, 0.0};
+            for (int q = lane; q < I.m; q += 32) nn[0] += S.b[q] * S.b[q];
+            for (int q = lane; q < I.n; q += 32) nn[1] += S.c[q] * S.c[q];
+            warp_allreduce<2>(nn);
+            w = (nn[0] > 0.0 && nn[1] > 0.0) ? sqrt(nn[1] / nn[0]) : 1.0;
+        }
+        const DevLP lp = warp_lp(I, S);
+        const MatView VA = global_view(I.A, 0u), VAT = global_view(I.AT, 0u);
+        double tau = eta / w, sigma = eta * w;
+        double fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
+        int k = 0, it = 0, restarts = 0, converged = 0;
+        double kk[10], dd[2];
+        warp_kkt(lp, VA, VAT, kk, dd);
+        while (it < max_iters) {
+            const double lam = (double)(k + 1) / (double)(k + 2);
+            const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iters);
+            const bool need_fpe = check || fpe_restart < 0.0;
+            double a2[2];
+            {
+                PrimalHalpernOp<false, SmemMem> op{lp, tau, lam};
+                double acc[NRED];
+                acc[0] = 0.0;
+                warp_tiles(VAT, op, acc);
+                a2[0] = acc[0];
+            }
+            {
+                DualHalpernOp<false, SmemMem> op{lp, sigma, lam};
+                double acc[NRED];
+                acc[0] = 0.0;
+                warp_tiles(VA, op, acc);
+                a2[1] = acc[0];
+            }
+            ++it; ++k;
+            if (need_fpe) {
+                warp_allreduce<2>(a2);
+                fpe = sqrt(w * a2[0] + a2[1] / w);
+                if (fpe_restart < 0.0) fpe_restart = fpe;
+            }
+            if (check) {
+                warp_kkt(lp, VA, VAT, kk, dd);
+                if (kk[8] <= tol) { converged = 1; break; }
+                const bool do_restart = (fpe <= 0.2 * fpe_restart) || (fpe <= 0.8 * fpe_restart && fpe > fpe_prev) ||
+                                        ((double)k >= 0.36 * (double)it);
+                fpe_prev = fpe;
+                if (do_restart) {
+                    const double ddx = sqrt(dd[0]), ddy = sqrt(dd[1]);
+                    if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
+                    tau = eta / w; sigma = eta * w;
+                    for (int q = lane; q < I.n; q += 32) S.x0[q] = S.x[q];
+                    for (int q = lane; q < I.m; q += 32) S.y0[q] = S.y[q];
+                    __syncwarp();
+                    k = 0; fpe_restart = -1.0; fpe_prev = INFINITY;
+                    ++restarts;
+                }
+            }
+        }
+        if (lane == 0) {
+            double* o = scalars + (size_t)inst * MLLP_NUM_SCALARS;
+            for (int q = 0; q < 10; ++q) o[q] = kk[q];
+            o[10] = (double)it; o[11] = (double)restarts; o[12] = (double)converged; o[13] = w; o[14] = fpe; o[15] = 0.0;
+        }
+        warp_store_instance(I, S, x, y);
+    }
+}
+
 // sigma_max(A) per instance by power iteration (same recurrence as oracle_power_iteration).
 __global__ void __launch_bounds__(1024, 1)
 k_batch_norm(const BatchInst* __restrict__ insts, int count, int shared, int iters, double* sigma_out)
@@ -990,6 +1260,10 @@ struct mllp_batch {
     int grid_run = 0, grid_solve = 0;
     size_t smem_run = 0, smem_solve = 0;
     BatchGeom g_run{}, g_solve{};
+    // one warp per instance (k_batch_run_warp / k_batch_solve_warp): large batches of small LPs without split rows
+    int use_warp = 0, grid_warp = 0;
+    uint32_t warp_lp_bytes = 0;
+    size_t smem_warp = 0;
 };
 
 namespace {
@@ -1088,6 +1362,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
         std::vector<MatOff> offA((size_t)nmat), offAT((size_t)nmat);
         std::vector<size_t> offOX((size_t)nmat), offOY((size_t)nmat), offDR((size_t)nmat), offDC((size_t)nmat);
         int max_tiles = 0, max_tiles_A = 0, max_tiles_AT = 0, max_steps_A = 0, max_steps_AT = 0;
+        bool any_split = false;
         for (int k = 0; k < nmat && rc == 0; ++k) {
             const int m = h_m[k], n = h_n[k];
             const int32_t* ip = h_indptr + h_indptr_off[k];
@@ -1131,6 +1406,7 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             offOX[k] = P.order.size(); P.order.insert(P.order.end(), orderX.begin(), orderX.end());
             offOY[k] = P.order.size(); P.order.insert(P.order.end(), orderY.begin(), orderY.end());
             max_tiles = std::max<int>(max_tiles, (int)std::max(HA.tiles.size(), HAT.tiles.size()));
+            any_split = any_split || !HA.splits.empty() || !HAT.splits.empty() || HA.cta_nsplit[0] != 0 || HAT.cta_nsplit[0] != 0;
             max_tiles_A = std::max<int>(max_tiles_A, (int)HA.tiles.size());
             max_tiles_AT = std::max<int>(max_tiles_AT, (int)HAT.tiles.size());
             max_steps_A = std::max<int>(max_steps_A, (int)HA.total_steps);
@@ -1254,7 +1530,8 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                     if (smem > 40 * 1024)
                         ck(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
                     int b = 0;
-                    ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, threads, smem), "occupancy");
+                    const bool warp_fn = fn == (const void*)k_batch_run_warp || fn == (const void*)k_batch_solve_warp;
+                    ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, warp_fn ? 32 * WARP_LPS : threads, smem), "occupancy");
                     if (rc == 0 && b < 1) rc = bfail(MLLP_E_STATE, "mllp_batch_create: kernel does not fit on an SM");
                     grid = (int)std::min<int64_t>(units, (int64_t)prop.multiProcessorCount * std::max(b, 1));
                 };
@@ -1265,6 +1542,25 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                 int gn = 0;
                 prepare((const void*)k_batch_norm, bt->dyn_smem, count, gn);
                 bt->grid = gn;
+                // one warp per instance: large batches of small LPs (see k_batch_solve_warp)
+                const size_t lpb = warp_lp_bytes(bt->max_m, bt->max_n);
+                const size_t sm_smem = (size_t)prop.sharedMemPerMultiprocessor;
+                // measured (scripts/small_batch_bench.py, profiles/r02_batch_experiments.md): 4096 x sc105 sharing one matrix
+                // +14 % LPs/s; 3072 LPs with their OWN matrices 0.4x -- a lone warp needs 11.7 us per iteration against the
+                // CTA's 1.6, and the few instances that run to the iteration cap then set the time: shared matrices only
+                bool warp = bt->shared && !any_split && count >= WARP_MIN_COUNT && lpb * WARP_MIN_PER_SM + 1024 * (WARP_MIN_PER_SM / WARP_LPS) <= sm_smem &&
+                            lpb * WARP_LPS <= smem_cap;
+                const char* wv = getenv("MLLP_BATCH_WARP");
+                if (wv && *wv) warp = atoi(wv) != 0 && !any_split && lpb * WARP_LPS <= smem_cap;
+                if (warp) {
+                    bt->use_warp = 1;
+                    bt->warp_lp_bytes = (uint32_t)lpb;
+                    bt->smem_warp = lpb * WARP_LPS;
+                    int gw = 0, gw2 = 0;
+                    prepare((const void*)k_batch_run_warp, bt->smem_warp, (count + WARP_LPS - 1) / WARP_LPS, gw);
+                    prepare((const void*)k_batch_solve_warp, bt->smem_warp, (count + WARP_LPS - 1) / WARP_LPS, gw2);
+                    bt->grid_warp = std::min(gw, gw2);
+                }
             }
             int64_t* I = bt->info;
             I[0] = count; I[1] = bt->sum_m; I[2] = bt->sum_n; I[3] = bt->sum_nnz; I[4] = bt->grid_run; I[5] = bt->threads;
@@ -1274,6 +1570,10 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             I[7] = 36 * bt->sum_m + 44 * bt->sum_n + 24 * bt->sum_nnz;
             I[8] = bt->R_run; I[9] = bt->R_solve; I[10] = bt->g_run.res_A; I[11] = bt->g_run.res_AT;
             I[12] = bt->g_solve.res_A; I[13] = bt->g_solve.res_AT; I[14] = (int64_t)bt->smem_solve; I[15] = bt->grid_solve;
+            if (bt->use_warp) {   // one warp per instance: WARP_LPS instances per CTA, no instance shares matrix steps with another
+                I[4] = bt->grid_warp; I[5] = 32 * WARP_LPS; I[6] = (int64_t)bt->smem_warp; I[8] = 1; I[9] = 1;
+                I[10] = I[11] = I[12] = I[13] = 0; I[14] = (int64_t)bt->smem_warp; I[15] = bt->grid_warp;
+            }
         }
     } catch (const std::bad_alloc&) {
         rc = bfail(MLLP_E_NOMEM, "mllp_batch_create: out of host memory");
@@ -1322,6 +1622,13 @@ int mllp_batch_run(mllp_batch_t bt, double* d_x, double* d_y, const double* d_b,
     DevGuard guard(bt->device);
     cudaStream_t st = (cudaStream_t)stream;
     mllp::count_launch(1);
+    if (bt->use_warp) {
+        k_batch_run_warp<<<bt->grid_warp, 32 * WARP_LPS, bt->smem_warp, st>>>(bt->d_insts, bt->count, bt->shared, bt->warp_lp_bytes, d_x, d_y,
+                                                                            d_b, d_c, d_tau, d_sigma, num_iters, d_scalars);
+        cudaError_t ew = cudaGetLastError();
+        if (ew != cudaSuccess) return bfail((int)ew, std::string("mllp_batch_run: ") + cudaGetErrorString(ew));
+        return 0;
+    }
 #define MLLP_RUN_R(RR) k_batch_run_r<RR><<<bt->grid_run, bt->threads, bt->smem_run, st>>>(bt->d_insts, bt->count, bt->g_run, d_x, d_y, d_b, d_c, d_tau, d_sigma, num_iters, d_scalars)
     switch (bt->R_run) {
         case 4: MLLP_RUN_R(4); break;
@@ -1347,6 +1654,14 @@ int mllp_batch_solve(mllp_batch_t bt, double* d_x, double* d_y, const double* d_
     if (e0 != cudaSuccess) return bfail((int)e0, std::string("mllp_batch_solve: ") + cudaGetErrorString(e0));
     cudaStream_t st = (cudaStream_t)stream;
     mllp::count_launch(1);
+    if (bt->use_warp) {
+        k_batch_solve_warp<<<bt->grid_warp, 32 * WARP_LPS, bt->smem_warp, st>>>(bt->d_insts, bt->count, bt->shared, bt->warp_lp_bytes, d_x,
+                                                                              d_y, d_b, d_c, d_eta, w0, max_iters, check_every, tol,
+                                                                              d_scalars, bt->d_next);
+        cudaError_t ew = cudaGetLastError();
+        if (ew != cudaSuccess) return bfail((int)ew, std::string("mllp_batch_solve: ") + cudaGetErrorString(ew));
+        return 0;
+    }
 #define MLLP_SOLVE_R(RR) k_batch_solve_r<RR><<<bt->grid_solve, bt->threads, bt->smem_solve, st>>>(bt->d_insts, bt->count, bt->g_solve, d_x, d_y, d_b, d_c, d_eta, w0, max_iters, check_every, tol, d_scalars, bt->d_next)
     switch (max_iters > 0 ? bt->R_solve : 1) {   // max_iters == 0 (scalars of the starting point): one-instance kernel
         case 4: MLLP_SOLVE_R(4); break;

@@ -218,3 +218,68 @@ def test_config5_shared_matrix_data_parallel_path_runs_the_real_kernels():
     # the same instances one by one through the single-LP solve: same optimum
     o1, _, _, i1 = M.solve_linear_program(A, A.data, bb[3], cb[3], tol=1e-6, max_iters=400000, precondition=True)
     assert i1["converged"] and abs(o1 - res[3][0]) <= 2e-5 * (1 + abs(o1))
+
+
+def test_warp_per_instance_kernels_match_the_cta_kernels_and_the_oracle(monkeypatch):
+    """Large batches of small LPs run with ONE WARP per instance (k_batch_run_warp / k_batch_solve_warp): forced here on a small
+    heterogeneous batch (37 instances: not a multiple of the 4 warps of a CTA).  Per row the summation order is the CTA
+    kernels', so parity-mode iterates are bitwise equal; solve mode reaches the same optimum (its sums over rows are added in
+    another order, so iteration counts may differ)."""
+    names = ["sc50a", "sc105", "blend", "afiro", "adlittle"]
+    base, mats0 = load_batch(names)
+    rng = np.random.default_rng(11)
+    insts, mats = [], []
+    for k in range(37):
+        constrs, w, b, c = base[k % len(base)]
+        A = mats0[k % len(base)][0]
+        ck = c * (1 + 0.05 * rng.uniform(-1, 1, c.shape[0]))
+        insts.append((constrs, w, b, ck))
+        mats.append((A, b, ck))
+    out = {}
+    for warp in ("0", "1"):
+        monkeypatch.setenv("MLLP_BATCH_WARP", warp)
+        bt = M.BatchLP(insts)
+        assert (bt.info()["threads"] == 128) == (warp == "1")
+        out[warp] = (M.pdhg_linear_program_batch(insts, num_iters=300, handle=bt),
+                     M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000, handle=bt))
+        sig = bt.sigma_max().cpu().numpy()
+        bt.close()
+    for k, (A, b, c) in enumerate(mats):
+        r0, r1 = out["0"][0][k], out["1"][0][k]
+        assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[2], r1[2])
+        if k < 10:
+            eta = 0.9 / sig[k]
+            xo, yo = O.pdhg_run(A, b, c, np.zeros(A.shape[1]), np.zeros(A.shape[0]), eta, eta, 300)
+            assert rel(r1[1], xo) < 1e-9 and rel(r1[2], yo) < 1e-9
+            kk = O.kkt(A, b, c, xo, yo)
+            assert abs(r1[3]["rel_kkt"] - kk[8]) <= 1e-6 * (1 + kk[8])
+        s0, s1 = out["0"][1][k], out["1"][1][k]
+        assert s1[3]["converged"] and s1[3]["rel_kkt"] <= 1e-6
+        assert abs(s1[0] - s0[0]) <= 1e-5 * (1 + abs(s0[0]))
+        kk = O.kkt(A, b, c, s1[1], s1[2])
+        assert abs(kk[0] - s1[0]) <= 1e-6 * (1 + abs(s1[0])) and abs(kk[8] - s1[3]["rel_kkt"]) <= 1e-9
+
+
+def test_warp_kernels_are_the_default_for_large_batches_of_small_lps_only(monkeypatch):
+    monkeypatch.delenv("MLLP_BATCH_WARP", raising=False)
+    A, b, c = D.load_csr("sc105")
+    m, n = A.shape
+    big = M.BatchLP([(A, A.data, b, c)], shared=True, count=2048)
+    small = M.BatchLP([(A, A.data, b, c)], shared=True, count=64)
+    assert big.info()["threads"] == 128 and small.info()["threads"] != 128
+    # shared matrix, warp path: instances 0, 1, last against the oracle
+    B = 2048
+    rng = np.random.default_rng(3)
+    cb = c * (1 + 0.05 * rng.uniform(-1, 1, (B, n)))
+    bb = np.tile(b, (B, 1))
+    res = M.pdhg_linear_program_batch([(A, A.data, b, c)], num_iters=100, handle=big, shared=True, rhs_batch=bb, coefs_batch=cb)
+    eta = 0.9 / O.power_iteration(A, 50)
+    for k in (0, 1, 1023, B - 1):
+        xo, yo = O.pdhg_run(A, bb[k], cb[k], np.zeros(n), np.zeros(m), eta, eta, 100)
+        assert rel(res[k][1], xo) < 1e-9 and rel(res[k][2], yo) < 1e-9
+    big.close(); small.close()
+    # 25fv47's vectors (80 KB per instance) do not fit 16 times into an SM: CTA kernels
+    A2, b2, c2 = D.load_csr("25fv47")
+    mid = M.BatchLP([(A2, A2.data, b2, c2)], shared=True, count=2048)
+    assert mid.info()["threads"] != 128
+    mid.close()
