@@ -70,10 +70,41 @@ class BipartiteData(_Base):
             src = self.__dict__.get("_mllp_source")
             if src is None:
                 raise ValueError("this BipartiteData was not made by mllp_b200's build_graph_from_weights_sets")
-            from .gnn import BipartiteGraph
-            g = BipartiteGraph(*src)
+            g = _cached_graph(src)
             self.__dict__["_mllp_graph"] = g
         return g
+
+
+# The reference's training loop rebuilds the graph of every instance in every epoch (linear_program_experiment.py:124) from
+# the SAME dataset arrays: the device CSR form (and the CUDA-graph plans captured on it) is kept per (arrays, device), so an
+# unchanged loop pays for it once.  Bounded; the arrays are held so that their identities stay valid.
+_GRAPH_CACHE = {}
+_GRAPH_CACHE_MAX = 256
+
+
+def _cached_graph(src):
+    from .gnn import BipartiteGraph
+    constrs, constr_weights, rhs, coefs, device = src
+    key = (id(constr_weights), id(rhs), id(coefs), device)
+    # identity alone would miss an in-place edit of the arrays: a content fingerprint (sums, O(nnz)) rides along
+    fp = tuple(float(np.asarray(a, dtype=np.float64).sum()) for a in (constr_weights, rhs, coefs)) + (len(rhs), len(coefs))
+    hit = _GRAPH_CACHE.get(key)
+    if hit is not None and hit[1] is constr_weights and hit[2] is rhs and hit[3] is coefs and hit[4] == fp:
+        return hit[0]
+    g = BipartiteGraph(*src)
+    if hit is not None:
+        _GRAPH_CACHE.pop(key)[0].close()
+    elif len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+        old_key = next(iter(_GRAPH_CACHE))
+        _GRAPH_CACHE.pop(old_key)[0].close()
+    _GRAPH_CACHE[key] = (g, constr_weights, rhs, coefs, fp)
+    return g
+
+
+def clear_graph_cache():
+    """release the cached device graphs (and their captured plans)"""
+    while _GRAPH_CACHE:
+        _GRAPH_CACHE.popitem()[1][0].close()
 
 
 def build_graph_from_weights_sets(constrs, constr_weights, rhs, coefs, device=0):

@@ -165,8 +165,11 @@ def test_gpu_training_loop_as_the_reference_runs_it():
     opt = torch.optim.Adam(model.parameters(), lr=1e-2)
     crit = torch.nn.BCEWithLogitsLoss()
     graph = build_graph_from_weights_sets(constrs, A.data, b, c, 0)
+    # the reference rebuilds the graph every epoch (:124): the device form is cached per (arrays, device)
+    assert build_graph_from_weights_sets(constrs, A.data, b, c, 0).bipartite_graph() is graph.bipartite_graph()
     losses = []
     for _ in range(30):
+        graph = build_graph_from_weights_sets(constrs, A.data, b, c, 0)
         obj = crit(model(graph), torch.as_tensor(basis, device="cuda"))
         obj.backward()
         opt.step()
@@ -184,3 +187,59 @@ def test_gpu_training_loop_as_the_reference_runs_it():
         ref.append(float(obj))
     assert losses[-1] < losses[0]
     assert np.max(np.abs(np.array(losses) - np.array(ref))) < 2e-3
+
+
+def test_device_graph_cache_follows_identity_and_content(monkeypatch):
+    """build_graph_from_weights_sets is called per instance per epoch by the reference's loop (:124): the device form is kept
+    per (arrays, device) and rebuilt when an array was edited in place"""
+    import mllp_b200.gnn as GN
+    import mllp_b200.graph as GR
+
+    class Stub:
+        made = 0
+
+        def __init__(self, *a):
+            Stub.made += 1
+            self.closed = False
+
+        def close(self):
+            self.closed = True
+
+    monkeypatch.setattr(GN, "BipartiteGraph", Stub)
+    monkeypatch.setattr(GR, "_GRAPH_CACHE", {})
+    w, b, c = np.ones(5), np.ones(2), np.ones(3)
+    g1, g2 = GR._cached_graph(([], w, b, c, 0)), GR._cached_graph(([], w, b, c, 0))
+    assert g1 is g2 and Stub.made == 1
+    assert GR._cached_graph(([], w, b, c.copy(), 0)) is not g1          # another array object
+    c[0] = 2.0                                                          # edited in place
+    g3 = GR._cached_graph(([], w, b, c, 0))
+    assert g3 is not g1 and g1.closed
+    GR.clear_graph_cache()
+    assert g3.closed and not GR._GRAPH_CACHE
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_gpu_backward_on_random_graphs(seed):
+    """random sparse matrices: empty rows and columns, a dense row and a dense column (cut into items when the forced lane
+    group makes them 'long'), sizes that are not multiples of the rows per warp"""
+    rng = np.random.default_rng(100 + seed)
+    m, n = int(rng.integers(1, 90)), int(rng.integers(1, 140))
+    dens = float(rng.choice([0.02, 0.1, 0.4]))
+    Ad = (rng.random((m, n)) < dens) * rng.standard_normal((m, n))
+    if seed % 2 == 0 and m > 2 and n > 2:
+        Ad[rng.integers(0, m)] = rng.standard_normal(n)        # a dense row
+        Ad[:, rng.integers(0, n)] = rng.standard_normal(m)     # a dense column
+    if m > 1:
+        Ad[rng.integers(0, m)] = 0.0                           # an empty row
+    A = sp.csr_matrix(Ad)
+    b, c = rng.standard_normal(m), rng.standard_normal(n)
+    st = G.init_state(seed)
+    dout = rng.standard_normal(n)
+    groups = (int(rng.choice([1, 2, 4, 8, 16, 32])), int(rng.choice([1, 2, 4, 8, 16, 32])))
+    out_ref, _, ref = T.torch_model_loss_and_grads(st, A, b, c, dout=dout)
+    out, _, got, _, g = _device_grads(st, A, b, c, dout=dout, groups=groups, use_plans=bool(seed % 2))
+    assert np.max(np.abs(out - out_ref)) <= 2e-4 * max(1.0, np.max(np.abs(out_ref)))
+    err = grad_errors(got, ref)
+    assert max(err.values()) < GTOL, (m, n, dens, groups, sorted(err.items(), key=lambda kv: -kv[1])[:4])
+    g.close()
