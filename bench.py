@@ -312,7 +312,9 @@ def measure_extras(M, torch, dev, local, rank, world, dist):
     sc = scal.cpu().numpy().reshape(B, _cabi.NUM_SCALARS)
     out["solve_4096x_sc105_shared"] = {"lps_solved_per_sec": world * B / sec, "instances_per_rank": B,
                                        "converged_fraction": float(sc[:, 12].mean()), "mean_iterations": float(sc[:, 10].mean()),
-                                       "instances_per_cta": bs.info()["instances_per_cta_solve"], "tol": 1e-6, "seconds": sec}
+                                       "instances_per_cta": bs.info()["instances_per_cta_solve"],
+                                       "kernel": "k_batch_solve_warp (one warp per instance)" if bs.info()["instances_per_cta_solve"] == 4 and bs.info()["res_steps_A_solve"] == 0 else "k_batch_solve_r<%d>" % bs.info()["instances_per_cta_solve"],
+                                       "tol": 1e-6, "seconds": sec}
     bs.close()
     del cb, bb
 

@@ -932,9 +932,9 @@ k_batch_solve_r(const BatchInst* __restrict__ insts, int count, BatchGeom geom, 
 // (split-row scratch, reduction scratch) caps the LPs in flight at 12 per SM.  Here a warp owns an instance: it walks
 // ALL tiles of A' and of A itself (two at a time), the phases are separated by __syncwarp(), every reduction is a
 // butterfly, and shared memory holds nothing but the instance's seven vectors, so ~30 instances are in flight per SM.
-// Chosen by the host (mllp_batch_create) for shared-matrix batches of >= WARP_MIN_COUNT instances without split rows whose
-// vectors fit WARP_MIN_PER_SM times into an SM's shared memory (MLLP_BATCH_WARP=1 forces it for any batch without split
-// rows: with one matrix per instance it measured slower, see there).  Per row the summation order is that of run_phase (same tiles, same
+// Chosen by the host (mllp_batch_create) for SOLVE mode on shared-matrix batches of >= WARP_MIN_COUNT instances without split
+// rows whose vectors fit WARP_MIN_PER_SM times into an SM's shared memory (MLLP_BATCH_WARP=1 forces both kernels for any
+// batch without split rows: with one matrix per instance, and in parity mode, they measured slower, see there).  Per row the summation order is that of run_phase (same tiles, same
 // lanes), so parity-mode iterates are bitwise those of the CTA kernels; the sums over rows (KKT scalars, fixed-point
 // error) are added in another order (lane-wise, then the butterfly), still fixed.
 constexpr int WARP_LPS = 4;            // warps (instances) per CTA
@@ -1261,7 +1261,7 @@ struct mllp_batch {
     size_t smem_run = 0, smem_solve = 0;
     BatchGeom g_run{}, g_solve{};
     // one warp per instance (k_batch_run_warp / k_batch_solve_warp): large batches of small LPs without split rows
-    int use_warp = 0, grid_warp = 0;
+    int use_warp = 0, use_warp_run = 0, grid_warp = 0;
     uint32_t warp_lp_bytes = 0;
     size_t smem_warp = 0;
 };
@@ -1550,10 +1550,15 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                 // CTA's 1.6, and the few instances that run to the iteration cap then set the time: shared matrices only
                 bool warp = bt->shared && !any_split && count >= WARP_MIN_COUNT && lpb * WARP_MIN_PER_SM + 1024 * (WARP_MIN_PER_SM / WARP_LPS) <= sm_smem &&
                             lpb * WARP_LPS <= smem_cap;
+                // ... and in SOLVE mode only: at a fixed iteration count (scripts/batch_bench.py sc105 4096) the solve loop runs at
+                // 4.3e8 LP-iterations/s on warps against 3.7e8 on CTAs (R = 2), the parity loop at 5.0e8 against 7.1e8 (there
+                // the R = 2 kernel with its resident matrix has nothing else to do): mllp_batch_run keeps the CTA kernels
+                bool warp_run = false;
                 const char* wv = getenv("MLLP_BATCH_WARP");
-                if (wv && *wv) warp = atoi(wv) != 0 && !any_split && lpb * WARP_LPS <= smem_cap;
+                if (wv && *wv) warp = warp_run = atoi(wv) != 0 && !any_split && lpb * WARP_LPS <= smem_cap;
                 if (warp) {
                     bt->use_warp = 1;
+                    bt->use_warp_run = warp_run ? 1 : 0;
                     bt->warp_lp_bytes = (uint32_t)lpb;
                     bt->smem_warp = lpb * WARP_LPS;
                     int gw = 0, gw2 = 0;
@@ -1570,9 +1575,11 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             I[7] = 36 * bt->sum_m + 44 * bt->sum_n + 24 * bt->sum_nnz;
             I[8] = bt->R_run; I[9] = bt->R_solve; I[10] = bt->g_run.res_A; I[11] = bt->g_run.res_AT;
             I[12] = bt->g_solve.res_A; I[13] = bt->g_solve.res_AT; I[14] = (int64_t)bt->smem_solve; I[15] = bt->grid_solve;
-            if (bt->use_warp) {   // one warp per instance: WARP_LPS instances per CTA, no instance shares matrix steps with another
-                I[4] = bt->grid_warp; I[5] = 32 * WARP_LPS; I[6] = (int64_t)bt->smem_warp; I[8] = 1; I[9] = 1;
-                I[10] = I[11] = I[12] = I[13] = 0; I[14] = (int64_t)bt->smem_warp; I[15] = bt->grid_warp;
+            if (bt->use_warp) {   // solve mode with one warp per instance: WARP_LPS instances per CTA, nothing resident
+                I[9] = WARP_LPS; I[12] = I[13] = 0; I[14] = (int64_t)bt->smem_warp; I[15] = bt->grid_warp;
+            }
+            if (bt->use_warp_run) {
+                I[4] = bt->grid_warp; I[5] = 32 * WARP_LPS; I[6] = (int64_t)bt->smem_warp; I[8] = WARP_LPS; I[10] = I[11] = 0;
             }
         }
     } catch (const std::bad_alloc&) {
@@ -1622,7 +1629,7 @@ int mllp_batch_run(mllp_batch_t bt, double* d_x, double* d_y, const double* d_b,
     DevGuard guard(bt->device);
     cudaStream_t st = (cudaStream_t)stream;
     mllp::count_launch(1);
-    if (bt->use_warp) {
+    if (bt->use_warp_run) {
         k_batch_run_warp<<<bt->grid_warp, 32 * WARP_LPS, bt->smem_warp, st>>>(bt->d_insts, bt->count, bt->shared, bt->warp_lp_bytes, d_x, d_y,
                                                                             d_b, d_c, d_tau, d_sigma, num_iters, d_scalars);
         cudaError_t ew = cudaGetLastError();

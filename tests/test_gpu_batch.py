@@ -239,7 +239,7 @@ def test_warp_per_instance_kernels_match_the_cta_kernels_and_the_oracle(monkeypa
     for warp in ("0", "1"):
         monkeypatch.setenv("MLLP_BATCH_WARP", warp)
         bt = M.BatchLP(insts)
-        assert (bt.info()["threads"] == 128) == (warp == "1")
+        assert (bt.info()["threads"] == 128) == (warp == "1") and (bt.info()["instances_per_cta_solve"] == 4) == (warp == "1")
         out[warp] = (M.pdhg_linear_program_batch(insts, num_iters=300, handle=bt),
                      M.solve_linear_program_batch(insts, tol=1e-6, max_iters=400000, handle=bt))
         sig = bt.sigma_max().cpu().numpy()
@@ -266,8 +266,10 @@ def test_warp_kernels_are_the_default_for_large_batches_of_small_lps_only(monkey
     m, n = A.shape
     big = M.BatchLP([(A, A.data, b, c)], shared=True, count=2048)
     small = M.BatchLP([(A, A.data, b, c)], shared=True, count=64)
-    assert big.info()["threads"] == 128 and small.info()["threads"] != 128
-    # shared matrix, warp path: instances 0, 1, last against the oracle
+    # solve mode on warps (4 instances per CTA, one per warp); parity mode stays on the CTA kernels (measured faster there)
+    assert big.info()["instances_per_cta_solve"] == 4 and big.info()["threads"] != 128
+    assert small.info()["instances_per_cta_solve"] != 4
+    # shared matrix, default kernels: instances 0, 1, last against the oracle (parity) and against HiGHS-checked objectives (solve)
     B = 2048
     rng = np.random.default_rng(3)
     cb = c * (1 + 0.05 * rng.uniform(-1, 1, (B, n)))
@@ -277,9 +279,14 @@ def test_warp_kernels_are_the_default_for_large_batches_of_small_lps_only(monkey
     for k in (0, 1, 1023, B - 1):
         xo, yo = O.pdhg_run(A, bb[k], cb[k], np.zeros(n), np.zeros(m), eta, eta, 100)
         assert rel(res[k][1], xo) < 1e-9 and rel(res[k][2], yo) < 1e-9
+    sol = M.solve_linear_program_batch([(A, A.data, b, c)], tol=1e-6, max_iters=200000, handle=big, shared=True, rhs_batch=bb, coefs_batch=cb)
+    for k in (0, 1, 1023, B - 1):
+        assert sol[k][3]["converged"]
+        kk = O.kkt(A, bb[k], cb[k], sol[k][1], sol[k][2])
+        assert kk[8] <= 1.0001e-6 and abs(kk[0] - sol[k][0]) <= 1e-6 * (1 + abs(sol[k][0]))
     big.close(); small.close()
     # 25fv47's vectors (80 KB per instance) do not fit 16 times into an SM: CTA kernels
     A2, b2, c2 = D.load_csr("25fv47")
     mid = M.BatchLP([(A2, A2.data, b2, c2)], shared=True, count=2048)
-    assert mid.info()["threads"] != 128
+    assert mid.info()["instances_per_cta_solve"] != 4
     mid.close()
