@@ -196,6 +196,19 @@ __device__ __forceinline__ void g_products(const float* prm, int c0, const float
     g_products_xs<DIN, CNT>(prm, c0, g, dxs);
 }
 
+// v[0..DIN) -> p[0..DIN): 128-bit stores when the row allows it (a lane writes its node's vectors: scattered rows)
+template <int DIN>
+__device__ __forceinline__ void store_vec(float* p, const float* v)
+{
+    if constexpr (DIN % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < DIN / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < DIN; ++d) p[d] = v[d];
+    }
+}
+
 // one edge of the second sweep
 template <int DIN>
 __device__ __forceinline__ void edge_ds(float a, const float* xj, const float* qt, float qe, float lse, const float* dxb, float dab,
@@ -351,8 +364,7 @@ __global__ void __launch_bounds__(256, 3) k_gnn_bwd_dst_stats(int nd, const int3
         const float abar = st.pa * inv;
         if (writer) {
             float* r = nr + (size_t)i * N::total;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) r[N::xbar + d] = st.acc[d];
+            store_vec<DIN>(r + N::xbar, st.acc);
             r[N::abar] = abar;
             r[N::any] = any ? 1.0f : 0.0f;
         }
@@ -486,8 +498,7 @@ __global__ void __launch_bounds__(256, 3) k_gnn_bwd_dst_sweep(int nd, const int3
         }
         if (live && gl == 0) {
             float* r = nr + (size_t)i * N::total;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) r[N::dqt + d] = dqt[d];
+            store_vec<DIN>(r + N::dqt, dqt);
             r[N::dqe] = dqe;
             if (dxdst) {
                 float park[DIN];
@@ -649,8 +660,7 @@ __global__ void __launch_bounds__(256) k_gnn_bwd_dst_long_final(int nlong, const
         }
         if (lane == 0) {
             float* q = nr + (size_t)i * N::total;
-#pragma unroll
-            for (int d = 0; d < DIN; ++d) q[N::dqt + d] = dqt[d];
+            store_vec<DIN>(q + N::dqt, dqt);
             q[N::dqe] = dqe;
             if (dxdst) {
                 float dxs[DIN];
@@ -819,16 +829,19 @@ __global__ void __launch_bounds__(256) k_gnn_param_partial(int nd, const float* 
 {
     using O = Off<DIN>;
     using N = NR<DIN>;
-    constexpr int TN = 32, NT = N::total, NV = NT / 4, W = NT + DIN + 1, WS = W | 1;
+    constexpr int TN = 32, NT = N::total, NV = NT / 4, W = NT + DIN + 1, WS = (W + 3) & ~3;
     constexpr int COL_X = NT, COL_ONE = NT + DIN;
-    constexpr int EPT = (O::total + 255) / 256;
     constexpr int LOADS = (TN * NV + 255) / 256;
-    __shared__ float T[TN][WS];
-    int ua[EPT], vb[EPT];
-    float acc[EPT];
+    static_assert(4 * 256 >= O::total, "four entries per thread cover the block");
+    __shared__ __align__(16) float T[TN][WS];
+    // a thread owns the four CONSECUTIVE entries e0 .. e0 + 3 of the block: in all blocks but wq / sq they share the U
+    // operand and their V operands are four consecutive floats (one 128-bit shared-memory load per node)
+    const int e0 = 4 * (int)threadIdx.x;
+    int ua[4], vb[4];
+    float acc[4];
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-        const int e = threadIdx.x + 256 * k;
+    for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k;
         int a = -1, b = 0;
         if (e < O::vq) { a = COL_X + e / DIN; b = N::dqt + e % DIN; }
         else if (e < O::wq) { a = COL_ONE; b = N::dqt + e - O::vq; }
@@ -842,6 +855,9 @@ __global__ void __launch_bounds__(256) k_gnn_param_partial(int nd, const float* 
         else if (e < O::total) { a = N::abar; b = N::g + e - O::we; }
         ua[k] = a; vb[k] = b; acc[k] = 0.0f;
     }
+    const bool fast = ua[0] >= 0 && ua[1] == ua[0] && ua[2] == ua[0] && ua[3] == ua[0] && (vb[0] & 3) == 0 && vb[1] == vb[0] + 1 &&
+                      vb[2] == vb[0] + 2 && vb[3] == vb[0] + 3;
+    const bool any_entry = ua[0] >= 0 || ua[1] >= 0 || ua[2] >= 0 || ua[3] >= 0;
     const int ntiles = (nd + TN - 1) / TN;
     float4 buf[LOADS];
     float4 xb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -870,29 +886,37 @@ __global__ void __launch_bounds__(256) k_gnn_param_partial(int nd, const float* 
         for (int u = 0; u < LOADS; ++u) {
             const int idx = threadIdx.x + 256 * u;
             const int r = idx / NV, q = idx % NV;
-            if (idx < TN * NV) { T[r][4 * q] = buf[u].x; T[r][4 * q + 1] = buf[u].y; T[r][4 * q + 2] = buf[u].z; T[r][4 * q + 3] = buf[u].w; }
+            if (idx < TN * NV) *reinterpret_cast<float4*>(&T[r][4 * q]) = buf[u];
         }
         if constexpr (DIN % 4 == 0) {
             const int r = threadIdx.x / (DIN / 4), q = threadIdx.x % (DIN / 4);
-            if (r < TN) { T[r][COL_X + 4 * q] = xb.x; T[r][COL_X + 4 * q + 1] = xb.y; T[r][COL_X + 4 * q + 2] = xb.z; T[r][COL_X + 4 * q + 3] = xb.w; }
+            if (r < TN) *reinterpret_cast<float4*>(&T[r][COL_X + 4 * q]) = xb;
         } else {
             if (threadIdx.x < TN) T[threadIdx.x][COL_X] = xb.x;
         }
         if (threadIdx.x < TN) T[threadIdx.x][COL_ONE] = (tile * TN + (int)threadIdx.x < nd) ? 1.0f : 0.0f;
         __syncthreads();
         if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);   // in flight while this tile is consumed
+        if (fast) {
 #pragma unroll 8
-        for (int r = 0; r < TN; ++r) {
+            for (int r = 0; r < TN; ++r) {
+                const float u = T[r][ua[0]];
+                const float4 v = *reinterpret_cast<const float4*>(&T[r][vb[0]]);
+                acc[0] = fmaf(u, v.x, acc[0]); acc[1] = fmaf(u, v.y, acc[1]);
+                acc[2] = fmaf(u, v.z, acc[2]); acc[3] = fmaf(u, v.w, acc[3]);
+            }
+        } else if (any_entry) {
+#pragma unroll 4
+            for (int r = 0; r < TN; ++r) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k)
-                if (ua[k] >= 0) acc[k] = fmaf(T[r][ua[k]], T[r][vb[k]], acc[k]);
+                for (int k = 0; k < 4; ++k)
+                    if (ua[k] >= 0) acc[k] = fmaf(T[r][ua[k]], T[r][vb[k]], acc[k]);
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-        const int e = threadIdx.x + 256 * k;
-        if (e < O::total) partial[(size_t)blockIdx.x * O::total + e] = acc[k];
-    }
+    for (int k = 0; k < 4; ++k)
+        if (e0 + k < O::total) partial[(size_t)blockIdx.x * O::total + e0 + k] = acc[k];
 }
 
 // out[e] = sum over the parts: 32 strided sub-sums per entry (four loads in flight each), added in a fixed order

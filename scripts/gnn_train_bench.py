@@ -81,7 +81,9 @@ def main(names, out=None):
                     "on the small graphs they are most of the step.  History of the backward on ken-18 / osa-60 / pds-20 (us): first version\n"
                     "1096 / 3647 / 738 (one CTA per cut row, one 255-register kernel per destination pass); cut rows through the forward's\n"
                     "items 1153 / 1329 / 766; destination pass split into row walk (80 registers) + dense maps (16 lanes per node) + sweep,\n"
-                    "float4-prefetched parameter-gradient tiles, parallel partial sums 836 / 1010 / 593; as CUDA graphs: the table.\n\n"
+                    "float4-prefetched parameter-gradient tiles, parallel partial sums 836 / 1010 / 593; as CUDA graphs 739 / 921 / 504; four\n"
+                    "consecutive entries per thread in the parameter-gradient kernel (one 128-bit shared-memory load per node instead of eight\n"
+                    "scalar ones: it was bound by shared-memory loads) and 128-bit stores of the per-node vectors: the table.\n\n"
                     "| instance | m | n | nnz | lanes per row (A' / A) | forward us | backward us | whole training step us | launches fwd / bwd |\n"
                     "|---|---:|---:|---:|---|---:|---:|---:|---|\n")
             for r in rows:
