@@ -1070,17 +1070,19 @@ int launch_param_grads(int nd, const float* hdst, const float* nr, float* partia
 }
 
 struct BwdWork {
-    float *d1b, *d1a, *d2b, *d2a, *rec1, *rec2, *nr, *hfc, *partial, *dpacked;
+    float *d1b, *d1a, *d2b, *d2a, *rec1, *rec2, *nr[5], *hfc, *partial, *dpacked;   // nr[k]: per-node vectors of conv k
 };
 size_t align4(size_t v) { return (v + 3) & ~(size_t)3; }
 size_t carve(BwdWork& w, float* base, size_t n, size_t m)
 {
-    const size_t mx = n > m ? n : m;
     size_t off = 0;
     auto take = [&](size_t cnt) { float* p = base ? base + off : nullptr; off += align4(cnt); return p; };
     w.d1b = take(16 * n); w.d1a = take(16 * n); w.d2b = take(16 * m); w.d2a = take(16 * m);
     w.rec1 = take(Rec<C>::total * n); w.rec2 = take(Rec<C>::total * m);
-    w.nr = take(NR<C>::total * mx); w.hfc = take(16 * n);
+    // one set of per-node vectors per conv: their parameter-gradient sums may run beside the next conv's passes
+    w.nr[0] = take(NR<1>::total * n); w.nr[1] = take(NR<1>::total * m);
+    w.nr[2] = take(NR<C>::total * n); w.nr[3] = take(NR<C>::total * m); w.nr[4] = take(NR<C>::total * n);
+    w.hfc = take(16 * n);
     w.partial = take((size_t)PGRID * Off<C>::total); w.dpacked = take(PACKED_TOTAL);
     return off;
 }
@@ -1111,9 +1113,12 @@ int64_t mllp_gnn_backward_workspace_floats(int32_t n, int32_t m)
 
 }  // extern "C"
 
+// With a second stream `s2` and events ev[0..5] (plan capture) the parameter-gradient sums of every conv (and of fc) run on
+// a parallel branch: they hang off the conv's destination pass and are only joined before the final unpack, so the chain
+// of dependent launches is the passes alone.  Without `s2` everything runs on `s` in order (same results: same kernels).
 static int backward_impl(const mllp_gnn_side* to_var, const mllp_gnn_side* to_con, const float* d_x1, const float* d_x2,
                          const float* d_flat, const float* d_packed, const float* d_work, float* d_bwork, const float* d_dout,
-                         float* d_dflat, cudaStream_t s, const char* who)
+                         float* d_dflat, cudaStream_t s, const char* who, cudaStream_t s2 = nullptr, cudaEvent_t* ev = nullptr)
 {
     if (!side_ok(to_var) || !side_ok(to_con) || !d_x1 || !d_x2 || !d_flat || !d_packed || !d_work || !d_bwork || !d_dout || !d_dflat)
         return gfail(MLLP_E_INVALID, std::string(who) + ": bad argument");
@@ -1137,30 +1142,45 @@ static int backward_impl(const mllp_gnn_side* to_var, const mllp_gnn_side* to_co
         if (cudaMemsetAsync(d_dflat, 0, sizeof(float) * FLAT_TOTAL, s) != cudaSuccess) return cuda_status("mllp_gnn_backward: memset");
         return 0;
     }
+    int forks = 0;
+    // the stream the parameter-gradient sums of the conv just finished on `s` go to
+    auto branch = [&]() -> cudaStream_t {
+        if (!s2) return s;
+        if (cudaEventRecord(ev[forks], s) != cudaSuccess || cudaStreamWaitEvent(s2, ev[forks], 0) != cudaSuccess) rc = cuda_status("mllp_gnn_backward: fork");
+        ++forks;
+        return s2;
+    };
     // layer 3: gconv3_w2s (destination = variables) with the folded Linear(16, 1)
-    rc = launch_bwd_dst<C>(*to_var, h1b, h2b, P[4], nullptr, d_dout, fcw, w.rec1, w.nr, w.d1b, w.hfc, s);
-    if (rc == 0) rc = launch_param_grads<C>((int)n, h1b, w.nr, w.partial, dP[4], s);
+    rc = launch_bwd_dst<C>(*to_var, h1b, h2b, P[4], nullptr, d_dout, fcw, w.rec1, w.nr[4], w.d1b, w.hfc, s);
     if (rc == 0) {
-        const int grid = (int)((n + 15) / 16 > PGRID ? PGRID : (n + 15) / 16);
-        count_launch(2);
-        k_gnn_fc_partial<<<grid, 256, 0, s>>>((int)n, w.hfc, d_dout, w.partial);
-        k_gnn_sum_parts<<<(C + 1 + 7) / 8, 256, 0, s>>>(grid, C + 1, w.partial, dfc);
-        rc = cuda_status("mllp_gnn_backward: fc");
+        cudaStream_t sp = branch();
+        if (rc == 0) rc = launch_param_grads<C>((int)n, h1b, w.nr[4], w.partial, dP[4], sp);
+        if (rc == 0) {
+            const int grid = (int)((n + 15) / 16 > PGRID ? PGRID : (n + 15) / 16);
+            count_launch(2);
+            k_gnn_fc_partial<<<grid, 256, 0, sp>>>((int)n, w.hfc, d_dout, w.partial);
+            k_gnn_sum_parts<<<(C + 1 + 7) / 8, 256, 0, sp>>>(grid, C + 1, w.partial, dfc);
+            rc = cuda_status("mllp_gnn_backward: fc");
+        }
     }
     if (rc == 0) rc = launch_bwd_src(*to_con, h2b, w.rec1, w.d2b, 0, s);
     // layer 2: gconv2_w2s (variables <- constraints) and gconv2_s2w (constraints <- variables)
-    if (rc == 0) rc = launch_bwd_dst<C>(*to_var, h1a, h2a, P[2], w.d1b, nullptr, nullptr, w.rec1, w.nr, w.d1a, nullptr, s);
-    if (rc == 0) rc = launch_param_grads<C>((int)n, h1a, w.nr, w.partial, dP[2], s);
-    if (rc == 0) rc = launch_bwd_dst<C>(*to_con, h2a, h1a, P[3], w.d2b, nullptr, nullptr, w.rec2, w.nr, w.d2a, nullptr, s);
-    if (rc == 0) rc = launch_param_grads<C>((int)m, h2a, w.nr, w.partial, dP[3], s);
+    if (rc == 0) rc = launch_bwd_dst<C>(*to_var, h1a, h2a, P[2], w.d1b, nullptr, nullptr, w.rec1, w.nr[2], w.d1a, nullptr, s);
+    if (rc == 0) { cudaStream_t sp = branch(); if (rc == 0) rc = launch_param_grads<C>((int)n, h1a, w.nr[2], w.partial, dP[2], sp); }
+    if (rc == 0) rc = launch_bwd_dst<C>(*to_con, h2a, h1a, P[3], w.d2b, nullptr, nullptr, w.rec2, w.nr[3], w.d2a, nullptr, s);
+    if (rc == 0) { cudaStream_t sp = branch(); if (rc == 0) rc = launch_param_grads<C>((int)m, h2a, w.nr[3], w.partial, dP[3], sp); }
     if (rc == 0) rc = launch_bwd_src(*to_con, h2a, w.rec1, w.d2a, 1, s);
     if (rc == 0) rc = launch_bwd_src(*to_var, h1a, w.rec2, w.d1a, 1, s);
     // layer 1: the inputs need no gradient
-    if (rc == 0) rc = launch_bwd_dst<1>(*to_var, d_x1, d_x2, P[0], w.d1a, nullptr, nullptr, w.rec1, w.nr, nullptr, nullptr, s);
-    if (rc == 0) rc = launch_param_grads<1>((int)n, d_x1, w.nr, w.partial, dP[0], s);
-    if (rc == 0) rc = launch_bwd_dst<1>(*to_con, d_x2, d_x1, P[1], w.d2a, nullptr, nullptr, w.rec2, w.nr, nullptr, nullptr, s);
-    if (rc == 0) rc = launch_param_grads<1>((int)m, d_x2, w.nr, w.partial, dP[1], s);
+    if (rc == 0) rc = launch_bwd_dst<1>(*to_var, d_x1, d_x2, P[0], w.d1a, nullptr, nullptr, w.rec1, w.nr[0], nullptr, nullptr, s);
+    if (rc == 0) { cudaStream_t sp = branch(); if (rc == 0) rc = launch_param_grads<1>((int)n, d_x1, w.nr[0], w.partial, dP[0], sp); }
+    if (rc == 0) rc = launch_bwd_dst<1>(*to_con, d_x2, d_x1, P[1], w.d2a, nullptr, nullptr, w.rec2, w.nr[1], nullptr, nullptr, s);
+    if (rc == 0) { cudaStream_t sp = branch(); if (rc == 0) rc = launch_param_grads<1>((int)m, d_x2, w.nr[1], w.partial, dP[1], sp); }
     if (rc != 0) return rc;
+    if (s2) {   // join: the unpack needs every conv's sums
+        if (cudaEventRecord(ev[forks], s2) != cudaSuccess || cudaStreamWaitEvent(s, ev[forks], 0) != cudaSuccess)
+            return cuda_status("mllp_gnn_backward: join");
+    }
     count_launch(1);
     k_gnn_unpack_grads<<<7, 256, 0, s>>>(d_flat, w.dpacked, d_dflat);
     return cuda_status("mllp_gnn_backward: unpack");
@@ -1183,10 +1203,10 @@ int mllp_gnn_backward_plan_create(const mllp_gnn_side* to_var, const mllp_gnn_si
 {
     if (!out) return gfail(MLLP_E_INVALID, "mllp_gnn_backward_plan_create: null output");
     *out = nullptr;
-    return capture_plan("mllp_gnn_backward_plan_create", out, [&](cudaStream_t s, cudaStream_t, cudaEvent_t*) {
+    return capture_plan("mllp_gnn_backward_plan_create", out, [&](cudaStream_t s, cudaStream_t s2, cudaEvent_t* ev) {
         int rc = mllp_gnn_pack_params(d_flat, d_packed, s);
         if (rc == 0) rc = backward_impl(to_var, to_con, d_x1, d_x2, d_flat, d_packed, d_work, d_bwork, d_dout, d_dflat, s,
-                                        "mllp_gnn_backward_plan_create");
+                                        "mllp_gnn_backward_plan_create", s2, ev);
         return rc;
     });
 }

@@ -324,12 +324,12 @@ struct mllp_gnn_plan {
 
 namespace mllp {
 namespace {
-// Capture what `body(stream, second stream, events[4])` launches into a CUDA graph and instantiate it.
+// Capture what `body(stream, second stream, events[8])` launches into a CUDA graph and instantiate it.
 template <class F>
 int capture_plan(const char* who, mllp_gnn_plan_t* out, F body)
 {
     cudaStream_t s = nullptr, s2 = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaGraph_t graph = nullptr;
     mllp_gnn_plan* plan = new (std::nothrow) mllp_gnn_plan();
     if (!plan) return gfail(MLLP_E_NOMEM, std::string(who) + ": out of host memory");
@@ -341,7 +341,7 @@ int capture_plan(const char* who, mllp_gnn_plan_t* out, F body)
     };
     cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
-    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { cleanup(); delete plan; return gfail((int)e, std::string(who) + ": " + cudaGetErrorString(e)); }
     int rc = body(s, s2, ev);

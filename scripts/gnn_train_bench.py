@@ -83,7 +83,8 @@ def main(names, out=None):
                     "items 1153 / 1329 / 766; destination pass split into row walk (80 registers) + dense maps (16 lanes per node) + sweep,\n"
                     "float4-prefetched parameter-gradient tiles, parallel partial sums 836 / 1010 / 593; as CUDA graphs 739 / 921 / 504; four\n"
                     "consecutive entries per thread in the parameter-gradient kernel (one 128-bit shared-memory load per node instead of eight\n"
-                    "scalar ones: it was bound by shared-memory loads) and 128-bit stores of the per-node vectors: the table.\n\n"
+                    "scalar ones: it was bound by shared-memory loads) and 128-bit stores of the per-node vectors 666 / 828 / 458; parameter-gradient\n"
+                    "sums on a parallel branch of the captured graph (joined before the unpack: afiro 139 -> 127, 25fv47 181 -> 158): the table.\n\n"
                     "| instance | m | n | nnz | lanes per row (A' / A) | forward us | backward us | whole training step us | launches fwd / bwd |\n"
                     "|---|---:|---:|---:|---|---:|---:|---:|---|\n")
             for r in rows:
