@@ -243,3 +243,25 @@ def test_gpu_backward_on_random_graphs(seed):
     err = grad_errors(got, ref)
     assert max(err.values()) < GTOL, (m, n, dens, groups, sorted(err.items(), key=lambda kv: -kv[1])[:4])
     g.close()
+
+
+def test_backward_restatement_property_random_graphs():
+    """hypothesis: on random bipartite graphs (empty rows / columns, duplicate-free random patterns, random upstream gradients)
+    the numpy restatement of the device algorithm equals autograd through the plain-PyTorch model"""
+    from hypothesis import given, settings, strategies as hs
+
+    @settings(max_examples=25, deadline=None)
+    @given(hs.integers(1, 12), hs.integers(1, 16), hs.floats(0.05, 0.9), hs.integers(0, 10 ** 6))
+    def check(m, n, dens, seed):
+        rng = np.random.default_rng(seed)
+        Ad = (rng.random((m, n)) < dens) * rng.standard_normal((m, n))
+        A = sp.csr_matrix(Ad)
+        b, c = rng.standard_normal(m), rng.standard_normal(n)
+        st = G.init_state(seed % 97)
+        dout = rng.standard_normal(n)
+        out, _, ref = T.torch_model_loss_and_grads(st, A, b, c, dout=dout)
+        out2, got = T.backward_numpy(st, A, b, c, dout)
+        assert np.allclose(out, out2, rtol=0, atol=1e-11)
+        assert max(grad_errors(got, ref).values()) < 1e-8
+
+    check()
