@@ -191,9 +191,10 @@ class GNNModel:
         L = _cabi.lib()
         if not use_plan:
             out = torch.empty(g.n, dtype=torch.float32, device=dev)
-            _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
-                                           g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), out.data_ptr(),
-                                           _torch_stream(dev)), "mllp_gnn_forward")
+            with torch.cuda.device(dev):   # the library launches on the calling thread's current device
+                _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(),
+                                               g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), out.data_ptr(),
+                                               _torch_stream(dev)), "mllp_gnn_forward")
             return out
         key = self.params.data_ptr()
         entry = g._plans.get(key)
@@ -205,7 +206,8 @@ class GNNModel:
                                                    g.x2.data_ptr(), self.params.data_ptr(), g.work.data_ptr(), buf.data_ptr(),
                                                    ctypes.byref(plan)), "mllp_gnn_plan_create")
             entry = g._plans[key] = (plan, buf, self.params)   # the plan holds these pointers: keep the tensors alive
-        _cabi.check(L.mllp_gnn_plan_run(entry[0], _torch_stream(dev)), "mllp_gnn_plan_run")
+        with torch.cuda.device(dev):
+            _cabi.check(L.mllp_gnn_plan_run(entry[0], _torch_stream(dev)), "mllp_gnn_plan_run")
         return entry[1].clone()
 
     __call__ = forward

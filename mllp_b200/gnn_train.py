@@ -77,15 +77,16 @@ class _Forward(torch.autograd.Function):
         flat_c = flat.detach()
         if not flat_c.is_contiguous():
             raise ValueError("the flat parameter vector must be contiguous")
-        if model.use_plans:
-            entry = _plans(g, model, flat_c)
-            _cabi.check(L.mllp_gnn_plan_run(entry[0], stream), "mllp_gnn_plan_run")
-            out = entry[2].clone()
-        else:
-            _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
-            out = torch.empty(g.n, dtype=torch.float32, device=dev)
-            _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
-                                           model._packed.data_ptr(), g.work.data_ptr(), out.data_ptr(), stream), "mllp_gnn_forward")
+        with torch.cuda.device(dev):   # the library launches on the calling thread's current device
+            if model.use_plans:
+                entry = _plans(g, model, flat_c)
+                _cabi.check(L.mllp_gnn_plan_run(entry[0], stream), "mllp_gnn_plan_run")
+                out = entry[2].clone()
+            else:
+                _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
+                out = torch.empty(g.n, dtype=torch.float32, device=dev)
+                _cabi.check(L.mllp_gnn_forward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
+                                               model._packed.data_ptr(), g.work.data_ptr(), out.data_ptr(), stream), "mllp_gnn_forward")
         g._forward_serial = getattr(g, "_forward_serial", 0) + 1
         ctx.g, ctx.model, ctx.serial = g, model, g._forward_serial
         ctx.save_for_backward(flat_c)
@@ -102,22 +103,23 @@ class _Forward(torch.autograd.Function):
         dev = flat_c.device
         stream = _torch_stream(dev)
         dout = dout.to(torch.float32).contiguous()
-        if model.use_plans:
-            entry = _plans(g, model, flat_c)
-            entry[3].copy_(dout)
-            _cabi.check(L.mllp_gnn_plan_run(entry[1], stream), "mllp_gnn_plan_run")
-            return entry[4].clone(), None, None
-        # the fused blocks of THIS forward's parameters (the model may have packed others since)
-        _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
-        need = int(L.mllp_gnn_backward_workspace_floats(g.n, g.m))
-        bw = getattr(g, "_bwork", None)
-        if bw is None or bw.numel() < need:
-            bw = g._bwork = torch.empty(need, dtype=torch.float32, device=dev)
-        dflat = torch.empty_like(flat_c)
-        _cabi.check(L.mllp_gnn_backward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
-                                        flat_c.data_ptr(), model._packed.data_ptr(), g.work.data_ptr(), bw.data_ptr(),
-                                        dout.data_ptr(), dflat.data_ptr(), stream), "mllp_gnn_backward")
-        return dflat, None, None
+        with torch.cuda.device(dev):   # the library launches on the calling thread's current device
+            if model.use_plans:
+                entry = _plans(g, model, flat_c)
+                entry[3].copy_(dout)
+                _cabi.check(L.mllp_gnn_plan_run(entry[1], stream), "mllp_gnn_plan_run")
+                return entry[4].clone(), None, None
+            # the fused blocks of THIS forward's parameters (the model may have packed others since)
+            _cabi.check(L.mllp_gnn_pack_params(flat_c.data_ptr(), model._packed.data_ptr(), stream), "mllp_gnn_pack_params")
+            need = int(L.mllp_gnn_backward_workspace_floats(g.n, g.m))
+            bw = getattr(g, "_bwork", None)
+            if bw is None or bw.numel() < need:
+                bw = g._bwork = torch.empty(need, dtype=torch.float32, device=dev)
+            dflat = torch.empty_like(flat_c)
+            _cabi.check(L.mllp_gnn_backward(ctypes.byref(g.to_var.c), ctypes.byref(g.to_con.c), g.x1.data_ptr(), g.x2.data_ptr(),
+                                            flat_c.data_ptr(), model._packed.data_ptr(), g.work.data_ptr(), bw.data_ptr(),
+                                            dout.data_ptr(), dflat.data_ptr(), stream), "mllp_gnn_backward")
+            return dflat, None, None
 
 
 class TrainableGNNModel(torch.nn.Module):
