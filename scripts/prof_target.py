@@ -66,7 +66,7 @@ elif what in ("batch_run", "batch_solve"):
     else:
         eta = (0.99 / bs.sigma_max_robust()).contiguous()
         meta.update(workload="4096 x sc105 (shared matrix, cost-perturbed), solve to 1e-6", instances_per_cta=info["instances_per_cta_solve"],
-                    kernel="k_batch_solve")
+                    kernel="k_batch_solve_warp" if info["instances_per_cta_solve"] == 4 and info["res_steps_A_solve"] == 0 else "k_batch_solve")
 
         def step():
             xb.zero_(); yb.zero_()
