@@ -1,6 +1,6 @@
 """dev lab: restart / primal-weight rule variants of solve mode on the hard Netlib files, on the CPU (scripts/dev/solve_lab.c).
 usage: python scripts/dev/solve_lab.py [max_iters]"""
-import ctypes, os, sys, time, itertools
+import ctypes, os, subprocess, sys, tempfile, time
 import numpy as np, scipy.sparse as sp
 from multiprocessing import Pool
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -9,7 +9,11 @@ from oracle.scaling_numpy import ruiz_pock_chambolle
 from oracle import pdhg_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LAB = ctypes.CDLL("/tmp/solve_lab.so")
+_SO = os.path.join(tempfile.gettempdir(), "mllp_solve_lab.so")
+if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(ROOT, "scripts", "dev", "solve_lab.c")):
+    subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", _SO,
+                           os.path.join(ROOT, "scripts", "dev", "solve_lab.c"), "-lm"])
+LAB = ctypes.CDLL(_SO)
 dp = ctypes.POINTER(ctypes.c_double); ip = ctypes.POINTER(ctypes.c_int32)
 
 def prep(name):
