@@ -91,6 +91,13 @@ int mllp_rowpart_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *ind
                            const int32_t *indices, const double *values, int32_t num_ctas,
                            int32_t nranks, double *out4);
 
+/* Host-only self check of the row-per-lane images the warp-per-instance batch kernels walk in solve mode (groups of 32
+ * internal rows, lane = row, slot-major entries): builds them for A and A' in the batch builder's internal orders and replays
+ * the lane walk on the CPU against the plain CSR products.  out4: [0] worst relative row error, [1] / [2] slots (of 32
+ * entries) of A / A', [3] padding factor (entries stored / nonzeros). */
+int mllp_ell_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices,
+                       const double *values, double *out4);
+
 /* Host-only statistic of the built format: distinct 128-byte lines touched by the warp-wide
  * gather instructions (the gather cost model).  out6: [0]/[1] total lines A / A', [2]/[3] the
  * largest per-CTA sum, [4]/[5] gather instructions.  `cluster` = cluster rows inside length

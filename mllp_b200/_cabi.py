@@ -24,6 +24,7 @@ SIGNATURES = {
     "mllp_launch_count": (ctypes.c_longlong, []),
     "mllp_format_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "mllp_rowpart_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "mllp_ell_selfcheck": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "mllp_format_gather_lines": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mllp_device_info": (ctypes.c_int, [ctypes.c_int, _vp]),
     "mllp_lp_create": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,

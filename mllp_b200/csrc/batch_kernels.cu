@@ -36,6 +36,9 @@ struct BatchInst {          // device-side descriptor of one instance
     const double* dc;
     int m, n;
     long long x_off, y_off; // offsets into the concatenated user vectors
+    // row-per-lane images of A / A' (lp_format.h: HostEll) for the warp-per-instance solve kernel, or null
+    const int32_t* eidxA; const double* evalA; const uint32_t* eoffA;
+    const int32_t* eidxT; const double* evalT; const uint32_t* eoffT;
 };
 
 // shared-memory vectors of one instance
@@ -1010,6 +1013,44 @@ __device__ __forceinline__ void warp_tiles(const MatView& V, const Op& op, doubl
     __syncwarp();   // the rows this phase wrote are gathered by the next one
 }
 
+// The same phase on the row-per-lane image: groups of 32 rows, lane = row, the group's slots one after the other (coalesced
+// 128 / 256-byte loads of indices / values, one gather and one DFMA per entry, no descriptor decoding, no shuffles, no owner
+// logic).  ncu of the tile walk on 4096 x sc105: 1 357 warp instructions per LP iteration with DFMA 6.8 % of them; this walk
+// needs ~7 per slot and sc105 has 31 slots per iteration.  Per row the entries are added in CSR order (the tile walk splits a
+// row over lanes), so the iterates differ from the tile walk's in rounding; the kernels below use it in SOLVE mode.
+template <class Op>
+__device__ __forceinline__ void warp_ell(int nrows, const int32_t* __restrict__ eidx, const double* __restrict__ eval,
+                                         const uint32_t* __restrict__ eoff, const Op& op, double* acc)
+{
+    const double* __restrict__ vec = op.vec();
+    const int lane = threadIdx.x & 31;
+    const int ngroups = (nrows + 31) >> 5;
+    uint32_t s0 = __ldg(eoff);
+    for (int g = 0; g < ngroups; ++g) {
+        const uint32_t s1 = __ldg(eoff + g + 1);
+        const int r = (g << 5) + lane;
+        const bool live = r < nrows;
+        typename Op::Pre pre{};
+        if (live) pre = op.prefetch(r);
+        double dot = 0.0;
+        uint32_t s = s0;
+        for (; s + 1 < s1; s += 2) {   // two slots in flight
+            const int32_t ja = __ldg(eidx + (size_t)s * 32 + lane), jb = __ldg(eidx + (size_t)(s + 1) * 32 + lane);
+            const double va = __ldg(eval + (size_t)s * 32 + lane), vb = __ldg(eval + (size_t)(s + 1) * 32 + lane);
+            dot = fma(va, Op::Mem::gather(vec + ja), dot);
+            dot = fma(vb, Op::Mem::gather(vec + jb), dot);
+        }
+        if (s < s1) {
+            const int32_t ja = __ldg(eidx + (size_t)s * 32 + lane);
+            const double va = __ldg(eval + (size_t)s * 32 + lane);
+            dot = fma(va, Op::Mem::gather(vec + ja), dot);
+        }
+        if (live) op.row(r, dot, pre, acc);
+        s0 = s1;
+    }
+    __syncwarp();   // the rows this phase wrote are gathered by the next one
+}
+
 template <int N>
 __device__ __forceinline__ void warp_allreduce(double* acc)
 {
@@ -1048,13 +1089,20 @@ __device__ __forceinline__ void warp_store_instance(const BatchInst& I, const Wa
 }
 
 // KKT scalars of (S.x, S.y) -> s[0..9] in every lane; also ||x-x0||^2, ||y-y0||^2 in dd[0..1]
-__device__ __forceinline__ void warp_kkt(const DevLP& lp, const MatView& VA, const MatView& VAT, double* s, double* dd)
+// (`E` = the instance when its row-per-lane images are to be walked, else null: the tile walk)
+__device__ __forceinline__ void warp_kkt(const DevLP& lp, const MatView& VA, const MatView& VAT, double* s, double* dd,
+                                         const BatchInst* E = nullptr)
 {
     double ap[NRED], ad[NRED];
 #pragma unroll
     for (int k = 0; k < NRED; ++k) { ap[k] = 0.0; ad[k] = 0.0; }
-    { EvalPrimalOp<false, SmemMem> op{lp}; warp_tiles(VAT, op, ap); }
-    { EvalDualOp<false, SmemMem> op{lp}; warp_tiles(VA, op, ad); }
+    if (E) {
+        { EvalPrimalOp<false, SmemMem> op{lp}; warp_ell(lp.n, E->eidxT, E->evalT, E->eoffT, op, ap); }
+        { EvalDualOp<false, SmemMem> op{lp}; warp_ell(lp.m, E->eidxA, E->evalA, E->eoffA, op, ad); }
+    } else {
+        { EvalPrimalOp<false, SmemMem> op{lp}; warp_tiles(VAT, op, ap); }
+        { EvalDualOp<false, SmemMem> op{lp}; warp_tiles(VA, op, ad); }
+    }
     warp_allreduce<7>(ap);
     warp_allreduce<6>(ad);
     const double pobj = ap[0], dobj = ad[0] + ap[1];
@@ -1136,11 +1184,12 @@ k_batch_solve_warp(const BatchInst* __restrict__ insts, int count, int shared, u
         }
         const DevLP lp = warp_lp(I, S);
         const MatView VA = global_view(I.A, 0u), VAT = global_view(I.AT, 0u);
+        const BatchInst* E = (I.eoffA && I.eoffT) ? &I : nullptr;   // row-per-lane images present: walk those
         double tau = eta / w, sigma = eta * w;
         double fpe_restart = -1.0, fpe_prev = INFINITY, fpe = 0.0;
         int k = 0, it = 0, restarts = 0, converged = 0;
         double kk[10], dd[2];
-        warp_kkt(lp, VA, VAT, kk, dd);
+        warp_kkt(lp, VA, VAT, kk, dd, E);
         while (it < max_iters) {
             const double lam = (double)(k + 1) / (double)(k + 2);
             const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iters);
@@ -1150,14 +1199,16 @@ k_batch_solve_warp(const BatchInst* __restrict__ insts, int count, int shared, u
                 PrimalHalpernOp<false, SmemMem> op{lp, tau, lam};
                 double acc[NRED];
                 acc[0] = 0.0;
-                warp_tiles(VAT, op, acc);
+                if (E) warp_ell(I.n, I.eidxT, I.evalT, I.eoffT, op, acc);
+                else warp_tiles(VAT, op, acc);
                 a2[0] = acc[0];
             }
             {
                 DualHalpernOp<false, SmemMem> op{lp, sigma, lam};
                 double acc[NRED];
                 acc[0] = 0.0;
-                warp_tiles(VA, op, acc);
+                if (E) warp_ell(I.m, I.eidxA, I.evalA, I.eoffA, op, acc);
+                else warp_tiles(VA, op, acc);
                 a2[1] = acc[0];
             }
             ++it; ++k;
@@ -1167,7 +1218,7 @@ k_batch_solve_warp(const BatchInst* __restrict__ insts, int count, int shared, u
                 if (fpe_restart < 0.0) fpe_restart = fpe;
             }
             if (check) {
-                warp_kkt(lp, VA, VAT, kk, dd);
+                warp_kkt(lp, VA, VAT, kk, dd, E);
                 if (kk[8] <= tol) { converged = 1; break; }
                 const bool do_restart = (fpe <= 0.2 * fpe_restart) || (fpe <= 0.8 * fpe_restart && fpe > fpe_prev) ||
                                         ((double)k >= 0.36 * (double)it);
@@ -1296,6 +1347,9 @@ struct Pools {
     std::vector<LocalSplit> lsplits;
     std::vector<int32_t> order;
     std::vector<double> scale;       // preconditioned batch: dr | dc of every matrix, internal order
+    std::vector<int32_t> ell_idx;    // row-per-lane images (HostEll) of A | A' of every small matrix
+    std::vector<double> ell_val;
+    std::vector<uint32_t> ell_off;
 };
 struct MatOff { size_t vals, idx, tiles, cb, csb, clb, cns, splits, lsplits; int nrows, ncols; };
 
@@ -1361,6 +1415,10 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
         Pools P;
         std::vector<MatOff> offA((size_t)nmat), offAT((size_t)nmat);
         std::vector<size_t> offOX((size_t)nmat), offOY((size_t)nmat), offDR((size_t)nmat), offDC((size_t)nmat);
+        // row-per-lane images: offsets of the entries (idx / val) and of the group table, A and A'; NO_ELL: not built
+        constexpr size_t NO_ELL = ~(size_t)0;
+        std::vector<size_t> offEAe((size_t)nmat, NO_ELL), offEAo((size_t)nmat, NO_ELL), offETe((size_t)nmat, NO_ELL), offETo((size_t)nmat, NO_ELL);
+        const size_t warp_cap = (size_t)prop.sharedMemPerBlockOptin - 4096;
         int max_tiles = 0, max_tiles_A = 0, max_tiles_AT = 0, max_steps_A = 0, max_steps_AT = 0;
         bool any_split = false;
         for (int k = 0; k < nmat && rc == 0; ++k) {
@@ -1403,6 +1461,19 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             build_host_mat(n, m, tptr.data(), tind.data(), tval.data(), orderX, posY, bp, HAT);
             offA[k] = append(P, HA);
             offAT[k] = append(P, HAT);
+            if (warp_lp_bytes(m, n) * WARP_LPS <= warp_cap) {   // small enough for the warp-per-instance kernels
+                HostEll EA, ET;
+                build_host_ell(m, ip, ii, vv, orderY, posX, EA);
+                build_host_ell(n, tptr.data(), tind.data(), tval.data(), orderX, posY, ET);
+                offEAe[k] = P.ell_idx.size(); offEAo[k] = P.ell_off.size();
+                P.ell_idx.insert(P.ell_idx.end(), EA.idx.begin(), EA.idx.end());
+                P.ell_val.insert(P.ell_val.end(), EA.val.begin(), EA.val.end());
+                P.ell_off.insert(P.ell_off.end(), EA.off.begin(), EA.off.end());
+                offETe[k] = P.ell_idx.size(); offETo[k] = P.ell_off.size();
+                P.ell_idx.insert(P.ell_idx.end(), ET.idx.begin(), ET.idx.end());
+                P.ell_val.insert(P.ell_val.end(), ET.val.begin(), ET.val.end());
+                P.ell_off.insert(P.ell_off.end(), ET.off.begin(), ET.off.end());
+            }
             offOX[k] = P.order.size(); P.order.insert(P.order.end(), orderX.begin(), orderX.end());
             offOY[k] = P.order.size(); P.order.insert(P.order.end(), orderY.begin(), orderY.end());
             max_tiles = std::max<int>(max_tiles, (int)std::max(HA.tiles.size(), HAT.tiles.size()));
@@ -1430,6 +1501,12 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
             ck(up(bt, &d_ls, P.lsplits), "upload local splits");
             ck(up(bt, &d_order, P.order), "upload orders");
             if (precondition) ck(up(bt, &d_scale, P.scale), "upload scaling vectors");
+            int32_t* d_eidx = nullptr; double* d_eval = nullptr; uint32_t* d_eoff = nullptr;
+            if (!P.ell_off.empty()) {
+                ck(up(bt, &d_eidx, P.ell_idx), "upload row-per-lane indices");
+                ck(up(bt, &d_eval, P.ell_val), "upload row-per-lane values");
+                ck(up(bt, &d_eoff, P.ell_off), "upload row-per-lane group table");
+            }
             ck(up(bt, &d_dummy_partials, std::vector<double>(P.splits.size() + 1, 0.0)), "alloc partials");
             ck(up(bt, &d_dummy_counters, std::vector<unsigned>(P.splits.size() + 1, 0u)), "alloc counters");
             ck(up(bt, &bt->d_next, std::vector<int>(4, 0)), "alloc work counter");
@@ -1456,6 +1533,11 @@ int mllp_batch_create(int32_t count, int32_t shared_matrix, const int32_t* h_m, 
                     I.dc = precondition ? d_scale + offDC[k] : nullptr;
                     I.m = h_m[k]; I.n = h_n[k];
                     I.x_off = xo; I.y_off = yo;
+                    const bool ell = offEAe[k] != NO_ELL && d_eoff;
+                    I.eidxA = ell ? d_eidx + offEAe[k] : nullptr; I.evalA = ell ? d_eval + offEAe[k] : nullptr;
+                    I.eoffA = ell ? d_eoff + offEAo[k] : nullptr;
+                    I.eidxT = ell ? d_eidx + offETe[k] : nullptr; I.evalT = ell ? d_eval + offETe[k] : nullptr;
+                    I.eoffT = ell ? d_eoff + offETo[k] : nullptr;
                     xo += h_n[k]; yo += h_m[k];
                 }
                 ck(up(bt, &bt->d_insts, insts), "upload instance table");

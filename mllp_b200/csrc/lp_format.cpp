@@ -449,6 +449,34 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
     out.cta_step_begin[G] = (uint32_t)step_cursor;
 }
 
+void build_host_ell(int nrows, const int32_t* ptr, const int32_t* ind, const double* val, const std::vector<int32_t>& order,
+                    const std::vector<int32_t>& colpos, HostEll& out)
+{
+    const int ngroups = (nrows + 31) / 32;
+    out.idx.clear(); out.val.clear();
+    out.off.assign((size_t)ngroups + 1, 0u);
+    for (int g = 0; g < ngroups; ++g) {
+        int w = 0;
+        for (int l = 0; l < 32 && g * 32 + l < nrows; ++l) {
+            const int r = order[(size_t)g * 32 + l];
+            w = std::max(w, (int)(ptr[r + 1] - ptr[r]));
+        }
+        out.off[(size_t)g + 1] = out.off[g] + (uint32_t)w;
+    }
+    out.idx.assign((size_t)32 * out.off.back(), 0);
+    out.val.assign((size_t)32 * out.off.back(), 0.0);
+    for (int g = 0; g < ngroups; ++g) {
+        for (int l = 0; l < 32 && g * 32 + l < nrows; ++l) {
+            const int r = order[(size_t)g * 32 + l];
+            uint32_t s = out.off[g];
+            for (int32_t q = ptr[r]; q < ptr[r + 1]; ++q, ++s) {
+                out.idx[(size_t)s * 32 + l] = colpos[ind[q]];
+                out.val[(size_t)s * 32 + l] = val[q];
+            }
+        }
+    }
+}
+
 }  // namespace mllp
 
 // ---------------------------------------------------------------------------------------
@@ -585,6 +613,71 @@ extern "C" int mllp_format_selfcheck(int32_t m, int32_t n, int64_t nnz, const in
     if (rc != 0) return 100 + rc;
     if (!(tmp[0] < 1e-9)) return 199;
     return format_selfcheck_impl(m, n, nnz, indptr, indices, values, num_ctas, pref_steps, max_steps, false, out8);
+}
+
+// Host-only self check of the row-per-lane images (build_host_ell) of A and A' in the batch builder's internal orders: the
+// lane walk of the warp-per-instance kernels replayed on the CPU (slot after slot, sequential sum per row) against the plain
+// CSR products.  out4: [0] worst relative row error, [1] / [2] slots of A / A', [3] padding factor (stored / nonzeros).
+extern "C" int mllp_ell_selfcheck(int32_t m, int32_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                                  const double* values, double* out4)
+{
+    using namespace mllp;
+    if (m < 0 || n < 0 || !indptr || !out4 || (int64_t)indptr[m] != nnz) return 1001;
+    BuildParams bp;
+    bp.num_ctas = 1;
+    bp.pref_steps = 2;
+    bp.max_steps = 4;
+    std::vector<int32_t> tptr, tind;
+    std::vector<double> tval;
+    csr_transpose(m, n, indptr, indices, values, tptr, tind, tval);
+    std::vector<int32_t> orderY, posY, orderX, posX;
+    plan_orders(m, n, indptr, indices, tptr.data(), tind.data(), bp, orderY, posY, orderX, posX);
+    HostEll EA, ET;
+    build_host_ell(m, indptr, indices, values, orderY, posX, EA);
+    build_host_ell(n, tptr.data(), tind.data(), tval.data(), orderX, posY, ET);
+    auto replay = [](const HostEll& E, int nrows, const std::vector<double>& vec_int, std::vector<double>& out_int) {
+        const int ngroups = (nrows + 31) / 32;
+        if ((int)E.off.size() != ngroups + 1 || E.idx.size() != (size_t)32 * E.off.back() || E.val.size() != E.idx.size()) return 2;
+        for (int g = 0; g < ngroups; ++g)
+            for (int l = 0; l < 32; ++l) {
+                double dot = 0.0;
+                for (uint32_t s = E.off[g]; s < E.off[(size_t)g + 1]; ++s) {
+                    const int32_t j = E.idx[(size_t)s * 32 + l];
+                    if (j < 0 || j >= (int32_t)vec_int.size()) return 3;
+                    dot = std::fma(E.val[(size_t)s * 32 + l], vec_int[j], dot);
+                }
+                if (g * 32 + l < nrows) out_int[(size_t)g * 32 + l] = dot;
+                else if (dot != 0.0) return 4;   // padding rows hold zeros only
+            }
+        return 0;
+    };
+    auto rel_err = [](const int32_t* ptr, const int32_t* ind, const double* val, const std::vector<double>& v, int r, double got) {
+        double ref = 0.0, mag = 0.0;
+        for (int32_t q = ptr[r]; q < ptr[r + 1]; ++q) { ref += val[q] * v[ind[q]]; mag += std::fabs(val[q] * v[ind[q]]); }
+        return std::fabs(got - ref) / (mag > 0.0 ? mag : 1.0);
+    };
+    double worst = 0.0;
+    {
+        std::vector<double> v_user((size_t)n), v_int((size_t)n), out_int((size_t)m, NAN);
+        for (int j = 0; j < n; ++j) v_user[j] = 0.25 + (double)((j * 2654435761u) % 1000u) / 997.0;
+        for (int k = 0; k < n; ++k) v_int[k] = v_user[orderX[k]];
+        const int rc = replay(EA, m, v_int, out_int);
+        if (rc != 0) return rc;
+        for (int r = 0; r < m; ++r) worst = std::max(worst, rel_err(indptr, indices, values, v_user, r, out_int[posY[r]]));
+    }
+    {
+        std::vector<double> w_user((size_t)m), w_int((size_t)m), out_int((size_t)n, NAN);
+        for (int i = 0; i < m; ++i) w_user[i] = 0.25 + (double)((i * 2654435761u) % 1000u) / 997.0;
+        for (int k = 0; k < m; ++k) w_int[k] = w_user[orderY[k]];
+        const int rc = replay(ET, n, w_int, out_int);
+        if (rc != 0) return rc;
+        for (int r = 0; r < n; ++r) worst = std::max(worst, rel_err(tptr.data(), tind.data(), tval.data(), w_user, r, out_int[posX[r]]));
+    }
+    out4[0] = worst;
+    out4[1] = (double)EA.off.back();
+    out4[2] = (double)ET.off.back();
+    out4[3] = nnz > 0 ? 32.0 * ((double)EA.off.back() + (double)ET.off.back()) / (2.0 * (double)nnz) : 1.0;
+    return 0;
 }
 
 // Host-only statistic of the built format: how many distinct 128 B lines the warp-wide gather

@@ -119,6 +119,19 @@ void build_host_mat(int nrows, int ncols, const int32_t* ptr, const int32_t* ind
                     const std::vector<int32_t>& colpos, const BuildParams& bp, HostMat& out,
                     uint32_t row_offset = 0, const DealFeedback* fb = nullptr);
 
+// Row-per-lane image of a small matrix (warp-per-instance batch kernels): groups of 32 consecutive internal rows, lane = row;
+// group g holds w_g = its longest row's length slots of 32 entries each (slot-major: entry s of the group's 32 rows is
+// contiguous), off[g] .. off[g+1] in slots.  Shorter rows and the rows past nrows are padded with (column 0, value 0).
+// Rows follow `order` (internal position -> original row), columns are renamed through `colpos`; the entries of a row keep
+// their CSR order.  The internal order sorts rows by length class, so the padding stays small.
+struct HostEll {
+    std::vector<int32_t> idx;    // 32 * off.back()
+    std::vector<double> val;     // 32 * off.back()
+    std::vector<uint32_t> off;   // ngroups + 1
+};
+void build_host_ell(int nrows, const int32_t* ptr, const int32_t* ind, const double* val, const std::vector<int32_t>& order,
+                    const std::vector<int32_t>& colpos, HostEll& out);
+
 // Row partition over `nranks` GPUs: rows go to ranks by longest-processing-time on their
 // nonzero counts; inside a rank the global (class, cluster) order is kept.  The global internal
 // order is [rank 0's rows | rank 1's rows | ...], every slice padded to the same even length L

@@ -158,3 +158,41 @@ def test_block_angular_structure_detection_and_images_on_the_host():
     found, ncomp, nlink, link_nnz, ea, et, smem, max_n = _blocks_selfcheck(A, 16)
     assert found == 1 and nlink == 5 and link_nnz == link.nnz and ncomp >= 120 and ea < 1e-13 and et < 1e-13
     assert _blocks_selfcheck(A, 148)[0] == 0            # fewer than 2 x 148 pieces
+
+
+@pytest.mark.parametrize("name", ["afiro", "sc50a", "sc105", "blend", "adlittle", "share2b", "kb2", "25fv47"])
+def test_row_per_lane_images_replay_on_the_cpu(name):
+    """the row-per-lane images (HostEll) the warp-per-instance solve kernel walks: the lane walk replayed on the host against
+    the plain CSR products, for A and A' in the batch builder's internal orders"""
+    import ctypes
+    import mllp_b200.linear_program_data as D
+    from mllp_b200 import _cabi
+    A, _, _ = D.load_csr(name)
+    A = A.tocsr()
+    A.sort_indices()
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ii = np.ascontiguousarray(A.indices, dtype=np.int32)
+    vv = np.ascontiguousarray(A.data, dtype=np.float64)
+    out = (ctypes.c_double * 4)()
+    rc = _cabi.lib().mllp_ell_selfcheck(A.shape[0], A.shape[1], A.nnz, ip.ctypes.data, ii.ctypes.data, vv.ctypes.data, out)
+    assert rc == 0 and out[0] < 1e-14
+    assert out[3] < 3.0          # padding factor: the internal order sorts the rows by length
+
+
+def test_row_per_lane_images_edge_cases():
+    import ctypes
+    import scipy.sparse as sp
+    from mllp_b200 import _cabi
+    rng = np.random.default_rng(5)
+    for m, n, dens in ((1, 1, 1.0), (33, 65, 0.1), (64, 32, 0.5), (40, 7, 0.0)):
+        Ad = (rng.random((m, n)) < dens) * rng.standard_normal((m, n))
+        if m > 2:
+            Ad[1] = 0.0                      # an empty row
+        A = sp.csr_matrix(Ad)
+        A.sort_indices()
+        ip = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        ii = np.ascontiguousarray(A.indices if A.nnz else np.zeros(1), dtype=np.int32)
+        vv = np.ascontiguousarray(A.data if A.nnz else np.zeros(1), dtype=np.float64)
+        out = (ctypes.c_double * 4)()
+        rc = _cabi.lib().mllp_ell_selfcheck(m, n, A.nnz, ip.ctypes.data, ii.ctypes.data, vv.ctypes.data, out)
+        assert rc == 0 and out[0] < 1e-14, (m, n, dens, rc)
